@@ -1,0 +1,18 @@
+"""audioanalysisdetector_b200 -- B200-native spectral front-end (log-mel / MFCC / LFCC + deltas).
+
+Drop-in for the feature-extraction hot path of IzaP1k/AudioAnalysisDetector
+(ASV_dl_func.py:404-439,522-538,1031-1049): same extractor names and call surface,
+arithmetic in hand-written sm_100a CUDA kernels behind the C ABI of include/aad.h.
+"""
+from . import _lib
+from ._lib import AadError
+from .frontend import Frontend, FrontendParams, delta, fp32_peak_tflops
+from .extractors import (extract_features, extract_lfcc, extract_mel_spectrogram, extract_mfcc,
+                         get_frontend)
+from .sharding import contiguous_shard, gather_features, partition_by_frames
+
+__all__ = [
+    "AadError", "Frontend", "FrontendParams", "delta", "fp32_peak_tflops",
+    "extract_features", "extract_lfcc", "extract_mel_spectrogram", "extract_mfcc", "get_frontend",
+    "contiguous_shard", "gather_features", "partition_by_frames",
+]

@@ -1,0 +1,99 @@
+"""ctypes binding of libaad_b200.so -- the C ABI declared in include/aad.h.
+
+The product path has NO fallback: if the shared library is missing or fails to
+load, importing anything that computes raises immediately.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libaad_b200.so")
+
+# enums (mirror include/aad.h)
+KIND_LOGMEL, KIND_MFCC, KIND_LFCC = 0, 1, 2
+F32, I16 = 0, 1
+WIN_HANN_PERIODIC, WIN_HAMMING_SYMMETRIC = 0, 1
+FB_MEL_SLANEY, FB_LINEAR_INTBIN, FB_LINEAR_CONT, FB_CUSTOM = 0, 1, 2, 3
+LOG_DB10, LOG_LN = 0, 1
+REF_ONE, REF_UTT_MAX = 0, 1
+LAYOUT_CT, LAYOUT_TC = 0, 1
+TABLE_WINDOW, TABLE_FILTERBANK, TABLE_DCT, TABLE_DELTA_TAPS = 0, 1, 2, 3
+
+ITEM_OK = 0
+ITEM_STATUS_NAMES = {
+    0: "ok", 1: "empty", 2: "too short for one frame", 3: "too short for delta",
+    4: "output too small", 5: "non-finite audio",
+}
+
+
+class AadParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("kind", C.c_int32), ("sample_rate", C.c_int32),
+        ("n_fft", C.c_int32), ("win_length", C.c_int32), ("hop_length", C.c_int32),
+        ("window", C.c_int32), ("center", C.c_int32), ("quantize_i16", C.c_int32),
+        ("pre_emph", C.c_float), ("n_filt", C.c_int32), ("fb_type", C.c_int32),
+        ("fmin", C.c_float), ("fmax", C.c_float), ("power_scale", C.c_float),
+        ("log_type", C.c_int32), ("ref_type", C.c_int32), ("amin", C.c_float),
+        ("top_db", C.c_float), ("n_ceps", C.c_int32), ("n_delta", C.c_int32),
+        ("delta_width", C.c_int32), ("layout", C.c_int32), ("time_mean", C.c_int32),
+        ("reserved0", C.c_int32), ("custom_fb", C.POINTER(C.c_float)),
+    ]
+
+
+# every symbol include/aad.h declares: name -> (restype, argtypes)
+_EXTRACT_ARGS = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64,
+                 C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                 C.c_void_p]
+SYMBOLS = {
+    "aad_version": (C.c_int, []),
+    "aad_strerror": (C.c_char_p, [C.c_int]),
+    "aad_params_default": (C.c_int, [C.POINTER(AadParams), C.c_int, C.c_int]),
+    "aad_plan_create": (C.c_int, [C.POINTER(AadParams), C.c_int, C.POINTER(C.c_void_p)]),
+    "aad_plan_destroy": (C.c_int, [C.c_void_p]),
+    "aad_query": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_int32),
+                            C.POINTER(C.c_int32), C.POINTER(C.c_size_t)]),
+    "aad_extract": (C.c_int, _EXTRACT_ARGS),
+    "aad_logmel": (C.c_int, _EXTRACT_ARGS),
+    "aad_mfcc": (C.c_int, _EXTRACT_ARGS),
+    "aad_lfcc": (C.c_int, _EXTRACT_ARGS),
+    "aad_delta": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int32, C.c_int, C.c_int,
+                            C.c_void_p, C.c_void_p]),
+    "aad_extract_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int,
+                                   C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_int]),
+    "aad_plan_table": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+    "aad_plan_launches": (C.c_int, [C.c_void_p]),
+    "aad_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
+}
+
+_lib = None
+
+
+class AadError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libaad_b200.so (once) and declare every prototype.  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AadError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built. Run "
+            "`python -m audioanalysisdetector_b200.build` (needs nvcc). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "aad call"):
+    if rc != 0:
+        msg = load().aad_strerror(rc).decode()
+        raise AadError(f"{what} failed: {msg} ({rc})")

@@ -1,0 +1,775 @@
+// C ABI + plan (host tables) + launch orchestration for libaad_b200.so.
+// See include/aad.h for the contract of every entry point.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/aad.h"
+#include "aad_kernels.cuh"
+
+using namespace aad;
+
+// ---------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------
+struct aad_plan {
+  aad_params p;
+  int device = 0;
+  int sm_count = 148;
+  int L = 0;          // n_fft / 64
+  int K = 0;          // bins
+  int warps = 0, ctas = 0;
+  size_t k1_smem = 0;
+  int c_feat = 0;     // rows before deltas
+  int c_out = 0;
+  int ncp = 0;
+  bool need_ws_E = false;     // filterbank energies go to workspace (cepstra / layout / mean follows)
+  bool need_ws_feat = false;  // features go to workspace (time_mean follows)
+  // host copies (introspection)
+  std::vector<float> h_window, h_fb, h_dct;
+  float taps[2][CEP_MAXW];
+  // device tables
+  float* d_window = nullptr;
+  float2* d_tw1 = nullptr;
+  float2* d_twp = nullptr;
+  float2* d_fbw = nullptr;
+  int32_t* d_seg = nullptr;
+  int32_t* d_warp_filt = nullptr;
+  float* d_dct_t = nullptr;
+  // host-path resources (lazy)
+  struct HostBuf {
+    cudaStream_t stream = nullptr;
+    void* d_wav = nullptr;
+    size_t wav_bytes = 0;
+    float* d_out = nullptr;
+    size_t out_bytes = 0;
+    int32_t *d_len = nullptr, *d_nf = nullptr, *d_st = nullptr;
+    int cap_b = 0;
+    void* d_ws = nullptr;
+    size_t ws_bytes = 0;
+  } hb[2];
+};
+
+static const double kPiD = 3.141592653589793238462643383279502884;
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+#define CUDA_TRY(expr)                       \
+  do {                                       \
+    cudaError_t e__ = (expr);                \
+    if (e__ != cudaSuccess) return AAD_ERR_CUDA; \
+  } while (0)
+
+// ---- Slaney mel scale (librosa.hz_to_mel / mel_to_hz, htk=False) ------------
+static double hz_to_mel(double f) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+  const double logstep = std::log(6.4) / 27.0;
+  if (f >= min_log_hz) return min_log_mel + std::log(f / min_log_hz) / logstep;
+  return f / f_sp;
+}
+static double mel_to_hz(double m) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+  const double logstep = std::log(6.4) / 27.0;
+  if (m >= min_log_mel) return min_log_hz * std::exp(logstep * (m - min_log_mel));
+  return f_sp * m;
+}
+static std::vector<double> linspace(double a, double b, int n) {
+  std::vector<double> y(n);
+  double step = n > 1 ? (b - a) / (n - 1) : 0.0;
+  for (int i = 0; i < n; ++i) y[i] = i * step + a;
+  if (n > 1) y[n - 1] = b;
+  return y;
+}
+
+// dense float32 filterbank [n_filt][K], reference rounding order reproduced
+static int build_filterbank(const aad_params& p, int K, std::vector<float>& fb) {
+  const int nf = p.n_filt;
+  const double sr = p.sample_rate;
+  const double fmax = p.fmax > 0 ? p.fmax : sr / 2;
+  const double fmin = p.fmin;
+  const double pscale = p.power_scale != 0.f ? (double)p.power_scale : 1.0;
+  fb.assign((size_t)nf * K, 0.f);
+  if (p.fb_type == AAD_FB_MEL_SLANEY) {
+    // librosa.filters.mel: float64 triangles -> float32 store -> in-place *= enorm (float64)
+    std::vector<double> mels = linspace(hz_to_mel(fmin), hz_to_mel(fmax), nf + 2), mel_f(nf + 2);
+    for (int i = 0; i < nf + 2; ++i) mel_f[i] = mel_to_hz(mels[i]);
+    const double val = 1.0 / (p.n_fft * (1.0 / sr));
+    for (int i = 0; i < nf; ++i) {
+      const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+      const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+      for (int k = 0; k < K; ++k) {
+        const double f = k * val;
+        const double lower = -(mel_f[i] - f) / fd0, upper = (mel_f[i + 2] - f) / fd1;
+        float w = (float)std::max(0.0, std::min(lower, upper));
+        w = (float)((double)w * enorm);
+        if (pscale != 1.0) w = (float)((double)w * pscale);
+        fb[(size_t)i * K + k] = w;
+      }
+    }
+  } else if (p.fb_type == AAD_FB_LINEAR_INTBIN) {
+    // spafe 0.3.x linear_filter_banks (scale="constant")
+    std::vector<double> pts = linspace(fmin, fmax, nf + 2), bins(nf + 2);
+    for (int i = 0; i < nf + 2; ++i) bins[i] = std::floor((p.n_fft + 1) * pts[i] / sr);
+    for (int j = 0; j < nf; ++j) {
+      const double b0 = bins[j], b1 = bins[j + 1], b2 = bins[j + 2];
+      for (int i = (int)b0; i < (int)b1 && i < K; ++i)
+        fb[(size_t)j * K + i] = (float)(std::fabs((i - (int)b0) / (b1 - b0)) * pscale);
+      for (int i = (int)b1; i < (int)b2 && i < K; ++i)
+        fb[(size_t)j * K + i] = (float)(std::fabs(((int)b2 - i) / (b2 - b1)) * pscale);
+    }
+  } else if (p.fb_type == AAD_FB_LINEAR_CONT) {
+    std::vector<double> edges = linspace(fmin, fmax, nf + 2), freqs = linspace(0.0, sr / 2, K);
+    for (int j = 0; j < nf; ++j) {
+      const double lo = edges[j], ce = edges[j + 1], hi = edges[j + 2];
+      for (int k = 0; k < K; ++k) {
+        const double f = freqs[k];
+        double w = 0.0;
+        if (f >= lo && f <= ce) w = (f - lo) / (ce - lo);
+        if (f >= ce && f <= hi) w = (hi - f) / (hi - ce);
+        fb[(size_t)j * K + k] = (float)(w * pscale);
+      }
+    }
+  } else if (p.fb_type == AAD_FB_CUSTOM) {
+    if (!p.custom_fb) return AAD_ERR_INVALID_ARG;
+    for (size_t i = 0; i < (size_t)nf * K; ++i) fb[i] = (float)((double)p.custom_fb[i] * pscale);
+  } else {
+    return AAD_ERR_INVALID_ARG;
+  }
+  return AAD_OK;
+}
+
+// dense -> banded two-tap form: per bin (rising weight of filter seg, falling weight of filter seg-1)
+static int band_filterbank(const std::vector<float>& fb, int nf, int K, std::vector<float2>& fbw,
+                           std::vector<int32_t>& seg_bounds) {
+  std::vector<int> seg(K);
+  int cur = 0;
+  for (int k = 0; k < K; ++k) {
+    int jmin = -1, jmax = -1;
+    for (int j = 0; j < nf; ++j)
+      if (fb[(size_t)j * K + k] != 0.f) {
+        if (jmin < 0) jmin = j;
+        jmax = j;
+      }
+    int s = cur;
+    if (jmin >= 0) {
+      if (jmax - jmin > 1) return AAD_ERR_FILTERBANK;
+      for (int j = jmin + 1; j < jmax; ++j)
+        if (fb[(size_t)j * K + k] != 0.f) return AAD_ERR_FILTERBANK;
+      if (jmax == jmin) {
+        if (cur <= jmin) s = jmin;
+        else if (cur == jmin + 1) s = cur;
+        else return AAD_ERR_FILTERBANK;
+      } else {
+        s = jmin + 1;
+        if (cur > s) return AAD_ERR_FILTERBANK;
+      }
+    }
+    seg[k] = cur = s;
+  }
+  fbw.assign(K, make_float2(0.f, 0.f));
+  for (int k = 0; k < K; ++k) {
+    int s = seg[k];
+    float wr = s < nf ? fb[(size_t)s * K + k] : 0.f;
+    float wf = s >= 1 ? fb[(size_t)(s - 1) * K + k] : 0.f;
+    fbw[k] = make_float2(wr, wf);
+  }
+  seg_bounds.assign(nf + 2, K);
+  int k = 0;
+  for (int s = 0; s <= nf + 1; ++s) {
+    while (k < K && seg[k] < s) ++k;
+    seg_bounds[s] = (s == nf + 1) ? K : k;
+  }
+  return AAD_OK;
+}
+
+static void savgol_taps(int width, float t1[CEP_MAXW], float t2[CEP_MAXW]) {
+  // least-squares polynomial fit of degree d, d-th derivative at the window centre
+  // (scipy.signal.savgol_coeffs(width, polyorder=d, deriv=d), d = 1, 2)
+  const int h = width / 2;
+  double s2 = 0, s4 = 0;
+  for (int x = -h; x <= h; ++x) {
+    s2 += (double)x * x;
+    s4 += (double)x * x * x * x;
+  }
+  const double n = width;
+  for (int i = 0; i < CEP_MAXW; ++i) t1[i] = t2[i] = 0.f;
+  for (int i = 0; i < width; ++i) {
+    const double x = i - h;
+    t1[i] = (float)(x / s2);
+    t2[i] = (float)(2.0 * (n * x * x - s2) / (n * s4 - s2 * s2));
+  }
+}
+
+template <typename T>
+static cudaError_t upload(T** dptr, const std::vector<T>& h) {
+  cudaError_t e = cudaMalloc((void**)dptr, std::max<size_t>(h.size(), 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  if (h.empty()) return cudaSuccess;
+  return cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+// ---- kernel dispatch table --------------------------------------------------
+typedef void (*stft_kernel_t)(const StftArgs);
+template <int L>
+static stft_kernel_t pick_stft_L(int mode, bool pre) {
+  switch (mode * 2 + (pre ? 1 : 0)) {
+    case 0: return k_stft_fb<L, IN_F32, false>;
+    case 1: return k_stft_fb<L, IN_F32, true>;
+    case 2: return k_stft_fb<L, IN_F32_Q16, false>;
+    case 3: return k_stft_fb<L, IN_F32_Q16, true>;
+    case 4: return k_stft_fb<L, IN_I16, false>;
+    default: return k_stft_fb<L, IN_I16, true>;
+  }
+}
+static stft_kernel_t pick_stft(int L, int mode, bool pre) {
+  switch (L) {
+    case 4: return pick_stft_L<4>(mode, pre);
+    case 8: return pick_stft_L<8>(mode, pre);
+    case 16: return pick_stft_L<16>(mode, pre);
+    case 32: return pick_stft_L<32>(mode, pre);
+  }
+  return nullptr;
+}
+static void stft_cfg(int L, int* warps, int* ctas, size_t* smem) {
+  switch (L) {
+    case 4: *warps = StftCfg<4>::WARPS; *ctas = StftCfg<4>::CTAS; *smem = StftCfg<4>::SMEM_BYTES; break;
+    case 8: *warps = StftCfg<8>::WARPS; *ctas = StftCfg<8>::CTAS; *smem = StftCfg<8>::SMEM_BYTES; break;
+    case 16: *warps = StftCfg<16>::WARPS; *ctas = StftCfg<16>::CTAS; *smem = StftCfg<16>::SMEM_BYTES; break;
+    default: *warps = StftCfg<32>::WARPS; *ctas = StftCfg<32>::CTAS; *smem = StftCfg<32>::SMEM_BYTES; break;
+  }
+}
+
+static size_t cep_smem_bytes(const aad_plan* pl) {
+  size_t f = (size_t)pl->p.n_filt * CEP_TS;
+  if (pl->p.n_ceps > 0) f += (size_t)pl->p.n_filt * pl->ncp + (size_t)pl->p.n_ceps * CEP_TS;
+  return f * 4;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int aad_version(void) { return AAD_VERSION; }
+
+const char* aad_strerror(int err) {
+  switch (err) {
+    case AAD_OK: return "ok";
+    case AAD_ERR_INVALID_ARG: return "invalid argument";
+    case AAD_ERR_UNSUPPORTED: return "unsupported configuration";
+    case AAD_ERR_CUDA: return "CUDA runtime error";
+    case AAD_ERR_WORKSPACE: return "workspace too small";
+    case AAD_ERR_KIND: return "plan kind does not match entry point";
+    case AAD_ERR_FILTERBANK: return "filterbank is not banded (at most two adjacent filters per bin)";
+  }
+  return "unknown error";
+}
+
+int aad_params_default(aad_params* p, int kind, int sample_rate) {
+  if (!p || sample_rate <= 0) return AAD_ERR_INVALID_ARG;
+  std::memset(p, 0, sizeof(*p));
+  p->struct_size = (int32_t)sizeof(aad_params);
+  p->kind = kind;
+  p->sample_rate = sample_rate;
+  p->amin = 1e-10f;
+  p->top_db = 80.f;
+  p->delta_width = 9;
+  p->fmin = 0.f;
+  p->fmax = 0.f;
+  p->power_scale = 1.f;
+  if (kind == AAD_KIND_LOGMEL || kind == AAD_KIND_MFCC) {
+    p->n_fft = 2048;
+    p->win_length = 2048;
+    p->hop_length = 512;
+    p->window = AAD_WIN_HANN_PERIODIC;
+    p->center = 1;
+    p->fb_type = AAD_FB_MEL_SLANEY;
+    p->log_type = AAD_LOG_DB10;
+    p->layout = AAD_LAYOUT_CT;
+    if (kind == AAD_KIND_LOGMEL) {
+      p->n_filt = 64;
+      p->ref_type = AAD_REF_UTT_MAX;
+      p->n_ceps = 0;
+    } else {
+      p->n_filt = 128;
+      p->ref_type = AAD_REF_ONE;
+      p->n_ceps = 13;
+    }
+  } else if (kind == AAD_KIND_LFCC) {
+    p->n_fft = 512;
+    p->win_length = (int)(0.025 * sample_rate);
+    p->hop_length = (int)(0.01 * sample_rate);
+    p->window = AAD_WIN_HAMMING_SYMMETRIC;
+    p->center = 0;
+    p->quantize_i16 = 1;
+    p->pre_emph = 0.97f;
+    p->n_filt = 24;
+    p->fb_type = AAD_FB_LINEAR_INTBIN;
+    p->power_scale = 1.0f / 512.0f;
+    p->log_type = AAD_LOG_LN;
+    p->ref_type = AAD_REF_ONE;
+    p->top_db = -1.f;
+    p->n_ceps = 13;
+    p->layout = AAD_LAYOUT_TC;
+  } else {
+    return AAD_ERR_INVALID_ARG;
+  }
+  return AAD_OK;
+}
+
+int aad_plan_destroy(aad_plan* pl) {
+  if (!pl) return AAD_OK;
+  cudaSetDevice(pl->device);
+  cudaFree(pl->d_window);
+  cudaFree(pl->d_tw1);
+  cudaFree(pl->d_twp);
+  cudaFree(pl->d_fbw);
+  cudaFree(pl->d_seg);
+  cudaFree(pl->d_warp_filt);
+  cudaFree(pl->d_dct_t);
+  for (auto& h : pl->hb) {
+    cudaFree(h.d_wav);
+    cudaFree(h.d_out);
+    cudaFree(h.d_len);
+    cudaFree(h.d_nf);
+    cudaFree(h.d_st);
+    cudaFree(h.d_ws);
+    if (h.stream) cudaStreamDestroy(h.stream);
+  }
+  delete pl;
+  return AAD_OK;
+}
+
+int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
+  if (!pp || !out) return AAD_ERR_INVALID_ARG;
+  if (pp->struct_size != (int32_t)sizeof(aad_params)) return AAD_ERR_INVALID_ARG;
+  const aad_params& p = *pp;
+  if (p.n_fft != 256 && p.n_fft != 512 && p.n_fft != 1024 && p.n_fft != 2048) return AAD_ERR_UNSUPPORTED;
+  if (p.win_length <= 0 || p.win_length > p.n_fft || p.hop_length <= 0) return AAD_ERR_INVALID_ARG;
+  if (p.n_filt <= 0 || p.n_filt > 512 || p.sample_rate <= 0) return AAD_ERR_INVALID_ARG;
+  if (p.n_ceps < 0 || p.n_ceps > p.n_filt) return AAD_ERR_INVALID_ARG;
+  if (p.n_delta < 0 || p.n_delta > 2) return AAD_ERR_INVALID_ARG;
+  if (p.n_delta > 0 && (p.delta_width < 3 || p.delta_width > CEP_MAXW || p.delta_width % 2 == 0))
+    return AAD_ERR_INVALID_ARG;
+  if (p.window != AAD_WIN_HANN_PERIODIC && p.window != AAD_WIN_HAMMING_SYMMETRIC) return AAD_ERR_INVALID_ARG;
+  if (p.log_type != AAD_LOG_DB10 && p.log_type != AAD_LOG_LN) return AAD_ERR_INVALID_ARG;
+  if (p.layout != AAD_LAYOUT_CT && p.layout != AAD_LAYOUT_TC) return AAD_ERR_INVALID_ARG;
+  if (p.fmax > 0 && p.fmax > p.sample_rate / 2.0f + 1e-3f) return AAD_ERR_INVALID_ARG;
+
+  CUDA_TRY(cudaSetDevice(device));
+  aad_plan* pl = new (std::nothrow) aad_plan();
+  if (!pl) return AAD_ERR_INVALID_ARG;
+  pl->p = p;
+  pl->p.custom_fb = nullptr;
+  pl->device = device;
+  cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, device);
+  pl->L = p.n_fft / 64;
+  pl->K = p.n_fft / 2 + 1;
+  stft_cfg(pl->L, &pl->warps, &pl->ctas, &pl->k1_smem);
+  pl->c_feat = p.n_ceps > 0 ? p.n_ceps : p.n_filt;
+  pl->c_out = pl->c_feat * (1 + p.n_delta);
+  pl->ncp = p.n_ceps > 0 ? (p.n_ceps + CEP_KC - 1) / CEP_KC * CEP_KC : 0;
+  const bool direct = (p.n_ceps == 0 && p.n_delta == 0 && p.layout == AAD_LAYOUT_CT && !p.time_mean);
+  pl->need_ws_E = !direct;
+  pl->need_ws_feat = p.time_mean != 0;
+
+  const int N = p.n_fft, M = N / 2, L = pl->L, K = pl->K;
+  // window (float64 -> float32), placed in the n_fft buffer
+  std::vector<double> w(p.win_length);
+  for (int n = 0; n < p.win_length; ++n) {
+    if (p.window == AAD_WIN_HANN_PERIODIC) w[n] = 0.5 - 0.5 * std::cos(2.0 * kPiD * n / p.win_length);
+    else w[n] = p.win_length > 1 ? 0.54 - 0.46 * std::cos(2.0 * kPiD * n / (p.win_length - 1)) : 1.0;
+  }
+  const int win_off = p.center ? (N - p.win_length) / 2 : 0;
+  pl->h_window.assign(N, 0.f);
+  std::vector<float> win_half(N, 0.f);
+  for (int n = 0; n < p.win_length; ++n) {
+    pl->h_window[win_off + n] = (float)w[n];
+    win_half[win_off + n] = 0.5f * (float)w[n];
+  }
+  std::vector<float2> tw1((size_t)32 * L), twp(M / 2);
+  for (int ka = 0; ka < 32; ++ka)
+    for (int b = 0; b < L; ++b) {
+      double ang = -2.0 * kPiD * (double)((long long)b * ka % M) / M;
+      tw1[(size_t)ka * L + b] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+  for (int k = 0; k < M / 2; ++k) {
+    double ang = -2.0 * kPiD * k / N;
+    twp[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+  }
+  int rc = build_filterbank(p, K, pl->h_fb);
+  std::vector<float2> fbw;
+  std::vector<int32_t> seg;
+  if (rc == AAD_OK) rc = band_filterbank(pl->h_fb, p.n_filt, K, fbw, seg);
+  if (rc != AAD_OK) {
+    delete pl;
+    return rc;
+  }
+  // filter ranges per warp of the filterbank phase, balanced by bins + a per-filter log cost
+  std::vector<int32_t> wfilt(pl->warps + 1, p.n_filt);
+  {
+    std::vector<double> cost(p.n_filt);
+    double tot = 0;
+    for (int j = 0; j < p.n_filt; ++j) {
+      cost[j] = (seg[j + 1] - seg[j]) + 10.0;
+      tot += cost[j];
+    }
+    tot += seg[p.n_filt + 1] - seg[p.n_filt];
+    wfilt[0] = 0;
+    double cum = 0;
+    int j = 0;
+    for (int wi = 1; wi < pl->warps; ++wi) {
+      const double target = tot * wi / pl->warps;
+      while (j < p.n_filt && cum + cost[j] * 0.5 < target) cum += cost[j++];
+      wfilt[wi] = j;
+    }
+    wfilt[pl->warps] = p.n_filt;
+  }
+  // DCT-II ortho (scipy.fftpack.dct type 2 norm='ortho'), first n_ceps rows; transposed + padded
+  std::vector<float> dct_t;
+  if (p.n_ceps > 0) {
+    const int Mf = p.n_filt;
+    pl->h_dct.assign((size_t)p.n_ceps * Mf, 0.f);
+    dct_t.assign((size_t)Mf * pl->ncp, 0.f);
+    for (int k = 0; k < p.n_ceps; ++k) {
+      const double fk = k == 0 ? std::sqrt(1.0 / (4.0 * Mf)) : std::sqrt(1.0 / (2.0 * Mf));
+      for (int m = 0; m < Mf; ++m) {
+        float v = (float)(2.0 * fk * std::cos(kPiD * k * (2.0 * m + 1.0) / (2.0 * Mf)));
+        pl->h_dct[(size_t)k * Mf + m] = v;
+        dct_t[(size_t)m * pl->ncp + k] = v;
+      }
+    }
+  }
+  savgol_taps(p.n_delta > 0 ? p.delta_width : 9, pl->taps[0], pl->taps[1]);
+
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = upload(&pl->d_window, win_half);
+  if (e == cudaSuccess) e = upload(&pl->d_tw1, tw1);
+  if (e == cudaSuccess) e = upload(&pl->d_twp, twp);
+  if (e == cudaSuccess) e = upload(&pl->d_fbw, fbw);
+  if (e == cudaSuccess) e = upload(&pl->d_seg, seg);
+  if (e == cudaSuccess) e = upload(&pl->d_warp_filt, wfilt);
+  if (e == cudaSuccess) e = upload(&pl->d_dct_t, dct_t);
+  // opt in to the large dynamic shared memory of every kernel variant this plan can launch
+  for (int mode = 0; mode < 3 && e == cudaSuccess; ++mode)
+    for (int pre = 0; pre < 2 && e == cudaSuccess; ++pre)
+      e = cudaFuncSetAttribute((const void*)pick_stft(L, mode, pre != 0),
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->k1_smem);
+  if (e == cudaSuccess && pl->need_ws_E) {
+    size_t cs = cep_smem_bytes(pl);
+    if (cs > 227 * 1024) {
+      aad_plan_destroy(pl);
+      return AAD_ERR_UNSUPPORTED;
+    }
+    e = cudaFuncSetAttribute((const void*)k_cepstra, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  }
+  if (e != cudaSuccess) {
+    aad_plan_destroy(pl);
+    return AAD_ERR_CUDA;
+  }
+  *out = pl;
+  return AAD_OK;
+}
+
+static int frames_for(const aad_params& p, int64_t len) {
+  if (len <= 0) return 0;
+  if (p.center) return (int)(1 + len / p.hop_length);
+  return len >= p.win_length ? (int)((len - p.win_length) / p.hop_length + 1) : 0;
+}
+
+struct WsLayout {
+  size_t off_frame_off, off_len, off_nf, off_max, off_E, off_feat, total;
+  int t_ws;
+};
+static WsLayout ws_layout(const aad_plan* pl, int B, int t_max) {
+  WsLayout w;
+  size_t o = 0;
+  w.off_frame_off = o; o = align_up(o + (size_t)(B + 1) * 4, 256);
+  w.off_len = o;       o = align_up(o + (size_t)B * 4, 256);
+  w.off_nf = o;        o = align_up(o + (size_t)B * 4, 256);
+  w.off_max = o;       o = align_up(o + (size_t)B * 4, 256);
+  w.t_ws = (t_max + 31) / 32 * 32;
+  w.off_E = o;
+  if (pl->need_ws_E) o = align_up(o + (size_t)B * pl->p.n_filt * w.t_ws * 4, 256);
+  w.off_feat = o;
+  if (pl->need_ws_feat) o = align_up(o + (size_t)B * pl->c_out * w.t_ws * 4, 256);
+  w.total = o;
+  return w;
+}
+
+int aad_query(const aad_plan* pl, int B, int64_t max_len, int32_t* t_max, int32_t* c_out,
+              size_t* workspace_bytes) {
+  if (!pl || B < 0 || max_len < 0) return AAD_ERR_INVALID_ARG;
+  if (max_len > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
+  int T = frames_for(pl->p, max_len);
+  if ((double)B * (double)std::max(T, 1) > 2.0e9) return AAD_ERR_UNSUPPORTED;
+  if (t_max) *t_max = T;
+  if (c_out) *c_out = pl->c_out;
+  if (workspace_bytes) *workspace_bytes = ws_layout(pl, std::max(B, 1), std::max(T, 1)).total;
+  return AAD_OK;
+}
+
+int aad_plan_launches(const aad_plan* pl) {
+  if (!pl) return AAD_ERR_INVALID_ARG;
+  return 2 + 1 + (pl->need_ws_feat ? 1 : 0);  // prepare, stft_fb, cepstra|finalize, [time_mean]
+}
+
+int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_stride,
+                const int32_t* lengths, int B, int64_t max_len, float* out, int64_t out_stride_b,
+                int32_t t_alloc, int32_t* n_frames, int32_t* status, void* workspace,
+                size_t workspace_bytes, void* stream_) {
+  if (!pl || !wav || !lengths || !out || !n_frames || !status || !workspace) return AAD_ERR_INVALID_ARG;
+  if (B <= 0 || max_len <= 0 || max_len > wav_stride || t_alloc <= 0) return AAD_ERR_INVALID_ARG;
+  if (wav_dtype != AAD_F32 && wav_dtype != AAD_I16) return AAD_ERR_INVALID_ARG;
+  const aad_params& p = pl->p;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int t_max = 0;
+  size_t need = 0;
+  int rc = aad_query(pl, B, max_len, &t_max, nullptr, &need);
+  if (rc != AAD_OK) return rc;
+  if (workspace_bytes < need) return AAD_ERR_WORKSPACE;
+  const int t_cap = std::min<int>(t_alloc, std::max(t_max, 1));
+  const WsLayout w = ws_layout(pl, B, std::max(t_max, 1));
+  char* ws = (char*)workspace;
+  int32_t* d_frame_off = (int32_t*)(ws + w.off_frame_off);
+  int32_t* d_len = (int32_t*)(ws + w.off_len);
+  int32_t* d_nf = (int32_t*)(ws + w.off_nf);
+  int32_t* d_max = (int32_t*)(ws + w.off_max);
+  float* d_E = (float*)(ws + w.off_E);
+  float* d_feat = (float*)(ws + w.off_feat);
+
+  if (p.time_mean) {
+    if (out_stride_b == 0) out_stride_b = pl->c_out;
+  } else if (out_stride_b == 0) {
+    out_stride_b = (int64_t)pl->c_out * t_alloc;
+  }
+
+  // K0
+  PrepArgs pa;
+  pa.lengths = lengths; pa.B = B; pa.max_len = max_len;
+  pa.hop = p.hop_length; pa.win_len = p.win_length; pa.center = p.center;
+  pa.n_delta = p.n_delta; pa.delta_width = p.delta_width;
+  pa.t_alloc = p.time_mean ? w.t_ws : t_cap;
+  pa.n_frames = n_frames; pa.status = status; pa.len_c = d_len; pa.nf_eff = d_nf;
+  pa.frame_off = d_frame_off; pa.utt_max = d_max;
+  k_prepare<<<1, 1024, 0, stream>>>(pa);
+
+  // K1
+  StftArgs sa;
+  sa.wav = wav; sa.wav_stride = wav_stride; sa.len_c = d_len; sa.frame_off = d_frame_off; sa.B = B;
+  sa.hop = p.hop_length; sa.s_off = p.center ? p.n_fft / 2 : 0;
+  sa.win_off = p.center ? (p.n_fft - p.win_length) / 2 : 0; sa.win_len = p.win_length;
+  sa.pre_emph = p.pre_emph;
+  sa.window = pl->d_window; sa.tw1 = pl->d_tw1; sa.twp = pl->d_twp; sa.fbw = pl->d_fbw;
+  sa.seg = pl->d_seg; sa.warp_filt = pl->d_warp_filt; sa.n_filt = p.n_filt;
+  sa.log_type = p.log_type; sa.amin = p.amin; sa.eps = 2.220446049250313e-16f;
+  if (pl->need_ws_E) {
+    sa.E = d_E; sa.e_stride_b = (long long)p.n_filt * w.t_ws; sa.e_stride_f = w.t_ws;
+  } else {
+    sa.E = out; sa.e_stride_b = out_stride_b; sa.e_stride_f = t_alloc;
+  }
+  sa.utt_max = p.log_type == AAD_LOG_DB10 ? d_max : nullptr;
+  sa.status = status;
+  const int mode = wav_dtype == AAD_I16 ? IN_I16 : (p.quantize_i16 ? IN_F32_Q16 : IN_F32);
+  stft_kernel_t kern = pick_stft(pl->L, mode, p.pre_emph != 0.f);
+  const long long max_tiles = ((long long)B * std::max(t_max, 1) + 31) / 32;
+  const int grid1 = (int)std::min<long long>((long long)pl->sm_count * pl->ctas, std::max<long long>(max_tiles, 1));
+  kern<<<grid1, pl->warps * 32, pl->k1_smem, stream>>>(sa);
+
+  // K2
+  if (pl->need_ws_E) {
+    CepArgs ca;
+    ca.E = d_E; ca.e_stride_b = sa.e_stride_b; ca.e_stride_f = sa.e_stride_f;
+    ca.nf_eff = d_nf; ca.utt_max = d_max; ca.n_filt = p.n_filt;
+    ca.log_type = p.log_type; ca.ref_type = p.ref_type; ca.top_db = p.top_db;
+    ca.n_ceps = p.n_ceps; ca.ncp = pl->ncp; ca.dct_t = pl->d_dct_t;
+    ca.n_delta = p.n_delta; ca.width = p.n_delta > 0 ? p.delta_width : 1;
+    std::memcpy(ca.taps, pl->taps, sizeof(ca.taps));
+    if (p.time_mean) {
+      ca.out = d_feat; ca.out_stride_b = (long long)pl->c_out * w.t_ws;
+      ca.out_stride_c = w.t_ws; ca.out_stride_t = 1;
+    } else if (p.layout == AAD_LAYOUT_CT) {
+      ca.out = out; ca.out_stride_b = out_stride_b; ca.out_stride_c = t_alloc; ca.out_stride_t = 1;
+    } else {
+      ca.out = out; ca.out_stride_b = out_stride_b; ca.out_stride_c = 1; ca.out_stride_t = pl->c_out;
+    }
+    ca.tile_out = CEP_TS - (p.n_delta > 0 ? 2 * (p.delta_width / 2) : 0);
+    const int gx = t_max <= CEP_TS ? 1 : (t_max + ca.tile_out - 1) / ca.tile_out;
+    dim3 grid(gx, B);
+    k_cepstra<<<grid, CEP_TS, cep_smem_bytes(pl), stream>>>(ca);
+    if (p.time_mean) {
+      dim3 gm((pl->c_out + 3) / 4, B);
+      k_time_mean<<<gm, 128, 0, stream>>>(d_feat, ca.out_stride_b, w.t_ws, d_nf, pl->c_out, out, out_stride_b);
+    }
+  } else {
+    FinArgs fa;
+    fa.out = out; fa.stride_b = out_stride_b; fa.stride_f = t_alloc; fa.nf_eff = d_nf; fa.utt_max = d_max;
+    fa.n_filt = p.n_filt; fa.ref_type = p.ref_type; fa.top_db = p.top_db;
+    if (p.log_type == AAD_LOG_DB10) {
+      const int gx = std::max(1, std::min(64, (p.n_filt * std::max(t_max, 1) + 255) / 256));
+      dim3 grid(gx, B);
+      k_db_finalize<<<grid, 256, 0, stream>>>(fa);
+    }
+  }
+  return cudaGetLastError() == cudaSuccess ? AAD_OK : AAD_ERR_CUDA;
+}
+
+#define AAD_KIND_ALIAS(NAME, KIND)                                                                        \
+  int NAME(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_stride, const int32_t* lengths, \
+           int B, int64_t max_len, float* out, int64_t out_stride_b, int32_t t_alloc, int32_t* n_frames,  \
+           int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {                      \
+    if (!pl) return AAD_ERR_INVALID_ARG;                                                                  \
+    if (pl->p.kind != KIND) return AAD_ERR_KIND;                                                          \
+    return aad_extract(pl, wav, wav_dtype, wav_stride, lengths, B, max_len, out, out_stride_b, t_alloc,   \
+                       n_frames, status, workspace, workspace_bytes, stream);                             \
+  }
+AAD_KIND_ALIAS(aad_logmel, AAD_KIND_LOGMEL)
+AAD_KIND_ALIAS(aad_mfcc, AAD_KIND_MFCC)
+AAD_KIND_ALIAS(aad_lfcc, AAD_KIND_LFCC)
+
+int aad_delta(const float* x, const int32_t* n_frames, int B, int C, int32_t t_stride, int width,
+              int order, float* out, void* stream) {
+  if (!x || !n_frames || !out || B <= 0 || C <= 0 || t_stride <= 0) return AAD_ERR_INVALID_ARG;
+  if (width < 3 || width > CEP_MAXW || width % 2 == 0 || order < 1 || order > 2) return AAD_ERR_INVALID_ARG;
+  if (B > 65535 || C > 65535) return AAD_ERR_UNSUPPORTED;
+  DeltaArgs da;
+  float t1[CEP_MAXW], t2[CEP_MAXW];
+  savgol_taps(width, t1, t2);
+  std::memcpy(da.taps, order == 1 ? t1 : t2, sizeof(da.taps));
+  da.x = x; da.out = out; da.n_frames = n_frames; da.C = C; da.t_stride = t_stride; da.width = width;
+  dim3 grid(std::max(1, std::min(64, (t_stride + 255) / 256)), C, B);
+  k_delta<<<grid, 256, 0, (cudaStream_t)stream>>>(da);
+  return cudaGetLastError() == cudaSuccess ? AAD_OK : AAD_ERR_CUDA;
+}
+
+int64_t aad_plan_table(const aad_plan* pl, int which, float* host_out, int64_t capacity) {
+  if (!pl) return AAD_ERR_INVALID_ARG;
+  const float* src = nullptr;
+  int64_t n = 0;
+  float tapbuf[2 * CEP_MAXW];
+  switch (which) {
+    case AAD_TABLE_WINDOW: src = pl->h_window.data(); n = (int64_t)pl->h_window.size(); break;
+    case AAD_TABLE_FILTERBANK: src = pl->h_fb.data(); n = (int64_t)pl->h_fb.size(); break;
+    case AAD_TABLE_DCT: src = pl->h_dct.data(); n = (int64_t)pl->h_dct.size(); break;
+    case AAD_TABLE_DELTA_TAPS: {
+      const int wdt = pl->p.n_delta > 0 ? pl->p.delta_width : 9;
+      for (int i = 0; i < wdt; ++i) {
+        tapbuf[i] = pl->taps[0][i];
+        tapbuf[wdt + i] = pl->taps[1][i];
+      }
+      src = tapbuf;
+      n = 2 * wdt;
+      break;
+    }
+    default: return AAD_ERR_INVALID_ARG;
+  }
+  if (host_out) {
+    if (capacity < n) return AAD_ERR_INVALID_ARG;
+    std::memcpy(host_out, src, (size_t)n * 4);
+  }
+  return n;
+}
+
+int aad_fp32_peak(int device, int iters, double* tflops_out) {
+  if (!tflops_out || iters <= 0) return AAD_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(device));
+  int sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  float* sink = nullptr;
+  CUDA_TRY(cudaMalloc(&sink, 4));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int grid = sms * 8, block = 256;
+  k_fma_peak<<<grid, block>>>(sink, 16);  // warm-up
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    k_fma_peak<<<grid, block>>>(sink, iters);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double flops = 2.0 * 8 * 16 * (double)iters * grid * block;
+    best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  *tflops_out = best;
+  return cudaGetLastError() == cudaSuccess ? AAD_OK : AAD_ERR_CUDA;
+}
+
+// ---- host-buffer path: chunked H2D -> kernels -> D2H on two internal streams ----
+static int ensure(void** p, size_t* cap, size_t need) {
+  if (*cap >= need) return AAD_OK;
+  cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  if (cudaMalloc(p, need) != cudaSuccess) return AAD_ERR_CUDA;
+  *cap = need;
+  return AAD_OK;
+}
+
+int aad_extract_host(aad_plan* pl, const void* wav_host, int wav_dtype, int64_t wav_stride,
+                     const int32_t* lengths_host, int B, int64_t max_len, float* out_host,
+                     int64_t out_stride_b, int32_t t_alloc, int32_t* n_frames_host,
+                     int32_t* status_host, int chunk_utts) {
+  if (!pl || !wav_host || !lengths_host || !out_host || !n_frames_host || !status_host)
+    return AAD_ERR_INVALID_ARG;
+  if (B <= 0 || max_len <= 0 || max_len > wav_stride || t_alloc <= 0) return AAD_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(pl->device));
+  const size_t esz = wav_dtype == AAD_I16 ? 2 : 4;
+  const int64_t row_out = pl->p.time_mean ? pl->c_out : (int64_t)pl->c_out * t_alloc;
+  if (out_stride_b == 0) out_stride_b = row_out;
+  if (chunk_utts <= 0) {
+    // ~32 MB of samples per chunk keeps both copy engines and the SMs busy
+    chunk_utts = (int)std::max<int64_t>(1, (32ll << 20) / (int64_t)(max_len * esz));
+  }
+  chunk_utts = std::min(chunk_utts, B);
+  int t_max = 0;
+  size_t ws_need = 0;
+  int rc = aad_query(pl, chunk_utts, max_len, &t_max, nullptr, &ws_need);
+  if (rc != AAD_OK) return rc;
+  for (auto& h : pl->hb) {
+    if (!h.stream) CUDA_TRY(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+    if ((rc = ensure(&h.d_wav, &h.wav_bytes, (size_t)chunk_utts * max_len * esz)) != AAD_OK) return rc;
+    if ((rc = ensure((void**)&h.d_out, &h.out_bytes, (size_t)chunk_utts * row_out * 4)) != AAD_OK) return rc;
+    if ((rc = ensure(&h.d_ws, &h.ws_bytes, ws_need)) != AAD_OK) return rc;
+    if (h.cap_b < chunk_utts) {
+      cudaFree(h.d_len); cudaFree(h.d_nf); cudaFree(h.d_st);
+      h.d_len = h.d_nf = h.d_st = nullptr;
+      h.cap_b = 0;
+      CUDA_TRY(cudaMalloc((void**)&h.d_len, (size_t)chunk_utts * 4));
+      CUDA_TRY(cudaMalloc((void**)&h.d_nf, (size_t)chunk_utts * 4));
+      CUDA_TRY(cudaMalloc((void**)&h.d_st, (size_t)chunk_utts * 4));
+      h.cap_b = chunk_utts;
+    }
+  }
+  int ci = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk_utts, ++ci) {
+    aad_plan::HostBuf& h = pl->hb[ci & 1];
+    const int nb = std::min(chunk_utts, B - b0);
+    const char* src = (const char*)wav_host + (size_t)b0 * wav_stride * esz;
+    CUDA_TRY(cudaMemcpy2DAsync(h.d_wav, (size_t)max_len * esz, src, (size_t)wav_stride * esz,
+                               (size_t)max_len * esz, nb, cudaMemcpyHostToDevice, h.stream));
+    CUDA_TRY(cudaMemcpyAsync(h.d_len, lengths_host + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, h.stream));
+    // rows with non-zero status are left untouched by the kernels: start from zeros
+    CUDA_TRY(cudaMemsetAsync(h.d_out, 0, (size_t)nb * row_out * 4, h.stream));
+    rc = aad_extract(pl, h.d_wav, wav_dtype, max_len, h.d_len, nb, max_len, h.d_out, row_out, t_alloc,
+                     h.d_nf, h.d_st, h.d_ws, h.ws_bytes, h.stream);
+    if (rc != AAD_OK) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(out_host + (size_t)b0 * out_stride_b, (size_t)out_stride_b * 4, h.d_out,
+                               (size_t)row_out * 4, (size_t)row_out * 4, nb, cudaMemcpyDeviceToHost, h.stream));
+    CUDA_TRY(cudaMemcpyAsync(n_frames_host + b0, h.d_nf, (size_t)nb * 4, cudaMemcpyDeviceToHost, h.stream));
+    CUDA_TRY(cudaMemcpyAsync(status_host + b0, h.d_st, (size_t)nb * 4, cudaMemcpyDeviceToHost, h.stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(pl->hb[0].stream));
+  CUDA_TRY(cudaStreamSynchronize(pl->hb[1].stream));
+  return AAD_OK;
+}
+
+}  // extern "C"

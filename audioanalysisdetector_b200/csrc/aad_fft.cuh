@@ -1,0 +1,143 @@
+// Register-resident radix-2 DIT FFT building blocks with compile-time twiddles.
+//
+// Every index is a template/constexpr value, so after inlining the `float2 v[N]`
+// arrays live entirely in registers and all twiddles are FFMA immediates.
+// Butterflies use the FMA form  a' = a + w*b,  b' = 2a - a'  (6 FFMA for a general
+// twiddle, 4 FADD for w in {1, -i}, 6 for the sqrt(1/2) twiddles).
+#pragma once
+#include <cuda_runtime.h>
+#include <utility>
+
+namespace aad {
+
+// ---------------------------------------------------------------- constexpr trig
+constexpr double kPi = 3.141592653589793238462643383279502884;
+
+constexpr double cx_sin_small(double x) {  // |x| <= pi/4
+  double x2 = x * x, term = x, sum = x;
+  for (int i = 1; i < 14; ++i) {
+    term *= -x2 / double((2 * i) * (2 * i + 1));
+    sum += term;
+  }
+  return sum;
+}
+constexpr double cx_cos_small(double x) {
+  double x2 = x * x, term = 1.0, sum = 1.0;
+  for (int i = 1; i < 14; ++i) {
+    term *= -x2 / double((2 * i - 1) * (2 * i));
+    sum += term;
+  }
+  return sum;
+}
+struct cx_cs {
+  double c, s;
+};
+// cos/sin of 2*pi*num/den with exact quadrant symmetry (integer range reduction).
+constexpr cx_cs cx_cossin_2pi(long long num, long long den) {
+  long long r = num % den;
+  if (r < 0) r += den;
+  long long q = (4 * r) / den;          // quadrant
+  long long rem = 4 * r - q * den;      // in [0, den): angle = (pi/2) * rem/den
+  double c = 0, s = 0;
+  if (rem == 0) {
+    c = 1.0;
+    s = 0.0;
+  } else if (2 * rem <= den) {
+    double a = (kPi / 2) * double(rem) / double(den);
+    c = cx_cos_small(a);
+    s = cx_sin_small(a);
+  } else {
+    double a = (kPi / 2) * double(den - rem) / double(den);
+    c = cx_sin_small(a);
+    s = cx_cos_small(a);
+  }
+  switch (q) {
+    case 0: return {c, s};
+    case 1: return {-s, c};
+    case 2: return {-c, -s};
+    default: return {s, -c};
+  }
+}
+
+// ---------------------------------------------------------------- static loops
+template <int I>
+using ic = std::integral_constant<int, I>;
+
+template <int B, int E, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(ic<B>{});
+    static_for<B + 1, E>(static_cast<F&&>(f));
+  }
+}
+
+constexpr int bitrev(int x, int bits) {
+  int r = 0;
+  for (int i = 0; i < bits; ++i) r |= ((x >> i) & 1) << (bits - 1 - i);
+  return r;
+}
+constexpr int ilog2(int x) {
+  int r = 0;
+  while ((1 << r) < x) ++r;
+  return r;
+}
+
+// ---------------------------------------------------------------- butterflies
+// W = exp(-2*pi*i*J/M) = (wr, wi) with wi = -sin.
+template <int J, int M>
+__device__ __forceinline__ void butterfly(float2& a, float2& b) {
+  if constexpr (J == 0) {
+    float2 t = b;
+    b = make_float2(a.x - t.x, a.y - t.y);
+    a = make_float2(a.x + t.x, a.y + t.y);
+  } else if constexpr (4 * J == M) {  // w = -i : w*b = (b.y, -b.x)
+    float2 t = make_float2(b.y, -b.x);
+    b = make_float2(a.x - t.x, a.y - t.y);
+    a = make_float2(a.x + t.x, a.y + t.y);
+  } else if constexpr (8 * J == M) {  // w = (1 - i)/sqrt2 : w*b = c*(b.x + b.y, b.y - b.x)
+    constexpr float c = 0.70710678118654752440f;
+    float s1 = b.x + b.y, s2 = b.y - b.x;
+    float nx = __fmaf_rn(c, s1, a.x), ny = __fmaf_rn(c, s2, a.y);
+    b = make_float2(__fmaf_rn(-c, s1, a.x), __fmaf_rn(-c, s2, a.y));
+    a = make_float2(nx, ny);
+  } else if constexpr (8 * J == 3 * M) {  // w = (-1 - i)/sqrt2 : w*b = c*(b.y - b.x, -(b.x + b.y))
+    constexpr float c = 0.70710678118654752440f;
+    float s1 = b.y - b.x, s2 = b.x + b.y;
+    float nx = __fmaf_rn(c, s1, a.x), ny = __fmaf_rn(-c, s2, a.y);
+    b = make_float2(__fmaf_rn(-c, s1, a.x), __fmaf_rn(c, s2, a.y));
+    a = make_float2(nx, ny);
+  } else {
+    constexpr cx_cs cs = cx_cossin_2pi(J, M);
+    constexpr float wr = float(cs.c), wi = float(-cs.s);
+    // t = w*b ; a' = a + t ; b' = 2a - a'
+    float nx = __fmaf_rn(wr, b.x, __fmaf_rn(-wi, b.y, a.x));
+    float ny = __fmaf_rn(wr, b.y, __fmaf_rn(wi, b.x, a.y));
+    b = make_float2(__fmaf_rn(2.0f, a.x, -nx), __fmaf_rn(2.0f, a.y, -ny));
+    a = make_float2(nx, ny);
+  }
+}
+
+// In-place DIT FFT of size N on v[OFF .. OFF+N).  Input must be stored in
+// bit-reversed order (element n at OFF + bitrev(n)); output is in natural order.
+template <int N, int OFF, int NV>
+__device__ __forceinline__ void fft_dit(float2 (&v)[NV]) {
+  constexpr int LOG2N = ilog2(N);
+  static_for<1, LOG2N + 1>([&](auto s_) {
+    constexpr int S = decltype(s_)::value;
+    constexpr int M = 1 << S;
+    constexpr int H = M / 2;
+    static_for<0, N / M>([&](auto g_) {
+      constexpr int K = decltype(g_)::value * M;
+      static_for<0, H>([&](auto j_) {
+        constexpr int J = decltype(j_)::value;
+        butterfly<J, M>(v[OFF + K + J], v[OFF + K + J + H]);
+      });
+    });
+  });
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(__fmaf_rn(a.x, b.x, -(a.y * b.y)), __fmaf_rn(a.x, b.y, a.y * b.x));
+}
+
+}  // namespace aad

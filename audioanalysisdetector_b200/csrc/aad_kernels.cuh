@@ -1,0 +1,654 @@
+// sm_100a kernels of the spectral front-end.
+//
+//   k_prepare   : per-utterance frame counts, status, exclusive scan of frames, max init
+//   k_stft_fb   : fused framing + window + real FFT + |X|^2 + banded filterbank + log
+//                 (persistent; one warp-iteration = 32/L frames, FFT entirely in registers)
+//   k_cepstra   : dB reference/floor + DCT-II + delta/delta-delta stencil + layout
+//   k_db_finalize, k_time_mean, k_delta : small epilogues
+//
+// Replaces (reference call chain): librosa.stft / np.abs()**2 / filters.mel einsum /
+// power_to_db / scipy dct inside librosa.feature.{melspectrogram,mfcc}
+// (ASV_dl_func.py:416,533-534) and spafe pre_emphasis / framing / windowing / fft /
+// linear filterbank / log / dct inside spafe.features.lfcc.lfcc (ASV_dl_func.py:435).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "aad_fft.cuh"
+
+namespace aad {
+
+enum InMode { IN_F32 = 0, IN_F32_Q16 = 1, IN_I16 = 2 };
+
+// ---------------------------------------------------------------------------
+// ordered-int encoding of floats (monotone), for atomicMax / redux on floats
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int enc_ordered(float f) {
+#ifdef __CUDA_ARCH__
+  int i = __float_as_int(f);
+#else
+  int i;
+  memcpy(&i, &f, 4);
+#endif
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float dec_ordered(int i) {
+  return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
+}
+#define AAD_ENC_NEG_INF ((int)0x807fffff)
+
+// ---------------------------------------------------------------------------
+// K0: prepare
+// ---------------------------------------------------------------------------
+struct PrepArgs {
+  const int32_t* lengths;
+  int B;
+  long long max_len;
+  int hop, win_len, center, n_delta, delta_width, t_alloc;
+  int32_t* n_frames;   // out (user)
+  int32_t* status;     // out (user)
+  int32_t* len_c;      // ws: clamped lengths
+  int32_t* nf_eff;     // ws: frames actually computed (0 when status != 0)
+  int32_t* frame_off;  // ws: [B+1] exclusive scan of nf_eff
+  int32_t* utt_max;    // ws: ordered-int encoded running max, init -inf
+};
+
+__global__ void __launch_bounds__(1024) k_prepare(PrepArgs a) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < a.B; base += 1024) {
+    int b = base + tid;
+    int nf = 0;
+    if (b < a.B) {
+      long long len = a.lengths[b];
+      if (len > a.max_len) len = a.max_len;
+      int st = 0;
+      int T = 0;
+      if (len <= 0) {
+        st = 1;
+        len = 0;
+      } else {
+        T = a.center ? (int)(1 + len / a.hop) : (len >= a.win_len ? (int)((len - a.win_len) / a.hop + 1) : 0);
+        if (T == 0) st = 2;
+        else if (a.n_delta > 0 && T < a.delta_width) st = 3;
+        else if (T > a.t_alloc) st = 4;
+      }
+      nf = st ? 0 : T;
+      a.n_frames[b] = T;
+      a.status[b] = st;
+      a.len_c[b] = (int)len;
+      a.nf_eff[b] = nf;
+      a.utt_max[b] = AAD_ENC_NEG_INF;
+    }
+    // block exclusive scan of nf
+    int x = nf;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warp_sums[lane] = w;  // inclusive
+    }
+    __syncthreads();
+    int carry = carry_s;
+    int excl = carry + (warp ? warp_sums[warp - 1] : 0) + (x - nf);
+    if (b < a.B) a.frame_off[b] = excl;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_sums[31];
+    __syncthreads();
+  }
+  if (tid == 0) a.frame_off[a.B] = carry_s;
+}
+
+// ---------------------------------------------------------------------------
+// K1: fused STFT + power + filterbank + log
+// ---------------------------------------------------------------------------
+template <int L>
+struct StftCfg {
+  static constexpr int Q = 32 / L;        // frames per warp-iteration
+  static constexpr int M = 32 * L;        // complex FFT length (n_fft / 2)
+  static constexpr int N = 2 * M;         // n_fft
+  static constexpr int K = M + 1;         // bins
+  static constexpr int SP = 33 * L + 1;   // power-row stride (odd; Q*SP >= 32*33 scratch words)
+  static constexpr int TILE = 32;         // frames per tile (= lanes of the filterbank phase)
+  static constexpr int ITERS = TILE / Q;  // warp-iterations per tile
+  static constexpr int WARPS = L == 32 ? 16 : (L == 16 ? 8 : 4);
+  static constexpr int CTAS = L == 32 ? 1 : (L == 16 ? 2 : 4);
+  static constexpr int KPAD = (K + 3) & ~3;
+  // shared memory carve-up, in floats
+  static constexpr int OFF_P = 0;
+  static constexpr int OFF_WIN = ((TILE * SP + 3) & ~3);
+  static constexpr int OFF_TW1 = OFF_WIN + N;
+  static constexpr int OFF_TWP = OFF_TW1 + 2 * 32 * L;
+  static constexpr int OFF_FBW = OFF_TWP + 2 * (M / 2);
+  static constexpr int OFF_META = OFF_FBW + 2 * KPAD;
+  static constexpr int SMEM_FLOATS = OFF_META + 2 * TILE;
+  static constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
+};
+
+struct StftArgs {
+  const void* wav;
+  long long wav_stride;     // elements
+  const int32_t* len_c;     // [B] clamped lengths
+  const int32_t* frame_off; // [B+1]
+  int B;
+  int hop, s_off;           // first sample of frame t is t*hop - s_off
+  int win_off, win_len;     // window support inside the n_fft buffer
+  float pre_emph;
+  const float* window;      // [N]   0.5 * window (zero outside support)
+  const float2* tw1;        // [32*L] exp(-2 pi i b kA / M) at [kA*L + b]
+  const float2* twp;        // [M/2]  exp(-2 pi i k / N)
+  const float2* fbw;        // [K]    (rising weight of segment's filter, falling weight of previous filter)
+  const int32_t* seg;       // [n_filt + 2] segment bin boundaries
+  const int32_t* warp_filt; // [WARPS + 1] filter range per warp
+  int n_filt;
+  int log_type;             // 0 dB, 1 ln
+  float amin, eps;
+  float* E;                 // log-energies out: E[b*stride_b + f*stride_f + t]
+  long long e_stride_b;
+  int e_stride_f;
+  int32_t* utt_max;         // ordered-int encoded, or null
+  int32_t* status;          // for NONFINITE flagging
+};
+
+template <int MODE>
+__device__ __forceinline__ float cvt_sample(float x) {
+  if constexpr (MODE == IN_F32_Q16) {
+    // (y * 32767).astype(np.int16): float32 multiply, truncate toward zero, keep low 16 bits
+    int q = __float2int_rz(x * 32767.0f);
+    return (float)(short)q;
+  } else {
+    return x;
+  }
+}
+
+// slow path: one sample with all masks (window support, utterance bounds)
+template <int MODE, bool PRE>
+__device__ __forceinline__ float load_masked(const void* row, int idx, int n, int len, int win_off,
+                                             int win_len, float pre) {
+  bool ok = (unsigned)(n - win_off) < (unsigned)win_len && (unsigned)idx < (unsigned)len;
+  float x = 0.f, xp = 0.f;
+  if (ok) {
+    if constexpr (MODE == IN_I16) {
+      x = (float)__ldg((const short*)row + idx);
+      if (PRE && idx >= 1) xp = (float)__ldg((const short*)row + idx - 1);
+    } else {
+      x = cvt_sample<MODE>(__ldg((const float*)row + idx));
+      if (PRE && idx >= 1) xp = cvt_sample<MODE>(__ldg((const float*)row + idx - 1));
+    }
+  }
+  if constexpr (PRE) x = __fmaf_rn(-pre, xp, x);
+  return x;
+}
+
+__device__ __forceinline__ float2 i16pair_to_float2(unsigned p) {
+  // exact int16 -> float via the 2^23 magic number (ALU + FADD instead of I2F)
+  float lo = __uint_as_float(0x4B000000u | ((p & 0xffffu) ^ 0x8000u)) - 8421376.0f;
+  float hi = __uint_as_float(0x4B000000u | ((p >> 16) ^ 0x8000u)) - 8421376.0f;
+  return make_float2(lo, hi);
+}
+
+template <int L, int MODE, bool PRE>
+__global__ void __launch_bounds__(StftCfg<L>::WARPS * 32, StftCfg<L>::CTAS) k_stft_fb(const StftArgs a) {
+  using C = StftCfg<L>;
+  constexpr int Q = C::Q, M = C::M, N = C::N, K = C::K, SP = C::SP;
+  constexpr int LOG2L = ilog2(L);
+  extern __shared__ __align__(16) float smem[];
+  float* sP = smem + C::OFF_P;
+  float* sWin = smem + C::OFF_WIN;
+  float2* sTw1 = reinterpret_cast<float2*>(smem + C::OFF_TW1);
+  float2* sTwp = reinterpret_cast<float2*>(smem + C::OFF_TWP);
+  float2* sFbw = reinterpret_cast<float2*>(smem + C::OFF_FBW);
+  int* sMetaB = reinterpret_cast<int*>(smem + C::OFF_META);
+  int* sMetaT = sMetaB + C::TILE;
+
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane / L, j = lane % L;  // frame-in-iteration, lane within the frame's group
+  const int partner = g * L + ((L - j) & (L - 1));
+
+  for (int i = tid; i < N; i += nthr) sWin[i] = a.window[i];
+  for (int i = tid; i < 32 * L; i += nthr) sTw1[i] = a.tw1[i];
+  for (int i = tid; i < M / 2; i += nthr) sTwp[i] = a.twp[i];
+  for (int i = tid; i < K; i += nthr) sFbw[i] = a.fbw[i];
+  const int wf0 = a.warp_filt[warp], wf1 = a.warp_filt[warp + 1];
+  const int total = a.frame_off[a.B];
+  const int n_tiles = (total + C::TILE - 1) / C::TILE;
+  const float2* sWin2 = reinterpret_cast<const float2*>(sWin);
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // ---- tile meta: global frame index -> (utterance, frame) -------------------
+    if (warp == 0) {
+      int gf = tile * C::TILE + lane;
+      int b = -1, t = 0;
+      if (gf < total) {
+        int lo = 0, hi = a.B;
+        while (lo < hi) {
+          int mid = (lo + hi) >> 1;
+          if (__ldg(a.frame_off + mid + 1) <= gf) lo = mid + 1;
+          else hi = mid;
+        }
+        b = lo;
+        t = gf - __ldg(a.frame_off + lo);
+      }
+      sMetaB[lane] = b;
+      sMetaT[lane] = t;
+    }
+    __syncthreads();  // meta visible; previous tile's filterbank phase is done with sP
+
+    // ---- FFT phase ---------------------------------------------------------------
+    for (int it = warp; it < C::ITERS; it += C::WARPS) {
+      const int fi = it * Q + g;
+      const int b = sMetaB[fi], t = sMetaT[fi];
+      const bool valid = b >= 0;
+      if (!__any_sync(0xffffffffu, valid)) continue;
+      const int len = valid ? __ldg(a.len_c + b) : 0;
+      const int s0 = t * a.hop - a.s_off;
+      const char* row = static_cast<const char*>(a.wav) +
+                        (valid ? (long long)b * a.wav_stride * (MODE == IN_I16 ? 2 : 4) : 0);
+      bool fast = valid && s0 >= (PRE ? 1 : 0) && (s0 + N) <= len;
+      if constexpr (MODE == IN_I16) fast = fast && (((uintptr_t)(row + 2ll * s0)) & 3) == 0;
+      else fast = fast && (((uintptr_t)(row + 4ll * s0)) & 7) == 0;
+
+      float2 v[32];
+      if (__all_sync(0xffffffffu, fast)) {
+        if constexpr (MODE == IN_I16) {
+          const unsigned* p = reinterpret_cast<const unsigned*>(row + 2ll * s0) + j;
+          unsigned raw[32];
+          static_for<0, 32>([&](auto a_) {
+            constexpr int A = decltype(a_)::value;
+            raw[A] = __ldg(p + L * A);
+          });
+          if constexpr (PRE) {
+            const short* ps = reinterpret_cast<const short*>(row + 2ll * s0) + 2 * j - 1;
+            static_for<0, 32>([&](auto a_) {
+              constexpr int A = decltype(a_)::value;
+              float xp = (float)__ldg(ps + 2 * L * A);
+              float2 x = i16pair_to_float2(raw[A]);
+              float2 w = sWin2[L * A + j];
+              float e0 = __fmaf_rn(-a.pre_emph, xp, x.x);
+              float e1 = __fmaf_rn(-a.pre_emph, x.x, x.y);
+              v[bitrev(A, 5)] = make_float2(e0 * w.x, e1 * w.y);
+            });
+          } else {
+            static_for<0, 32>([&](auto a_) {
+              constexpr int A = decltype(a_)::value;
+              float2 x = i16pair_to_float2(raw[A]);
+              float2 w = sWin2[L * A + j];
+              v[bitrev(A, 5)] = make_float2(x.x * w.x, x.y * w.y);
+            });
+          }
+        } else {
+          const float2* p = reinterpret_cast<const float2*>(row + 4ll * s0) + j;
+          static_for<0, 32>([&](auto a_) {
+            constexpr int A = decltype(a_)::value;
+            v[bitrev(A, 5)] = __ldg(p + L * A);
+          });
+          if constexpr (PRE) {
+            const float* ps = reinterpret_cast<const float*>(row + 4ll * s0) + 2 * j - 1;
+            static_for<0, 32>([&](auto a_) {
+              constexpr int A = decltype(a_)::value;
+              float xp = cvt_sample<MODE>(__ldg(ps + 2 * L * A));
+              float2 x = v[bitrev(A, 5)];
+              x.x = cvt_sample<MODE>(x.x);
+              x.y = cvt_sample<MODE>(x.y);
+              float2 w = sWin2[L * A + j];
+              float e0 = __fmaf_rn(-a.pre_emph, xp, x.x);
+              float e1 = __fmaf_rn(-a.pre_emph, x.x, x.y);
+              v[bitrev(A, 5)] = make_float2(e0 * w.x, e1 * w.y);
+            });
+          } else {
+            static_for<0, 32>([&](auto a_) {
+              constexpr int A = decltype(a_)::value;
+              float2 x = v[bitrev(A, 5)];
+              float2 w = sWin2[L * A + j];
+              v[bitrev(A, 5)] = make_float2(cvt_sample<MODE>(x.x) * w.x, cvt_sample<MODE>(x.y) * w.y);
+            });
+          }
+        }
+      } else {
+        // edge frames: centre padding, utterance tail, zero-extended window, unaligned rows
+        static_for<0, 32>([&](auto a_) {
+          constexpr int A = decltype(a_)::value;
+          const int n0 = 2 * (L * A + j);
+          float x0 = load_masked<MODE, PRE>(row, s0 + n0, n0, len, a.win_off, a.win_len, a.pre_emph);
+          float x1 = load_masked<MODE, PRE>(row, s0 + n0 + 1, n0 + 1, len, a.win_off, a.win_len, a.pre_emph);
+          float2 w = sWin2[L * A + j];
+          v[bitrev(A, 5)] = make_float2(x0 * w.x, x1 * w.y);
+        });
+      }
+
+      // pass 1: 32-point DFT over a (stride L), then twiddle W_M^(b*kA)
+      fft_dit<32, 0>(v);
+      static_for<1, 32>([&](auto k_) {
+        constexpr int KA = decltype(k_)::value;
+        v[KA] = cmul(v[KA], sTw1[KA * L + j]);
+      });
+
+      // transpose through the warp's scratch (= its own power rows), re then im
+      float* scr = sP + (it * Q) * SP;
+      float* scr_w = scr + lane;
+      const float* scr_r = scr + j * 33 + g * L;
+      static_for<0, 32>([&](auto k_) {
+        constexpr int KA = decltype(k_)::value;
+        scr_w[KA * 33] = v[KA].x;
+      });
+      __syncwarp();
+      static_for<0, Q>([&](auto q_) {
+        constexpr int QQ = decltype(q_)::value;
+        static_for<0, L>([&](auto b_) {
+          constexpr int BB = decltype(b_)::value;
+          v[QQ * L + bitrev(BB, LOG2L)].x = scr_r[QQ * L * 33 + BB];
+        });
+      });
+      __syncwarp();
+      static_for<0, 32>([&](auto k_) {
+        constexpr int KA = decltype(k_)::value;
+        scr_w[KA * 33] = v[KA].y;
+      });
+      __syncwarp();
+      static_for<0, Q>([&](auto q_) {
+        constexpr int QQ = decltype(q_)::value;
+        static_for<0, L>([&](auto b_) {
+          constexpr int BB = decltype(b_)::value;
+          v[QQ * L + bitrev(BB, LOG2L)].y = scr_r[QQ * L * 33 + BB];
+        });
+      });
+      __syncwarp();
+
+      // pass 2: Q DFTs of length L over b  ->  v[q*L + kB] = Z[(j + L q) + 32 kB]
+      static_for<0, Q>([&](auto q_) {
+        constexpr int QQ = decltype(q_)::value;
+        fft_dit<L, QQ * L>(v);
+      });
+
+      // real-input split + power:  X[k] = E - T,  X[M-k] = conj(E + T)
+      float* prow = sP + fi * SP;
+      static_for<0, Q>([&](auto q_) {
+        constexpr int QQ = decltype(q_)::value;
+        static_for<0, L / 2>([&](auto s_) {
+          constexpr int S = decltype(s_)::value;
+          constexpr int GEN = (Q - 1 - QQ) * L + (L - 1 - S);
+          constexpr int ALT = QQ == 0 ? ((L - S) % L) : (Q - QQ) * L + (L - 1 - S);
+          float2 snd = (j == 0) ? v[ALT] : v[GEN];
+          float rx = __shfl_sync(0xffffffffu, snd.x, partner);
+          float ry = __shfl_sync(0xffffffffu, snd.y, partner);
+          float2 A = v[QQ * L + S];
+          float2 E = make_float2(A.x + rx, A.y - ry);
+          float2 O = make_float2(A.x - rx, A.y + ry);
+          const int k = j + L * QQ + 32 * S;
+          float2 w = sTwp[k];
+          float2 wO = cmul(w, O);
+          float x1r = E.x + wO.y, x1i = E.y - wO.x;  // E - T, T = i*wO = (-wO.y, wO.x)
+          float x2r = E.x - wO.y, x2i = E.y + wO.x;  // E + T
+          prow[k] = __fmaf_rn(x1r, x1r, x1i * x1i);
+          prow[M - k] = __fmaf_rn(x2r, x2r, x2i * x2i);
+        });
+      });
+      if (j == 0) {
+        float2 A = v[L / 2];
+        prow[M / 2] = 4.0f * __fmaf_rn(A.x, A.x, A.y * A.y);
+      }
+    }
+    __syncthreads();
+
+    // ---- filterbank + log phase: lane = frame, warps split the filters ----------
+    if (wf0 < wf1) {
+      const int b = sMetaB[lane], t = sMetaT[lane];
+      const bool valid = b >= 0;
+      const float* prow = sP + lane * SP;
+      float* erow = a.E + (valid ? (long long)b * a.e_stride_b + t : 0);
+      float rprev = 0.f, vmax = -INFINITY;
+      bool bad = false;
+      for (int s = wf0; s <= wf1; ++s) {
+        const int k0 = __ldg(a.seg + s), k1 = __ldg(a.seg + s + 1);
+        float r = 0.f, f = 0.f;
+        int k = k0;
+#pragma unroll 4
+        for (; k < k1; ++k) {
+          float p = prow[k];
+          float2 w = sFbw[k];
+          r = __fmaf_rn(w.x, p, r);
+          f = __fmaf_rn(w.y, p, f);
+        }
+        if (s > wf0) {
+          float e = rprev + f;
+          float val = a.log_type == 0 ? 10.0f * log10f(fmaxf(a.amin, e)) : logf(e == 0.f ? a.eps : e);
+          if (valid) erow[(long long)(s - 1) * a.e_stride_f] = val;
+          vmax = fmaxf(vmax, val);
+          bad |= !(fabsf(val) <= 3.0e38f);
+        }
+        rprev = r;
+      }
+      if (valid) {
+        if (a.utt_max) {
+          unsigned peers = __match_any_sync(__activemask(), b);
+          int enc = __reduce_max_sync(peers, enc_ordered(vmax));
+          if ((int)(__ffs(peers) - 1) == lane) atomicMax(a.utt_max + b, enc);
+        }
+        if (bad) a.status[b] = 5;
+      }
+    }
+    // the __syncthreads at the top of the next tile protects sP and the meta arrays
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2: dB reference / floor + DCT-II + deltas + layout
+// ---------------------------------------------------------------------------
+constexpr int CEP_TS = 128;       // frames per tile held in smem (threads per CTA)
+constexpr int CEP_KC = 20;        // DCT coefficients accumulated per pass
+constexpr int CEP_MAXW = 9;
+
+struct CepArgs {
+  const float* E;         // [B][n_filt][e_stride_f]
+  long long e_stride_b;
+  int e_stride_f;
+  const int32_t* nf_eff;  // [B]
+  const int32_t* utt_max; // ordered-int encoded (dB only)
+  int n_filt;
+  int log_type, ref_type;
+  float top_db;           // < 0: none
+  int n_ceps;             // 0: identity
+  int ncp;                // padded n_ceps (multiple of CEP_KC)
+  const float* dct_t;     // [n_filt][ncp]  (transposed DCT matrix, zero padded)
+  int n_delta, width;
+  float taps[2][CEP_MAXW];
+  float* out;
+  long long out_stride_b;
+  int out_stride_c, out_stride_t;  // CT: (t_alloc, 1); TC: (1, c_out)
+  int tile_out;           // output frames per tile when T > CEP_TS
+};
+
+__global__ void __launch_bounds__(CEP_TS) k_cepstra(const CepArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int b = blockIdx.y;
+  const int T = a.nf_eff[b];
+  if (T == 0) return;
+  int o0, o1;
+  if (T <= CEP_TS) {
+    if (blockIdx.x > 0) return;
+    o0 = 0;
+    o1 = T;
+  } else {
+    o0 = blockIdx.x * a.tile_out;
+    if (o0 >= T) return;
+    o1 = min(T, o0 + a.tile_out);
+  }
+  const int h = a.width >> 1;
+  int lo = o0, hi = o1;
+  if (a.n_delta > 0) {
+    int c0 = min(max(o0, h), T - 1 - h), c1 = min(max(o1 - 1, h), T - 1 - h);
+    lo = min(lo, c0 - h);
+    hi = max(hi, c1 + h + 1);
+  }
+  const int nload = hi - lo;  // <= CEP_TS by construction
+  const int tid = threadIdx.x;
+  const int C = a.n_ceps > 0 ? a.n_ceps : a.n_filt;
+
+  float* sE = smem;                                   // [n_filt][CEP_TS]
+  float* sD = sE + a.n_filt * CEP_TS;                 // [n_filt][ncp]
+  float* sC = a.n_ceps > 0 ? sD + a.n_filt * a.ncp : sE;  // [C][CEP_TS]
+
+  // reference / floor (librosa.power_to_db):  ls = E - ref ; ls = max(ls, max(ls) - top_db)
+  float ref = 0.f, floorv = -INFINITY;
+  if (a.log_type == 0) {
+    float m = dec_ordered(a.utt_max[b]);
+    if (a.ref_type == 1) ref = m;
+    if (a.top_db >= 0.f) floorv = (m - ref) - a.top_db;
+  }
+  const float* Eb = a.E + (long long)b * a.e_stride_b + lo;
+  if (tid < nload) {
+    for (int m = 0; m < a.n_filt; ++m) {
+      float e = __ldg(Eb + (long long)m * a.e_stride_f + tid);
+      sE[m * CEP_TS + tid] = fmaxf(e - ref, floorv);
+    }
+  } else {
+    for (int m = 0; m < a.n_filt; ++m) sE[m * CEP_TS + tid] = 0.f;
+  }
+  if (a.n_ceps > 0) {
+    const int nd = a.n_filt * a.ncp;
+    for (int i = tid * 4; i < nd; i += CEP_TS * 4)
+      *reinterpret_cast<float4*>(sD + i) = __ldg(reinterpret_cast<const float4*>(a.dct_t + i));
+  }
+  __syncthreads();
+
+  if (a.n_ceps > 0) {
+    for (int c0 = 0; c0 < a.n_ceps; c0 += CEP_KC) {
+      float acc[CEP_KC];
+#pragma unroll
+      for (int i = 0; i < CEP_KC; ++i) acc[i] = 0.f;
+      for (int m = 0; m < a.n_filt; ++m) {
+        const float e = sE[m * CEP_TS + tid];
+        const float4* d4 = reinterpret_cast<const float4*>(sD + m * a.ncp + c0);
+#pragma unroll
+        for (int i = 0; i < CEP_KC / 4; ++i) {
+          float4 d = d4[i];
+          acc[4 * i + 0] = __fmaf_rn(d.x, e, acc[4 * i + 0]);
+          acc[4 * i + 1] = __fmaf_rn(d.y, e, acc[4 * i + 1]);
+          acc[4 * i + 2] = __fmaf_rn(d.z, e, acc[4 * i + 2]);
+          acc[4 * i + 3] = __fmaf_rn(d.w, e, acc[4 * i + 3]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < CEP_KC; ++i)
+        if (c0 + i < a.n_ceps) sC[(c0 + i) * CEP_TS + tid] = acc[i];
+    }
+    __syncthreads();
+  }
+
+  const int t = lo + tid;
+  if (t >= o0 && t < o1) {
+    float* ob = a.out + (long long)b * a.out_stride_b + (long long)t * a.out_stride_t;
+    const int te = min(max(t, h), T - 1 - h) - lo;  // stencil centre (edges replicate the interior fit)
+    for (int k = 0; k < C; ++k) {
+      const float* row = sC + k * CEP_TS;
+      ob[(long long)k * a.out_stride_c] = row[tid];
+      if (a.n_delta > 0) {
+        float d1 = 0.f, d2 = 0.f;
+        for (int i = 0; i < a.width; ++i) {
+          float x = row[te - h + i];
+          d1 = __fmaf_rn(a.taps[0][i], x, d1);
+          d2 = __fmaf_rn(a.taps[1][i], x, d2);
+        }
+        ob[(long long)(C + k) * a.out_stride_c] = d1;
+        if (a.n_delta > 1) ob[(long long)(2 * C + k) * a.out_stride_c] = d2;
+      }
+    }
+  }
+}
+
+// log-mel without DCT/deltas in CT layout: in-place reference subtraction + floor
+struct FinArgs {
+  float* out;
+  long long stride_b;
+  int stride_f;
+  const int32_t* nf_eff;
+  const int32_t* utt_max;
+  int n_filt, ref_type;
+  float top_db;
+};
+__global__ void __launch_bounds__(256) k_db_finalize(const FinArgs a) {
+  const int b = blockIdx.y;
+  const int T = a.nf_eff[b];
+  if (T == 0) return;
+  const float m = dec_ordered(a.utt_max[b]);
+  const float ref = a.ref_type == 1 ? m : 0.f;
+  const float floorv = a.top_db >= 0.f ? (m - ref) - a.top_db : -INFINITY;
+  float* ob = a.out + (long long)b * a.stride_b;
+  const int total = a.n_filt * T;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int f = i / T, t = i - f * T;
+    float* p = ob + (long long)f * a.stride_f + t;
+    *p = fmaxf(*p - ref, floorv);
+  }
+}
+
+// mean over frames of feat[b][c][0..T_b): one warp per (b, c)
+__global__ void __launch_bounds__(128) k_time_mean(const float* feat, long long stride_b, int stride_c,
+                                                   const int32_t* nf_eff, int C, float* out,
+                                                   long long out_stride_b) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int T = nf_eff[b];
+  if (c >= C || T == 0) return;
+  const float* row = feat + (long long)b * stride_b + (long long)c * stride_c;
+  float s = 0.f;
+  for (int t = lane; t < T; t += 32) s += row[t];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[(long long)b * out_stride_b + c] = s / (float)T;
+}
+
+// standalone delta: librosa.feature.delta(x, width, order, mode='interp') on [B][C][t_stride]
+struct DeltaArgs {
+  const float* x;
+  float* out;
+  const int32_t* n_frames;
+  int C, t_stride, width;
+  float taps[CEP_MAXW];
+};
+__global__ void __launch_bounds__(256) k_delta(const DeltaArgs a) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int T = a.n_frames[b];
+  const int h = a.width >> 1;
+  if (T < a.width) return;
+  const long long base = ((long long)b * a.C + c) * a.t_stride;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    int te = min(max(t, h), T - 1 - h);
+    float d = 0.f;
+    for (int i = 0; i < a.width; ++i) d = __fmaf_rn(a.taps[i], __ldg(a.x + base + te - h + i), d);
+    a.out[base + t] = d;
+  }
+}
+
+// dense FP32 FMA peak: 8 independent chains per thread, 2 flops per FFMA
+__global__ void __launch_bounds__(256) k_fma_peak(float* sink, int iters) {
+  float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
+  float x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+  const float a = 0.999f, c = 1e-4f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = __fmaf_rn(x0, a, c); x1 = __fmaf_rn(x1, a, c); x2 = __fmaf_rn(x2, a, c); x3 = __fmaf_rn(x3, a, c);
+      x4 = __fmaf_rn(x4, a, c); x5 = __fmaf_rn(x5, a, c); x6 = __fmaf_rn(x6, a, c); x7 = __fmaf_rn(x7, a, c);
+    }
+  }
+  float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 123.456f) sink[0] = s;
+}
+
+}  // namespace aad

@@ -1,0 +1,219 @@
+"""Drop-in replacements for the reference's feature extractors and dispatcher.
+
+Same names, arguments, return shapes/dtypes and error convention as
+  extract_mel_spectrogram  ASV_dl_func.py:522-538  -> (n_mels, T) float32
+  extract_mfcc             ASV_dl_func.py:404-420  -> (n_mfcc, T) float32
+  extract_lfcc             ASV_dl_func.py:423-439  -> (T, n_ceps) float64
+  extract_features         ASV_dl_func.py:1031-1049
+but the arithmetic runs in the sm_100a kernels of libaad_b200.so.  The per-file
+functions are thin B=1 wrappers over the batched op; `extract_features` recognises
+them in the extractor map and runs ONE batched GPU call per feature instead of a
+joblib process pool (a CUDA context per loky worker is exactly what the GPU path must
+avoid).  Any other callable in the map is called per row, as the reference does.
+
+On any per-item failure the reference prints "[BŁĄD ...]" and returns None; so do we.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import audio_io
+from .frontend import Frontend, FrontendParams
+
+_plans: Dict[tuple, Frontend] = {}
+
+
+def get_frontend(params: FrontendParams, device=None) -> Frontend:
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (params.key(), str(dev))
+    fe = _plans.get(key)
+    if fe is None:
+        fe = _plans[key] = Frontend(params, dev)
+    return fe
+
+
+def augment_audio(data, sr, mode="change pitch", factor=None):
+    """ASV_dl_func.py:78-93.  'noise' is reproduced; 'change pitch' needs
+    librosa.effects.pitch_shift (resampling + phase vocoder), which is outside the
+    front-end: it raises, and the caller's error convention turns that into None."""
+    if mode == "change pitch":
+        raise NotImplementedError("pitch-shift augmentation is outside the spectral front-end")
+    if mode == "noise":
+        if factor is None:
+            factor = 1.022
+        noise = np.random.randn(len(data))
+        return (data + factor * noise).astype(data.dtype), sr
+    return data, sr
+
+
+def _prepare_clip(filepath, chunk_start, chunk_end, sr, augment):
+    y, sr = audio_io.load(filepath, sr=sr)
+    if chunk_start is not None and chunk_end is not None and not (
+            isinstance(chunk_start, float) and math.isnan(chunk_start)):
+        start_sample = int(chunk_start * sr)
+        end_sample = min(int(chunk_end * sr), len(y))
+        y = y[start_sample:end_sample]
+    if augment is not None and not (isinstance(augment, float) and math.isnan(augment)):
+        y, sr = augment_audio(y, sr, mode=augment)
+    return np.ascontiguousarray(y, dtype=np.float32), sr
+
+
+def _run_batch(params: FrontendParams, clips: Sequence[np.ndarray]):
+    """Pad clips to one [B, Lmax] batch, run the plan, return per-clip arrays (None on item error)."""
+    fe = get_frontend(params)
+    B = len(clips)
+    lens = np.array([len(c) for c in clips], dtype=np.int32)
+    Lmax = max(int(lens.max()), 1)
+    Lmax = (Lmax + 3) // 4 * 4          # keeps rows 16-byte aligned for the vector loads
+    host = torch.zeros((B, Lmax), dtype=torch.float32, pin_memory=True)
+    hv = host.numpy()
+    for i, c in enumerate(clips):
+        hv[i, :len(c)] = c
+    wav = host.to(fe.device, non_blocking=True)
+    feats, n_frames, status = fe(wav, torch.from_numpy(lens).to(fe.device))
+    feats, n_frames, status = feats.cpu().numpy(), n_frames.cpu().numpy(), status.cpu().numpy()
+    out: List[Optional[np.ndarray]] = []
+    for i in range(B):
+        if status[i] != 0:
+            out.append(None)
+        elif params.time_mean:
+            out.append(feats[i].copy())
+        elif params.layout == L.LAYOUT_CT:
+            out.append(feats[i, :, :n_frames[i]].copy())
+        else:
+            out.append(feats[i, :n_frames[i], :].copy())
+    return out, status
+
+
+# --------------------------------------------------------------------------- params per call
+def _mel_params(sr, n_mels, fmax, mean):
+    return FrontendParams.logmel(sr, n_mels=n_mels, fmax=fmax or sr / 2, time_mean=bool(mean))
+
+
+def _mfcc_params(sr, n_mfcc, mean):
+    return FrontendParams.mfcc(sr, n_mfcc=n_mfcc, time_mean=bool(mean))
+
+
+def _lfcc_params(sr, n_ceps):
+    return FrontendParams.lfcc(sr, n_ceps=n_ceps)
+
+
+def _lfcc_post(x, mean):
+    x = x.astype(np.float64)                       # spafe returns float64 (T, n_ceps)
+    return np.mean(x, axis=1) if mean else x       # ASV_dl_func.py:436 averages axis=1
+
+
+# --------------------------------------------------------------------------- per-file drop-ins
+def extract_mel_spectrogram(filepath, chunk_start=None, chunk_end=None, sr=None, n_mels=64, fmax=None,
+                            mean=False, augment=None):
+    try:
+        y, sr = _prepare_clip(filepath, chunk_start, chunk_end, sr, augment)
+        out, status = _run_batch(_mel_params(sr, n_mels, fmax, mean), [y])
+        if out[0] is None:
+            raise ValueError(L.ITEM_STATUS_NAMES.get(int(status[0]), "item failed"))
+        return out[0]
+    except Exception as e:
+        print(f"[BŁĄD MEL] {filepath if isinstance(filepath, str) else '<array>'}: {e}")
+        return None
+
+
+def extract_mfcc(filepath, chunk_start=None, chunk_end=None, sr=None, n_mfcc=13, mean=False, augment=None):
+    try:
+        y, sr = _prepare_clip(filepath, chunk_start, chunk_end, sr, augment)
+        out, status = _run_batch(_mfcc_params(sr, n_mfcc, mean), [y])
+        if out[0] is None:
+            raise ValueError(L.ITEM_STATUS_NAMES.get(int(status[0]), "item failed"))
+        return out[0]
+    except Exception as e:
+        print(f"[BŁĄD MFCC] {filepath if isinstance(filepath, str) else '<array>'}: {e}")
+        return None
+
+
+def extract_lfcc(filepath, chunk_start=None, chunk_end=None, n_ceps=13, mean=False, augment=None):
+    try:
+        y, sr = _prepare_clip(filepath, chunk_start, chunk_end, None, augment)
+        out, status = _run_batch(_lfcc_params(sr, n_ceps), [y])
+        if out[0] is None:
+            raise ValueError(L.ITEM_STATUS_NAMES.get(int(status[0]), "item failed"))
+        return _lfcc_post(out[0], mean)
+    except Exception as e:
+        print(f"[BŁĄD LFCC] {filepath if isinstance(filepath, str) else '<array>'}: {e}")
+        return None
+
+
+# how extract_features batches each recognised extractor: (params builder, post-processing, tag)
+_BATCHED = {
+    extract_mel_spectrogram: ("MEL", lambda sr, mean: _mel_params(sr, 64, None, mean), lambda x, mean: x),
+    extract_mfcc: ("MFCC", lambda sr, mean: _mfcc_params(sr, 13, mean), lambda x, mean: x),
+    extract_lfcc: ("LFCC", lambda sr, mean: _lfcc_params(sr, 13), _lfcc_post),
+}
+
+
+def _row_get(row, key, default=None):
+    try:
+        v = row.get(key, default)
+    except AttributeError:
+        v = row[key] if key in row else default
+    if isinstance(v, float) and math.isnan(v):
+        return default
+    return v
+
+
+def extract_features(final_df, feature_extractors_map: Dict[str, Callable], col_name="filepath",
+                     mean=False, aug_col="augmentationType", max_batch_samples: int = 1 << 28):
+    """Reference dispatcher (ASV_dl_func.py:1031-1049): adds one object column per map key.
+
+    Recognised extractors (the three above) run as batched GPU calls; every file is
+    decoded once per feature and sliced into its chunks on the host."""
+    rows = [row for _, row in final_df.iterrows()]
+    for name, func in feature_extractors_map.items():
+        print(f"   - Ekstrahuję: {name}")
+        if func not in _BATCHED:
+            final_df[name] = [
+                func(_row_get(r, col_name), chunk_start=_row_get(r, "chunk_start"),
+                     chunk_end=_row_get(r, "chunk_end"), mean=mean, augment=_row_get(r, aug_col))
+                for r in rows]
+            continue
+        tag, mk_params, post = _BATCHED[func]
+        results: List[Optional[np.ndarray]] = [None] * len(rows)
+        decoded: Dict[object, tuple] = {}
+        by_sr: Dict[int, List[tuple]] = {}
+        for i, r in enumerate(rows):
+            src = _row_get(r, col_name)
+            try:
+                key = src if isinstance(src, str) else id(src)
+                if key not in decoded:
+                    decoded[key] = audio_io.load(src)
+                y, sr = _prepare_clip(decoded[key], _row_get(r, "chunk_start"), _row_get(r, "chunk_end"),
+                                      None, _row_get(r, aug_col))
+                by_sr.setdefault(sr, []).append((i, y))
+            except Exception as e:
+                print(f"[BŁĄD {tag}] {src if isinstance(src, str) else '<array>'}: {e}")
+        for sr, items in by_sr.items():
+            params = mk_params(sr, mean)
+            start = 0
+            while start < len(items):        # bound the padded batch (samples) per GPU call
+                end, lmax = start, 0
+                while end < len(items):
+                    lm = max(lmax, len(items[end][1]))
+                    if end > start and lm * (end - start + 1) > max_batch_samples:
+                        break
+                    lmax, end = lm, end + 1
+                chunk = items[start:end]
+                try:
+                    outs, status = _run_batch(params, [y for _, y in chunk])
+                    for (i, _), o, st in zip(chunk, outs, status):
+                        if o is None:
+                            print(f"[BŁĄD {tag}] row {i}: {L.ITEM_STATUS_NAMES.get(int(st), 'item failed')}")
+                        else:
+                            results[i] = post(o, mean)
+                except Exception as e:
+                    print(f"[BŁĄD {tag}] batch {start}:{end}: {e}")
+                start = end
+        final_df[name] = results
+    return final_df

@@ -1,0 +1,288 @@
+"""Batched spectral front-end: PyTorch tensors in/out over the C ABI (include/aad.h).
+
+`FrontendParams` mirrors `aad_params`; the three constructors reproduce the
+parameters the reference's extractors pass to librosa / spafe:
+
+  FrontendParams.logmel(sr, n_mels=64)  extract_mel_spectrogram  ASV_dl_func.py:522-538
+  FrontendParams.mfcc(sr, n_mfcc=13)    extract_mfcc             ASV_dl_func.py:404-420
+  FrontendParams.lfcc(sr, n_ceps=13)    extract_lfcc             ASV_dl_func.py:423-439
+
+`Frontend` owns one plan (device tables) and runs batches on the caller's current
+CUDA stream.  torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+@dataclass
+class FrontendParams:
+    kind: int = L.KIND_LOGMEL
+    sample_rate: int = 16000
+    n_fft: int = 2048
+    win_length: int = 2048
+    hop_length: int = 512
+    window: int = L.WIN_HANN_PERIODIC
+    center: bool = True
+    quantize_i16: bool = False
+    pre_emph: float = 0.0
+    n_filt: int = 64
+    fb_type: int = L.FB_MEL_SLANEY
+    fmin: float = 0.0
+    fmax: float = 0.0            # <= 0: sr / 2
+    power_scale: float = 1.0
+    log_type: int = L.LOG_DB10
+    ref_type: int = L.REF_UTT_MAX
+    amin: float = 1e-10
+    top_db: float = 80.0         # < 0 disables
+    n_ceps: int = 0
+    n_delta: int = 0
+    delta_width: int = 9
+    layout: int = L.LAYOUT_CT
+    time_mean: bool = False
+    custom_fb: Optional[np.ndarray] = None   # (n_filt, n_fft//2+1) float32, FB_CUSTOM only
+
+    # ---- reference presets ---------------------------------------------------
+    @classmethod
+    def logmel(cls, sample_rate, n_mels=64, fmax=None, n_fft=2048, hop_length=512, **kw):
+        """librosa.feature.melspectrogram(n_mels, fmax=fmax or sr/2) + power_to_db(ref=np.max)."""
+        return cls(kind=L.KIND_LOGMEL, sample_rate=int(sample_rate), n_fft=n_fft, win_length=n_fft,
+                   hop_length=hop_length, n_filt=n_mels, fmax=float(fmax or 0.0),
+                   ref_type=L.REF_UTT_MAX, n_ceps=0, **kw)
+
+    @classmethod
+    def mfcc(cls, sample_rate, n_mfcc=13, n_mels=128, n_fft=2048, hop_length=512, **kw):
+        """librosa.feature.mfcc(n_mfcc): 128 mels, power_to_db(ref=1.0, top_db=80), DCT-II ortho."""
+        return cls(kind=L.KIND_MFCC, sample_rate=int(sample_rate), n_fft=n_fft, win_length=n_fft,
+                   hop_length=hop_length, n_filt=n_mels, ref_type=L.REF_ONE, n_ceps=n_mfcc, **kw)
+
+    @classmethod
+    def lfcc(cls, sample_rate, n_ceps=13, nfilts=24, nfft=512, win_len=0.025, win_hop=0.01,
+             pre_emph=0.97, quantize_i16=True, layout=L.LAYOUT_TC, fb_type=L.FB_LINEAR_INTBIN, **kw):
+        """(y*32767).astype(int16) + spafe lfcc(num_ceps, nfilts=24, nfft=512, 25/10 ms hamming)."""
+        sr = int(sample_rate)
+        return cls(kind=L.KIND_LFCC, sample_rate=sr, n_fft=nfft, win_length=int(win_len * sr),
+                   hop_length=int(win_hop * sr), window=L.WIN_HAMMING_SYMMETRIC, center=False,
+                   quantize_i16=quantize_i16, pre_emph=pre_emph, n_filt=nfilts, fb_type=fb_type,
+                   power_scale=1.0 / nfft, log_type=L.LOG_LN, ref_type=L.REF_ONE, top_db=-1.0,
+                   n_ceps=n_ceps, layout=layout, **kw)
+
+    def replace(self, **kw) -> "FrontendParams":
+        return dataclasses.replace(self, **kw)
+
+    def key(self):
+        d = dataclasses.asdict(self)
+        fb = d.pop("custom_fb")
+        return tuple(sorted(d.items())) + ((None if fb is None else np.asarray(fb).tobytes()),)
+
+    def to_c(self):
+        p = L.AadParams()
+        p.struct_size = C.sizeof(L.AadParams)
+        for f in ("kind", "sample_rate", "n_fft", "win_length", "hop_length", "window", "n_filt",
+                  "fb_type", "log_type", "ref_type", "n_ceps", "n_delta", "delta_width", "layout"):
+            setattr(p, f, int(getattr(self, f)))
+        p.center = int(bool(self.center))
+        p.quantize_i16 = int(bool(self.quantize_i16))
+        p.time_mean = int(bool(self.time_mean))
+        for f in ("pre_emph", "fmin", "fmax", "power_scale", "amin", "top_db"):
+            setattr(p, f, float(getattr(self, f)))
+        keep = None
+        if self.custom_fb is not None:
+            keep = np.ascontiguousarray(self.custom_fb, dtype=np.float32)
+            p.custom_fb = keep.ctypes.data_as(C.POINTER(C.c_float))
+        return p, keep
+
+    # ---- geometry (host mirror of the kernel's frame arithmetic) -------------
+    def n_frames(self, length: int) -> int:
+        if length <= 0:
+            return 0
+        if self.center:
+            return 1 + length // self.hop_length
+        return (length - self.win_length) // self.hop_length + 1 if length >= self.win_length else 0
+
+    @property
+    def c_out(self) -> int:
+        return (self.n_ceps if self.n_ceps > 0 else self.n_filt) * (1 + self.n_delta)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Frontend:
+    """One plan on one GPU.  Thread-compatible: use one instance per host thread / stream."""
+
+    def __init__(self, params: FrontendParams, device=None):
+        if not torch.cuda.is_available():
+            raise L.AadError("Frontend needs a CUDA device; there is no CPU fallback")
+        self.lib = L.load()
+        self.params = params
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise L.AadError("Frontend runs on CUDA devices only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        cp, keep = params.to_c()
+        h = C.c_void_p()
+        L.check(self.lib.aad_plan_create(C.byref(cp), self.device.index, C.byref(h)), "aad_plan_create")
+        self._h = h
+        self._ws = None
+        self.launches_per_call = int(self.lib.aad_plan_launches(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.aad_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- introspection --------------------------------------------------------
+    def table(self, which: int) -> np.ndarray:
+        n = int(self.lib.aad_plan_table(self._h, which, None, 0))
+        if n < 0:
+            L.check(n, "aad_plan_table")
+        out = np.empty(n, dtype=np.float32)
+        self.lib.aad_plan_table(self._h, which, out.ctypes.data_as(C.c_void_p), n)
+        p = self.params
+        if which == L.TABLE_FILTERBANK:
+            return out.reshape(p.n_filt, p.n_fft // 2 + 1)
+        if which == L.TABLE_DCT:
+            return out.reshape(p.n_ceps, p.n_filt)
+        if which == L.TABLE_DELTA_TAPS:
+            return out.reshape(2, -1)
+        return out
+
+    def query(self, B: int, max_len: int) -> Tuple[int, int, int]:
+        t, c, ws = C.c_int32(), C.c_int32(), C.c_size_t()
+        L.check(self.lib.aad_query(self._h, B, max_len, C.byref(t), C.byref(c), C.byref(ws)), "aad_query")
+        return t.value, c.value, ws.value
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ---- the batched op ----------------------------------------------------------
+    def __call__(self, wav: torch.Tensor, lengths: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None):
+        """wav [B, Lmax] float32|int16 on this device, lengths [B] int32 (default: all Lmax).
+
+        Returns (features, n_frames, status):
+          features  CT: [B, C, Tmax]   TC: [B, Tmax, C]   time_mean: [B, C]   float32
+          n_frames  [B] int32, status [B] int32 (0 = ok; rows with status != 0 are zeros)
+        """
+        if wav.dim() != 2 or not wav.is_cuda or wav.device != self.device:
+            raise L.AadError(f"wav must be a 2-D tensor on {self.device}")
+        if wav.dtype == torch.float32:
+            dt = L.F32
+        elif wav.dtype == torch.int16:
+            dt = L.I16
+        else:
+            raise L.AadError("wav must be float32 or int16")
+        if wav.stride(1) != 1:
+            wav = wav.contiguous()
+        B, Lmax = wav.shape
+        if lengths is None:
+            lengths = torch.full((B,), Lmax, dtype=torch.int32, device=self.device)
+        elif lengths.dtype != torch.int32 or lengths.device != self.device or not lengths.is_contiguous():
+            lengths = lengths.to(device=self.device, dtype=torch.int32).contiguous()
+        t_max, c_out, ws_bytes = self.query(B, Lmax)
+        t_alloc = max(t_max, 1)
+        p = self.params
+        if out is None:
+            if p.time_mean:
+                shape = (B, c_out)
+            elif p.layout == L.LAYOUT_CT:
+                shape = (B, c_out, t_alloc)
+            else:
+                shape = (B, t_alloc, c_out)
+            out = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        n_frames = torch.empty(B, dtype=torch.int32, device=self.device)
+        status = torch.empty(B, dtype=torch.int32, device=self.device)
+        ws = self._workspace(ws_bytes)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = self.lib.aad_extract(self._h, _ptr(wav), dt, wav.stride(0), _ptr(lengths), B, Lmax,
+                                      _ptr(out), out.stride(0), t_alloc, _ptr(n_frames), _ptr(status),
+                                      _ptr(ws), ws.numel(), C.c_void_p(stream))
+        L.check(rc, "aad_extract")
+        return out, n_frames, status
+
+    # ---- host buffers in / out (pipelined H2D -> kernels -> D2H inside the library) ----
+    def extract_host(self, wav: np.ndarray, lengths: Optional[np.ndarray] = None,
+                     out: Optional[np.ndarray] = None, chunk_utts: int = 0):
+        """wav [B, Lmax] float32|int16 HOST array (numpy, or a pinned torch CPU tensor's .numpy())."""
+        if isinstance(wav, torch.Tensor):
+            wav = wav.numpy()
+        if wav.ndim != 2 or wav.strides[1] != wav.itemsize:
+            wav = np.ascontiguousarray(wav)
+        if wav.dtype == np.float32:
+            dt = L.F32
+        elif wav.dtype == np.int16:
+            dt = L.I16
+        else:
+            raise L.AadError("wav must be float32 or int16")
+        B, Lmax = wav.shape
+        if lengths is None:
+            lengths = np.full(B, Lmax, dtype=np.int32)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+        t_max, c_out, _ = self.query(B, Lmax)
+        t_alloc = max(t_max, 1)
+        p = self.params
+        if out is None:
+            if p.time_mean:
+                shape = (B, c_out)
+            elif p.layout == L.LAYOUT_CT:
+                shape = (B, c_out, t_alloc)
+            else:
+                shape = (B, t_alloc, c_out)
+            out = np.zeros(shape, dtype=np.float32)
+        elif isinstance(out, torch.Tensor):
+            out = out.numpy()
+        n_frames = np.empty(B, dtype=np.int32)
+        status = np.empty(B, dtype=np.int32)
+        rc = self.lib.aad_extract_host(
+            self._h, C.c_void_p(wav.ctypes.data), dt, wav.strides[0] // wav.itemsize,
+            C.c_void_p(lengths.ctypes.data), B, Lmax, C.c_void_p(out.ctypes.data),
+            out.strides[0] // 4, t_alloc, C.c_void_p(n_frames.ctypes.data),
+            C.c_void_p(status.ctypes.data), int(chunk_utts))
+        L.check(rc, "aad_extract_host")
+        return out, n_frames, status
+
+
+def delta(x: torch.Tensor, n_frames: Optional[torch.Tensor] = None, width: int = 9, order: int = 1):
+    """librosa.feature.delta(x, width, order, axis=-1, mode='interp') on [B, C, T] (CUDA, float32)."""
+    lib = L.load()
+    if x.dim() == 2:
+        return delta(x.unsqueeze(0), n_frames, width, order)[0]
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise L.AadError("delta needs a CUDA float32 tensor")
+    x = x.contiguous()
+    B, Cc, T = x.shape
+    if n_frames is None:
+        n_frames = torch.full((B,), T, dtype=torch.int32, device=x.device)
+    n_frames = n_frames.to(device=x.device, dtype=torch.int32).contiguous()
+    out = torch.zeros_like(x)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    with torch.cuda.device(x.device):
+        rc = lib.aad_delta(_ptr(x), _ptr(n_frames), B, Cc, T, width, order, _ptr(out), C.c_void_p(stream))
+    L.check(rc, "aad_delta")
+    return out
+
+
+def fp32_peak_tflops(device: int = 0, iters: int = 4096) -> float:
+    v = C.c_double()
+    L.check(L.load().aad_fp32_peak(device, iters, C.byref(v)), "aad_fp32_peak")
+    return v.value

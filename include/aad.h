@@ -1,0 +1,197 @@
+/*
+ * aad.h -- C ABI of the B200-native spectral front-end (libaad_b200.so).
+ *
+ * Drop-in boundary for the feature-extraction hot path of
+ * IzaP1k/AudioAnalysisDetector.  The reference has no FFI of its own (it is pure
+ * Python); each entry point below cites the reference interface it replaces.
+ * Signatures are plain C: pointers, sizes, a CUDA stream passed as void*.  All
+ * data pointers are DEVICE pointers unless the name says host.  The library
+ * never allocates in the hot calls (caller owns inputs, outputs, workspace and
+ * status), never synchronises the stream, and never throws across the ABI:
+ * every call returns 0 or a negative aad_error; per-utterance problems are
+ * reported in status[B] (the reference's "print and return None" convention,
+ * ASV_dl_func.py:418-420,437-439,536-538).
+ */
+#ifndef AAD_H_
+#define AAD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AAD_VERSION 100 /* 0.1.0 */
+
+typedef struct aad_plan aad_plan;
+
+/* ---- enums ------------------------------------------------------------- */
+enum aad_kind {        /* which reference extractor the plan mirrors */
+  AAD_KIND_LOGMEL = 0, /* extract_mel_spectrogram  ASV_dl_func.py:522-538 */
+  AAD_KIND_MFCC = 1,   /* extract_mfcc             ASV_dl_func.py:404-420 */
+  AAD_KIND_LFCC = 2    /* extract_lfcc             ASV_dl_func.py:423-439 */
+};
+enum aad_dtype { AAD_F32 = 0, AAD_I16 = 1 };
+enum aad_window {
+  AAD_WIN_HANN_PERIODIC = 0,    /* scipy get_window('hann', fftbins=True): librosa.stft */
+  AAD_WIN_HAMMING_SYMMETRIC = 1 /* np.hamming(win_length): spafe windowing */
+};
+enum aad_fb {
+  AAD_FB_MEL_SLANEY = 0,    /* librosa.filters.mel(htk=False, norm='slaney') */
+  AAD_FB_LINEAR_INTBIN = 1, /* spafe 0.3.x linear_filter_banks (integer FFT bins) */
+  AAD_FB_LINEAR_CONT = 2,   /* triangles on continuous bin frequencies */
+  AAD_FB_CUSTOM = 3         /* caller matrix, at most two adjacent filters per bin */
+};
+enum aad_log {
+  AAD_LOG_DB10 = 0, /* 10*log10(max(amin, S))            librosa.power_to_db */
+  AAD_LOG_LN = 1    /* ln(S == 0 ? eps : S)              spafe zero_handling + np.log */
+};
+enum aad_ref {
+  AAD_REF_ONE = 0,    /* power_to_db(S) inside librosa.feature.mfcc */
+  AAD_REF_UTT_MAX = 1 /* power_to_db(S, ref=np.max)  ASV_dl_func.py:534 */
+};
+enum aad_layout {
+  AAD_LAYOUT_CT = 0, /* out[b][c][t]  (librosa orientation; cnn_bilstm_hybrid.py:56 wants (B,F,T)) */
+  AAD_LAYOUT_TC = 1  /* out[b][t][c]  (spafe orientation; BiLSTM collate ASV_dl_func.py:1206-1227) */
+};
+
+enum aad_error {
+  AAD_OK = 0,
+  AAD_ERR_INVALID_ARG = -1,
+  AAD_ERR_UNSUPPORTED = -2, /* e.g. n_fft not in {256,512,1024,2048} */
+  AAD_ERR_CUDA = -3,
+  AAD_ERR_WORKSPACE = -4, /* workspace too small */
+  AAD_ERR_KIND = -5,      /* plan kind does not match the entry point */
+  AAD_ERR_FILTERBANK = -6 /* custom filterbank is not two-adjacent-filters-per-bin */
+};
+
+enum aad_item_status { /* status[b] */
+  AAD_ITEM_OK = 0,
+  AAD_ITEM_EMPTY = 1,               /* length <= 0 */
+  AAD_ITEM_TOO_SHORT_FOR_FRAME = 2, /* spafe framing: L < win_length */
+  AAD_ITEM_TOO_SHORT_FOR_DELTA = 3, /* librosa.feature.delta: T < width */
+  AAD_ITEM_OUT_TOO_SMALL = 4,       /* T > T_alloc of the output buffer */
+  AAD_ITEM_NONFINITE = 5            /* NaN/Inf reached the log-energies (librosa.util.valid_audio) */
+};
+
+/* ---- plan parameters (POD) ---------------------------------------------- */
+typedef struct aad_params {
+  int32_t struct_size; /* sizeof(aad_params), for ABI versioning */
+  int32_t kind;        /* aad_kind */
+  int32_t sample_rate;
+  int32_t n_fft;      /* 256 | 512 | 1024 | 2048 */
+  int32_t win_length; /* <= n_fft */
+  int32_t hop_length;
+  int32_t window; /* aad_window */
+  int32_t center; /* 1: librosa.stft(center=True, pad_mode='constant'): zero-pad n_fft/2
+                        both sides, T = 1 + L/hop, window centred in the n_fft buffer.
+                     0: spafe framing: no padding, T = (L-win)/hop + 1, window at the
+                        start of the buffer, zero-extended to n_fft. */
+  int32_t quantize_i16; /* float input only: y -> (int16)trunc(y*32767)  ASV_dl_func.py:434 */
+  float pre_emph;       /* 0 = off; spafe default 0.97, first sample unchanged */
+  int32_t n_filt;       /* n_mels / nfilts */
+  int32_t fb_type;      /* aad_fb */
+  float fmin;
+  float fmax;         /* <= 0: sample_rate / 2 */
+  float power_scale;  /* power spectrum multiplier folded into the filterbank (spafe: 1/nfft); 0 -> 1 */
+  int32_t log_type;   /* aad_log */
+  int32_t ref_type;   /* aad_ref (dB only) */
+  float amin;         /* 1e-10 */
+  float top_db;       /* 80; < 0 disables the floor */
+  int32_t n_ceps;     /* 0: no DCT (log-mel); else DCT-II ortho, first n_ceps (scipy.fftpack.dct) */
+  int32_t n_delta;    /* 0 | 1 | 2: append delta (and delta-delta) rows: librosa.feature.delta */
+  int32_t delta_width; /* odd, 3..9 (9 = librosa default) */
+  int32_t layout;      /* aad_layout */
+  int32_t time_mean;   /* 1: out[b][c] = mean over frames (the reference's mean=True, axis=1 of (C,T)) */
+  int32_t reserved0;
+  const float* custom_fb; /* HOST pointer, row-major n_filt x (n_fft/2+1); AAD_FB_CUSTOM only */
+} aad_params;
+
+/* Fill *p with the parameters of the named reference extractor:
+ *   AAD_KIND_LOGMEL: melspectrogram(n_fft 2048, hop 512, hann, center, n_mels 64, fmax sr/2)
+ *                    + power_to_db(ref=np.max)                    ASV_dl_func.py:533-534
+ *   AAD_KIND_MFCC:   librosa.feature.mfcc(n_mfcc 13; 128 mels)    ASV_dl_func.py:416
+ *   AAD_KIND_LFCC:   int16 quantise + spafe lfcc(num_ceps 13, 24 filters, nfft 512,
+ *                    25 ms / 10 ms hamming, pre-emphasis 0.97), TC layout  ASV_dl_func.py:434-435 */
+int aad_params_default(aad_params* p, int kind, int sample_rate);
+
+/* ---- plan life cycle ------------------------------------------------------
+ * Builds the device tables (window, twiddles, banded filterbank, DCT matrix,
+ * Savitzky-Golay taps) once.  Replaces the per-call table construction inside
+ * librosa.filters.mel / get_window / spafe linear_filter_banks. */
+int aad_plan_create(const aad_params* p, int device, aad_plan** out);
+int aad_plan_destroy(aad_plan* plan);
+
+/* Output geometry and workspace size for a batch of B utterances of at most
+ * max_len samples.  *t_max = frames of a max_len utterance; *c_out = rows per
+ * frame (n_filt or n_ceps, times 1 + n_delta). */
+int aad_query(const aad_plan* plan, int B, int64_t max_len, int32_t* t_max, int32_t* c_out,
+              size_t* workspace_bytes);
+
+/* ---- the hot call -----------------------------------------------------------
+ * Batched replacement for one pass of extract_features' inner loop
+ * (ASV_dl_func.py:1036-1045) over B in-memory utterances.
+ *   wav        [B][wav_stride] float32 or int16 (wav_dtype), row b valid for lengths[b] samples
+ *   lengths    [B] int32 (device)
+ *   out        CT: [B][c_out][t_alloc]; TC: [B][t_alloc][c_out]; time_mean: [B][c_out]
+ *              out_stride_b in elements (0 = dense)
+ *   n_frames   [B] int32 out: frames of utterance b (the reference's T)
+ *   status     [B] int32 out: aad_item_status; rows with non-zero status are left untouched
+ *   workspace  device scratch of at least aad_query's workspace_bytes
+ *   stream     cudaStream_t; work is enqueued, never synchronised
+ */
+int aad_extract(const aad_plan* plan, const void* wav, int wav_dtype, int64_t wav_stride,
+                const int32_t* lengths, int B, int64_t max_len, float* out, int64_t out_stride_b,
+                int32_t t_alloc, int32_t* n_frames, int32_t* status, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/* Kind-checked aliases of aad_extract (return AAD_ERR_KIND on mismatch). */
+int aad_logmel(const aad_plan* plan, const void* wav, int wav_dtype, int64_t wav_stride,
+               const int32_t* lengths, int B, int64_t max_len, float* out, int64_t out_stride_b,
+               int32_t t_alloc, int32_t* n_frames, int32_t* status, void* workspace,
+               size_t workspace_bytes, void* stream);
+int aad_mfcc(const aad_plan* plan, const void* wav, int wav_dtype, int64_t wav_stride,
+             const int32_t* lengths, int B, int64_t max_len, float* out, int64_t out_stride_b,
+             int32_t t_alloc, int32_t* n_frames, int32_t* status, void* workspace,
+             size_t workspace_bytes, void* stream);
+int aad_lfcc(const aad_plan* plan, const void* wav, int wav_dtype, int64_t wav_stride,
+             const int32_t* lengths, int B, int64_t max_len, float* out, int64_t out_stride_b,
+             int32_t t_alloc, int32_t* n_frames, int32_t* status, void* workspace,
+             size_t workspace_bytes, void* stream);
+
+/* Standalone delta stencil: librosa.feature.delta(x, width, order, axis=-1, mode='interp')
+ * on x[B][C][t_stride] with per-utterance n_frames (edges replicate at each utterance's
+ * own T).  Rows with n_frames[b] < width are left untouched. */
+int aad_delta(const float* x, const int32_t* n_frames, int B, int C, int32_t t_stride,
+              int width, int order, float* out, void* stream);
+
+/* Host-buffer convenience path (what the reference-facing Python drop-ins use for
+ * host arrays): pinned-or-pageable HOST wav/lengths in, HOST out/n_frames/status back,
+ * chunked H2D -> kernels -> D2H pipelined on internal streams.  Synchronous. */
+int aad_extract_host(aad_plan* plan, const void* wav_host, int wav_dtype, int64_t wav_stride,
+                     const int32_t* lengths_host, int B, int64_t max_len, float* out_host,
+                     int64_t out_stride_b, int32_t t_alloc, int32_t* n_frames_host,
+                     int32_t* status_host, int chunk_utts);
+
+/* ---- introspection (tests / parity) ---------------------------------------- */
+enum aad_table { AAD_TABLE_WINDOW = 0, AAD_TABLE_FILTERBANK = 1, AAD_TABLE_DCT = 2, AAD_TABLE_DELTA_TAPS = 3 };
+/* Copies a plan table to HOST memory as float32: WINDOW [n_fft] (unscaled, zero-extended),
+ * FILTERBANK dense [n_filt][n_fft/2+1] (power_scale folded in), DCT [n_ceps][n_filt],
+ * DELTA_TAPS [2][delta_width].  Returns the element count or a negative error. */
+int64_t aad_plan_table(const aad_plan* plan, int which, float* host_out, int64_t capacity);
+
+/* Number of kernel launches one aad_extract call enqueues for this plan. */
+int aad_plan_launches(const aad_plan* plan);
+
+/* Dense FP32 FMA micro-benchmark (roofline denominator; not in MEASURED_PEAKS.json):
+ * runs `iters` dependent-chain FFMA blocks on `device`, returns achieved TFLOP/s. */
+int aad_fp32_peak(int device, int iters, double* tflops_out);
+
+const char* aad_strerror(int err);
+int aad_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AAD_H_ */

@@ -1,0 +1,151 @@
+"""Oracle: numpy/scipy restatement of spafe 0.3.x `spafe.features.lfcc.lfcc`.
+
+TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  PARITY UNPINNED (spafe is
+not installed in this image; the reference has no fixtures).
+
+Reference call sites:
+  ASV_dl_func.py:434-435   y_int16 = (y * 32767).astype(np.int16)
+                           lfcc(sig=y_int16, fs=sr, num_ceps=n_ceps)
+  ASV_func.py:68-69 ; train_fun.py:84-85   (same)
+
+spafe 0.3.x chain restated (spafe/features/lfcc.py, spafe/utils/preprocessing.py,
+spafe/fbanks/linear_fbanks.py), all float64:
+  pre_emphasis (0.97, first sample kept) -> framing (win 25 ms / hop 10 ms, no
+  padding, tail dropped) -> np.hamming(frame_len) -> |np.fft.fft(frames, nfft)|
+  -> (1/nfft) * |X|^2 -> @ linear filterbank^T -> zero_handling (0 -> eps)
+  -> np.log -> scipy.fftpack.dct(type=2, norm='ortho', axis=1)[:, :num_ceps].
+
+Least-certain step: the filterbank construction.  `linear_filter_banks`
+restates the integer-FFT-bin triangles of spafe 0.3.x; the continuous-frequency
+construction found in other spafe versions is `linear_filter_banks_continuous`.
+Everything downstream takes the matrix as data, so parity of the CUDA path with
+this oracle holds for either (both are exercised in tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.fft
+
+EPS = np.finfo(float).eps
+
+
+def quantize_int16(y):
+    """ASV_dl_func.py:434 -- float32 multiply, then C-style truncation toward zero.
+
+    numpy's float32->int16 `astype` goes through a 32-bit integer and keeps the low
+    16 bits (wrap-around) for out-of-range values on x86; in-range values are
+    truncated toward zero.
+    """
+    y = np.asarray(y, dtype=np.float32)
+    scaled = y * np.float32(32767)
+    with np.errstate(invalid="ignore"):
+        return scaled.astype(np.int32).astype(np.int16)
+
+
+def pre_emphasis(sig, pre_emph_coeff=0.97):
+    """spafe.utils.preprocessing.pre_emphasis: [s0, s[1:] - c*s[:-1]] (float64)."""
+    sig = np.asarray(sig)
+    return np.append(sig[0], sig[1:] - pre_emph_coeff * sig[:-1])
+
+
+def frame_params(fs, win_len=0.025, win_hop=0.01):
+    return int(win_len * fs), int(win_hop * fs)
+
+
+def n_frames_uncentered(length, frame_length, frame_step):
+    if length < frame_length:
+        return 0
+    return (int(length) - frame_length) // frame_step + 1
+
+
+def framing(sig, fs=16000, win_len=0.025, win_hop=0.01):
+    """spafe.utils.preprocessing.framing via stride_trick: no padding, tail dropped."""
+    if win_len < win_hop:
+        raise ValueError("win_len must be >= win_hop")
+    frame_length, frame_step = frame_params(fs, win_len, win_hop)
+    sig = np.asarray(sig)
+    nrows = n_frames_uncentered(sig.size, frame_length, frame_step)
+    if nrows <= 0:
+        raise ValueError("signal shorter than one frame")
+    idx = np.arange(frame_length)[None, :] + frame_step * np.arange(nrows)[:, None]
+    return sig[idx], frame_length
+
+
+def linear_filter_banks(nfilts=24, nfft=512, fs=16000, low_freq=0, high_freq=None,
+                        scale="constant"):
+    """spafe 0.3.x linear_filter_banks: triangles on integer FFT bins, unit peak.
+
+    bins = floor((nfft + 1) * hz / fs) for nfilts + 2 equally spaced edge
+    frequencies; filter j rises over [b_j, b_{j+1}) and falls over [b_{j+1}, b_{j+2}).
+    """
+    high_freq = high_freq or fs / 2
+    low_freq = low_freq or 0
+    if low_freq < 0 or high_freq > fs / 2:
+        raise ValueError("bad frequency range")
+    linear_points = np.linspace(low_freq, high_freq, nfilts + 2)
+    bins = np.floor((nfft + 1) * linear_points / fs)
+    fbank = np.zeros([nfilts, nfft // 2 + 1])
+    c = 1.0 if scale in ("descendant", "constant") else 0.0
+    for j in range(nfilts):
+        b0, b1, b2 = bins[j], bins[j + 1], bins[j + 2]
+        if scale == "descendant":
+            c -= 1 / nfilts
+            c = c * (c > 0) + 0 * (c < 0)
+        elif scale == "ascendant":
+            c += 1 / nfilts
+            c = c * (c < 1) + 1 * (c > 1)
+        fbank[j, int(b0):int(b1)] = c * (np.arange(int(b0), int(b1)) - int(b0)) / (b1 - b0)
+        fbank[j, int(b1):int(b2)] = c * (int(b2) - np.arange(int(b1), int(b2))) / (b2 - b1)
+    return np.abs(fbank)
+
+
+def linear_filter_banks_continuous(nfilts=24, nfft=512, fs=16000, low_freq=0,
+                                   high_freq=None):
+    """Alternative construction (triangles on continuous bin frequencies)."""
+    high_freq = high_freq or fs / 2
+    low_freq = low_freq or 0
+    edges = np.linspace(low_freq, high_freq, nfilts + 2)
+    freqs = np.linspace(0, fs / 2, nfft // 2 + 1)
+    fbank = np.zeros((nfilts, nfft // 2 + 1))
+    for j in range(nfilts):
+        lo, ce, hi = edges[j], edges[j + 1], edges[j + 2]
+        left = (freqs >= lo) & (freqs <= ce)
+        fbank[j, left] = (freqs[left] - lo) / (ce - lo)
+        right = (freqs >= ce) & (freqs <= hi)
+        fbank[j, right] = (hi - freqs[right]) / (hi - ce)
+    return fbank
+
+
+def zero_handling(x):
+    return np.where(x == 0, EPS, x)
+
+
+def linear_spectrogram(sig, fs=16000, pre_emph=True, pre_emph_coeff=0.97,
+                       win_len=0.025, win_hop=0.01, nfilts=24, nfft=512,
+                       low_freq=0, high_freq=None, fbanks=None):
+    """spafe.features.lfcc.linear_spectrogram -> (T, nfilts) float64 energies."""
+    if fbanks is None:
+        fbanks = linear_filter_banks(nfilts, nfft, fs, low_freq, high_freq)
+    sig = np.asarray(sig)
+    if pre_emph:
+        sig = pre_emphasis(sig, pre_emph_coeff)
+    frames, frame_length = framing(sig, fs, win_len, win_hop)
+    windows = np.hamming(frame_length) * frames
+    mag = np.absolute(np.fft.fft(windows, nfft))[:, : nfft // 2 + 1]
+    power = (1.0 / nfft) * np.square(mag)
+    return np.dot(power, fbanks.T)
+
+
+def lfcc(sig, fs=16000, num_ceps=13, pre_emph=True, pre_emph_coeff=0.97,
+         win_len=0.025, win_hop=0.01, nfilts=24, nfft=512, low_freq=0,
+         high_freq=None, fbanks=None):
+    """spafe.features.lfcc.lfcc defaults (dct_type=2, no energy/lifter/normalise).
+
+    Returns float64 (T, num_ceps), T = (L - frame_len)//frame_step + 1.
+    """
+    if nfilts < num_ceps:
+        raise ValueError("nfilts must be >= num_ceps")
+    feats = linear_spectrogram(sig, fs, pre_emph, pre_emph_coeff, win_len, win_hop,
+                               nfilts, nfft, low_freq, high_freq, fbanks)
+    log_feats = np.log(zero_handling(feats))
+    return scipy.fft.dct(log_feats, type=2, axis=1, norm="ortho")[:, :num_ceps]
