@@ -65,6 +65,8 @@ SYMBOLS = {
                                    C.c_void_p, C.c_int]),
     "aad_plan_table": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "aad_plan_launches": (C.c_int, [C.c_void_p]),
+    "aad_plan_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "aad_plan_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "aad_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
 

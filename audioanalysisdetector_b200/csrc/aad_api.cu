@@ -41,6 +41,9 @@ struct aad_plan {
   int32_t* d_seg = nullptr;
   int32_t* d_warp_filt = nullptr;
   float* d_dct_t = nullptr;
+  // optional per-kernel timing (bench roofline): events recorded around each launch
+  bool profile = false;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   // host-path resources (lazy)
   struct HostBuf {
     cudaStream_t stream = nullptr;
@@ -330,6 +333,8 @@ int aad_plan_destroy(aad_plan* pl) {
   cudaFree(pl->d_seg);
   cudaFree(pl->d_warp_filt);
   cudaFree(pl->d_dct_t);
+  for (auto& e : pl->ev)
+    if (e) cudaEventDestroy(e);
   for (auto& h : pl->hb) {
     cudaFree(h.d_wav);
     cudaFree(h.d_out);
@@ -555,7 +560,10 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
   pa.t_alloc = p.time_mean ? w.t_ws : t_cap;
   pa.n_frames = n_frames; pa.status = status; pa.len_c = d_len; pa.nf_eff = d_nf;
   pa.frame_off = d_frame_off; pa.utt_max = d_max;
+  const bool prof = pl->profile;
+  if (prof) cudaEventRecord(pl->ev[0], stream);
   k_prepare<<<1, 1024, 0, stream>>>(pa);
+  if (prof) cudaEventRecord(pl->ev[1], stream);
 
   // K1
   StftArgs sa;
@@ -578,6 +586,7 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
   const long long max_tiles = ((long long)B * std::max(t_max, 1) + 31) / 32;
   const int grid1 = (int)std::min<long long>((long long)pl->sm_count * pl->ctas, std::max<long long>(max_tiles, 1));
   kern<<<grid1, pl->warps * 32, pl->k1_smem, stream>>>(sa);
+  if (prof) cudaEventRecord(pl->ev[2], stream);
 
   // K2
   if (pl->need_ws_E) {
@@ -600,6 +609,7 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
     const int gx = t_max <= CEP_TS ? 1 : (t_max + ca.tile_out - 1) / ca.tile_out;
     dim3 grid(gx, B);
     k_cepstra<<<grid, CEP_TS, cep_smem_bytes(pl), stream>>>(ca);
+    if (prof) cudaEventRecord(pl->ev[3], stream);
     if (p.time_mean) {
       dim3 gm((pl->c_out + 3) / 4, B);
       k_time_mean<<<gm, 128, 0, stream>>>(d_feat, ca.out_stride_b, w.t_ws, d_nf, pl->c_out, out, out_stride_b);
@@ -613,7 +623,9 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
       dim3 grid(gx, B);
       k_db_finalize<<<grid, 256, 0, stream>>>(fa);
     }
+    if (prof) cudaEventRecord(pl->ev[3], stream);
   }
+  if (prof) cudaEventRecord(pl->ev[4], stream);
   return cudaGetLastError() == cudaSuccess ? AAD_OK : AAD_ERR_CUDA;
 }
 
@@ -671,6 +683,25 @@ int64_t aad_plan_table(const aad_plan* pl, int which, float* host_out, int64_t c
     std::memcpy(host_out, src, (size_t)n * 4);
   }
   return n;
+}
+
+int aad_plan_set_profiling(aad_plan* pl, int enable) {
+  if (!pl) return AAD_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(pl->device));
+  if (enable)
+    for (auto& e : pl->ev)
+      if (!e) CUDA_TRY(cudaEventCreate(&e));
+  pl->profile = enable != 0;
+  return AAD_OK;
+}
+
+int aad_plan_kernel_times(const aad_plan* pl, float* ms_out) {
+  if (!pl || !ms_out || !pl->ev[0]) return AAD_ERR_INVALID_ARG;
+  for (int i = 0; i < 4; ++i) {
+    ms_out[i] = 0.f;
+    if (cudaEventElapsedTime(&ms_out[i], pl->ev[i], pl->ev[i + 1]) != cudaSuccess) return AAD_ERR_CUDA;
+  }
+  return AAD_OK;
 }
 
 int aad_fp32_peak(int device, int iters, double* tflops_out) {

@@ -148,6 +148,16 @@ class Frontend:
         except Exception:
             pass
 
+    # ---- per-kernel device timing (bench roofline) --------------------------------
+    def set_profiling(self, enable: bool):
+        L.check(self.lib.aad_plan_set_profiling(self._h, int(enable)), "aad_plan_set_profiling")
+
+    def kernel_times_ms(self):
+        """{prepare, stft_fb, epilogue, time_mean} of the last call; synchronise first."""
+        buf = (C.c_float * 4)()
+        L.check(self.lib.aad_plan_kernel_times(self._h, buf), "aad_plan_kernel_times")
+        return {"prepare": buf[0], "stft_fb": buf[1], "epilogue": buf[2], "time_mean": buf[3]}
+
     # ---- introspection --------------------------------------------------------
     def table(self, which: int) -> np.ndarray:
         n = int(self.lib.aad_plan_table(self._h, which, None, 0))

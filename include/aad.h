@@ -184,6 +184,13 @@ int64_t aad_plan_table(const aad_plan* plan, int which, float* host_out, int64_t
 /* Number of kernel launches one aad_extract call enqueues for this plan. */
 int aad_plan_launches(const aad_plan* plan);
 
+/* Per-kernel device timing for the roofline report.  When enabled, aad_extract records CUDA
+ * events on the caller's stream around each launch; after the caller has synchronised,
+ * aad_plan_kernel_times fills ms_out[4] = {prepare, stft_fb, cepstra|finalize, time_mean}
+ * for the most recent call.  Off by default (the timed bench loop runs without it). */
+int aad_plan_set_profiling(aad_plan* plan, int enable);
+int aad_plan_kernel_times(const aad_plan* plan, float* ms_out);
+
 /* Dense FP32 FMA micro-benchmark (roofline denominator; not in MEASURED_PEAKS.json):
  * runs `iters` dependent-chain FFMA blocks on `device`, returns achieved TFLOP/s. */
 int aad_fp32_peak(int device, int iters, double* tflops_out);

@@ -1,0 +1,98 @@
+"""CPU: the C-ABI library builds, loads, and exports every symbol include/aad.h declares.
+No compute calls (no GPU here); host-only entry points are exercised."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "aad.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(aad_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(built_lib):
+    from audioanalysisdetector_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(built_lib, n), f"{n} declared in aad.h but not exported"
+        assert n in _lib.SYMBOLS, f"{n} has no ctypes prototype in _lib.SYMBOLS"
+    assert sorted(_lib.SYMBOLS) == names
+
+
+def test_version_and_strerror(built_lib):
+    assert built_lib.aad_version() == 100
+    assert built_lib.aad_strerror(0) == b"ok"
+    assert b"workspace" in built_lib.aad_strerror(-4)
+
+
+def test_params_default_mirrors_reference_defaults(built_lib):
+    from audioanalysisdetector_b200 import _lib as L
+    p = L.AadParams()
+    assert built_lib.aad_params_default(C.byref(p), L.KIND_LOGMEL, 16000) == 0
+    assert p.struct_size == C.sizeof(L.AadParams)
+    assert (p.n_fft, p.hop_length, p.n_filt, p.center, p.ref_type, p.n_ceps) == (2048, 512, 64, 1, L.REF_UTT_MAX, 0)
+    assert built_lib.aad_params_default(C.byref(p), L.KIND_MFCC, 16000) == 0
+    assert (p.n_filt, p.n_ceps, p.ref_type, p.top_db) == (128, 13, L.REF_ONE, 80.0)
+    assert built_lib.aad_params_default(C.byref(p), L.KIND_LFCC, 16000) == 0
+    assert (p.n_fft, p.win_length, p.hop_length, p.n_filt, p.n_ceps) == (512, 400, 160, 24, 13)
+    assert p.quantize_i16 == 1 and abs(p.pre_emph - 0.97) < 1e-7 and p.layout == L.LAYOUT_TC
+    assert built_lib.aad_params_default(C.byref(p), 99, 16000) == -1
+    assert built_lib.aad_params_default(None, 0, 16000) == -1
+
+
+def test_python_params_match_c_defaults(built_lib):
+    from audioanalysisdetector_b200 import _lib as L
+    from audioanalysisdetector_b200.frontend import FrontendParams
+    for kind, fp in [(L.KIND_LOGMEL, FrontendParams.logmel(16000)), (L.KIND_MFCC, FrontendParams.mfcc(16000)),
+                     (L.KIND_LFCC, FrontendParams.lfcc(16000))]:
+        c = L.AadParams()
+        assert built_lib.aad_params_default(C.byref(c), kind, 16000) == 0
+        mine, _ = fp.to_c()
+        for name, _t in L.AadParams._fields_:
+            if name in ("custom_fb", "reserved0"):
+                continue
+            a, b = getattr(c, name), getattr(mine, name)
+            assert a == pytest.approx(b), name
+
+
+def test_invalid_arguments_are_rejected_without_gpu(built_lib):
+    assert built_lib.aad_plan_create(None, 0, None) == -1
+    assert built_lib.aad_plan_destroy(None) == 0
+    assert built_lib.aad_query(None, 1, 10, None, None, None) == -1
+    assert built_lib.aad_plan_launches(None) == -1
+    assert built_lib.aad_delta(None, None, 1, 1, 1, 9, 1, None, None) == -1
+
+
+def test_frontend_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import audioanalysisdetector_b200 as aad
+    with pytest.raises(aad.AadError):
+        aad.Frontend(aad.FrontendParams.mfcc(16000))
+    # the per-file drop-ins keep the reference's error convention: print and return None
+    assert aad.extract_mfcc((np.zeros(16000, np.float32), 16000)) is None
+
+
+def test_missing_library_is_an_error(monkeypatch, tmp_path):
+    from audioanalysisdetector_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.AadError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "audioanalysisdetector_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

@@ -1,0 +1,109 @@
+"""GPU: the reference-facing drop-ins (same names / arguments / shapes / dtypes / None-on-error
+as ASV_dl_func.py:404-439,522-538,1031-1049), checked against the oracle."""
+import wave
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import noise, speech
+
+pytestmark = pytest.mark.gpu
+SR = 16000
+
+
+def _write_wav(path, y, sr=SR):
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(sr)
+        w.writeframes(np.round(y * 32767).astype("<i2").tobytes())
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("wavs")
+    paths = []
+    for i, n in enumerate((4 * SR + 123, 2 * SR, 6 * SR)):
+        p = d / f"clip{i}.wav"
+        _write_wav(p, speech(i, n) if i % 2 else noise(i, n))
+        paths.append(str(p))
+    return paths
+
+
+def _decoded(path):
+    from audioanalysisdetector_b200 import audio_io
+    return audio_io.load(path)
+
+
+def test_per_file_extractors_shapes_dtypes_and_values(files):
+    import audioanalysisdetector_b200 as aad
+    y, sr = _decoded(files[1])                                       # 2-s chunk -> T = 63 / 198
+    mel = aad.extract_mel_spectrogram(files[1])
+    assert mel.shape == (64, 63) and mel.dtype == np.float32
+    assert np.abs(mel - oracle.extract_mel_spectrogram_ref(y, sr)).max() <= 1e-3
+    mf = aad.extract_mfcc(files[1])
+    assert mf.shape == (13, 63) and mf.dtype == np.float32
+    assert np.abs(mf - oracle.extract_mfcc_ref(y, sr)).max() <= 1e-3
+    lf = aad.extract_lfcc(files[1])
+    assert lf.shape == (198, 13) and lf.dtype == np.float64
+    assert np.abs(lf - oracle.extract_lfcc_ref(y, sr)).max() <= 1e-3
+    # keyword variants of the reference signatures
+    y0, _ = _decoded(files[0])
+    got = aad.extract_mfcc(files[0], chunk_start=1.0, chunk_end=3.0, n_mfcc=20)
+    want = oracle.extract_mfcc_ref(y0, sr, chunk_start=1.0, chunk_end=3.0, n_mfcc=20)
+    assert got.shape == want.shape == (20, 63) and np.abs(got - want).max() <= 1e-3
+    got = aad.extract_mel_spectrogram(files[0], n_mels=80, fmax=4000, mean=True)
+    want = oracle.extract_mel_spectrogram_ref(y0, sr, n_mels=80, fmax=4000, mean=True)
+    assert got.shape == (80,) and np.abs(got - want).max() <= 1e-3
+    got = aad.extract_lfcc(files[0], n_ceps=20, mean=True)
+    want = oracle.extract_lfcc_ref(y0, sr, n_ceps=20, mean=True)
+    assert got.shape == want.shape and np.abs(got - want).max() <= 1e-3
+
+
+def test_error_convention_returns_none(files, tmp_path, capsys):
+    import audioanalysisdetector_b200 as aad
+    assert aad.extract_mfcc(str(tmp_path / "missing.wav")) is None
+    assert "[BŁĄD MFCC]" in capsys.readouterr().out
+    assert aad.extract_mel_spectrogram(files[0], chunk_start=100.0, chunk_end=102.0) is None   # empty slice
+    assert aad.extract_lfcc((np.zeros(100, np.float32), SR)) is None                            # < one window
+    assert aad.extract_mfcc(files[0], augment="change pitch") is None                          # out of scope -> None
+    out = aad.extract_mfcc(files[0], augment="noise")
+    assert out is not None and out.shape[0] == 13
+
+
+def test_extract_features_dispatcher(files, tmp_path):
+    pd = pytest.importorskip("pandas")
+    import audioanalysisdetector_b200 as aad
+    rows = []
+    for p in files:
+        y, sr = _decoded(p)
+        for k in range(int(len(y) / sr // 2.0)):                    # the reference's 2-s chunk index
+            rows.append({"filepath": p, "chunk_index": k, "chunk_start": 2.0 * k, "chunk_end": 2.0 * (k + 1),
+                         "augmentationType": None})
+    rows.append({"filepath": str(tmp_path / "nope.wav"), "chunk_index": 0, "chunk_start": 0.0, "chunk_end": 2.0,
+                 "augmentationType": None})
+    df = pd.DataFrame(rows)
+
+    def custom(path, chunk_start=None, chunk_end=None, mean=False, augment=None):
+        return np.array([chunk_start, chunk_end])
+
+    fmap = {"mel-spect": aad.extract_mel_spectrogram, "mfcc": aad.extract_mfcc, "lfcc": aad.extract_lfcc,
+            "custom": custom}
+    df = aad.extract_features(df, fmap)
+    assert list(df.columns[-4:]) == list(fmap)
+    assert df["mfcc"].iloc[-1] is None and df["mel-spect"].iloc[-1] is None and df["lfcc"].iloc[-1] is None
+    cache = {p: _decoded(p) for p in files}
+    for _, r in df.iloc[:-1].iterrows():
+        y, sr = cache[r["filepath"]]
+        assert r["mel-spect"].shape == (64, 63) and r["mfcc"].shape == (13, 63) and r["lfcc"].shape == (198, 13)
+        kw = dict(chunk_start=r["chunk_start"], chunk_end=r["chunk_end"])
+        assert np.abs(r["mel-spect"] - oracle.extract_mel_spectrogram_ref(y, sr, **kw)).max() <= 1e-3
+        assert np.abs(r["mfcc"] - oracle.extract_mfcc_ref(y, sr, **kw)).max() <= 1e-3
+        assert np.abs(r["lfcc"] - oracle.extract_lfcc_ref(y, sr, **kw)).max() <= 1e-3
+        assert list(r["custom"]) == [r["chunk_start"], r["chunk_end"]]
+    # mean=True variant of the dispatcher (ASV_func.py defaults)
+    df2 = aad.extract_features(pd.DataFrame(rows[:3]), {"mfcc": aad.extract_mfcc}, mean=True)
+    y, sr = cache[rows[0]["filepath"]]
+    want = oracle.extract_mfcc_ref(y, sr, chunk_start=0.0, chunk_end=2.0, mean=True)
+    assert df2["mfcc"].iloc[0].shape == (13,) and np.abs(df2["mfcc"].iloc[0] - want).max() <= 1e-3

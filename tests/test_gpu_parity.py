@@ -1,0 +1,323 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the oracle.
+
+Tolerances are BASELINE.json's: max abs error <= 1e-3 on log features (dB, ln, cepstra,
+deltas); <= 1e-4 on linear spectra, peak-normalised per utterance, and element-wise on the
+flat-spectrum noise input.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import librosa_ref as LR, spafe_ref as SR, delta_ref as DR
+from helpers import golden, noise, pad_batch, speech
+
+pytestmark = pytest.mark.gpu
+
+TOL_LOG = 1e-3
+TOL_LIN = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def run(params, clips, dev, dtype=np.float32):
+    from audioanalysisdetector_b200.frontend import Frontend
+    fe = Frontend(params, dev)
+    w, lens = pad_batch(clips, dtype)
+    out, nf, st = fe(torch.from_numpy(w).to(dev), torch.from_numpy(lens).to(dev))
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), nf.cpu().numpy(), st.cpu().numpy(), fe
+
+
+def FP():
+    from audioanalysisdetector_b200.frontend import FrontendParams
+    return FrontendParams
+
+
+def LIB():
+    from audioanalysisdetector_b200 import _lib
+    return _lib
+
+
+# ----------------------------------------------------------------------------- log-mel
+@pytest.mark.parametrize("n_fft,hop,n_mels,sr", [
+    (2048, 512, 64, 16000),      # reference default (ASV_dl_func.py:533)
+    (512, 160, 80, 16000),       # BASELINE configs[0]
+    (1024, 256, 40, 16000),
+    (256, 64, 32, 8000),
+    (2048, 480, 128, 48000),     # BASELINE configs[4] framing
+])
+def test_logmel_matches_oracle(dev, n_fft, hop, n_mels, sr):
+    clips = [noise(1, 32000), speech(2, 47999, sr), noise(3, 5000), noise(4, 300)]
+    out, nf, st, fe = run(FP().logmel(sr, n_mels=n_mels, n_fft=n_fft, hop_length=hop), clips, dev)
+    for i, c in enumerate(clips):
+        want = LR.logmel_db(c, sr, n_mels=n_mels, n_fft=n_fft, hop_length=hop)
+        assert st[i] == 0 and nf[i] == want.shape[1]
+        assert np.abs(out[i, :, :nf[i]] - want).max() <= TOL_LOG
+        assert np.all(out[i, :, nf[i]:] == 0)
+    np.testing.assert_allclose(fe.table(LIB().TABLE_FILTERBANK), LR.mel_filterbank(sr, n_fft, n_mels), atol=1e-7)
+
+
+def test_linear_mel_energies_tolerance(dev):
+    L = LIB()
+    p = FP().logmel(16000, n_mels=128).replace(log_type=L.LOG_LN, top_db=-1.0)
+    clips = [noise(5, 64000), speech(6, 64000)]
+    out, nf, st, _ = run(p, clips, dev)
+    for i, c in enumerate(clips):
+        want = LR.melspectrogram(c, 16000, n_mels=128).astype(np.float64)
+        got = np.exp(out[i, :, :nf[i]].astype(np.float64))
+        assert np.abs(got - want).max() / want.max() <= TOL_LIN          # peak-normalised
+        if i == 0:                                                        # flat spectrum: element-wise
+            assert np.abs(got / want - 1).max() <= TOL_LIN
+
+
+# ----------------------------------------------------------------------------- MFCC (+ deltas)
+@pytest.mark.parametrize("n_mfcc,n_delta", [(13, 0), (40, 2), (20, 1), (64, 2)])
+def test_mfcc_matches_oracle(dev, n_mfcc, n_delta):
+    clips = [noise(7, 64000), speech(8, 64000), noise(9, 32000), speech(10, 5000)]
+    out, nf, st, fe = run(FP().mfcc(16000, n_mfcc=n_mfcc, n_delta=n_delta), clips, dev)
+    assert out.shape[1] == n_mfcc * (1 + n_delta)
+    for i, c in enumerate(clips):
+        want = oracle.mfcc_with_deltas_ref(c, 16000, n_mfcc=n_mfcc, n_delta=n_delta)
+        assert st[i] == 0 and nf[i] == want.shape[1]
+        assert np.abs(out[i, :, :nf[i]] - want).max() <= TOL_LOG
+    k = np.arange(n_mfcc)[:, None]
+    m = np.arange(128)[None, :]
+    D = 2 * np.where(k == 0, np.sqrt(1 / 512), np.sqrt(1 / 256)) * np.cos(np.pi * k * (2 * m + 1) / 256)
+    np.testing.assert_allclose(fe.table(LIB().TABLE_DCT), D, atol=1e-7)
+
+
+def test_mfcc_small_fft_variant(dev):
+    clips = [noise(11, 48000), speech(12, 30000)]
+    p = FP().mfcc(16000, n_mfcc=40, n_mels=80, n_fft=512, hop_length=160, n_delta=2)
+    out, nf, st, _ = run(p, clips, dev)
+    for i, c in enumerate(clips):
+        want = oracle.mfcc_with_deltas_ref(c, 16000, n_mfcc=40, n_fft=512, hop_length=160, n_mels=80)
+        assert st[i] == 0 and np.abs(out[i, :, :nf[i]] - want).max() <= TOL_LOG
+
+
+# ----------------------------------------------------------------------------- LFCC
+def test_lfcc_reference_defaults(dev):
+    clips = [noise(13, 32000), speech(14, 40001), noise(15, 16000), noise(16, 500)]
+    out, nf, st, fe = run(FP().lfcc(16000, n_ceps=13), clips, dev)
+    assert out.shape[2] == 13                                     # time-major like spafe
+    for i, c in enumerate(clips):
+        want = oracle.extract_lfcc_ref(c, 16000)
+        assert st[i] == 0 and nf[i] == want.shape[0]
+        assert np.abs(out[i, :nf[i], :] - want).max() <= TOL_LOG
+    np.testing.assert_allclose(fe.table(LIB().TABLE_FILTERBANK), SR.linear_filter_banks(24, 512, 16000) / 512,
+                               rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("fb", ["intbin", "cont", "custom"])
+def test_lfcc_config3_int16_with_deltas(dev, fb):
+    L = LIB()
+    clips = [SR.quantize_int16(noise(20 + i, n)) for i, n in enumerate((16000, 77777, 128000, 31999))]
+    kw = dict(n_ceps=20, nfilts=20, win_len=0.02, n_delta=2, layout=L.LAYOUT_CT)
+    if fb == "intbin":
+        p, fbm = FP().lfcc(16000, **kw), SR.linear_filter_banks(20, 512, 16000)
+    elif fb == "cont":
+        p = FP().lfcc(16000, fb_type=L.FB_LINEAR_CONT, **kw)
+        fbm = SR.linear_filter_banks_continuous(20, 512, 16000)
+    else:
+        fbm = SR.linear_filter_banks_continuous(20, 512, 16000)
+        p = FP().lfcc(16000, fb_type=L.FB_CUSTOM, custom_fb=fbm.astype(np.float32), **kw)
+    out, nf, st, _ = run(p, clips, dev, dtype=np.int16)
+    for i, c in enumerate(clips):
+        want = oracle.lfcc_with_deltas_ref(c, 16000, fbanks=fbm)
+        assert st[i] == 0 and nf[i] == want.shape[1]
+        assert np.abs(out[i, :, :nf[i]] - want).max() <= TOL_LOG
+
+
+def test_int16_input_equals_float_quantised_input(dev):
+    clips = [noise(30, 20000), speech(31, 33333)]
+    p = FP().lfcc(16000)
+    a, nfa, _, _ = run(p, clips, dev)
+    b, nfb, _, _ = run(p, [SR.quantize_int16(c) for c in clips], dev, dtype=np.int16)
+    assert np.array_equal(nfa, nfb) and np.array_equal(a, b)      # bit-exact: same arithmetic after the cast
+
+
+def test_non_banded_custom_filterbank_is_rejected(dev):
+    from audioanalysisdetector_b200 import AadError, Frontend
+    L = LIB()
+    fbm = np.ones((20, 257), dtype=np.float32)
+    with pytest.raises(AadError, match="banded"):
+        Frontend(FP().lfcc(16000, n_ceps=20, nfilts=20, fb_type=L.FB_CUSTOM, custom_fb=fbm), dev)
+    with pytest.raises(AadError, match="unsupported"):
+        Frontend(FP().mfcc(16000, n_fft=4096), dev)
+
+
+# ----------------------------------------------------------------------------- golden fixtures
+def test_committed_golden_vectors(dev):
+    L = LIB()
+    g = golden("oracle_outputs.npz")
+    for name in ("noise", "speech"):
+        y = g[f"{name}_wave"]
+        for params, key, tc in [
+            (FP().logmel(16000), "logmel64", False),
+            (FP().mfcc(16000), "mfcc13", False),
+            (FP().lfcc(16000), "lfcc13", True),
+            (FP().mfcc(16000, n_mfcc=40, n_delta=2), "mfcc40_d2", False),
+            (FP().lfcc(16000, n_ceps=20, nfilts=20, win_len=0.02, n_delta=2, layout=L.LAYOUT_CT), "lfcc20_d2", False),
+            (FP().logmel(16000, n_mels=80, n_fft=512, hop_length=160), "logmel80_c1", False),
+        ]:
+            out, nf, st, _ = run(params, [y], dev)
+            want = g[f"{name}_{key}"]
+            got = out[0, :nf[0], :] if tc else out[0, :, :nf[0]]
+            assert st[0] == 0 and got.shape == want.shape
+            assert np.abs(got - want).max() <= TOL_LOG, (name, key)
+
+
+# ----------------------------------------------------------------------------- known answers
+def test_zero_input_known_answers(dev):
+    z = [np.zeros(32000, np.float32)]
+    out, nf, st, _ = run(FP().logmel(16000), z, dev)
+    assert nf[0] == 63 and np.all(out[0] == 0.0)                  # 10log10(amin) - 10log10(amin)
+    out, nf, st, _ = run(FP().mfcc(16000), z, dev)
+    np.testing.assert_allclose(out[0, 0, :63], -100.0 * np.sqrt(128), rtol=1e-6)
+    assert np.abs(out[0, 1:, :63]).max() < 1e-3
+    out, nf, st, _ = run(FP().lfcc(16000), z, dev)
+    np.testing.assert_allclose(out[0, :198, 0], np.log(np.finfo(float).eps) * np.sqrt(24), rtol=1e-6)
+    assert np.abs(out[0, :198, 1:]).max() < 1e-4
+
+
+def test_bin_centred_sinusoid(dev):
+    L = LIB()
+    n_fft, k0, A = 512, 37, 0.5
+    y = (A * np.cos(2 * np.pi * k0 * np.arange(8192) / n_fft)).astype(np.float32)
+    # identity "filterbank": one filter per bin pair is not banded, so probe through a 3-filter custom bank
+    fbm = np.zeros((3, 257), np.float32)
+    fbm[0, k0 - 1], fbm[1, k0], fbm[2, k0 + 1] = 1, 1, 1
+    p = FP().logmel(16000, n_mels=3, n_fft=n_fft, hop_length=128).replace(
+        fb_type=L.FB_CUSTOM, custom_fb=fbm, log_type=L.LOG_LN, top_db=-1.0)
+    out, nf, st, _ = run(p, [y], dev)
+    pw = np.exp(out[0, :, 10].astype(np.float64))
+    np.testing.assert_allclose(np.sqrt(pw), [A * n_fft / 8, A * n_fft / 4, A * n_fft / 8], rtol=1e-4)
+
+
+# ----------------------------------------------------------------------------- edges / status
+def test_length_edge_cases_and_status(dev):
+    n_fft, hop = 512, 160
+    lens = [1, hop - 1, hop, n_fft - 1, n_fft, n_fft + 1, 2 * n_fft + 3]
+    clips = [noise(40 + i, n) for i, n in enumerate(lens)]
+    out, nf, st, _ = run(FP().logmel(16000, n_mels=40, n_fft=n_fft, hop_length=hop), clips, dev)
+    for i, c in enumerate(clips):
+        want = LR.logmel_db(c, 16000, n_mels=40, n_fft=n_fft, hop_length=hop)
+        assert st[i] == 0 and nf[i] == want.shape[1] == 1 + len(c) // hop
+        assert np.abs(out[i, :, :nf[i]] - want).max() <= TOL_LOG
+    # delta needs T >= 9 (librosa raises -> the reference returns None)
+    out, nf, st, _ = run(FP().mfcc(16000, n_delta=2), [noise(50, 512 * 8), np.zeros(0, np.float32), noise(51, 512 * 7)], dev)
+    assert list(st) == [0, 1, 3] and list(nf) == [9, 0, 8]
+    assert np.all(out[1] == 0) and np.all(out[2] == 0)
+    # spafe framing needs one full window
+    out, nf, st, _ = run(FP().lfcc(16000), [noise(52, 399), noise(53, 400), noise(54, 559), noise(55, 560)], dev)
+    assert list(st) == [2, 0, 0, 0] and list(nf) == [0, 1, 1, 2]
+
+
+def test_padding_content_is_ignored_and_batch_invariant(dev):
+    from audioanalysisdetector_b200.frontend import Frontend
+    p = FP().mfcc(16000, n_mfcc=20, n_delta=2)
+    fe = Frontend(p, dev)
+    clips = [noise(60, 16000), speech(61, 50001), noise(62, 128000), noise(63, 7000), speech(64, 99999)]
+    w, lens = pad_batch(clips)
+    garbage = w.copy()
+    for i, c in enumerate(clips):
+        garbage[i, len(c):] = 1e6 * (i + 1)                      # junk beyond lengths must not matter
+    a, nfa, _ = fe(torch.from_numpy(w).to(dev), torch.from_numpy(lens).to(dev))
+    b, nfb, _ = fe(torch.from_numpy(garbage).to(dev), torch.from_numpy(lens).to(dev))
+    assert torch.equal(a, b)
+    perm = [3, 0, 4, 2, 1]
+    c_, _, _ = fe(torch.from_numpy(w[perm]).to(dev), torch.from_numpy(lens[perm]).to(dev))
+    assert torch.equal(c_, a[perm])                              # order/batch independent, bit-exact
+    for i, c in enumerate(clips):
+        single, nf1, _ = fe(torch.from_numpy(pad_batch([c])[0]).to(dev),
+                            torch.tensor([len(c)], dtype=torch.int32, device=dev))
+        t = int(nf1[0])
+        assert t == int(nfa[i]) and torch.equal(single[0, :, :t], a[i, :, :t])
+
+
+def test_layouts_and_time_mean(dev):
+    L = LIB()
+    clips = [noise(70, 30000), speech(71, 64000)]
+    ct, nf, _, _ = run(FP().mfcc(16000, n_mfcc=13, n_delta=1), clips, dev)
+    tc, nf2, _, _ = run(FP().mfcc(16000, n_mfcc=13, n_delta=1, layout=L.LAYOUT_TC), clips, dev)
+    assert np.array_equal(ct.transpose(0, 2, 1), tc)
+    mean, _, _, _ = run(FP().mfcc(16000, n_mfcc=13, time_mean=True), clips, dev)
+    full, nf3, _, _ = run(FP().mfcc(16000, n_mfcc=13), clips, dev)
+    for i in range(2):
+        np.testing.assert_allclose(mean[i], full[i, :, :nf3[i]].mean(axis=1), atol=2e-4)
+    lm_mean, _, _, _ = run(FP().logmel(16000, time_mean=True), clips, dev)
+    for i, c in enumerate(clips):
+        np.testing.assert_allclose(lm_mean[i], oracle.extract_mel_spectrogram_ref(c, 16000, mean=True), atol=TOL_LOG)
+
+
+def test_standalone_delta_matches_oracle(dev):
+    import audioanalysisdetector_b200 as aad
+    x = np.random.default_rng(5).standard_normal((3, 7, 50)).astype(np.float32)
+    nfr = np.array([50, 9, 8], dtype=np.int32)
+    for order in (1, 2):
+        got = aad.delta(torch.from_numpy(x).to(dev), torch.from_numpy(nfr).to(dev), order=order).cpu().numpy()
+        for b in (0, 1):
+            want = DR.delta(x[b, :, :nfr[b]], order=order)
+            assert np.abs(got[b, :, :nfr[b]] - want).max() <= 1e-5
+        assert np.all(got[2] == 0)                               # T < width: left untouched
+    t = np.arange(40, dtype=np.float32)
+    got = aad.delta(torch.from_numpy((t ** 2)[None, None, :]).to(dev), order=2).cpu().numpy()
+    np.testing.assert_allclose(got, 2.0, atol=1e-3)
+    got = aad.delta(torch.from_numpy((3 * t + 1)[None, None, :]).to(dev), order=1).cpu().numpy()
+    np.testing.assert_allclose(got, 3.0, atol=1e-4)
+
+
+def test_long_form_48k_multi_tile(dev):
+    sr = 48000
+    y = speech(80, 30 * sr, sr)
+    out, nf, st, _ = run(FP().logmel(sr, n_mels=128, n_fft=2048, hop_length=480), [y], dev)
+    want = LR.logmel_db(y, sr, n_mels=128, n_fft=2048, hop_length=480)
+    assert nf[0] == want.shape[1] == 3001 and np.abs(out[0, :, :nf[0]] - want).max() <= TOL_LOG
+    out, nf, st, _ = run(FP().mfcc(sr, n_mfcc=20, n_fft=2048, hop_length=480, n_delta=2), [y, y[:100000]], dev)
+    for i, c in enumerate((y, y[:100000])):
+        want = oracle.mfcc_with_deltas_ref(c, sr, n_mfcc=20, hop_length=480)
+        assert np.abs(out[i, :, :nf[i]] - want).max() <= TOL_LOG
+
+
+def test_host_path_equals_device_path(dev):
+    from audioanalysisdetector_b200.frontend import Frontend
+    p = FP().mfcc(16000, n_mfcc=40, n_delta=2)
+    fe = Frontend(p, dev)
+    clips = [noise(90 + i, n) for i, n in enumerate((64000, 12345, 0, 64000, 33000, 4000, 64000))]
+    w, lens = pad_batch(clips)
+    a, nfa, sta = fe(torch.from_numpy(w).to(dev), torch.from_numpy(lens).to(dev))
+    for chunk in (0, 2, 3):
+        b, nfb, stb = fe.extract_host(w, lens, chunk_utts=chunk)
+        assert np.array_equal(a.cpu().numpy(), b) and np.array_equal(nfa.cpu().numpy(), nfb)
+        assert np.array_equal(sta.cpu().numpy(), stb) and stb[2] == 1
+
+
+# ----------------------------------------------------------------------------- full size (configs[1])
+def test_full_size_config2_properties(dev):
+    """4096 x 4 s clips, MFCC-40 + d + dd: replicas of 8 distinct clips must be bit-identical
+    to their first occurrence (no cross-utterance leakage at scale), those 8 match the oracle,
+    and the delta rows equal the standalone stencil applied to the static rows."""
+    import audioanalysisdetector_b200 as aad
+    from audioanalysisdetector_b200.frontend import Frontend
+    B, Ls = 4096, 64000
+    base = np.stack([noise(100 + i, Ls) if i % 2 == 0 else speech(100 + i, Ls) for i in range(8)])
+    wav = torch.from_numpy(base).to(dev).repeat(B // 8, 1)
+    fe = Frontend(FP().mfcc(16000, n_mfcc=40, n_delta=2), dev)
+    out, nf, st = fe(wav)
+    torch.cuda.synchronize()
+    assert int(st.sum()) == 0 and int(nf.min()) == int(nf.max()) == 126
+    ref8 = out[:8]
+    assert torch.equal(out.view(B // 8, 8, 120, 126), ref8.unsqueeze(0).expand(B // 8, -1, -1, -1))
+    got = ref8.cpu().numpy()
+    for i in range(8):
+        want = oracle.mfcc_with_deltas_ref(base[i], 16000, n_mfcc=40)
+        assert np.abs(got[i] - want).max() <= TOL_LOG
+    static = out[:64, :40].contiguous()
+    d1 = aad.delta(static, order=1)
+    d2 = aad.delta(static, order=2)
+    assert (out[:64, 40:80] - d1).abs().max().item() <= 1e-5
+    assert (out[:64, 80:120] - d2).abs().max().item() <= 1e-5

@@ -1,0 +1,95 @@
+"""CPU: host-side logic -- frame arithmetic, sharding, WAV decode, bench accounting, gloo gather."""
+import os
+import sys
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+from audioanalysisdetector_b200.frontend import FrontendParams
+from audioanalysisdetector_b200 import audio_io, sharding
+from oracle import librosa_ref as LR, spafe_ref as SR
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_frame_counts_match_oracle():
+    mf, lf = FrontendParams.mfcc(16000), FrontendParams.lfcc(16000)
+    for n in (0, 1, 159, 160, 399, 400, 401, 511, 512, 513, 2047, 2048, 2049, 32000, 64000):
+        assert mf.n_frames(n) == (LR.n_frames_centered(n, 512) if n > 0 else 0)
+        assert lf.n_frames(n) == SR.n_frames_uncentered(n, 400, 160)
+    assert FrontendParams.mfcc(16000, n_mfcc=40, n_delta=2).c_out == 120
+    assert FrontendParams.logmel(16000).c_out == 64
+    assert FrontendParams.lfcc(16000, n_ceps=20, nfilts=20, n_delta=2).c_out == 60
+
+
+def test_partition_by_frames_balanced_and_complete():
+    rng = np.random.default_rng(0)
+    nf = rng.integers(99, 800, size=4096)
+    for ws in (1, 2, 4, 8):
+        parts = sharding.partition_by_frames(nf, ws)
+        allidx = np.sort(np.concatenate(parts))
+        assert np.array_equal(allidx, np.arange(4096))
+        loads = np.array([nf[p].sum() for p in parts])
+        assert loads.max() - loads.min() <= nf.max()
+    sl = [sharding.contiguous_shard(10, r, 4) for r in range(4)]
+    assert sum(s.stop - s.start for s in sl) == 10 and sl[0] == slice(0, 3) and sl[3] == slice(9, 10)
+
+
+def test_wav_loader_round_trip(tmp_path):
+    y = (np.sin(np.arange(8000) * 0.05) * 0.5).astype(np.float32)
+    path = str(tmp_path / "a.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(16000)
+        w.writeframes((y * 32767).astype("<i2").tobytes())
+    z, sr = audio_io.load(path)
+    assert sr == 16000 and z.dtype == np.float32 and np.abs(z - y).max() < 1e-4
+    with pytest.raises(ValueError):
+        audio_io.load(path, sr=8000)
+    z2, sr2 = audio_io.load((y, 22050))
+    assert sr2 == 22050 and z2 is not None
+
+
+def test_bench_algorithmic_work_matches_survey():
+    sys.path.insert(0, ROOT)
+    import bench
+    w = bench.algorithmic_work(2048, 512, 128, 40, 2, 2020, 120)
+    assert round(w["flops"]) == 77291 and w["bytes"] == 2528
+    w = bench.algorithmic_work(512, 160, 80, 0, 0, 500, 80)
+    assert round(w["flops"]) == 13883 and w["bytes"] == 960           # config C1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_total = 37
+    nf = (np.arange(n_total) * 7919 % 500) + 9
+    parts = sharding.partition_by_frames(nf, world)
+    idx = torch.from_numpy(parts[rank])
+    local = torch.stack([torch.full((3, 5), float(i)) for i in parts[rank]]) if len(idx) else torch.zeros((0, 3, 5))
+    full = sharding.gather_features(local, idx, n_total)
+    ok = all(bool((full[i] == float(i)).all()) for i in range(n_total))
+    q.put((rank, ok, int(nf[parts[rank]].sum())))
+    dist.destroy_process_group()
+
+
+def test_sharded_gather_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
+    loads = [l for _, _, l in res]
+    assert abs(loads[0] - loads[1]) <= 509

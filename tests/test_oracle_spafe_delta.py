@@ -1,0 +1,102 @@
+"""CPU: the spafe restatement and the delta semantics against independent checks."""
+import numpy as np
+import pytest
+import scipy.signal
+
+from oracle import spafe_ref as SR, delta_ref as DR
+from helpers import golden, noise
+
+
+def test_quantize_int16_truncates_toward_zero():
+    y = np.array([0.99999, -0.99999, 1.0, -1.0, 0.5, -0.5, 1e-5, -1e-5, 0.0], dtype=np.float32)
+    q = SR.quantize_int16(y)
+    assert q.dtype == np.int16
+    assert list(q) == [32766, -32766, 32767, -32767, 16383, -16383, 0, 0, 0]
+    assert SR.quantize_int16(np.array([1.5], np.float32))[0] == np.int16((int(1.5 * 32767) + 2**15) % 2**16 - 2**15)
+
+
+def test_pre_emphasis_and_framing():
+    s = np.arange(1, 11, dtype=np.int16)
+    e = SR.pre_emphasis(s)
+    assert e.dtype == np.float64 and e[0] == 1.0
+    np.testing.assert_allclose(e[1:], s[1:] - 0.97 * s[:-1])
+    fr, flen = SR.framing(np.arange(1000.0), fs=16000)
+    assert flen == 400 and fr.shape == ((1000 - 400) // 160 + 1, 400)
+    assert fr[2, 0] == 320.0
+    with pytest.raises(ValueError):
+        SR.framing(np.arange(399.0), fs=16000)
+
+
+def test_linear_filterbank_structure():
+    for fbk in (SR.linear_filter_banks(24, 512, 16000), SR.linear_filter_banks(20, 512, 16000),
+                SR.linear_filter_banks_continuous(24, 512, 16000)):
+        assert fbk.shape[1] == 257 and fbk.min() >= 0 and fbk.max() <= 1.0
+        nz = (fbk > 0).sum(axis=0)
+        assert nz.max() <= 2
+        for k in np.nonzero(nz == 2)[0]:
+            j = np.nonzero(fbk[:, k])[0]
+            assert j[1] - j[0] == 1
+    fbk = SR.linear_filter_banks(24, 512, 16000)
+    # unit peaks at the centre bins, adjacent falling/rising slopes sum to one
+    bins = np.floor(513 * np.linspace(0, 8000, 26) / 16000).astype(int)
+    for j in range(24):
+        assert fbk[j, bins[j + 1]] == 1.0
+
+
+def test_lfcc_known_answers_and_shapes():
+    z = np.zeros(32000, dtype=np.int16)
+    lf = SR.lfcc(z, fs=16000, num_ceps=13)
+    assert lf.shape == (198, 13) and lf.dtype == np.float64
+    np.testing.assert_allclose(lf[:, 0], np.log(SR.EPS) * np.sqrt(24), rtol=1e-12)
+    assert np.abs(lf[:, 1:]).max() < 1e-9
+    with pytest.raises(ValueError):
+        SR.lfcc(z, num_ceps=30)
+
+
+def test_lfcc_matches_direct_dft_formulation():
+    y = SR.quantize_int16(noise(4, 4000))
+    lf = SR.lfcc(y, fs=16000, num_ceps=13)
+    # independent re-derivation of frame 3 with an explicit DFT matrix
+    e = np.concatenate([[float(y[0])], y[1:].astype(np.float64) - 0.97 * y[:-1].astype(np.float64)])
+    fr = e[3 * 160:3 * 160 + 400] * (0.54 - 0.46 * np.cos(2 * np.pi * np.arange(400) / 399))
+    n, k = np.arange(400)[None, :], np.arange(257)[:, None]
+    X = (fr[None, :] * np.exp(-2j * np.pi * k * n / 512)).sum(axis=1)
+    en = (np.abs(X) ** 2 / 512) @ SR.linear_filter_banks(24, 512, 16000).T
+    m = np.arange(24)
+    c = [np.sqrt((1 if q == 0 else 2) / 24) * (np.log(en) * np.cos(np.pi * q * (2 * m + 1) / 48)).sum() for q in range(13)]
+    np.testing.assert_allclose(lf[3], c, rtol=1e-9, atol=1e-9)
+
+
+def test_delta_taps_and_known_answers():
+    np.testing.assert_allclose(DR.savgol_taps(9, 1) * 60, np.arange(-4, 5), atol=1e-12)
+    np.testing.assert_allclose(DR.savgol_taps(9, 2) * 462, [28, 7, -8, -17, -20, -17, -8, 7, 28], atol=1e-10)
+    t = np.arange(30, dtype=np.float64)
+    np.testing.assert_allclose(DR.delta(3.5 * t[None, :] + 1, order=1), 3.5, atol=1e-10)      # ramp incl. edges
+    np.testing.assert_allclose(DR.delta((t ** 2)[None, :], order=2), 2.0, atol=1e-9)           # t^2 -> 2
+    x = golden("independent.npz")["delta_in"]
+    ind = golden("independent.npz")
+    np.testing.assert_allclose(DR.delta(x, order=1), ind["scipy_savgol_d1"], atol=1e-6)
+    np.testing.assert_allclose(DR.delta(x, order=2), ind["scipy_savgol_d2"], atol=1e-6)
+    d = DR.delta(x, order=1)
+    assert np.allclose(d[:, :4], d[:, 4:5], atol=1e-6) and np.allclose(d[:, -4:], d[:, -5:-4], atol=1e-6)
+    with pytest.raises(ValueError):
+        DR.delta(x[:, :8])
+
+
+def test_delta_interior_matches_torchaudio():
+    ta = pytest.importorskip("torchaudio")
+    import torch
+    x = golden("independent.npz")["delta_in"]
+    ref = ta.functional.compute_deltas(torch.from_numpy(x), win_length=9).numpy()
+    np.testing.assert_allclose(DR.delta(x, order=1)[:, 4:-4], ref[:, 4:-4], atol=1e-6)
+
+
+def test_oracle_regression_against_committed_outputs():
+    import oracle
+    g = golden("oracle_outputs.npz")
+    for name in ("noise", "speech"):
+        y = g[f"{name}_wave"]
+        np.testing.assert_allclose(oracle.extract_mel_spectrogram_ref(y, 16000), g[f"{name}_logmel64"], atol=2e-4)
+        np.testing.assert_allclose(oracle.extract_mfcc_ref(y, 16000), g[f"{name}_mfcc13"], atol=2e-4)
+        np.testing.assert_allclose(oracle.extract_lfcc_ref(y, 16000), g[f"{name}_lfcc13"], atol=1e-8)
+        np.testing.assert_allclose(oracle.mfcc_with_deltas_ref(y, 16000, n_mfcc=40), g[f"{name}_mfcc40_d2"], atol=2e-4)
