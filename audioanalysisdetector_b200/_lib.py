@@ -49,6 +49,7 @@ _EXTRACT_ARGS = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int
 SYMBOLS = {
     "aad_version": (C.c_int, []),
     "aad_strerror": (C.c_char_p, [C.c_int]),
+    "aad_last_error_detail": (C.c_char_p, []),
     "aad_params_default": (C.c_int, [C.POINTER(AadParams), C.c_int, C.c_int]),
     "aad_plan_create": (C.c_int, [C.POINTER(AadParams), C.c_int, C.POINTER(C.c_void_p)]),
     "aad_plan_destroy": (C.c_int, [C.c_void_p]),
@@ -97,5 +98,7 @@ def load():
 
 def check(rc: int, what: str = "aad call"):
     if rc != 0:
-        msg = load().aad_strerror(rc).decode()
-        raise AadError(f"{what} failed: {msg} ({rc})")
+        lib = load()
+        msg = lib.aad_strerror(rc).decode()
+        detail = lib.aad_last_error_detail().decode() if rc == -3 else ""
+        raise AadError(f"{what} failed: {msg} ({rc})" + (f" [{detail}]" if detail else ""))

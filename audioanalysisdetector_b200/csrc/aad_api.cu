@@ -62,10 +62,21 @@ static const double kPiD = 3.141592653589793238462643383279502884;
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-#define CUDA_TRY(expr)                       \
-  do {                                       \
-    cudaError_t e__ = (expr);                \
-    if (e__ != cudaSuccess) return AAD_ERR_CUDA; \
+static thread_local char g_err_detail[256] = "";
+static int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err_detail, sizeof(g_err_detail), "%s: %s (%d)", what, cudaGetErrorString(e), (int)e);
+  return AAD_ERR_CUDA;
+}
+#define CUDA_TRY(expr)                                  \
+  do {                                                  \
+    cudaError_t e__ = (expr);                           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
+  } while (0)
+// launch check: cudaErrorNotReady can be left behind by event/stream queries and is not a failure
+#define LAUNCH_CHECK(what)                                             \
+  do {                                                                 \
+    cudaError_t e__ = cudaGetLastError();                              \
+    if (e__ != cudaSuccess && e__ != cudaErrorNotReady) return cuda_fail(e__, what); \
   } while (0)
 
 // ---- Slaney mel scale (librosa.hz_to_mel / mel_to_hz, htk=False) ------------
@@ -249,7 +260,7 @@ static void stft_cfg(int L, int* warps, int* ctas, size_t* smem) {
 
 static size_t cep_smem_bytes(const aad_plan* pl) {
   size_t f = (size_t)pl->p.n_filt * CEP_TS;
-  if (pl->p.n_ceps > 0) f += (size_t)pl->p.n_filt * pl->ncp + (size_t)pl->p.n_ceps * CEP_TS;
+  if (pl->p.n_ceps > 0) f += (size_t)(pl->p.n_filt + 1) * pl->ncp + (size_t)pl->p.n_ceps * CEP_TS;
   return f * 4;
 }
 
@@ -257,6 +268,8 @@ static size_t cep_smem_bytes(const aad_plan* pl) {
 extern "C" {
 
 int aad_version(void) { return AAD_VERSION; }
+
+const char* aad_last_error_detail(void) { return g_err_detail; }
 
 const char* aad_strerror(int err) {
   switch (err) {
@@ -438,14 +451,17 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   if (p.n_ceps > 0) {
     const int Mf = p.n_filt;
     pl->h_dct.assign((size_t)p.n_ceps * Mf, 0.f);
-    dct_t.assign((size_t)Mf * pl->ncp, 0.f);
+    dct_t.assign((size_t)(Mf + 1) * pl->ncp, 0.f);
     for (int k = 0; k < p.n_ceps; ++k) {
       const double fk = k == 0 ? std::sqrt(1.0 / (4.0 * Mf)) : std::sqrt(1.0 / (2.0 * Mf));
+      double colsum = 0.0;
       for (int m = 0; m < Mf; ++m) {
         float v = (float)(2.0 * fk * std::cos(kPiD * k * (2.0 * m + 1.0) / (2.0 * Mf)));
         pl->h_dct[(size_t)k * Mf + m] = v;
         dct_t[(size_t)m * pl->ncp + k] = v;
+        colsum += (double)v;
       }
+      dct_t[(size_t)Mf * pl->ncp + k] = (float)colsum;  // exact re-addition of the per-frame mean
     }
   }
   savgol_taps(p.n_delta > 0 ? p.delta_width : 9, pl->taps[0], pl->taps[1]);
@@ -464,12 +480,14 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
       e = cudaFuncSetAttribute((const void*)pick_stft(L, mode, pre != 0),
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->k1_smem);
   if (e == cudaSuccess && pl->need_ws_E) {
-    size_t cs = cep_smem_bytes(pl);
-    if (cs > 227 * 1024) {
+    // the attribute is per function, not per plan: opt in to the device maximum once
+    int optin = 0;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (cep_smem_bytes(pl) > (size_t)optin) {
       aad_plan_destroy(pl);
       return AAD_ERR_UNSUPPORTED;
     }
-    e = cudaFuncSetAttribute((const void*)k_cepstra, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+    e = cudaFuncSetAttribute((const void*)k_cepstra, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   }
   if (e != cudaSuccess) {
     aad_plan_destroy(pl);
@@ -562,7 +580,9 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
   pa.frame_off = d_frame_off; pa.utt_max = d_max;
   const bool prof = pl->profile;
   if (prof) cudaEventRecord(pl->ev[0], stream);
+  (void)cudaGetLastError();  // clear stale non-sticky state left by earlier calls in this thread
   k_prepare<<<1, 1024, 0, stream>>>(pa);
+  LAUNCH_CHECK("k_prepare launch");
   if (prof) cudaEventRecord(pl->ev[1], stream);
 
   // K1
@@ -586,6 +606,7 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
   const long long max_tiles = ((long long)B * std::max(t_max, 1) + 31) / 32;
   const int grid1 = (int)std::min<long long>((long long)pl->sm_count * pl->ctas, std::max<long long>(max_tiles, 1));
   kern<<<grid1, pl->warps * 32, pl->k1_smem, stream>>>(sa);
+  LAUNCH_CHECK("k_stft_fb launch");
   if (prof) cudaEventRecord(pl->ev[2], stream);
 
   // K2
@@ -609,6 +630,7 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
     const int gx = t_max <= CEP_TS ? 1 : (t_max + ca.tile_out - 1) / ca.tile_out;
     dim3 grid(gx, B);
     k_cepstra<<<grid, CEP_TS, cep_smem_bytes(pl), stream>>>(ca);
+    LAUNCH_CHECK("k_cepstra launch");
     if (prof) cudaEventRecord(pl->ev[3], stream);
     if (p.time_mean) {
       dim3 gm((pl->c_out + 3) / 4, B);
@@ -626,7 +648,8 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
     if (prof) cudaEventRecord(pl->ev[3], stream);
   }
   if (prof) cudaEventRecord(pl->ev[4], stream);
-  return cudaGetLastError() == cudaSuccess ? AAD_OK : AAD_ERR_CUDA;
+  LAUNCH_CHECK("epilogue launch");
+  return AAD_OK;
 }
 
 #define AAD_KIND_ALIAS(NAME, KIND)                                                                        \
@@ -653,8 +676,10 @@ int aad_delta(const float* x, const int32_t* n_frames, int B, int C, int32_t t_s
   std::memcpy(da.taps, order == 1 ? t1 : t2, sizeof(da.taps));
   da.x = x; da.out = out; da.n_frames = n_frames; da.C = C; da.t_stride = t_stride; da.width = width;
   dim3 grid(std::max(1, std::min(64, (t_stride + 255) / 256)), C, B);
+  (void)cudaGetLastError();
   k_delta<<<grid, 256, 0, (cudaStream_t)stream>>>(da);
-  return cudaGetLastError() == cudaSuccess ? AAD_OK : AAD_ERR_CUDA;
+  LAUNCH_CHECK("k_delta launch");
+  return AAD_OK;
 }
 
 int64_t aad_plan_table(const aad_plan* pl, int which, float* host_out, int64_t capacity) {

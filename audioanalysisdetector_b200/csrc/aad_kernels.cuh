@@ -463,7 +463,7 @@ struct CepArgs {
   float top_db;           // < 0: none
   int n_ceps;             // 0: identity
   int ncp;                // padded n_ceps (multiple of CEP_KC)
-  const float* dct_t;     // [n_filt][ncp]  (transposed DCT matrix, zero padded)
+  const float* dct_t;     // [n_filt + 1][ncp]  (transposed DCT matrix, zero padded; last row = column sums)
   int n_delta, width;
   float taps[2][CEP_MAXW];
   float* out;
@@ -499,8 +499,8 @@ __global__ void __launch_bounds__(CEP_TS) k_cepstra(const CepArgs a) {
   const int C = a.n_ceps > 0 ? a.n_ceps : a.n_filt;
 
   float* sE = smem;                                   // [n_filt][CEP_TS]
-  float* sD = sE + a.n_filt * CEP_TS;                 // [n_filt][ncp]
-  float* sC = a.n_ceps > 0 ? sD + a.n_filt * a.ncp : sE;  // [C][CEP_TS]
+  float* sD = sE + a.n_filt * CEP_TS;                 // [n_filt + 1][ncp] (last row: column sums)
+  float* sC = a.n_ceps > 0 ? sD + (a.n_filt + 1) * a.ncp : sE;  // [C][CEP_TS]
 
   // reference / floor (librosa.power_to_db):  ls = E - ref ; ls = max(ls, max(ls) - top_db)
   float ref = 0.f, floorv = -INFINITY;
@@ -519,19 +519,25 @@ __global__ void __launch_bounds__(CEP_TS) k_cepstra(const CepArgs a) {
     for (int m = 0; m < a.n_filt; ++m) sE[m * CEP_TS + tid] = 0.f;
   }
   if (a.n_ceps > 0) {
-    const int nd = a.n_filt * a.ncp;
+    const int nd = (a.n_filt + 1) * a.ncp;
     for (int i = tid * 4; i < nd; i += CEP_TS * 4)
       *reinterpret_cast<float4*>(sD + i) = __ldg(reinterpret_cast<const float4*>(a.dct_t + i));
   }
   __syncthreads();
 
   if (a.n_ceps > 0) {
+    // The DCT is linear: accumulate on the per-frame-centred energies (small partial sums,
+    // so float32 accumulation of ~100 same-sign dB values loses nothing) and add the mean
+    // back through the table's column sums (row n_filt of dct_t).
+    float mean = 0.f;
+    for (int m = 0; m < a.n_filt; ++m) mean += sE[m * CEP_TS + tid];
+    mean *= 1.0f / (float)a.n_filt;
     for (int c0 = 0; c0 < a.n_ceps; c0 += CEP_KC) {
       float acc[CEP_KC];
 #pragma unroll
       for (int i = 0; i < CEP_KC; ++i) acc[i] = 0.f;
       for (int m = 0; m < a.n_filt; ++m) {
-        const float e = sE[m * CEP_TS + tid];
+        const float e = sE[m * CEP_TS + tid] - mean;
         const float4* d4 = reinterpret_cast<const float4*>(sD + m * a.ncp + c0);
 #pragma unroll
         for (int i = 0; i < CEP_KC / 4; ++i) {
@@ -542,9 +548,10 @@ __global__ void __launch_bounds__(CEP_TS) k_cepstra(const CepArgs a) {
           acc[4 * i + 3] = __fmaf_rn(d.w, e, acc[4 * i + 3]);
         }
       }
+      const float* colsum = sD + a.n_filt * a.ncp + c0;
 #pragma unroll
       for (int i = 0; i < CEP_KC; ++i)
-        if (c0 + i < a.n_ceps) sC[(c0 + i) * CEP_TS + tid] = acc[i];
+        if (c0 + i < a.n_ceps) sC[(c0 + i) * CEP_TS + tid] = __fmaf_rn(mean, colsum[i], acc[i]);
     }
     __syncthreads();
   }

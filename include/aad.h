@@ -196,6 +196,8 @@ int aad_plan_kernel_times(const aad_plan* plan, float* ms_out);
 int aad_fp32_peak(int device, int iters, double* tflops_out);
 
 const char* aad_strerror(int err);
+/* Text of the most recent CUDA failure seen by this thread inside the library ("" if none). */
+const char* aad_last_error_detail(void);
 int aad_version(void);
 
 #ifdef __cplusplus
