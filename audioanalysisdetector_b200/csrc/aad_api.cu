@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -23,8 +24,11 @@ struct aad_plan {
   int sm_count = 148;
   int L = 0;          // n_fft / 64
   int K = 0;          // bins
+  int tile = 32;      // frames per K1 tile (16 or 32)
   int warps = 0, ctas = 0;
   size_t k1_smem = 0;
+  int n_w4 = 0;
+  int kc = 20, cep_groups = 1;
   int c_feat = 0;     // rows before deltas
   int c_out = 0;
   int ncp = 0;
@@ -37,8 +41,8 @@ struct aad_plan {
   float* d_window = nullptr;
   float2* d_tw1 = nullptr;
   float2* d_twp = nullptr;
-  float2* d_fbw = nullptr;
-  int32_t* d_seg = nullptr;
+  int2* d_filt_hdr = nullptr;
+  float4* d_filt_w = nullptr;
   int32_t* d_warp_filt = nullptr;
   float* d_dct_t = nullptr;
   // optional per-kernel timing (bench roofline): events recorded around each launch
@@ -229,32 +233,48 @@ static cudaError_t upload(T** dptr, const std::vector<T>& h) {
 
 // ---- kernel dispatch table --------------------------------------------------
 typedef void (*stft_kernel_t)(const StftArgs);
-template <int L>
-static stft_kernel_t pick_stft_L(int mode, bool pre) {
+template <int L, int TILE>
+static stft_kernel_t pick_stft_LT(int mode, bool pre) {
   switch (mode * 2 + (pre ? 1 : 0)) {
-    case 0: return k_stft_fb<L, IN_F32, false>;
-    case 1: return k_stft_fb<L, IN_F32, true>;
-    case 2: return k_stft_fb<L, IN_F32_Q16, false>;
-    case 3: return k_stft_fb<L, IN_F32_Q16, true>;
-    case 4: return k_stft_fb<L, IN_I16, false>;
-    default: return k_stft_fb<L, IN_I16, true>;
+    case 0: return k_stft_fb<L, IN_F32, false, TILE>;
+    case 1: return k_stft_fb<L, IN_F32, true, TILE>;
+    case 2: return k_stft_fb<L, IN_F32_Q16, false, TILE>;
+    case 3: return k_stft_fb<L, IN_F32_Q16, true, TILE>;
+    case 4: return k_stft_fb<L, IN_I16, false, TILE>;
+    default: return k_stft_fb<L, IN_I16, true, TILE>;
   }
 }
-static stft_kernel_t pick_stft(int L, int mode, bool pre) {
+static stft_kernel_t pick_stft(int L, int tile, int mode, bool pre) {
   switch (L) {
-    case 4: return pick_stft_L<4>(mode, pre);
-    case 8: return pick_stft_L<8>(mode, pre);
-    case 16: return pick_stft_L<16>(mode, pre);
-    case 32: return pick_stft_L<32>(mode, pre);
+    case 4: return pick_stft_LT<4, 32>(mode, pre);
+    case 8: return pick_stft_LT<8, 32>(mode, pre);
+    case 16: return pick_stft_LT<16, 32>(mode, pre);
+    case 32: return tile == 16 ? pick_stft_LT<32, 16>(mode, pre) : pick_stft_LT<32, 32>(mode, pre);
   }
   return nullptr;
 }
-static void stft_cfg(int L, int* warps, int* ctas, size_t* smem) {
+template <int L, int TILE>
+static void stft_cfg_LT(int* warps, int* ctas, size_t* fixed, int* npar) {
+  using C = StftCfg<L, TILE>;
+  *warps = C::WARPS; *ctas = C::CTAS; *fixed = C::FIXED_BYTES; *npar = C::NPAR;
+}
+static void stft_cfg(int L, int tile, int* warps, int* ctas, size_t* fixed, int* npar) {
   switch (L) {
-    case 4: *warps = StftCfg<4>::WARPS; *ctas = StftCfg<4>::CTAS; *smem = StftCfg<4>::SMEM_BYTES; break;
-    case 8: *warps = StftCfg<8>::WARPS; *ctas = StftCfg<8>::CTAS; *smem = StftCfg<8>::SMEM_BYTES; break;
-    case 16: *warps = StftCfg<16>::WARPS; *ctas = StftCfg<16>::CTAS; *smem = StftCfg<16>::SMEM_BYTES; break;
-    default: *warps = StftCfg<32>::WARPS; *ctas = StftCfg<32>::CTAS; *smem = StftCfg<32>::SMEM_BYTES; break;
+    case 4: stft_cfg_LT<4, 32>(warps, ctas, fixed, npar); break;
+    case 8: stft_cfg_LT<8, 32>(warps, ctas, fixed, npar); break;
+    case 16: stft_cfg_LT<16, 32>(warps, ctas, fixed, npar); break;
+    default:
+      if (tile == 16) stft_cfg_LT<32, 16>(warps, ctas, fixed, npar);
+      else stft_cfg_LT<32, 32>(warps, ctas, fixed, npar);
+  }
+}
+
+typedef void (*cep_kernel_t)(const CepArgs);
+static cep_kernel_t pick_cep(int kc) {
+  switch (kc) {
+    case 8: return k_cepstra<8>;
+    case 12: return k_cepstra<12>;
+    default: return k_cepstra<20>;
   }
 }
 
@@ -342,8 +362,8 @@ int aad_plan_destroy(aad_plan* pl) {
   cudaFree(pl->d_window);
   cudaFree(pl->d_tw1);
   cudaFree(pl->d_twp);
-  cudaFree(pl->d_fbw);
-  cudaFree(pl->d_seg);
+  cudaFree(pl->d_filt_hdr);
+  cudaFree(pl->d_filt_w);
   cudaFree(pl->d_warp_filt);
   cudaFree(pl->d_dct_t);
   for (auto& e : pl->ev)
@@ -386,10 +406,21 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, device);
   pl->L = p.n_fft / 64;
   pl->K = p.n_fft / 2 + 1;
-  stft_cfg(pl->L, &pl->warps, &pl->ctas, &pl->k1_smem);
+  // n_fft 2048: one 16-warp CTA per SM on 32-frame tiles.  AAD_TILE=16 selects the
+  // two-CTAs-per-SM variant on 16-frame tiles (kept for comparison runs; measured equal).
+  pl->tile = 32;
+  if (pl->L == 32) {
+    const char* env = getenv("AAD_TILE");
+    pl->tile = (env && atoi(env) == 16) ? 16 : 32;
+  }
+  size_t k1_fixed = 0;
+  int npar = 1;
+  stft_cfg(pl->L, pl->tile, &pl->warps, &pl->ctas, &k1_fixed, &npar);
   pl->c_feat = p.n_ceps > 0 ? p.n_ceps : p.n_filt;
   pl->c_out = pl->c_feat * (1 + p.n_delta);
-  pl->ncp = p.n_ceps > 0 ? (p.n_ceps + CEP_KC - 1) / CEP_KC * CEP_KC : 0;
+  pl->kc = p.n_ceps >= 40 ? 20 : (p.n_ceps > 16 ? 12 : 8);
+  pl->ncp = p.n_ceps > 0 ? (p.n_ceps + pl->kc - 1) / pl->kc * pl->kc : 0;
+  pl->cep_groups = p.n_ceps > 0 ? std::min(CEP_MAXG, pl->ncp / pl->kc) : 2;
   const bool direct = (p.n_ceps == 0 && p.n_delta == 0 && p.layout == AAD_LAYOUT_CT && !p.time_mean);
   pl->need_ws_E = !direct;
   pl->need_ws_feat = p.time_mean != 0;
@@ -426,16 +457,37 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
     delete pl;
     return rc;
   }
-  // filter ranges per warp of the filterbank phase, balanced by bins + a per-filter log cost
+  // Filterbank tables: per filter the dense band [seg[j], seg[j+2]) of the float32 matrix, in
+  // groups of 4*npar taps (zero padded); per warp a contiguous filter range balanced by cost.
   std::vector<int32_t> wfilt(pl->warps + 1, p.n_filt);
+  std::vector<int2> fhdr(p.n_filt);
+  std::vector<float4> fw4;
   {
+    const int gt = 4 * npar;  // taps per group
     std::vector<double> cost(p.n_filt);
     double tot = 0;
     for (int j = 0; j < p.n_filt; ++j) {
-      cost[j] = (seg[j + 1] - seg[j]) + 10.0;
+      int k0 = seg[j], k1 = seg[j + 2];
+      while (k0 < k1 && pl->h_fb[(size_t)j * K + k0] == 0.f) ++k0;       // trim zero taps
+      while (k1 > k0 && pl->h_fb[(size_t)j * K + k1 - 1] == 0.f) --k1;
+      const int ng = (k1 - k0 + gt - 1) / gt;
+      if (k0 > 0xffff || ng > 0x7fff) {
+        delete pl;
+        return AAD_ERR_UNSUPPORTED;
+      }
+      fhdr[j] = make_int2(k0 | (ng << 16), (int)fw4.size());
+      for (int g = 0; g < ng; ++g)
+        for (int h = 0; h < npar; ++h) {
+          float w[4];
+          for (int i = 0; i < 4; ++i) {
+            const int k = k0 + g * gt + npar * i + h;
+            w[i] = k < k1 ? pl->h_fb[(size_t)j * K + k] : 0.f;
+          }
+          fw4.push_back(make_float4(w[0], w[1], w[2], w[3]));
+        }
+      cost[j] = 9.0 * ng + 30.0;  // ~instructions: tap groups + one emit
       tot += cost[j];
     }
-    tot += seg[p.n_filt + 1] - seg[p.n_filt];
     wfilt[0] = 0;
     double cum = 0;
     int j = 0;
@@ -446,6 +498,8 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
     }
     wfilt[pl->warps] = p.n_filt;
   }
+  pl->n_w4 = (int)fw4.size();
+  pl->k1_smem = k1_fixed + (size_t)((2 * p.n_filt + 3) & ~3) * 4 + fw4.size() * sizeof(float4);
   // DCT-II ortho (scipy.fftpack.dct type 2 norm='ortho'), first n_ceps rows; transposed + padded
   std::vector<float> dct_t;
   if (p.n_ceps > 0) {
@@ -470,24 +524,28 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   if (e == cudaSuccess) e = upload(&pl->d_window, win_half);
   if (e == cudaSuccess) e = upload(&pl->d_tw1, tw1);
   if (e == cudaSuccess) e = upload(&pl->d_twp, twp);
-  if (e == cudaSuccess) e = upload(&pl->d_fbw, fbw);
-  if (e == cudaSuccess) e = upload(&pl->d_seg, seg);
+  if (e == cudaSuccess) e = upload(&pl->d_filt_hdr, fhdr);
+  if (e == cudaSuccess) e = upload(&pl->d_filt_w, fw4);
   if (e == cudaSuccess) e = upload(&pl->d_warp_filt, wfilt);
   if (e == cudaSuccess) e = upload(&pl->d_dct_t, dct_t);
   // opt in to the large dynamic shared memory of every kernel variant this plan can launch
+  // (the attribute is per function, not per plan: opt in to the device maximum)
+  int optin = 0;
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if (pl->k1_smem > (size_t)optin) {
+    aad_plan_destroy(pl);
+    return AAD_ERR_UNSUPPORTED;
+  }
   for (int mode = 0; mode < 3 && e == cudaSuccess; ++mode)
     for (int pre = 0; pre < 2 && e == cudaSuccess; ++pre)
-      e = cudaFuncSetAttribute((const void*)pick_stft(L, mode, pre != 0),
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->k1_smem);
+      e = cudaFuncSetAttribute((const void*)pick_stft(L, pl->tile, mode, pre != 0),
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   if (e == cudaSuccess && pl->need_ws_E) {
-    // the attribute is per function, not per plan: opt in to the device maximum once
-    int optin = 0;
-    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (cep_smem_bytes(pl) > (size_t)optin) {
       aad_plan_destroy(pl);
       return AAD_ERR_UNSUPPORTED;
     }
-    e = cudaFuncSetAttribute((const void*)k_cepstra, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    e = cudaFuncSetAttribute((const void*)pick_cep(pl->kc), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   }
   if (e != cudaSuccess) {
     aad_plan_destroy(pl);
@@ -504,8 +562,9 @@ static int frames_for(const aad_params& p, int64_t len) {
 }
 
 struct WsLayout {
-  size_t off_frame_off, off_len, off_nf, off_max, off_E, off_feat, total;
+  size_t off_frame_off, off_len, off_nf, off_max, off_tile, off_E, off_feat, total;
   int t_ws;
+  int max_tiles;
 };
 static WsLayout ws_layout(const aad_plan* pl, int B, int t_max) {
   WsLayout w;
@@ -514,6 +573,8 @@ static WsLayout ws_layout(const aad_plan* pl, int B, int t_max) {
   w.off_len = o;       o = align_up(o + (size_t)B * 4, 256);
   w.off_nf = o;        o = align_up(o + (size_t)B * 4, 256);
   w.off_max = o;       o = align_up(o + (size_t)B * 4, 256);
+  w.max_tiles = (int)(((long long)B * t_max + pl->tile - 1) / pl->tile);
+  w.off_tile = o;      o = align_up(o + (size_t)(w.max_tiles + 1) * 4, 256);
   w.t_ws = (t_max + 31) / 32 * 32;
   w.off_E = o;
   if (pl->need_ws_E) o = align_up(o + (size_t)B * pl->p.n_filt * w.t_ws * 4, 256);
@@ -578,6 +639,7 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
   pa.t_alloc = p.time_mean ? w.t_ws : t_cap;
   pa.n_frames = n_frames; pa.status = status; pa.len_c = d_len; pa.nf_eff = d_nf;
   pa.frame_off = d_frame_off; pa.utt_max = d_max;
+  pa.tile_b0 = (int32_t*)(ws + w.off_tile); pa.tile = pl->tile; pa.max_tiles = w.max_tiles;
   const bool prof = pl->profile;
   if (prof) cudaEventRecord(pl->ev[0], stream);
   (void)cudaGetLastError();  // clear stale non-sticky state left by earlier calls in this thread
@@ -591,8 +653,9 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
   sa.hop = p.hop_length; sa.s_off = p.center ? p.n_fft / 2 : 0;
   sa.win_off = p.center ? (p.n_fft - p.win_length) / 2 : 0; sa.win_len = p.win_length;
   sa.pre_emph = p.pre_emph;
-  sa.window = pl->d_window; sa.tw1 = pl->d_tw1; sa.twp = pl->d_twp; sa.fbw = pl->d_fbw;
-  sa.seg = pl->d_seg; sa.warp_filt = pl->d_warp_filt; sa.n_filt = p.n_filt;
+  sa.window = pl->d_window; sa.tw1 = pl->d_tw1; sa.twp = pl->d_twp;
+  sa.filt_hdr = pl->d_filt_hdr; sa.filt_w = pl->d_filt_w; sa.n_w4 = pl->n_w4;
+  sa.warp_filt = pl->d_warp_filt; sa.tile_b0 = pa.tile_b0; sa.n_filt = p.n_filt;
   sa.log_type = p.log_type; sa.amin = p.amin; sa.eps = 2.220446049250313e-16f;
   if (pl->need_ws_E) {
     sa.E = d_E; sa.e_stride_b = (long long)p.n_filt * w.t_ws; sa.e_stride_f = w.t_ws;
@@ -602,8 +665,8 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
   sa.utt_max = p.log_type == AAD_LOG_DB10 ? d_max : nullptr;
   sa.status = status;
   const int mode = wav_dtype == AAD_I16 ? IN_I16 : (p.quantize_i16 ? IN_F32_Q16 : IN_F32);
-  stft_kernel_t kern = pick_stft(pl->L, mode, p.pre_emph != 0.f);
-  const long long max_tiles = ((long long)B * std::max(t_max, 1) + 31) / 32;
+  stft_kernel_t kern = pick_stft(pl->L, pl->tile, mode, p.pre_emph != 0.f);
+  const long long max_tiles = w.max_tiles;
   const int grid1 = (int)std::min<long long>((long long)pl->sm_count * pl->ctas, std::max<long long>(max_tiles, 1));
   kern<<<grid1, pl->warps * 32, pl->k1_smem, stream>>>(sa);
   LAUNCH_CHECK("k_stft_fb launch");
@@ -629,7 +692,7 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
     ca.tile_out = CEP_TS - (p.n_delta > 0 ? 2 * (p.delta_width / 2) : 0);
     const int gx = t_max <= CEP_TS ? 1 : (t_max + ca.tile_out - 1) / ca.tile_out;
     dim3 grid(gx, B);
-    k_cepstra<<<grid, CEP_TS, cep_smem_bytes(pl), stream>>>(ca);
+    pick_cep(pl->kc)<<<grid, CEP_TS * pl->cep_groups, cep_smem_bytes(pl), stream>>>(ca);
     LAUNCH_CHECK("k_cepstra launch");
     if (prof) cudaEventRecord(pl->ev[3], stream);
     if (p.time_mean) {

@@ -51,6 +51,8 @@ struct PrepArgs {
   int32_t* nf_eff;     // ws: frames actually computed (0 when status != 0)
   int32_t* frame_off;  // ws: [B+1] exclusive scan of nf_eff
   int32_t* utt_max;    // ws: ordered-int encoded running max, init -inf
+  int32_t* tile_b0;    // ws: [max_tiles] utterance holding the first frame of each K1 tile
+  int tile, max_tiles;
 };
 
 __global__ void __launch_bounds__(1024) k_prepare(PrepArgs a) {
@@ -110,32 +112,52 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepArgs a) {
     __syncthreads();
   }
   if (tid == 0) a.frame_off[a.B] = carry_s;
+  __syncthreads();
+  // tile -> utterance index for k_stft_fb (global frame g belongs to utterance b iff
+  // frame_off[b] <= g < frame_off[b+1]); __ldcg: frame_off was written by this CTA just above
+  const int total = carry_s;
+  const int n_tiles = min(a.max_tiles, (total + a.tile - 1) / a.tile);
+  for (int tl = tid; tl < n_tiles; tl += 1024) {
+    const int gf = tl * a.tile;
+    int lo = 0, hi = a.B;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (__ldcg(a.frame_off + mid + 1) <= gf) lo = mid + 1;
+      else hi = mid;
+    }
+    a.tile_b0[tl] = lo;
+  }
 }
 
 // ---------------------------------------------------------------------------
 // K1: fused STFT + power + filterbank + log
 // ---------------------------------------------------------------------------
-template <int L>
+template <int L, int TILE_>
 struct StftCfg {
   static constexpr int Q = 32 / L;        // frames per warp-iteration
   static constexpr int M = 32 * L;        // complex FFT length (n_fft / 2)
   static constexpr int N = 2 * M;         // n_fft
   static constexpr int K = M + 1;         // bins
-  static constexpr int SP = 33 * L + 1;   // power-row stride (odd; Q*SP >= 32*33 scratch words)
-  static constexpr int TILE = 32;         // frames per tile (= lanes of the filterbank phase)
+  static constexpr int TILE = TILE_;      // frames per tile
+  static constexpr int NPAR = 32 / TILE;  // filterbank phase: lane = frame + TILE * (bin parity class)
+  // power-row stride: the filterbank phase reads P[frame][bin] with lane = frame (+ parity), so
+  // banks (frame*SP + parity) must be distinct: SP odd for NPAR=1, SP = 2 (mod 4) for NPAR=2.
+  // Q*SP >= 32*33 words because the rows double as the warp's transpose scratch.
+  static constexpr int SP = NPAR == 1 ? 33 * L + 1 : 33 * L + 2;
   static constexpr int ITERS = TILE / Q;  // warp-iterations per tile
-  static constexpr int WARPS = L == 32 ? 16 : (L == 16 ? 8 : 4);
-  static constexpr int CTAS = L == 32 ? 1 : (L == 16 ? 2 : 4);
-  static constexpr int KPAD = (K + 3) & ~3;
-  // shared memory carve-up, in floats
+  static constexpr int WARPS = ITERS >= 8 ? ITERS / 2 : 4;
+  static constexpr int CTAS = L == 32 ? (TILE == 32 ? 1 : 2) : (L == 16 ? 2 : 4);
+  // shared memory carve-up, in floats (the filterbank program follows at OFF_PROG)
   static constexpr int OFF_P = 0;
   static constexpr int OFF_WIN = ((TILE * SP + 3) & ~3);
   static constexpr int OFF_TW1 = OFF_WIN + N;
   static constexpr int OFF_TWP = OFF_TW1 + 2 * 32 * L;
-  static constexpr int OFF_FBW = OFF_TWP + 2 * (M / 2);
-  static constexpr int OFF_META = OFF_FBW + 2 * KPAD;
-  static constexpr int SMEM_FLOATS = OFF_META + 2 * TILE;
-  static constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
+  static constexpr int OFF_META = OFF_TWP + 2 * (M / 2);      // 2 x {b[TILE], t[TILE]} (double buffered)
+  static constexpr int OFF_PROG = OFF_META + 4 * TILE;        // filter headers + tap weights follow
+  static constexpr size_t FIXED_BYTES = size_t(OFF_PROG) * 4;
+  static_assert(NPAR == 1 || NPAR == 2, "tile must be 16 or 32 frames");
+  static_assert(Q * SP >= 32 * 33, "power rows must hold the transpose scratch");
+  static_assert(OFF_PROG % 4 == 0, "program stream must be 16-byte aligned");
 };
 
 struct StftArgs {
@@ -150,9 +172,14 @@ struct StftArgs {
   const float* window;      // [N]   0.5 * window (zero outside support)
   const float2* tw1;        // [32*L] exp(-2 pi i b kA / M) at [kA*L + b]
   const float2* twp;        // [M/2]  exp(-2 pi i k / N)
-  const float2* fbw;        // [K]    (rising weight of segment's filter, falling weight of previous filter)
-  const int32_t* seg;       // [n_filt + 2] segment bin boundaries
+  // filterbank tables (copied to smem): per filter a header {first bin | n_groups << 16, weight
+  // offset in float4 units}, then the dense band weights in groups of 4*NPAR taps (zero padded;
+  // for NPAR = 2 each group holds the even-tap float4 then the odd-tap float4)
+  const int2* filt_hdr;     // [n_filt]
+  const float4* filt_w;     // [n_w4]
+  int n_w4;
   const int32_t* warp_filt; // [WARPS + 1] filter range per warp
+  const int32_t* tile_b0;   // [n_tiles] from k_prepare
   int n_filt;
   int log_type;             // 0 dB, 1 ln
   float amin, eps;
@@ -200,19 +227,20 @@ __device__ __forceinline__ float2 i16pair_to_float2(unsigned p) {
   return make_float2(lo, hi);
 }
 
-template <int L, int MODE, bool PRE>
-__global__ void __launch_bounds__(StftCfg<L>::WARPS * 32, StftCfg<L>::CTAS) k_stft_fb(const StftArgs a) {
-  using C = StftCfg<L>;
-  constexpr int Q = C::Q, M = C::M, N = C::N, K = C::K, SP = C::SP;
+template <int L, int MODE, bool PRE, int TILE>
+__global__ void __launch_bounds__(StftCfg<L, TILE>::WARPS * 32, StftCfg<L, TILE>::CTAS)
+k_stft_fb(const StftArgs a) {
+  using C = StftCfg<L, TILE>;
+  constexpr int Q = C::Q, M = C::M, N = C::N, SP = C::SP, NPAR = C::NPAR;
   constexpr int LOG2L = ilog2(L);
   extern __shared__ __align__(16) float smem[];
   float* sP = smem + C::OFF_P;
   float* sWin = smem + C::OFF_WIN;
   float2* sTw1 = reinterpret_cast<float2*>(smem + C::OFF_TW1);
   float2* sTwp = reinterpret_cast<float2*>(smem + C::OFF_TWP);
-  float2* sFbw = reinterpret_cast<float2*>(smem + C::OFF_FBW);
-  int* sMetaB = reinterpret_cast<int*>(smem + C::OFF_META);
-  int* sMetaT = sMetaB + C::TILE;
+  int* sMeta = reinterpret_cast<int*>(smem + C::OFF_META);
+  int2* sHdr = reinterpret_cast<int2*>(smem + C::OFF_PROG);
+  float4* sW4 = reinterpret_cast<float4*>(smem + C::OFF_PROG + ((2 * a.n_filt + 3) & ~3));
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -222,31 +250,51 @@ __global__ void __launch_bounds__(StftCfg<L>::WARPS * 32, StftCfg<L>::CTAS) k_st
   for (int i = tid; i < N; i += nthr) sWin[i] = a.window[i];
   for (int i = tid; i < 32 * L; i += nthr) sTw1[i] = a.tw1[i];
   for (int i = tid; i < M / 2; i += nthr) sTwp[i] = a.twp[i];
-  for (int i = tid; i < K; i += nthr) sFbw[i] = a.fbw[i];
+  for (int i = tid; i < a.n_filt; i += nthr) sHdr[i] = a.filt_hdr[i];
+  for (int i = tid; i < a.n_w4; i += nthr) sW4[i] = a.filt_w[i];
   const int wf0 = a.warp_filt[warp], wf1 = a.warp_filt[warp + 1];
   const int total = a.frame_off[a.B];
   const int n_tiles = (total + C::TILE - 1) / C::TILE;
   const float2* sWin2 = reinterpret_cast<const float2*>(sWin);
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    // ---- tile meta: global frame index -> (utterance, frame) -------------------
-    if (warp == 0) {
-      int gf = tile * C::TILE + lane;
+  // tile meta: global frame index -> (utterance, frame); computed one tile ahead by warp 0 so the
+  // dependent index loads never sit on the critical path, and used to prefetch the next tile's
+  // new samples into L2 (bulk prefetch: one instruction per frame)
+  auto tile_meta = [&](int tile, int buf) {
+    if (lane < C::TILE) {
+      const int gf = tile * C::TILE + lane;
       int b = -1, t = 0;
-      if (gf < total) {
-        int lo = 0, hi = a.B;
-        while (lo < hi) {
-          int mid = (lo + hi) >> 1;
-          if (__ldg(a.frame_off + mid + 1) <= gf) lo = mid + 1;
-          else hi = mid;
-        }
-        b = lo;
-        t = gf - __ldg(a.frame_off + lo);
+      if (tile < n_tiles && gf < total) {
+        b = __ldg(a.tile_b0 + tile);
+        int nxt = __ldg(a.frame_off + b + 1);
+        while (gf >= nxt) nxt = __ldg(a.frame_off + (++b) + 1);
+        t = gf - __ldg(a.frame_off + b);
       }
-      sMetaB[lane] = b;
-      sMetaT[lane] = t;
+      sMeta[buf * 2 * C::TILE + lane] = b;
+      sMeta[buf * 2 * C::TILE + C::TILE + lane] = t;
+      if (b >= 0) {
+        constexpr int ES = MODE == IN_I16 ? 2 : 4;
+        const long long len = __ldg(a.len_c + b);
+        long long s_lo = (long long)t * a.hop - a.s_off + (t == 0 ? 0 : N - a.hop);
+        long long s_hi = (long long)t * a.hop - a.s_off + N;
+        if (s_lo < 0) s_lo = 0;
+        if (s_hi > len) s_hi = len;
+        const char* row = static_cast<const char*>(a.wav) + (long long)b * a.wav_stride * ES;
+        uintptr_t p0 = ((uintptr_t)(row + s_lo * ES) + 15) & ~(uintptr_t)15;
+        uintptr_t p1 = (uintptr_t)(row + s_hi * ES) & ~(uintptr_t)15;
+        if (p1 > p0)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"((unsigned)(p1 - p0)) : "memory");
+      }
     }
-    __syncthreads();  // meta visible; previous tile's filterbank phase is done with sP
+  };
+  if (warp == 0) tile_meta(blockIdx.x, 0);
+  __syncthreads();
+
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    const int* sMetaB = sMeta + buf * 2 * C::TILE;
+    const int* sMetaT = sMetaB + C::TILE;
+    if (warp == 0) tile_meta(tile + gridDim.x, buf ^ 1);  // consumed after the bottom barrier
 
     // ---- FFT phase ---------------------------------------------------------------
     for (int it = warp; it < C::ITERS; it += C::WARPS) {
@@ -404,33 +452,40 @@ __global__ void __launch_bounds__(StftCfg<L>::WARPS * 32, StftCfg<L>::CTAS) k_st
     }
     __syncthreads();
 
-    // ---- filterbank + log phase: lane = frame, warps split the filters ----------
+    // ---- filterbank + log phase: lane = frame (+ tap parity class), warps split the filters ----
+    // Per filter: dense band of taps in groups of four (weights: one LDS.128, powers: four LDS at
+    // immediate offsets from one pointer), then log, store, running max.
     if (wf0 < wf1) {
-      const int b = sMetaB[lane], t = sMetaT[lane];
+      const int fr = lane % C::TILE, par = lane / C::TILE;
+      const int b = sMetaB[fr], t = sMetaT[fr];
       const bool valid = b >= 0;
-      const float* prow = sP + lane * SP;
-      float* erow = a.E + (valid ? (long long)b * a.e_stride_b + t : 0);
-      float rprev = 0.f, vmax = -INFINITY;
-      bool bad = false;
-      for (int s = wf0; s <= wf1; ++s) {
-        const int k0 = __ldg(a.seg + s), k1 = __ldg(a.seg + s + 1);
-        float r = 0.f, f = 0.f;
-        int k = k0;
-#pragma unroll 4
-        for (; k < k1; ++k) {
-          float p = prow[k];
-          float2 w = sFbw[k];
-          r = __fmaf_rn(w.x, p, r);
-          f = __fmaf_rn(w.y, p, f);
+      const float* pbase = sP + fr * SP + par;
+      float* eptr = a.E + (valid ? (long long)b * a.e_stride_b + (long long)wf0 * a.e_stride_f + t : 0);
+      float vmax = -INFINITY, chk = 0.f;
+      for (int jf = wf0; jf < wf1; ++jf) {
+        const int2 hd = sHdr[jf];
+        const float* pp = pbase + (hd.x & 0xffff);
+        const float4* wp = sW4 + hd.y + par;
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int gq = hd.x >> 16; gq > 0; --gq) {
+          const float4 w = *wp;
+          acc0 = __fmaf_rn(w.x, pp[0], acc0);
+          acc1 = __fmaf_rn(w.y, pp[NPAR], acc1);
+          acc0 = __fmaf_rn(w.z, pp[2 * NPAR], acc0);
+          acc1 = __fmaf_rn(w.w, pp[3 * NPAR], acc1);
+          wp += NPAR;
+          pp += 4 * NPAR;
         }
-        if (s > wf0) {
-          float e = rprev + f;
-          float val = a.log_type == 0 ? 10.0f * log10f(fmaxf(a.amin, e)) : logf(e == 0.f ? a.eps : e);
-          if (valid) erow[(long long)(s - 1) * a.e_stride_f] = val;
-          vmax = fmaxf(vmax, val);
-          bad |= !(fabsf(val) <= 3.0e38f);
-        }
-        rprev = r;
+        float en = acc0 + acc1;
+        if constexpr (NPAR == 2) en += __shfl_xor_sync(0xffffffffu, en, 16);
+        // 10*log10(x) = 3.0103*log2(x), ln(x) = 0.6931*log2(x); MUFU.LG2 is accurate to 2 ulp,
+        // i.e. <= 3e-5 dB / 4e-6 nepers here, far inside the 1e-3 parity tolerance
+        const float val = a.log_type == 0 ? 3.01029995663981195f * __log2f(fmaxf(a.amin, en))
+                                          : 0.69314718055994531f * __log2f(en == 0.f ? a.eps : en);
+        if (valid && par == 0) *eptr = val;
+        eptr += a.e_stride_f;
+        vmax = fmaxf(vmax, val);
+        chk = __fmaf_rn(val, 0.f, chk);  // NaN/Inf poison
       }
       if (valid) {
         if (a.utt_max) {
@@ -438,19 +493,19 @@ __global__ void __launch_bounds__(StftCfg<L>::WARPS * 32, StftCfg<L>::CTAS) k_st
           int enc = __reduce_max_sync(peers, enc_ordered(vmax));
           if ((int)(__ffs(peers) - 1) == lane) atomicMax(a.utt_max + b, enc);
         }
-        if (bad) a.status[b] = 5;
+        if (chk != chk) a.status[b] = 5;
       }
     }
-    // the __syncthreads at the top of the next tile protects sP and the meta arrays
+    __syncthreads();  // sP free for the next tile's FFTs; next tile's meta (written above) visible
   }
 }
 
 // ---------------------------------------------------------------------------
 // K2: dB reference / floor + DCT-II + deltas + layout
 // ---------------------------------------------------------------------------
-constexpr int CEP_TS = 128;       // frames per tile held in smem (threads per CTA)
-constexpr int CEP_KC = 20;        // DCT coefficients accumulated per pass
+constexpr int CEP_TS = 128;       // frames per tile held in smem
 constexpr int CEP_MAXW = 9;
+constexpr int CEP_MAXG = 4;       // thread groups per CTA (each: one thread per frame column)
 
 struct CepArgs {
   const float* E;         // [B][n_filt][e_stride_f]
@@ -462,7 +517,7 @@ struct CepArgs {
   int log_type, ref_type;
   float top_db;           // < 0: none
   int n_ceps;             // 0: identity
-  int ncp;                // padded n_ceps (multiple of CEP_KC)
+  int ncp;                // padded n_ceps (multiple of the chunk size KC)
   const float* dct_t;     // [n_filt + 1][ncp]  (transposed DCT matrix, zero padded; last row = column sums)
   int n_delta, width;
   float taps[2][CEP_MAXW];
@@ -472,7 +527,11 @@ struct CepArgs {
   int tile_out;           // output frames per tile when T > CEP_TS
 };
 
-__global__ void __launch_bounds__(CEP_TS) k_cepstra(const CepArgs a) {
+// One CTA = (utterance, tile of <= 128 frames).  blockDim = 128 * G: thread (col, grp) owns frame
+// column `col`; the G groups split the filterbank rows when loading, the DCT coefficient chunks
+// when contracting and the coefficient rows when writing.
+template <int KC>
+__global__ void __launch_bounds__(CEP_TS * CEP_MAXG) k_cepstra(const CepArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int b = blockIdx.y;
   const int T = a.nf_eff[b];
@@ -495,7 +554,7 @@ __global__ void __launch_bounds__(CEP_TS) k_cepstra(const CepArgs a) {
     hi = max(hi, c1 + h + 1);
   }
   const int nload = hi - lo;  // <= CEP_TS by construction
-  const int tid = threadIdx.x;
+  const int col = threadIdx.x & (CEP_TS - 1), grp = threadIdx.x >> 7, G = blockDim.x >> 7;
   const int C = a.n_ceps > 0 ? a.n_ceps : a.n_filt;
 
   float* sE = smem;                                   // [n_filt][CEP_TS]
@@ -509,18 +568,23 @@ __global__ void __launch_bounds__(CEP_TS) k_cepstra(const CepArgs a) {
     if (a.ref_type == 1) ref = m;
     if (a.top_db >= 0.f) floorv = (m - ref) - a.top_db;
   }
-  const float* Eb = a.E + (long long)b * a.e_stride_b + lo;
-  if (tid < nload) {
-    for (int m = 0; m < a.n_filt; ++m) {
-      float e = __ldg(Eb + (long long)m * a.e_stride_f + tid);
-      sE[m * CEP_TS + tid] = fmaxf(e - ref, floorv);
+  const float* Eb = a.E + (long long)b * a.e_stride_b + lo + col;
+  if (col < nload) {
+    int m = grp;
+    for (; m + 7 * G < a.n_filt; m += 8 * G) {   // 8 independent loads in flight per thread
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(Eb + (long long)(m + u * G) * a.e_stride_f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) sE[(m + u * G) * CEP_TS + col] = fmaxf(v[u] - ref, floorv);
     }
+    for (; m < a.n_filt; m += G) sE[m * CEP_TS + col] = fmaxf(__ldg(Eb + (long long)m * a.e_stride_f) - ref, floorv);
   } else {
-    for (int m = 0; m < a.n_filt; ++m) sE[m * CEP_TS + tid] = 0.f;
+    for (int m = grp; m < a.n_filt; m += G) sE[m * CEP_TS + col] = 0.f;
   }
   if (a.n_ceps > 0) {
     const int nd = (a.n_filt + 1) * a.ncp;
-    for (int i = tid * 4; i < nd; i += CEP_TS * 4)
+    for (int i = threadIdx.x * 4; i < nd; i += blockDim.x * 4)
       *reinterpret_cast<float4*>(sD + i) = __ldg(reinterpret_cast<const float4*>(a.dct_t + i));
   }
   __syncthreads();
@@ -530,17 +594,18 @@ __global__ void __launch_bounds__(CEP_TS) k_cepstra(const CepArgs a) {
     // so float32 accumulation of ~100 same-sign dB values loses nothing) and add the mean
     // back through the table's column sums (row n_filt of dct_t).
     float mean = 0.f;
-    for (int m = 0; m < a.n_filt; ++m) mean += sE[m * CEP_TS + tid];
+    for (int m = 0; m < a.n_filt; ++m) mean += sE[m * CEP_TS + col];
     mean *= 1.0f / (float)a.n_filt;
-    for (int c0 = 0; c0 < a.n_ceps; c0 += CEP_KC) {
-      float acc[CEP_KC];
+    for (int c0 = grp * KC; c0 < a.n_ceps; c0 += G * KC) {
+      float acc[KC];
 #pragma unroll
-      for (int i = 0; i < CEP_KC; ++i) acc[i] = 0.f;
+      for (int i = 0; i < KC; ++i) acc[i] = 0.f;
+#pragma unroll 2
       for (int m = 0; m < a.n_filt; ++m) {
-        const float e = sE[m * CEP_TS + tid] - mean;
+        const float e = sE[m * CEP_TS + col] - mean;
         const float4* d4 = reinterpret_cast<const float4*>(sD + m * a.ncp + c0);
 #pragma unroll
-        for (int i = 0; i < CEP_KC / 4; ++i) {
+        for (int i = 0; i < KC / 4; ++i) {
           float4 d = d4[i];
           acc[4 * i + 0] = __fmaf_rn(d.x, e, acc[4 * i + 0]);
           acc[4 * i + 1] = __fmaf_rn(d.y, e, acc[4 * i + 1]);
@@ -550,25 +615,28 @@ __global__ void __launch_bounds__(CEP_TS) k_cepstra(const CepArgs a) {
       }
       const float* colsum = sD + a.n_filt * a.ncp + c0;
 #pragma unroll
-      for (int i = 0; i < CEP_KC; ++i)
-        if (c0 + i < a.n_ceps) sC[(c0 + i) * CEP_TS + tid] = __fmaf_rn(mean, colsum[i], acc[i]);
+      for (int i = 0; i < KC; ++i)
+        if (c0 + i < a.n_ceps) sC[(c0 + i) * CEP_TS + col] = __fmaf_rn(mean, colsum[i], acc[i]);
     }
     __syncthreads();
   }
 
-  const int t = lo + tid;
+  const int t = lo + col;
   if (t >= o0 && t < o1) {
     float* ob = a.out + (long long)b * a.out_stride_b + (long long)t * a.out_stride_t;
     const int te = min(max(t, h), T - 1 - h) - lo;  // stencil centre (edges replicate the interior fit)
-    for (int k = 0; k < C; ++k) {
+    for (int k = grp; k < C; k += G) {
       const float* row = sC + k * CEP_TS;
-      ob[(long long)k * a.out_stride_c] = row[tid];
+      ob[(long long)k * a.out_stride_c] = row[col];
       if (a.n_delta > 0) {
         float d1 = 0.f, d2 = 0.f;
-        for (int i = 0; i < a.width; ++i) {
-          float x = row[te - h + i];
-          d1 = __fmaf_rn(a.taps[0][i], x, d1);
-          d2 = __fmaf_rn(a.taps[1][i], x, d2);
+#pragma unroll
+        for (int i = 0; i < CEP_MAXW; ++i) {
+          if (i < a.width) {
+            float x = row[te - h + i];
+            d1 = __fmaf_rn(a.taps[0][i], x, d1);
+            d2 = __fmaf_rn(a.taps[1][i], x, d2);
+          }
         }
         ob[(long long)(C + k) * a.out_stride_c] = d1;
         if (a.n_delta > 1) ob[(long long)(2 * C + k) * a.out_stride_c] = d2;
