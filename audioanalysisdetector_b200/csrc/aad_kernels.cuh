@@ -107,26 +107,24 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepArgs a) {
     int carry = carry_s;
     int excl = carry + (warp ? warp_sums[warp - 1] : 0) + (x - nf);
     if (b < a.B) a.frame_off[b] = excl;
+    // tile -> utterance index for k_stft_fb: tile tl (first frame tl*tile) starts inside utterance b
+    // iff frame_off[b] <= tl*tile < frame_off[b+1].  The warp walks its 32 utterances and the lanes
+    // write each one's tiles cooperatively (long utterances own thousands of tiles).
+#pragma unroll 1
+    for (int src = 0; src < 32; ++src) {
+      const int e0 = __shfl_sync(0xffffffffu, excl, src);
+      const int n0 = __shfl_sync(0xffffffffu, nf, src);
+      const int b0 = __shfl_sync(0xffffffffu, b, src);
+      if (n0 == 0) continue;
+      const int t_first = (e0 + a.tile - 1) / a.tile, t_end = (e0 + n0 + a.tile - 1) / a.tile;
+      for (int tl = t_first + lane; tl < t_end; tl += 32)
+        if (tl < a.max_tiles) a.tile_b0[tl] = b0;
+    }
     __syncthreads();
     if (tid == 1023) carry_s = carry + warp_sums[31];
     __syncthreads();
   }
   if (tid == 0) a.frame_off[a.B] = carry_s;
-  __syncthreads();
-  // tile -> utterance index for k_stft_fb (global frame g belongs to utterance b iff
-  // frame_off[b] <= g < frame_off[b+1]); __ldcg: frame_off was written by this CTA just above
-  const int total = carry_s;
-  const int n_tiles = min(a.max_tiles, (total + a.tile - 1) / a.tile);
-  for (int tl = tid; tl < n_tiles; tl += 1024) {
-    const int gf = tl * a.tile;
-    int lo = 0, hi = a.B;
-    while (lo < hi) {
-      int mid = (lo + hi) >> 1;
-      if (__ldcg(a.frame_off + mid + 1) <= gf) lo = mid + 1;
-      else hi = mid;
-    }
-    a.tile_b0[tl] = lo;
-  }
 }
 
 // ---------------------------------------------------------------------------
