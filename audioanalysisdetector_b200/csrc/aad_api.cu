@@ -406,12 +406,12 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, device);
   pl->L = p.n_fft / 64;
   pl->K = p.n_fft / 2 + 1;
-  // n_fft 2048: one 16-warp CTA per SM on 32-frame tiles.  AAD_TILE=16 selects the
-  // two-CTAs-per-SM variant on 16-frame tiles (kept for comparison runs; measured equal).
+  // frames per K1 tile.  n_fft 2048: 32 (one 16-warp CTA per SM) or, with AAD_TILE=16 in the
+  // environment, 16 (two 8-warp CTAs per SM whose FFT and filterbank phases interleave).
   pl->tile = 32;
   if (pl->L == 32) {
     const char* env = getenv("AAD_TILE");
-    pl->tile = (env && atoi(env) == 16) ? 16 : 32;
+    if (env && atoi(env) == 16) pl->tile = 16;
   }
   size_t k1_fixed = 0;
   int npar = 1;
@@ -457,36 +457,41 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
     delete pl;
     return rc;
   }
-  // Filterbank tables: per filter the dense band [seg[j], seg[j+2]) of the float32 matrix, in
-  // groups of 4*npar taps (zero padded); per warp a contiguous filter range balanced by cost.
+  // Filterbank program, two-tap banded form (see StftArgs): per segment the bins [seg[s], seg[s+1])
+  // with all-zero ends trimmed, first bin rounded down to a multiple of 4, in rounds of npar groups of
+  // 4 bins; per warp a contiguous filter range balanced by cost.
   std::vector<int32_t> wfilt(pl->warps + 1, p.n_filt);
-  std::vector<int2> fhdr(p.n_filt);
+  std::vector<int2> fhdr(p.n_filt + 1);
   std::vector<float4> fw4;
   {
-    const int gt = 4 * npar;  // taps per group
-    std::vector<double> cost(p.n_filt);
+    std::vector<double> cost(p.n_filt + 1);
     double tot = 0;
-    for (int j = 0; j < p.n_filt; ++j) {
-      int k0 = seg[j], k1 = seg[j + 2];
-      while (k0 < k1 && pl->h_fb[(size_t)j * K + k0] == 0.f) ++k0;       // trim zero taps
-      while (k1 > k0 && pl->h_fb[(size_t)j * K + k1 - 1] == 0.f) --k1;
-      const int ng = (k1 - k0 + gt - 1) / gt;
-      if (k0 > 0xffff || ng > 0x7fff) {
+    for (int sgi = 0; sgi <= p.n_filt; ++sgi) {
+      int k0 = seg[sgi], k1 = seg[sgi + 1];
+      auto zero = [&](int k) { return fbw[k].x == 0.f && fbw[k].y == 0.f; };
+      while (k0 < k1 && zero(k0)) ++k0;
+      while (k1 > k0 && zero(k1 - 1)) --k1;
+      k0 &= ~3;
+      const int ng = (k1 - k0 + 3) / 4;
+      const int rounds = (ng + npar - 1) / npar;
+      if (k0 > 0xffff || rounds > 0x7fff) {
         delete pl;
         return AAD_ERR_UNSUPPORTED;
       }
-      fhdr[j] = make_int2(k0 | (ng << 16), (int)fw4.size());
-      for (int g = 0; g < ng; ++g)
-        for (int h = 0; h < npar; ++h) {
-          float w[4];
-          for (int i = 0; i < 4; ++i) {
-            const int k = k0 + g * gt + npar * i + h;
-            w[i] = k < k1 ? pl->h_fb[(size_t)j * K + k] : 0.f;
-          }
-          fw4.push_back(make_float4(w[0], w[1], w[2], w[3]));
+      fhdr[sgi] = make_int2(k0 | (rounds << 16), (int)fw4.size());
+      for (int g = 0; g < rounds * npar; ++g) {
+        float w[8];
+        for (int i = 0; i < 4; ++i) {
+          const int k = k0 + g * 4 + i;
+          const bool in = k >= seg[sgi] && k < k1;
+          w[2 * i] = in ? fbw[k].x : 0.f;
+          w[2 * i + 1] = in ? fbw[k].y : 0.f;
         }
-      cost[j] = 9.0 * ng + 30.0;  // ~instructions: tap groups + one emit
-      tot += cost[j];
+        fw4.push_back(make_float4(w[0], w[1], w[2], w[3]));
+        fw4.push_back(make_float4(w[4], w[5], w[6], w[7]));
+      }
+      cost[sgi] = 8.0 * rounds + 24.0;  // ~instructions: tap rounds + one emit
+      tot += cost[sgi];
     }
     wfilt[0] = 0;
     double cum = 0;
@@ -499,7 +504,7 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
     wfilt[pl->warps] = p.n_filt;
   }
   pl->n_w4 = (int)fw4.size();
-  pl->k1_smem = k1_fixed + (size_t)((2 * p.n_filt + 3) & ~3) * 4 + fw4.size() * sizeof(float4);
+  pl->k1_smem = k1_fixed + (size_t)((2 * (p.n_filt + 1) + 3) & ~3) * 4 + fw4.size() * sizeof(float4);
   // DCT-II ortho (scipy.fftpack.dct type 2 norm='ortho'), first n_ceps rows; transposed + padded
   std::vector<float> dct_t;
   if (p.n_ceps > 0) {

@@ -1,9 +1,10 @@
-// Register-resident radix-2 DIT FFT building blocks with compile-time twiddles.
+// Register-resident radix-2 DIT FFT building blocks with compile-time twiddles, written for the
+// packed FP32 instructions of sm_100a (FFMA2 / FADD2 / FMUL2 on float2 = one complex number).
 //
 // Every index is a template/constexpr value, so after inlining the `float2 v[N]`
-// arrays live entirely in registers and all twiddles are FFMA immediates.
-// Butterflies use the FMA form  a' = a + w*b,  b' = 2a - a'  (6 FFMA for a general
-// twiddle, 4 FADD for w in {1, -i}, 6 for the sqrt(1/2) twiddles).
+// arrays live entirely in registers and all twiddles are instruction immediates.
+// Butterflies use the FMA form  a' = a + w*b,  b' = 2a - a'  (3 FFMA2 for a general
+// twiddle, 2 FADD2 for w in {1, -i}, 3 for the sqrt(1/2) twiddles).
 #pragma once
 #include <cuda_runtime.h>
 #include <utility>
@@ -82,38 +83,57 @@ constexpr int ilog2(int x) {
   return r;
 }
 
+// ---------------------------------------------------------------- packed FP32 helpers
+// sm_100a executes FFMA2 / FADD2 / FMUL2 on float2 register pairs: one issue slot for two
+// FP32 lane-ops (measured: same 128 lane-ops/clk/SM as scalar FFMA, half the issue slots;
+// tools/microbench/mb_ffma2.cu).  Operand swap (.LO_HI), per-half negation and scalar broadcast
+// (.F32) are instruction modifiers, so with a complex number held as one float2 the products
+// by -i, conj() and i*w*z cost nothing extra: ptxas folds the make_float2() shuffles below.
+__device__ __forceinline__ float2 pk_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 pk_sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 pk_mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+// a * s + c with the scalar s broadcast to both halves
+__device__ __forceinline__ float2 pk_fma_s(float2 a, float s, float2 c) { return __ffma2_rn(a, make_float2(s, s), c); }
+
+// complex product a * w  (2 packed instructions)
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+  // a*w = w.x * (a.x, a.y) + w.y * (-a.y, a.x): swap/negate on the register pair, scalars broadcast
+  const float2 t = __fmul2_rn(make_float2(-a.y, a.x), make_float2(w.y, w.y));
+  return __ffma2_rn(a, make_float2(w.x, w.x), t);
+}
+
 // ---------------------------------------------------------------- butterflies
-// W = exp(-2*pi*i*J/M) = (wr, wi) with wi = -sin.
+// W = exp(-2*pi*i*J/M) = (wr, wi) with wi = -sin.  (a, b) <- (a + W b, a - W b).
+// Packed cost: 2 for W in {1, -i}, 3 otherwise (general: t = a + wr*b; a' = t + wi*(-b.y, b.x);
+// b' = 2a - a').
 template <int J, int M>
 __device__ __forceinline__ void butterfly(float2& a, float2& b) {
   if constexpr (J == 0) {
-    float2 t = b;
-    b = make_float2(a.x - t.x, a.y - t.y);
-    a = make_float2(a.x + t.x, a.y + t.y);
+    const float2 t = b;
+    b = pk_sub(a, t);
+    a = pk_add(a, t);
   } else if constexpr (4 * J == M) {  // w = -i : w*b = (b.y, -b.x)
-    float2 t = make_float2(b.y, -b.x);
-    b = make_float2(a.x - t.x, a.y - t.y);
-    a = make_float2(a.x + t.x, a.y + t.y);
+    const float2 t = b;
+    b = __fadd2_rn(a, make_float2(-t.y, t.x));
+    a = __fadd2_rn(a, make_float2(t.y, -t.x));
   } else if constexpr (8 * J == M) {  // w = (1 - i)/sqrt2 : w*b = c*(b.x + b.y, b.y - b.x)
     constexpr float c = 0.70710678118654752440f;
-    float s1 = b.x + b.y, s2 = b.y - b.x;
-    float nx = __fmaf_rn(c, s1, a.x), ny = __fmaf_rn(c, s2, a.y);
-    b = make_float2(__fmaf_rn(-c, s1, a.x), __fmaf_rn(-c, s2, a.y));
-    a = make_float2(nx, ny);
-  } else if constexpr (8 * J == 3 * M) {  // w = (-1 - i)/sqrt2 : w*b = c*(b.y - b.x, -(b.x + b.y))
+    const float2 s = __fadd2_rn(b, make_float2(b.y, -b.x));
+    b = pk_fma_s(s, -c, a);
+    a = pk_fma_s(s, c, a);
+  } else if constexpr (8 * J == 3 * M) {  // w = (-1 - i)/sqrt2 : w*b = -c*(b.x - b.y, b.x + b.y)
     constexpr float c = 0.70710678118654752440f;
-    float s1 = b.y - b.x, s2 = b.x + b.y;
-    float nx = __fmaf_rn(c, s1, a.x), ny = __fmaf_rn(-c, s2, a.y);
-    b = make_float2(__fmaf_rn(-c, s1, a.x), __fmaf_rn(c, s2, a.y));
-    a = make_float2(nx, ny);
+    const float2 s = __fadd2_rn(b, make_float2(-b.y, b.x));
+    b = pk_fma_s(s, c, a);
+    a = pk_fma_s(s, -c, a);
   } else {
     constexpr cx_cs cs = cx_cossin_2pi(J, M);
     constexpr float wr = float(cs.c), wi = float(-cs.s);
-    // t = w*b ; a' = a + t ; b' = 2a - a'
-    float nx = __fmaf_rn(wr, b.x, __fmaf_rn(-wi, b.y, a.x));
-    float ny = __fmaf_rn(wr, b.y, __fmaf_rn(wi, b.x, a.y));
-    b = make_float2(__fmaf_rn(2.0f, a.x, -nx), __fmaf_rn(2.0f, a.y, -ny));
-    a = make_float2(nx, ny);
+    const float2 t = pk_fma_s(b, wr, a);
+    const float2 na = __ffma2_rn(make_float2(-b.y, b.x), make_float2(wi, wi), t);
+    b = __ffma2_rn(a, make_float2(2.0f, 2.0f), make_float2(-na.x, -na.y));
+    a = na;
   }
 }
 
@@ -134,10 +154,6 @@ __device__ __forceinline__ void fft_dit(float2 (&v)[NV]) {
       });
     });
   });
-}
-
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(__fmaf_rn(a.x, b.x, -(a.y * b.y)), __fmaf_rn(a.x, b.y, a.y * b.x));
 }
 
 }  // namespace aad

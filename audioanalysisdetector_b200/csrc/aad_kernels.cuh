@@ -2,7 +2,8 @@
 //
 //   k_prepare   : per-utterance frame counts, status, exclusive scan of frames, max init
 //   k_stft_fb   : fused framing + window + real FFT + |X|^2 + banded filterbank + log
-//                 (persistent; one warp-iteration = 32/L frames, FFT entirely in registers)
+//                 (persistent; one warp-iteration = 32/L frames, FFT entirely in registers,
+//                 packed FP32: FFMA2 / FADD2 / FMUL2 on float2 = one complex number)
 //   k_cepstra   : dB reference/floor + DCT-II + delta/delta-delta stencil + layout
 //   k_db_finalize, k_time_mean, k_delta : small epilogues
 //
@@ -137,25 +138,28 @@ struct StftCfg {
   static constexpr int N = 2 * M;         // n_fft
   static constexpr int K = M + 1;         // bins
   static constexpr int TILE = TILE_;      // frames per tile
-  static constexpr int NPAR = 32 / TILE;  // filterbank phase: lane = frame + TILE * (bin parity class)
-  // power-row stride: the filterbank phase reads P[frame][bin] with lane = frame (+ parity), so
-  // banks (frame*SP + parity) must be distinct: SP odd for NPAR=1, SP = 2 (mod 4) for NPAR=2.
-  // Q*SP >= 32*33 words because the rows double as the warp's transpose scratch.
-  static constexpr int SP = NPAR == 1 ? 33 * L + 1 : 33 * L + 2;
+  static constexpr int NPAR = 32 / TILE;  // filterbank phase: lane = frame + TILE * (tap-group parity)
+  // power-row stride in floats.  The filterbank phase reads P[frame][4g .. 4g+3] as one LDS.128 per
+  // lane: conflict-free iff SP/4 is odd.  Q rows double as the warp's 32x33 transpose scratch
+  // (Q*SP >= 1056), and the row holds K bins plus zeroed padding (PAD words).
+  static constexpr int SP = L == 4 ? 132 : (L == 8 ? 292 : (L == 16 ? 548 : 1060));
+  static constexpr int PAD = NPAR == 1 ? 3 : 7;
   static constexpr int ITERS = TILE / Q;  // warp-iterations per tile
   static constexpr int WARPS = ITERS >= 8 ? ITERS / 2 : 4;
   static constexpr int CTAS = L == 32 ? (TILE == 32 ? 1 : 2) : (L == 16 ? 2 : 4);
   // shared memory carve-up, in floats (the filterbank program follows at OFF_PROG)
   static constexpr int OFF_P = 0;
-  static constexpr int OFF_WIN = ((TILE * SP + 3) & ~3);
+  static constexpr int OFF_WIN = TILE * SP;
   static constexpr int OFF_TW1 = OFF_WIN + N;
   static constexpr int OFF_TWP = OFF_TW1 + 2 * 32 * L;
   static constexpr int OFF_META = OFF_TWP + 2 * (M / 2);      // 2 x {b[TILE], t[TILE]} (double buffered)
-  static constexpr int OFF_PROG = OFF_META + 4 * TILE;        // filter headers + tap weights follow
+  static constexpr int OFF_PROG = OFF_META + 4 * TILE;        // segment headers + tap weights follow
   static constexpr size_t FIXED_BYTES = size_t(OFF_PROG) * 4;
   static_assert(NPAR == 1 || NPAR == 2, "tile must be 16 or 32 frames");
+  static_assert(SP % 8 == 4, "LDS.128 over lane = frame needs an odd number of 16-byte units per row");
   static_assert(Q * SP >= 32 * 33, "power rows must hold the transpose scratch");
-  static_assert(OFF_PROG % 4 == 0, "program stream must be 16-byte aligned");
+  static_assert(SP >= K + PAD, "row must hold the bins and the zero padding");
+  static_assert(OFF_PROG % 4 == 0 && OFF_WIN % 4 == 0, "tables must be 16-byte aligned");
 };
 
 struct StftArgs {
@@ -170,13 +174,16 @@ struct StftArgs {
   const float* window;      // [N]   0.5 * window (zero outside support)
   const float2* tw1;        // [32*L] exp(-2 pi i b kA / M) at [kA*L + b]
   const float2* twp;        // [M/2]  exp(-2 pi i k / N)
-  // filterbank tables (copied to smem): per filter a header {first bin | n_groups << 16, weight
-  // offset in float4 units}, then the dense band weights in groups of 4*NPAR taps (zero padded;
-  // for NPAR = 2 each group holds the even-tap float4 then the odd-tap float4)
-  const int2* filt_hdr;     // [n_filt]
+  // filterbank program (copied to smem), two-tap banded form: the bins split into n_filt + 1
+  // segments; inside segment s bin k feeds filter s with its rising weight wr[k] and filter s - 1
+  // with its falling weight wf[k], so  energy[j] = R[j] + F[j + 1]  with (R, F)[s] the two
+  // weighted sums over segment s and every power value is read once.  Per segment a header
+  // {first bin (multiple of 4) | n_rounds << 16, weight offset in float4 units}; per round NPAR
+  // groups of 4 bins, each group two float4 {wr0, wf0, wr1, wf1}, {wr2, wf2, wr3, wf3} (zero padded).
+  const int2* filt_hdr;     // [n_filt + 1]
   const float4* filt_w;     // [n_w4]
   int n_w4;
-  const int32_t* warp_filt; // [WARPS + 1] filter range per warp
+  const int32_t* warp_filt; // [WARPS + 1] filter range per warp (segments wf0 .. wf1 inclusive)
   const int32_t* tile_b0;   // [n_tiles] from k_prepare
   int n_filt;
   int log_type;             // 0 dB, 1 ln
@@ -220,9 +227,9 @@ __device__ __forceinline__ float load_masked(const void* row, int idx, int n, in
 
 __device__ __forceinline__ float2 i16pair_to_float2(unsigned p) {
   // exact int16 -> float via the 2^23 magic number (ALU + FADD instead of I2F)
-  float lo = __uint_as_float(0x4B000000u | ((p & 0xffffu) ^ 0x8000u)) - 8421376.0f;
-  float hi = __uint_as_float(0x4B000000u | ((p >> 16) ^ 0x8000u)) - 8421376.0f;
-  return make_float2(lo, hi);
+  float2 m = make_float2(__uint_as_float(0x4B000000u | ((p & 0xffffu) ^ 0x8000u)),
+                         __uint_as_float(0x4B000000u | ((p >> 16) ^ 0x8000u)));
+  return __fadd2_rn(m, make_float2(-8421376.0f, -8421376.0f));
 }
 
 template <int L, int MODE, bool PRE, int TILE>
@@ -238,7 +245,7 @@ k_stft_fb(const StftArgs a) {
   float2* sTwp = reinterpret_cast<float2*>(smem + C::OFF_TWP);
   int* sMeta = reinterpret_cast<int*>(smem + C::OFF_META);
   int2* sHdr = reinterpret_cast<int2*>(smem + C::OFF_PROG);
-  float4* sW4 = reinterpret_cast<float4*>(smem + C::OFF_PROG + ((2 * a.n_filt + 3) & ~3));
+  float4* sW4 = reinterpret_cast<float4*>(smem + C::OFF_PROG + ((2 * (a.n_filt + 1) + 3) & ~3));
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -248,7 +255,7 @@ k_stft_fb(const StftArgs a) {
   for (int i = tid; i < N; i += nthr) sWin[i] = a.window[i];
   for (int i = tid; i < 32 * L; i += nthr) sTw1[i] = a.tw1[i];
   for (int i = tid; i < M / 2; i += nthr) sTwp[i] = a.twp[i];
-  for (int i = tid; i < a.n_filt; i += nthr) sHdr[i] = a.filt_hdr[i];
+  for (int i = tid; i <= a.n_filt; i += nthr) sHdr[i] = a.filt_hdr[i];
   for (int i = tid; i < a.n_w4; i += nthr) sW4[i] = a.filt_w[i];
   const int wf0 = a.warp_filt[warp], wf1 = a.warp_filt[warp + 1];
   const int total = a.frame_off[a.B];
@@ -259,30 +266,29 @@ k_stft_fb(const StftArgs a) {
   // dependent index loads never sit on the critical path, and used to prefetch the next tile's
   // new samples into L2 (bulk prefetch: one instruction per frame)
   auto tile_meta = [&](int tile, int buf) {
-    if (lane < C::TILE) {
-      const int gf = tile * C::TILE + lane;
-      int b = -1, t = 0;
-      if (tile < n_tiles && gf < total) {
-        b = __ldg(a.tile_b0 + tile);
-        int nxt = __ldg(a.frame_off + b + 1);
-        while (gf >= nxt) nxt = __ldg(a.frame_off + (++b) + 1);
-        t = gf - __ldg(a.frame_off + b);
-      }
-      sMeta[buf * 2 * C::TILE + lane] = b;
-      sMeta[buf * 2 * C::TILE + C::TILE + lane] = t;
-      if (b >= 0) {
-        constexpr int ES = MODE == IN_I16 ? 2 : 4;
-        const long long len = __ldg(a.len_c + b);
-        long long s_lo = (long long)t * a.hop - a.s_off + (t == 0 ? 0 : N - a.hop);
-        long long s_hi = (long long)t * a.hop - a.s_off + N;
-        if (s_lo < 0) s_lo = 0;
-        if (s_hi > len) s_hi = len;
-        const char* row = static_cast<const char*>(a.wav) + (long long)b * a.wav_stride * ES;
-        uintptr_t p0 = ((uintptr_t)(row + s_lo * ES) + 15) & ~(uintptr_t)15;
-        uintptr_t p1 = (uintptr_t)(row + s_hi * ES) & ~(uintptr_t)15;
-        if (p1 > p0)
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"((unsigned)(p1 - p0)) : "memory");
-      }
+    if (lane >= C::TILE) return;
+    const int gf = tile * C::TILE + lane;
+    int b = -1, t = 0;
+    if (tile < n_tiles && gf < total) {
+      b = __ldg(a.tile_b0 + tile);
+      int nxt = __ldg(a.frame_off + b + 1);
+      while (gf >= nxt) nxt = __ldg(a.frame_off + (++b) + 1);
+      t = gf - __ldg(a.frame_off + b);
+    }
+    sMeta[buf * 2 * C::TILE + lane] = b;
+    sMeta[buf * 2 * C::TILE + C::TILE + lane] = t;
+    if (b >= 0) {
+      constexpr int ES = MODE == IN_I16 ? 2 : 4;
+      const long long len = __ldg(a.len_c + b);
+      long long s_lo = (long long)t * a.hop - a.s_off + (t == 0 ? 0 : N - a.hop);
+      long long s_hi = (long long)t * a.hop - a.s_off + N;
+      if (s_lo < 0) s_lo = 0;
+      if (s_hi > len) s_hi = len;
+      const char* row = static_cast<const char*>(a.wav) + (long long)b * a.wav_stride * ES;
+      uintptr_t p0 = ((uintptr_t)(row + s_lo * ES) + 15) & ~(uintptr_t)15;
+      uintptr_t p1 = (uintptr_t)(row + s_hi * ES) & ~(uintptr_t)15;
+      if (p1 > p0)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"((unsigned)(p1 - p0)) : "memory");
     }
   };
   if (warp == 0) tile_meta(blockIdx.x, 0);
@@ -323,17 +329,13 @@ k_stft_fb(const StftArgs a) {
               constexpr int A = decltype(a_)::value;
               float xp = (float)__ldg(ps + 2 * L * A);
               float2 x = i16pair_to_float2(raw[A]);
-              float2 w = sWin2[L * A + j];
-              float e0 = __fmaf_rn(-a.pre_emph, xp, x.x);
-              float e1 = __fmaf_rn(-a.pre_emph, x.x, x.y);
-              v[bitrev(A, 5)] = make_float2(e0 * w.x, e1 * w.y);
+              float2 e = make_float2(__fmaf_rn(-a.pre_emph, xp, x.x), __fmaf_rn(-a.pre_emph, x.x, x.y));
+              v[bitrev(A, 5)] = pk_mul(e, sWin2[L * A + j]);
             });
           } else {
             static_for<0, 32>([&](auto a_) {
               constexpr int A = decltype(a_)::value;
-              float2 x = i16pair_to_float2(raw[A]);
-              float2 w = sWin2[L * A + j];
-              v[bitrev(A, 5)] = make_float2(x.x * w.x, x.y * w.y);
+              v[bitrev(A, 5)] = pk_mul(i16pair_to_float2(raw[A]), sWin2[L * A + j]);
             });
           }
         } else {
@@ -350,17 +352,15 @@ k_stft_fb(const StftArgs a) {
               float2 x = v[bitrev(A, 5)];
               x.x = cvt_sample<MODE>(x.x);
               x.y = cvt_sample<MODE>(x.y);
-              float2 w = sWin2[L * A + j];
-              float e0 = __fmaf_rn(-a.pre_emph, xp, x.x);
-              float e1 = __fmaf_rn(-a.pre_emph, x.x, x.y);
-              v[bitrev(A, 5)] = make_float2(e0 * w.x, e1 * w.y);
+              float2 e = make_float2(__fmaf_rn(-a.pre_emph, xp, x.x), __fmaf_rn(-a.pre_emph, x.x, x.y));
+              v[bitrev(A, 5)] = pk_mul(e, sWin2[L * A + j]);
             });
           } else {
             static_for<0, 32>([&](auto a_) {
               constexpr int A = decltype(a_)::value;
               float2 x = v[bitrev(A, 5)];
-              float2 w = sWin2[L * A + j];
-              v[bitrev(A, 5)] = make_float2(cvt_sample<MODE>(x.x) * w.x, cvt_sample<MODE>(x.y) * w.y);
+              if constexpr (MODE == IN_F32_Q16) x = make_float2(cvt_sample<MODE>(x.x), cvt_sample<MODE>(x.y));
+              v[bitrev(A, 5)] = pk_mul(x, sWin2[L * A + j]);
             });
           }
         }
@@ -371,8 +371,7 @@ k_stft_fb(const StftArgs a) {
           const int n0 = 2 * (L * A + j);
           float x0 = load_masked<MODE, PRE>(row, s0 + n0, n0, len, a.win_off, a.win_len, a.pre_emph);
           float x1 = load_masked<MODE, PRE>(row, s0 + n0 + 1, n0 + 1, len, a.win_off, a.win_len, a.pre_emph);
-          float2 w = sWin2[L * A + j];
-          v[bitrev(A, 5)] = make_float2(x0 * w.x, x1 * w.y);
+          v[bitrev(A, 5)] = pk_mul(make_float2(x0, x1), sWin2[L * A + j]);
         });
       }
 
@@ -420,7 +419,7 @@ k_stft_fb(const StftArgs a) {
         fft_dit<L, QQ * L>(v);
       });
 
-      // real-input split + power:  X[k] = E - T,  X[M-k] = conj(E + T)
+      // real-input split + power:  X[k] = E - T,  X[M-k] = conj(E + T),  T = i*w*O
       float* prow = sP + fi * SP;
       static_for<0, Q>([&](auto q_) {
         constexpr int QQ = decltype(q_)::value;
@@ -428,62 +427,76 @@ k_stft_fb(const StftArgs a) {
           constexpr int S = decltype(s_)::value;
           constexpr int GEN = (Q - 1 - QQ) * L + (L - 1 - S);
           constexpr int ALT = QQ == 0 ? ((L - S) % L) : (Q - QQ) * L + (L - 1 - S);
-          float2 snd = (j == 0) ? v[ALT] : v[GEN];
-          float rx = __shfl_sync(0xffffffffu, snd.x, partner);
-          float ry = __shfl_sync(0xffffffffu, snd.y, partner);
-          float2 A = v[QQ * L + S];
-          float2 E = make_float2(A.x + rx, A.y - ry);
-          float2 O = make_float2(A.x - rx, A.y + ry);
+          const float2 snd = (j == 0) ? v[ALT] : v[GEN];
+          float2 r;  // Z[M - k]
+          r.x = __shfl_sync(0xffffffffu, snd.x, partner);
+          r.y = __shfl_sync(0xffffffffu, snd.y, partner);
+          const float2 A = v[QQ * L + S];
+          const float2 E = __fadd2_rn(A, make_float2(r.x, -r.y));   // A + conj(r)
+          const float2 O = __fadd2_rn(A, make_float2(-r.x, r.y));   // A - conj(r)
           const int k = j + L * QQ + 32 * S;
-          float2 w = sTwp[k];
-          float2 wO = cmul(w, O);
-          float x1r = E.x + wO.y, x1i = E.y - wO.x;  // E - T, T = i*wO = (-wO.y, wO.x)
-          float x2r = E.x - wO.y, x2i = E.y + wO.x;  // E + T
-          prow[k] = __fmaf_rn(x1r, x1r, x1i * x1i);
-          prow[M - k] = __fmaf_rn(x2r, x2r, x2i * x2i);
+          const float2 wO = cmul(O, sTwp[k]);
+          const float2 x1 = __fadd2_rn(E, make_float2(wO.y, -wO.x));  // E - i*wO
+          const float2 x2 = __fadd2_rn(E, make_float2(-wO.y, wO.x));  // E + i*wO
+          prow[k] = __fmaf_rn(x1.x, x1.x, x1.y * x1.y);
+          prow[M - k] = __fmaf_rn(x2.x, x2.x, x2.y * x2.y);
         });
       });
       if (j == 0) {
         float2 A = v[L / 2];
         prow[M / 2] = 4.0f * __fmaf_rn(A.x, A.x, A.y * A.y);
+        // padding read by the last tap groups of a segment that reaches the Nyquist bin
+#pragma unroll
+        for (int i = 1; i <= C::PAD; ++i) prow[M + i] = 0.f;
       }
     }
     __syncthreads();
 
-    // ---- filterbank + log phase: lane = frame (+ tap parity class), warps split the filters ----
-    // Per filter: dense band of taps in groups of four (weights: one LDS.128, powers: four LDS at
-    // immediate offsets from one pointer), then log, store, running max.
+    // ---- filterbank + log phase: lane = frame (+ group parity), warps split the filters ----
+    // Per segment: 4 bins per step (powers: one conflict-free LDS.128 per lane; weights: two
+    // LDS.128 broadcasts; four FFMA2 accumulate (rising, falling) sums with the power broadcast to
+    // both halves), then filter s-1 = R[s-1] + F[s]: log, store, running max.
     if (wf0 < wf1) {
       const int fr = lane % C::TILE, par = lane / C::TILE;
       const int b = sMetaB[fr], t = sMetaT[fr];
       const bool valid = b >= 0;
-      const float* pbase = sP + fr * SP + par;
+      const float* pbase = sP + fr * SP + 4 * par;
       float* eptr = a.E + (valid ? (long long)b * a.e_stride_b + (long long)wf0 * a.e_stride_f + t : 0);
-      float vmax = -INFINITY, chk = 0.f;
-      for (int jf = wf0; jf < wf1; ++jf) {
-        const int2 hd = sHdr[jf];
-        const float* pp = pbase + (hd.x & 0xffff);
-        const float4* wp = sW4 + hd.y + par;
-        float acc0 = 0.f, acc1 = 0.f;
+      const float lscale = a.log_type == 0 ? 3.01029995663981195f : 0.69314718055994531f;
+      float vmax = -INFINITY, chk = 0.f, rprev = 0.f;
+      for (int sg = wf0; sg <= wf1; ++sg) {
+        const int2 hd = sHdr[sg];
+        const float4* pp = reinterpret_cast<const float4*>(pbase + (hd.x & 0xffff));
+        const float4* wp = sW4 + hd.y + 2 * par;
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll 2
         for (int gq = hd.x >> 16; gq > 0; --gq) {
-          const float4 w = *wp;
-          acc0 = __fmaf_rn(w.x, pp[0], acc0);
-          acc1 = __fmaf_rn(w.y, pp[NPAR], acc1);
-          acc0 = __fmaf_rn(w.z, pp[2 * NPAR], acc0);
-          acc1 = __fmaf_rn(w.w, pp[3 * NPAR], acc1);
-          wp += NPAR;
-          pp += 4 * NPAR;
+          const float4 p = *pp;
+          const float4 wa = wp[0], wb = wp[1];
+          pp += NPAR;
+          wp += 2 * NPAR;
+          acc0 = __ffma2_rn(make_float2(p.x, p.x), make_float2(wa.x, wa.y), acc0);
+          acc1 = __ffma2_rn(make_float2(p.y, p.y), make_float2(wa.z, wa.w), acc1);
+          acc0 = __ffma2_rn(make_float2(p.z, p.z), make_float2(wb.x, wb.y), acc0);
+          acc1 = __ffma2_rn(make_float2(p.w, p.w), make_float2(wb.z, wb.w), acc1);
         }
-        float en = acc0 + acc1;
-        if constexpr (NPAR == 2) en += __shfl_xor_sync(0xffffffffu, en, 16);
-        // 10*log10(x) = 3.0103*log2(x), ln(x) = 0.6931*log2(x); MUFU.LG2 is accurate to 2 ulp,
-        // i.e. <= 3e-5 dB / 4e-6 nepers here, far inside the 1e-3 parity tolerance
-        const float val = a.log_type == 0 ? 3.01029995663981195f * __log2f(fmaxf(a.amin, en))
-                                          : 0.69314718055994531f * __log2f(en == 0.f ? a.eps : en);
-        if (valid && par == 0) *eptr = val;
-        eptr += a.e_stride_f;
-        vmax = fmaxf(vmax, val);
-        chk = __fmaf_rn(val, 0.f, chk);  // NaN/Inf poison
+        float2 rf = __fadd2_rn(acc0, acc1);  // (R[sg], F[sg])
+        if constexpr (NPAR == 2) {
+          rf.x += __shfl_xor_sync(0xffffffffu, rf.x, 16);
+          rf.y += __shfl_xor_sync(0xffffffffu, rf.y, 16);
+        }
+        if (sg > wf0) {
+          const float en = rprev + rf.y;
+          // 10*log10(x) = 3.0103*log2(x), ln(x) = 0.6931*log2(x); MUFU.LG2 is accurate to 2 ulp,
+          // i.e. <= 3e-5 dB / 4e-6 nepers here, far inside the 1e-3 parity tolerance
+          const float arg = a.log_type == 0 ? fmaxf(a.amin, en) : (en == 0.f ? a.eps : en);
+          const float val = lscale * __log2f(arg);
+          if (valid && par == 0) *eptr = val;
+          eptr += a.e_stride_f;
+          vmax = fmaxf(vmax, val);
+          chk = __fmaf_rn(val, 0.f, chk);  // NaN/Inf poison
+        }
+        rprev = rf.x;
       }
       if (valid) {
         if (a.utt_max) {

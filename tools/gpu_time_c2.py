@@ -1,4 +1,4 @@
-"""Time configs on the GPU with per-kernel breakdown (dev tool). Usage: python tools/gpu_time_c2.py [tile ...]"""
+"""Time configs on the GPU with per-kernel breakdown (dev tool). Usage: python tools/gpu_time_c2.py [--quick]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -26,12 +26,11 @@ def timeit(name, params, wav, lengths=None, iters=10):
     return ms
 
 wav = (0.1 * torch.randn((4096, 64000), generator=g, device=dev)).clamp_(-1, 1)
-tiles = sys.argv[1:] or ["16", "32"]
-for tile in tiles:
-    os.environ["AAD_TILE"] = tile
-    timeit(f"C2 mfcc40+d+dd 2048/512 tile{tile}", FrontendParams.mfcc(16000, n_mfcc=40, n_delta=2), wav)
-    timeit(f"   mfcc13 2048/512 tile{tile}", FrontendParams.mfcc(16000, n_mfcc=13), wav)
-    timeit(f"   logmel64 2048/512 tile{tile}", FrontendParams.logmel(16000), wav)
+timeit("C2 mfcc40+d+dd 2048/512", FrontendParams.mfcc(16000, n_mfcc=40, n_delta=2), wav)
+timeit("   mfcc13 2048/512", FrontendParams.mfcc(16000, n_mfcc=13), wav)
+timeit("   logmel64 2048/512", FrontendParams.logmel(16000), wav)
+if "--quick" in sys.argv:
+    sys.exit(0)
 timeit("C2b mfcc40+d+dd 512/160/80", FrontendParams.mfcc(16000, n_mfcc=40, n_mels=80, n_fft=512, hop_length=160, n_delta=2), wav)
 timeit("C1 logmel80 512/160 (B=4096)", FrontendParams.logmel(16000, n_mels=80, n_fft=512, hop_length=160), wav)
 timeit("C1 logmel80 512/160 (B=64)", FrontendParams.logmel(16000, n_mels=80, n_fft=512, hop_length=160), wav[:64].contiguous(), iters=50)
