@@ -28,7 +28,7 @@ struct aad_plan {
   int warps = 0, ctas = 0;
   size_t k1_smem = 0;
   int n_w4 = 0;
-  int kc = 20, cep_groups = 1;
+  int kc = 10;
   int c_feat = 0;     // rows before deltas
   int c_out = 0;
   int ncp = 0;
@@ -272,14 +272,17 @@ static void stft_cfg(int L, int tile, int* warps, int* ctas, size_t* fixed, int*
 typedef void (*cep_kernel_t)(const CepArgs);
 static cep_kernel_t pick_cep(int kc) {
   switch (kc) {
+    case 2: return k_cepstra<2>;
+    case 4: return k_cepstra<4>;
+    case 6: return k_cepstra<6>;
     case 8: return k_cepstra<8>;
-    case 12: return k_cepstra<12>;
-    default: return k_cepstra<20>;
+    case 10: return k_cepstra<10>;
+    default: return k_cepstra<12>;
   }
 }
 
 static size_t cep_smem_bytes(const aad_plan* pl) {
-  size_t f = (size_t)pl->p.n_filt * CEP_TS;
+  size_t f = (size_t)pl->p.n_filt * CEP_TS + 8 * CEP_TS;
   if (pl->p.n_ceps > 0) f += (size_t)(pl->p.n_filt + 1) * pl->ncp + (size_t)pl->p.n_ceps * CEP_TS;
   return f * 4;
 }
@@ -418,9 +421,9 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   stft_cfg(pl->L, pl->tile, &pl->warps, &pl->ctas, &k1_fixed, &npar);
   pl->c_feat = p.n_ceps > 0 ? p.n_ceps : p.n_filt;
   pl->c_out = pl->c_feat * (1 + p.n_delta);
-  pl->kc = p.n_ceps >= 40 ? 20 : (p.n_ceps > 16 ? 12 : 8);
+  // K2: four thread groups split the coefficient chunks of kc (even, <= 12) coefficients each
+  pl->kc = std::min(12, std::max(2, ((p.n_ceps + 3) / 4 + 1) & ~1));
   pl->ncp = p.n_ceps > 0 ? (p.n_ceps + pl->kc - 1) / pl->kc * pl->kc : 0;
-  pl->cep_groups = p.n_ceps > 0 ? std::min(CEP_MAXG, pl->ncp / pl->kc) : 2;
   const bool direct = (p.n_ceps == 0 && p.n_delta == 0 && p.layout == AAD_LAYOUT_CT && !p.time_mean);
   pl->need_ws_E = !direct;
   pl->need_ws_feat = p.time_mean != 0;
@@ -697,7 +700,7 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
     ca.tile_out = CEP_TS - (p.n_delta > 0 ? 2 * (p.delta_width / 2) : 0);
     const int gx = t_max <= CEP_TS ? 1 : (t_max + ca.tile_out - 1) / ca.tile_out;
     dim3 grid(gx, B);
-    pick_cep(pl->kc)<<<grid, CEP_TS * pl->cep_groups, cep_smem_bytes(pl), stream>>>(ca);
+    pick_cep(pl->kc)<<<grid, CEP_THREADS, cep_smem_bytes(pl), stream>>>(ca);
     LAUNCH_CHECK("k_cepstra launch");
     if (prof) cudaEventRecord(pl->ev[3], stream);
     if (p.time_mean) {

@@ -109,17 +109,23 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepArgs a) {
     int excl = carry + (warp ? warp_sums[warp - 1] : 0) + (x - nf);
     if (b < a.B) a.frame_off[b] = excl;
     // tile -> utterance index for k_stft_fb: tile tl (first frame tl*tile) starts inside utterance b
-    // iff frame_off[b] <= tl*tile < frame_off[b+1].  The warp walks its 32 utterances and the lanes
-    // write each one's tiles cooperatively (long utterances own thousands of tiles).
-#pragma unroll 1
-    for (int src = 0; src < 32; ++src) {
-      const int e0 = __shfl_sync(0xffffffffu, excl, src);
-      const int n0 = __shfl_sync(0xffffffffu, nf, src);
-      const int b0 = __shfl_sync(0xffffffffu, b, src);
-      if (n0 == 0) continue;
-      const int t_first = (e0 + a.tile - 1) / a.tile, t_end = (e0 + n0 + a.tile - 1) / a.tile;
-      for (int tl = t_first + lane; tl < t_end; tl += 32)
-        if (tl < a.max_tiles) a.tile_b0[tl] = b0;
+    // iff frame_off[b] <= tl*tile < frame_off[b+1].  Each thread writes the few tiles of its own
+    // utterance; utterances that own many tiles (long-form audio) are written by the whole warp.
+    {
+      const int t_first = (excl + a.tile - 1) / a.tile, t_end = nf ? (excl + nf + a.tile - 1) / a.tile : t_first;
+      const bool big = t_end - t_first > 32;
+      if (!big)
+        for (int tl = t_first; tl < t_end; ++tl)
+          if (tl < a.max_tiles) a.tile_b0[tl] = b;
+      unsigned todo = __ballot_sync(0xffffffffu, big);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int f0 = __shfl_sync(0xffffffffu, t_first, src), f1 = __shfl_sync(0xffffffffu, t_end, src);
+        const int b0 = __shfl_sync(0xffffffffu, b, src);
+        for (int tl = f0 + lane; tl < f1; tl += 32)
+          if (tl < a.max_tiles) a.tile_b0[tl] = b0;
+      }
     }
     __syncthreads();
     if (tid == 1023) carry_s = carry + warp_sums[31];
@@ -516,7 +522,7 @@ k_stft_fb(const StftArgs a) {
 // ---------------------------------------------------------------------------
 constexpr int CEP_TS = 128;       // frames per tile held in smem
 constexpr int CEP_MAXW = 9;
-constexpr int CEP_MAXG = 4;       // thread groups per CTA (each: one thread per frame column)
+constexpr int CEP_THREADS = 256;  // 8 warps: 4 coefficient groups x 64 frame pairs
 
 struct CepArgs {
   const float* E;         // [B][n_filt][e_stride_f]
@@ -538,11 +544,16 @@ struct CepArgs {
   int tile_out;           // output frames per tile when T > CEP_TS
 };
 
-// One CTA = (utterance, tile of <= 128 frames).  blockDim = 128 * G: thread (col, grp) owns frame
-// column `col`; the G groups split the filterbank rows when loading, the DCT coefficient chunks
-// when contracting and the coefficient rows when writing.
+// One CTA = (utterance, tile of <= 128 frames).  Three phases:
+//  load : E tile -> sE[m][t] with the dB reference / floor applied (float4 along t, warp w owns the
+//         filterbank rows m = w (mod 8)), per-warp partial column sums for the per-frame mean
+//  DCT  : thread (p, grp) owns the frame PAIR (2p, 2p+1) and the coefficient chunks grp, grp+4, ..:
+//         acc[k] (float2 = the two frames) += (e - mean) * D[m][k] as one FFMA2 per (m, k) with the
+//         table value broadcast to both halves; the mean is added back through the column sums
+//  out  : thread = frame column; static rows and the delta / delta-delta stencils as one FFMA2 per
+//         tap ((d1, d2) accumulated together), coalesced stores along t (CT) or along c (TC)
 template <int KC>
-__global__ void __launch_bounds__(CEP_TS * CEP_MAXG) k_cepstra(const CepArgs a) {
+__global__ void __launch_bounds__(CEP_THREADS) k_cepstra(const CepArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int b = blockIdx.y;
   const int T = a.nf_eff[b];
@@ -565,11 +576,12 @@ __global__ void __launch_bounds__(CEP_TS * CEP_MAXG) k_cepstra(const CepArgs a) 
     hi = max(hi, c1 + h + 1);
   }
   const int nload = hi - lo;  // <= CEP_TS by construction
-  const int col = threadIdx.x & (CEP_TS - 1), grp = threadIdx.x >> 7, G = blockDim.x >> 7;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = a.n_ceps > 0 ? a.n_ceps : a.n_filt;
 
   float* sE = smem;                                   // [n_filt][CEP_TS]
-  float* sD = sE + a.n_filt * CEP_TS;                 // [n_filt + 1][ncp] (last row: column sums)
+  float* sPart = sE + a.n_filt * CEP_TS;              // [8][CEP_TS] per-warp partial column sums
+  float* sD = sPart + 8 * CEP_TS;                     // [n_filt + 1][ncp] (last row: column sums)
   float* sC = a.n_ceps > 0 ? sD + (a.n_filt + 1) * a.ncp : sE;  // [C][CEP_TS]
 
   // reference / floor (librosa.power_to_db):  ls = E - ref ; ls = max(ls, max(ls) - top_db)
@@ -579,78 +591,117 @@ __global__ void __launch_bounds__(CEP_TS * CEP_MAXG) k_cepstra(const CepArgs a) 
     if (a.ref_type == 1) ref = m;
     if (a.top_db >= 0.f) floorv = (m - ref) - a.top_db;
   }
-  const float* Eb = a.E + (long long)b * a.e_stride_b + lo + col;
-  if (col < nload) {
-    int m = grp;
-    for (; m + 7 * G < a.n_filt; m += 8 * G) {   // 8 independent loads in flight per thread
-      float v[8];
+  // ---- load ---------------------------------------------------------------------------
+  {
+    const float* Eb = a.E + (long long)b * a.e_stride_b + lo;
+    const bool vec = ((lo | a.e_stride_f) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.E) & 15) == 0 &&
+                     (a.e_stride_b & 3) == 0;
+    const int t4 = 4 * lane;
+    float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto xf = [&](float v, int t) { return t < nload ? fmaxf(v - ref, floorv) : 0.f; };
+    if (vec) {
+      int m = warp;
+      for (; m + 24 < a.n_filt; m += 32) {  // 4 independent 16-byte loads in flight per thread
+        float4 v[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldg(Eb + (long long)(m + u * G) * a.e_stride_f);
+        for (int u = 0; u < 4; ++u)
+          v[u] = t4 < nload ? __ldg(reinterpret_cast<const float4*>(Eb + (long long)(m + 8 * u) * a.e_stride_f + t4))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) sE[(m + u * G) * CEP_TS + col] = fmaxf(v[u] - ref, floorv);
+        for (int u = 0; u < 4; ++u) {
+          float4 r = make_float4(xf(v[u].x, t4), xf(v[u].y, t4 + 1), xf(v[u].z, t4 + 2), xf(v[u].w, t4 + 3));
+          *reinterpret_cast<float4*>(sE + (m + 8 * u) * CEP_TS + t4) = r;
+          ps.x += r.x; ps.y += r.y; ps.z += r.z; ps.w += r.w;
+        }
+      }
+      for (; m < a.n_filt; m += 8) {
+        float4 v = t4 < nload ? __ldg(reinterpret_cast<const float4*>(Eb + (long long)m * a.e_stride_f + t4))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 r = make_float4(xf(v.x, t4), xf(v.y, t4 + 1), xf(v.z, t4 + 2), xf(v.w, t4 + 3));
+        *reinterpret_cast<float4*>(sE + m * CEP_TS + t4) = r;
+        ps.x += r.x; ps.y += r.y; ps.z += r.z; ps.w += r.w;
+      }
+    } else {
+      for (int m = warp; m < a.n_filt; m += 8) {
+        float r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t4 + u;
+          r[u] = t < nload ? fmaxf(__ldg(Eb + (long long)m * a.e_stride_f + t) - ref, floorv) : 0.f;
+        }
+        *reinterpret_cast<float4*>(sE + m * CEP_TS + t4) = make_float4(r[0], r[1], r[2], r[3]);
+        ps.x += r[0]; ps.y += r[1]; ps.z += r[2]; ps.w += r[3];
+      }
     }
-    for (; m < a.n_filt; m += G) sE[m * CEP_TS + col] = fmaxf(__ldg(Eb + (long long)m * a.e_stride_f) - ref, floorv);
-  } else {
-    for (int m = grp; m < a.n_filt; m += G) sE[m * CEP_TS + col] = 0.f;
-  }
-  if (a.n_ceps > 0) {
-    const int nd = (a.n_filt + 1) * a.ncp;
-    for (int i = threadIdx.x * 4; i < nd; i += blockDim.x * 4)
-      *reinterpret_cast<float4*>(sD + i) = __ldg(reinterpret_cast<const float4*>(a.dct_t + i));
+    *reinterpret_cast<float4*>(sPart + warp * CEP_TS + t4) = ps;
+    if (a.n_ceps > 0) {
+      const int nd = (a.n_filt + 1) * a.ncp;  // ncp is even and dct_t comes from cudaMalloc: 8-byte units
+      for (int i = tid * 2; i < nd; i += CEP_THREADS * 2)
+        *reinterpret_cast<float2*>(sD + i) = __ldg(reinterpret_cast<const float2*>(a.dct_t + i));
+    }
   }
   __syncthreads();
 
+  // ---- DCT ----------------------------------------------------------------------------
   if (a.n_ceps > 0) {
     // The DCT is linear: accumulate on the per-frame-centred energies (small partial sums,
     // so float32 accumulation of ~100 same-sign dB values loses nothing) and add the mean
     // back through the table's column sums (row n_filt of dct_t).
-    float mean = 0.f;
-    for (int m = 0; m < a.n_filt; ++m) mean += sE[m * CEP_TS + col];
-    mean *= 1.0f / (float)a.n_filt;
-    for (int c0 = grp * KC; c0 < a.n_ceps; c0 += G * KC) {
-      float acc[KC];
+    const int p = tid & 63, grp = tid >> 6;
+    const float2* sE2 = reinterpret_cast<const float2*>(sE) + p;
+    float2 mean2 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < KC; ++i) acc[i] = 0.f;
-#pragma unroll 2
+    for (int w = 0; w < 8; ++w) mean2 = __fadd2_rn(mean2, *reinterpret_cast<const float2*>(sPart + w * CEP_TS + 2 * p));
+    const float inv = 1.0f / (float)a.n_filt;
+    mean2 = __fmul2_rn(mean2, make_float2(inv, inv));
+    const float2 nmean2 = make_float2(-mean2.x, -mean2.y);
+    for (int c0 = grp * KC; c0 < a.ncp; c0 += 4 * KC) {
+      float2 acc[KC];
+#pragma unroll
+      for (int i = 0; i < KC; ++i) acc[i] = make_float2(0.f, 0.f);
+      const float* drow = sD + c0;
+#pragma unroll 4
       for (int m = 0; m < a.n_filt; ++m) {
-        const float e = sE[m * CEP_TS + col] - mean;
-        const float4* d4 = reinterpret_cast<const float4*>(sD + m * a.ncp + c0);
+        const float2 e = __fadd2_rn(sE2[m * (CEP_TS / 2)], nmean2);
+        const float2* d2 = reinterpret_cast<const float2*>(drow + m * a.ncp);
 #pragma unroll
-        for (int i = 0; i < KC / 4; ++i) {
-          float4 d = d4[i];
-          acc[4 * i + 0] = __fmaf_rn(d.x, e, acc[4 * i + 0]);
-          acc[4 * i + 1] = __fmaf_rn(d.y, e, acc[4 * i + 1]);
-          acc[4 * i + 2] = __fmaf_rn(d.z, e, acc[4 * i + 2]);
-          acc[4 * i + 3] = __fmaf_rn(d.w, e, acc[4 * i + 3]);
+        for (int i = 0; i < KC / 2; ++i) {
+          const float2 d = d2[i];
+          acc[2 * i] = __ffma2_rn(e, make_float2(d.x, d.x), acc[2 * i]);
+          acc[2 * i + 1] = __ffma2_rn(e, make_float2(d.y, d.y), acc[2 * i + 1]);
         }
       }
       const float* colsum = sD + a.n_filt * a.ncp + c0;
 #pragma unroll
       for (int i = 0; i < KC; ++i)
-        if (c0 + i < a.n_ceps) sC[(c0 + i) * CEP_TS + col] = __fmaf_rn(mean, colsum[i], acc[i]);
+        if (c0 + i < a.n_ceps) {
+          const float cs = colsum[i];
+          *reinterpret_cast<float2*>(sC + (c0 + i) * CEP_TS + 2 * p) = __ffma2_rn(mean2, make_float2(cs, cs), acc[i]);
+        }
     }
     __syncthreads();
   }
 
+  // ---- static rows + delta stencils + layout -------------------------------------------
+  const int col = tid & (CEP_TS - 1), half = tid >> 7;
   const int t = lo + col;
   if (t >= o0 && t < o1) {
     float* ob = a.out + (long long)b * a.out_stride_b + (long long)t * a.out_stride_t;
     const int te = min(max(t, h), T - 1 - h) - lo;  // stencil centre (edges replicate the interior fit)
-    for (int k = grp; k < C; k += G) {
+    for (int k = half; k < C; k += 2) {
       const float* row = sC + k * CEP_TS;
       ob[(long long)k * a.out_stride_c] = row[col];
       if (a.n_delta > 0) {
-        float d1 = 0.f, d2 = 0.f;
+        float2 d12 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < CEP_MAXW; ++i) {
           if (i < a.width) {
-            float x = row[te - h + i];
-            d1 = __fmaf_rn(a.taps[0][i], x, d1);
-            d2 = __fmaf_rn(a.taps[1][i], x, d2);
+            const float x = row[te - h + i];
+            d12 = __ffma2_rn(make_float2(x, x), make_float2(a.taps[0][i], a.taps[1][i]), d12);
           }
         }
-        ob[(long long)(C + k) * a.out_stride_c] = d1;
-        if (a.n_delta > 1) ob[(long long)(2 * C + k) * a.out_stride_c] = d2;
+        ob[(long long)(C + k) * a.out_stride_c] = d12.x;
+        if (a.n_delta > 1) ob[(long long)(2 * C + k) * a.out_stride_c] = d12.y;
       }
     }
   }
