@@ -59,7 +59,11 @@ struct aad_plan {
     int cap_b = 0;
     void* d_ws = nullptr;
     size_t ws_bytes = 0;
-  } hb[2];
+  } hb[3];
+  // pinned staging for the small per-utterance arrays of the host path: async copies to or from
+  // pageable memory block the calling thread until they complete, which would serialise the chunks
+  int32_t* h_stage = nullptr;  // [3][cap] lengths, n_frames, status
+  int h_stage_cap = 0;
 };
 
 static const double kPiD = 3.141592653589793238462643383279502884;
@@ -371,6 +375,7 @@ int aad_plan_destroy(aad_plan* pl) {
   cudaFree(pl->d_dct_t);
   for (auto& e : pl->ev)
     if (e) cudaEventDestroy(e);
+  if (pl->h_stage) cudaFreeHost(pl->h_stage);
   for (auto& h : pl->hb) {
     cudaFree(h.d_wav);
     cudaFree(h.d_out);
@@ -830,7 +835,7 @@ int aad_fp32_peak(int device, int iters, double* tflops_out) {
   return cudaGetLastError() == cudaSuccess ? AAD_OK : AAD_ERR_CUDA;
 }
 
-// ---- host-buffer path: chunked H2D -> kernels -> D2H on two internal streams ----
+// ---- host-buffer path: chunked H2D -> kernels -> D2H on three internal streams ----
 static int ensure(void** p, size_t* cap, size_t need) {
   if (*cap >= need) return AAD_OK;
   cudaFree(*p);
@@ -876,26 +881,45 @@ int aad_extract_host(aad_plan* pl, const void* wav_host, int wav_dtype, int64_t 
       h.cap_b = chunk_utts;
     }
   }
+  if (pl->h_stage_cap < B) {
+    if (pl->h_stage) cudaFreeHost(pl->h_stage);
+    pl->h_stage = nullptr;
+    pl->h_stage_cap = 0;
+    CUDA_TRY(cudaHostAlloc((void**)&pl->h_stage, (size_t)3 * B * sizeof(int32_t), cudaHostAllocDefault));
+    pl->h_stage_cap = B;
+  }
+  int32_t* st_len = pl->h_stage;
+  int32_t* st_nf = pl->h_stage + pl->h_stage_cap;
+  int32_t* st_st = pl->h_stage + 2 * (size_t)pl->h_stage_cap;
+  std::memcpy(st_len, lengths_host, (size_t)B * sizeof(int32_t));
   int ci = 0;
   for (int b0 = 0; b0 < B; b0 += chunk_utts, ++ci) {
-    aad_plan::HostBuf& h = pl->hb[ci & 1];
+    aad_plan::HostBuf& h = pl->hb[ci % 3];
     const int nb = std::min(chunk_utts, B - b0);
     const char* src = (const char*)wav_host + (size_t)b0 * wav_stride * esz;
-    CUDA_TRY(cudaMemcpy2DAsync(h.d_wav, (size_t)max_len * esz, src, (size_t)wav_stride * esz,
-                               (size_t)max_len * esz, nb, cudaMemcpyHostToDevice, h.stream));
-    CUDA_TRY(cudaMemcpyAsync(h.d_len, lengths_host + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, h.stream));
+    if (wav_stride == max_len)
+      CUDA_TRY(cudaMemcpyAsync(h.d_wav, src, (size_t)nb * max_len * esz, cudaMemcpyHostToDevice, h.stream));
+    else
+      CUDA_TRY(cudaMemcpy2DAsync(h.d_wav, (size_t)max_len * esz, src, (size_t)wav_stride * esz,
+                                 (size_t)max_len * esz, nb, cudaMemcpyHostToDevice, h.stream));
+    CUDA_TRY(cudaMemcpyAsync(h.d_len, st_len + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, h.stream));
     // rows with non-zero status are left untouched by the kernels: start from zeros
     CUDA_TRY(cudaMemsetAsync(h.d_out, 0, (size_t)nb * row_out * 4, h.stream));
     rc = aad_extract(pl, h.d_wav, wav_dtype, max_len, h.d_len, nb, max_len, h.d_out, row_out, t_alloc,
                      h.d_nf, h.d_st, h.d_ws, h.ws_bytes, h.stream);
     if (rc != AAD_OK) return rc;
-    CUDA_TRY(cudaMemcpy2DAsync(out_host + (size_t)b0 * out_stride_b, (size_t)out_stride_b * 4, h.d_out,
-                               (size_t)row_out * 4, (size_t)row_out * 4, nb, cudaMemcpyDeviceToHost, h.stream));
-    CUDA_TRY(cudaMemcpyAsync(n_frames_host + b0, h.d_nf, (size_t)nb * 4, cudaMemcpyDeviceToHost, h.stream));
-    CUDA_TRY(cudaMemcpyAsync(status_host + b0, h.d_st, (size_t)nb * 4, cudaMemcpyDeviceToHost, h.stream));
+    if (out_stride_b == row_out)
+      CUDA_TRY(cudaMemcpyAsync(out_host + (size_t)b0 * out_stride_b, h.d_out, (size_t)nb * row_out * 4,
+                               cudaMemcpyDeviceToHost, h.stream));
+    else
+      CUDA_TRY(cudaMemcpy2DAsync(out_host + (size_t)b0 * out_stride_b, (size_t)out_stride_b * 4, h.d_out,
+                                 (size_t)row_out * 4, (size_t)row_out * 4, nb, cudaMemcpyDeviceToHost, h.stream));
+    CUDA_TRY(cudaMemcpyAsync(st_nf + b0, h.d_nf, (size_t)nb * 4, cudaMemcpyDeviceToHost, h.stream));
+    CUDA_TRY(cudaMemcpyAsync(st_st + b0, h.d_st, (size_t)nb * 4, cudaMemcpyDeviceToHost, h.stream));
   }
-  CUDA_TRY(cudaStreamSynchronize(pl->hb[0].stream));
-  CUDA_TRY(cudaStreamSynchronize(pl->hb[1].stream));
+  for (auto& h : pl->hb) CUDA_TRY(cudaStreamSynchronize(h.stream));
+  std::memcpy(n_frames_host, st_nf, (size_t)B * sizeof(int32_t));
+  std::memcpy(status_host, st_st, (size_t)B * sizeof(int32_t));
   return AAD_OK;
 }
 
