@@ -286,8 +286,10 @@ static cep_kernel_t pick_cep(int kc) {
 }
 
 static size_t cep_smem_bytes(const aad_plan* pl) {
-  size_t f = (size_t)pl->p.n_filt * CEP_TS + 8 * CEP_TS;
-  if (pl->p.n_ceps > 0) f += (size_t)(pl->p.n_filt + 1) * pl->ncp + (size_t)pl->p.n_ceps * CEP_TS;
+  const int kcp = (pl->kc + 3) & ~3;
+  size_t f = 4 + (size_t)pl->p.n_filt * CEP_TS + 8 * CEP_TS;
+  if (pl->p.n_ceps > 0)
+    f += (size_t)(pl->ncp / pl->kc) * (pl->p.n_filt + 1) * kcp + (size_t)pl->p.n_ceps * CEP_TS;
   return f * 4;
 }
 
@@ -513,22 +515,25 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   }
   pl->n_w4 = (int)fw4.size();
   pl->k1_smem = k1_fixed + (size_t)((2 * (p.n_filt + 1) + 3) & ~3) * 4 + fw4.size() * sizeof(float4);
-  // DCT-II ortho (scipy.fftpack.dct type 2 norm='ortho'), first n_ceps rows; transposed + padded
+  // DCT-II ortho (scipy.fftpack.dct type 2 norm='ortho'), first n_ceps rows.  Device layout for K2:
+  // [chunk][m = 0..n_filt][kcp] with chunk = kc consecutive coefficients padded to kcp (16-byte rows);
+  // row n_filt of every chunk holds the column sums.
   std::vector<float> dct_t;
   if (p.n_ceps > 0) {
-    const int Mf = p.n_filt;
+    const int Mf = p.n_filt, kc = pl->kc, kcp = (kc + 3) & ~3, n_chunks = pl->ncp / kc;
     pl->h_dct.assign((size_t)p.n_ceps * Mf, 0.f);
-    dct_t.assign((size_t)(Mf + 1) * pl->ncp, 0.f);
+    dct_t.assign((size_t)n_chunks * (Mf + 1) * kcp, 0.f);
     for (int k = 0; k < p.n_ceps; ++k) {
       const double fk = k == 0 ? std::sqrt(1.0 / (4.0 * Mf)) : std::sqrt(1.0 / (2.0 * Mf));
+      const size_t base = (size_t)(k / kc) * (Mf + 1) * kcp + (k % kc);
       double colsum = 0.0;
       for (int m = 0; m < Mf; ++m) {
         float v = (float)(2.0 * fk * std::cos(kPiD * k * (2.0 * m + 1.0) / (2.0 * Mf)));
         pl->h_dct[(size_t)k * Mf + m] = v;
-        dct_t[(size_t)m * pl->ncp + k] = v;
+        dct_t[base + (size_t)m * kcp] = v;
         colsum += (double)v;
       }
-      dct_t[(size_t)Mf * pl->ncp + k] = (float)colsum;  // exact re-addition of the per-frame mean
+      dct_t[base + (size_t)Mf * kcp] = (float)colsum;  // exact re-addition of the per-frame mean
     }
   }
   savgol_taps(p.n_delta > 0 ? p.delta_width : 9, pl->taps[0], pl->taps[1]);

@@ -553,7 +553,8 @@ struct CepArgs {
 //  out  : thread = frame column; static rows and the delta / delta-delta stencils as one FFMA2 per
 //         tap ((d1, d2) accumulated together), coalesced stores along t (CT) or along c (TC)
 template <int KC>
-__global__ void __launch_bounds__(CEP_THREADS) k_cepstra(const CepArgs a) {
+__global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
+  constexpr int KCP = (KC + 3) & ~3;  // chunk stride in the table: 16-byte aligned rows
   extern __shared__ __align__(16) float smem[];
   const int b = blockIdx.y;
   const int T = a.nf_eff[b];
@@ -578,11 +579,14 @@ __global__ void __launch_bounds__(CEP_THREADS) k_cepstra(const CepArgs a) {
   const int nload = hi - lo;  // <= CEP_TS by construction
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = a.n_ceps > 0 ? a.n_ceps : a.n_filt;
+  const int n_chunks = a.ncp / KC;
 
-  float* sE = smem;                                   // [n_filt][CEP_TS]
+  // 4 floats of slack in front: the fixed 9-tap stencil of a narrower delta window may read up to 3
+  // columns before a row (with a zero tap)
+  float* sE = smem + 4;                               // [n_filt][CEP_TS]
   float* sPart = sE + a.n_filt * CEP_TS;              // [8][CEP_TS] per-warp partial column sums
-  float* sD = sPart + 8 * CEP_TS;                     // [n_filt + 1][ncp] (last row: column sums)
-  float* sC = a.n_ceps > 0 ? sD + (a.n_filt + 1) * a.ncp : sE;  // [C][CEP_TS]
+  float* sD = sPart + 8 * CEP_TS;                     // [n_chunks][n_filt + 1][KCP] (last row: column sums)
+  float* sC = a.n_ceps > 0 ? sD + n_chunks * (a.n_filt + 1) * KCP : sE;  // [C][CEP_TS]
 
   // reference / floor (librosa.power_to_db):  ls = E - ref ; ls = max(ls, max(ls) - top_db)
   float ref = 0.f, floorv = -INFINITY;
@@ -601,14 +605,14 @@ __global__ void __launch_bounds__(CEP_THREADS) k_cepstra(const CepArgs a) {
     auto xf = [&](float v, int t) { return t < nload ? fmaxf(v - ref, floorv) : 0.f; };
     if (vec) {
       int m = warp;
-      for (; m + 24 < a.n_filt; m += 32) {  // 4 independent 16-byte loads in flight per thread
-        float4 v[4];
+      for (; m + 56 < a.n_filt; m += 64) {  // 8 independent 16-byte loads in flight per thread
+        float4 v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 8; ++u)
           v[u] = t4 < nload ? __ldg(reinterpret_cast<const float4*>(Eb + (long long)(m + 8 * u) * a.e_stride_f + t4))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           float4 r = make_float4(xf(v[u].x, t4), xf(v[u].y, t4 + 1), xf(v[u].z, t4 + 2), xf(v[u].w, t4 + 3));
           *reinterpret_cast<float4*>(sE + (m + 8 * u) * CEP_TS + t4) = r;
           ps.x += r.x; ps.y += r.y; ps.z += r.z; ps.w += r.w;
@@ -635,9 +639,9 @@ __global__ void __launch_bounds__(CEP_THREADS) k_cepstra(const CepArgs a) {
     }
     *reinterpret_cast<float4*>(sPart + warp * CEP_TS + t4) = ps;
     if (a.n_ceps > 0) {
-      const int nd = (a.n_filt + 1) * a.ncp;  // ncp is even and dct_t comes from cudaMalloc: 8-byte units
-      for (int i = tid * 2; i < nd; i += CEP_THREADS * 2)
-        *reinterpret_cast<float2*>(sD + i) = __ldg(reinterpret_cast<const float2*>(a.dct_t + i));
+      const int nd = n_chunks * (a.n_filt + 1) * KCP;  // multiple of 4 floats, cudaMalloc-aligned source
+      for (int i = tid * 4; i < nd; i += CEP_THREADS * 4)
+        *reinterpret_cast<float4*>(sD + i) = __ldg(reinterpret_cast<const float4*>(a.dct_t + i));
     }
   }
   __syncthreads();
@@ -646,7 +650,7 @@ __global__ void __launch_bounds__(CEP_THREADS) k_cepstra(const CepArgs a) {
   if (a.n_ceps > 0) {
     // The DCT is linear: accumulate on the per-frame-centred energies (small partial sums,
     // so float32 accumulation of ~100 same-sign dB values loses nothing) and add the mean
-    // back through the table's column sums (row n_filt of dct_t).
+    // back through the table's column sums (row n_filt of each chunk).
     const int p = tid & 63, grp = tid >> 6;
     const float2* sE2 = reinterpret_cast<const float2*>(sE) + p;
     float2 mean2 = make_float2(0.f, 0.f);
@@ -655,28 +659,29 @@ __global__ void __launch_bounds__(CEP_THREADS) k_cepstra(const CepArgs a) {
     const float inv = 1.0f / (float)a.n_filt;
     mean2 = __fmul2_rn(mean2, make_float2(inv, inv));
     const float2 nmean2 = make_float2(-mean2.x, -mean2.y);
-    for (int c0 = grp * KC; c0 < a.ncp; c0 += 4 * KC) {
+    for (int ch = grp; ch < n_chunks; ch += 4) {
       float2 acc[KC];
 #pragma unroll
       for (int i = 0; i < KC; ++i) acc[i] = make_float2(0.f, 0.f);
-      const float* drow = sD + c0;
+      const float4* dch = reinterpret_cast<const float4*>(sD + ch * (a.n_filt + 1) * KCP);
 #pragma unroll 4
       for (int m = 0; m < a.n_filt; ++m) {
         const float2 e = __fadd2_rn(sE2[m * (CEP_TS / 2)], nmean2);
-        const float2* d2 = reinterpret_cast<const float2*>(drow + m * a.ncp);
+        float d[KCP];
 #pragma unroll
-        for (int i = 0; i < KC / 2; ++i) {
-          const float2 d = d2[i];
-          acc[2 * i] = __ffma2_rn(e, make_float2(d.x, d.x), acc[2 * i]);
-          acc[2 * i + 1] = __ffma2_rn(e, make_float2(d.y, d.y), acc[2 * i + 1]);
+        for (int i = 0; i < KCP / 4; ++i) {
+          const float4 q = dch[m * (KCP / 4) + i];
+          d[4 * i] = q.x; d[4 * i + 1] = q.y; d[4 * i + 2] = q.z; d[4 * i + 3] = q.w;
         }
+#pragma unroll
+        for (int i = 0; i < KC; ++i) acc[i] = __ffma2_rn(e, make_float2(d[i], d[i]), acc[i]);
       }
-      const float* colsum = sD + a.n_filt * a.ncp + c0;
+      const float* colsum = reinterpret_cast<const float*>(dch) + a.n_filt * KCP;
 #pragma unroll
       for (int i = 0; i < KC; ++i)
-        if (c0 + i < a.n_ceps) {
+        if (ch * KC + i < a.n_ceps) {
           const float cs = colsum[i];
-          *reinterpret_cast<float2*>(sC + (c0 + i) * CEP_TS + 2 * p) = __ffma2_rn(mean2, make_float2(cs, cs), acc[i]);
+          *reinterpret_cast<float2*>(sC + (ch * KC + i) * CEP_TS + 2 * p) = __ffma2_rn(mean2, make_float2(cs, cs), acc[i]);
         }
     }
     __syncthreads();
@@ -686,22 +691,26 @@ __global__ void __launch_bounds__(CEP_THREADS) k_cepstra(const CepArgs a) {
   const int col = tid & (CEP_TS - 1), half = tid >> 7;
   const int t = lo + col;
   if (t >= o0 && t < o1) {
-    float* ob = a.out + (long long)b * a.out_stride_b + (long long)t * a.out_stride_t;
+    float* ob = a.out + (long long)b * a.out_stride_b + (long long)t * a.out_stride_t + (long long)half * a.out_stride_c;
+    const long long cstep = 2ll * a.out_stride_c, dstep = (long long)C * a.out_stride_c;
     const int te = min(max(t, h), T - 1 - h) - lo;  // stencil centre (edges replicate the interior fit)
-    for (int k = half; k < C; k += 2) {
-      const float* row = sC + k * CEP_TS;
-      ob[(long long)k * a.out_stride_c] = row[col];
+    // taps centred in a fixed 9-wide window (zero outside the delta width): immediate offsets
+    float2 tp[CEP_MAXW];
+#pragma unroll
+    for (int i = 0; i < CEP_MAXW; ++i) {
+      const int src = i - (CEP_MAXW / 2) + h;
+      tp[i] = (src >= 0 && src < a.width) ? make_float2(a.taps[0][src], a.taps[1][src]) : make_float2(0.f, 0.f);
+    }
+    const float* row = sC + half * CEP_TS;
+    for (int k = half; k < C; k += 2, row += 2 * CEP_TS, ob += cstep) {
+      ob[0] = row[col];
       if (a.n_delta > 0) {
+        const float* rc = row + te - CEP_MAXW / 2;
         float2 d12 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < CEP_MAXW; ++i) {
-          if (i < a.width) {
-            const float x = row[te - h + i];
-            d12 = __ffma2_rn(make_float2(x, x), make_float2(a.taps[0][i], a.taps[1][i]), d12);
-          }
-        }
-        ob[(long long)(C + k) * a.out_stride_c] = d12.x;
-        if (a.n_delta > 1) ob[(long long)(2 * C + k) * a.out_stride_c] = d12.y;
+        for (int i = 0; i < CEP_MAXW; ++i) d12 = __ffma2_rn(make_float2(rc[i], rc[i]), tp[i], d12);
+        ob[dstep] = d12.x;
+        if (a.n_delta > 1) ob[2 * dstep] = d12.y;
       }
     }
   }
