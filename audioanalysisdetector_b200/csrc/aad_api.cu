@@ -27,7 +27,7 @@ struct aad_plan {
   int tile = 32;      // frames per K1 tile (16 or 32)
   int warps = 0, ctas = 0;
   size_t k1_smem = 0;
-  int n_w4 = 0;
+  int n_w4 = 0, n_hdr = 0;
   int kc = 10;
   int c_feat = 0;     // rows before deltas
   int c_out = 0;
@@ -43,7 +43,7 @@ struct aad_plan {
   float2* d_twp = nullptr;
   int2* d_filt_hdr = nullptr;
   float4* d_filt_w = nullptr;
-  int32_t* d_warp_filt = nullptr;
+  int4* d_warp_prog = nullptr;
   float* d_dct_t = nullptr;
   // optional per-kernel timing (bench roofline): events recorded around each launch
   bool profile = false;
@@ -373,7 +373,7 @@ int aad_plan_destroy(aad_plan* pl) {
   cudaFree(pl->d_twp);
   cudaFree(pl->d_filt_hdr);
   cudaFree(pl->d_filt_w);
-  cudaFree(pl->d_warp_filt);
+  cudaFree(pl->d_warp_prog);
   cudaFree(pl->d_dct_t);
   for (auto& e : pl->ev)
     if (e) cudaEventDestroy(e);
@@ -467,42 +467,29 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
     delete pl;
     return rc;
   }
-  // Filterbank program, two-tap banded form (see StftArgs): per segment the bins [seg[s], seg[s+1])
-  // with all-zero ends trimmed, first bin rounded down to a multiple of 4, in rounds of npar groups of
-  // 4 bins; per warp a contiguous filter range balanced by cost.
-  std::vector<int32_t> wfilt(pl->warps + 1, p.n_filt);
-  std::vector<int2> fhdr(p.n_filt + 1);
+  // Filterbank program, two-tap banded form (see StftArgs).  Segment s = bins [seg[s], seg[s+1]) with
+  // all-zero ends trimmed, first bin rounded down to a multiple of 4, in rounds of 4 bins.  Warps get
+  // contiguous filter ranges balanced by cost; each warp's entry list is its segments wf0 .. wf1.
+  std::vector<int2> fhdr;
   std::vector<float4> fw4;
+  std::vector<int4> wprog(pl->warps, make_int4(0, 0, 0, 0));
   {
-    std::vector<double> cost(p.n_filt + 1);
+    const int nseg = p.n_filt + 1;
+    std::vector<int> sk0(nseg), sk1(nseg), srounds(nseg);
+    std::vector<double> cost(nseg);
     double tot = 0;
-    for (int sgi = 0; sgi <= p.n_filt; ++sgi) {
+    for (int sgi = 0; sgi < nseg; ++sgi) {
       int k0 = seg[sgi], k1 = seg[sgi + 1];
       auto zero = [&](int k) { return fbw[k].x == 0.f && fbw[k].y == 0.f; };
       while (k0 < k1 && zero(k0)) ++k0;
       while (k1 > k0 && zero(k1 - 1)) --k1;
-      k0 &= ~3;
-      const int ng = (k1 - k0 + 3) / 4;
-      const int rounds = (ng + npar - 1) / npar;
-      if (k0 > 0xffff || rounds > 0x7fff) {
-        delete pl;
-        return AAD_ERR_UNSUPPORTED;
-      }
-      fhdr[sgi] = make_int2(k0 | (rounds << 16), (int)fw4.size());
-      for (int g = 0; g < rounds * npar; ++g) {
-        float w[8];
-        for (int i = 0; i < 4; ++i) {
-          const int k = k0 + g * 4 + i;
-          const bool in = k >= seg[sgi] && k < k1;
-          w[2 * i] = in ? fbw[k].x : 0.f;
-          w[2 * i + 1] = in ? fbw[k].y : 0.f;
-        }
-        fw4.push_back(make_float4(w[0], w[1], w[2], w[3]));
-        fw4.push_back(make_float4(w[4], w[5], w[6], w[7]));
-      }
-      cost[sgi] = 8.0 * rounds + 24.0;  // ~instructions: tap rounds + one emit
+      sk0[sgi] = k0;
+      sk1[sgi] = k1;
+      srounds[sgi] = (k1 - (k0 & ~3) + 3) / 4;
+      cost[sgi] = 8.0 * srounds[sgi] + 24.0;  // ~instructions: tap rounds + one emit
       tot += cost[sgi];
     }
+    std::vector<int> wfilt(pl->warps + 1, p.n_filt);
     wfilt[0] = 0;
     double cum = 0;
     int j = 0;
@@ -511,10 +498,45 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
       while (j < p.n_filt && cum + cost[j] * 0.5 < target) cum += cost[j++];
       wfilt[wi] = j;
     }
-    wfilt[pl->warps] = p.n_filt;
+    const int row_limit = (K + 3) & ~3;  // bins + zeroed padding of a power row
+    for (int wi = 0; wi < pl->warps; ++wi) {
+      const int f0 = wfilt[wi], f1 = wfilt[wi + 1];
+      if (f1 <= f0) continue;
+      std::vector<int> ents;
+      for (int sgi = f0; sgi <= f1; ++sgi) ents.push_back(sgi);
+      if (npar == 2 && (ents.size() & 1)) ents.push_back(-1);  // empty entry
+      wprog[wi] = make_int4(f0, (int)fhdr.size(), (int)ents.size(), f1 - f0);
+      for (size_t e = 0; e < ents.size(); ++e) {
+        const int sgi = ents[e];
+        int k0 = sgi >= 0 ? sk0[sgi] : 0, k1 = sgi >= 0 ? sk1[sgi] : 0;
+        int rounds = sgi >= 0 ? srounds[sgi] : 0;
+        if (npar == 2) {  // both half-warps run the same number of rounds
+          const int mate = ents[e ^ 1];
+          rounds = std::max(rounds, mate >= 0 ? srounds[mate] : 0);
+        }
+        int k0a = std::min(k0 & ~3, row_limit - 4 * rounds);
+        if (k0a < 0 || k0a > 0xffff || rounds > 0x7fff) {
+          delete pl;
+          return AAD_ERR_UNSUPPORTED;
+        }
+        fhdr.push_back(make_int2(k0a | (rounds << 16), (int)fw4.size()));
+        for (int g = 0; g < rounds; ++g) {
+          float w[8];
+          for (int i = 0; i < 4; ++i) {
+            const int k = k0a + g * 4 + i;
+            const bool in = k >= k0 && k < k1;
+            w[2 * i] = in ? fbw[k].x : 0.f;
+            w[2 * i + 1] = in ? fbw[k].y : 0.f;
+          }
+          fw4.push_back(make_float4(w[0], w[1], w[2], w[3]));
+          fw4.push_back(make_float4(w[4], w[5], w[6], w[7]));
+        }
+      }
+    }
   }
+  pl->n_hdr = (int)fhdr.size();
   pl->n_w4 = (int)fw4.size();
-  pl->k1_smem = k1_fixed + (size_t)((2 * (p.n_filt + 1) + 3) & ~3) * 4 + fw4.size() * sizeof(float4);
+  pl->k1_smem = k1_fixed + (size_t)((2 * fhdr.size() + 3) & ~3) * 4 + fw4.size() * sizeof(float4);
   // DCT-II ortho (scipy.fftpack.dct type 2 norm='ortho'), first n_ceps rows.  Device layout for K2:
   // [chunk][m = 0..n_filt][kcp] with chunk = kc consecutive coefficients padded to kcp (16-byte rows);
   // row n_filt of every chunk holds the column sums.
@@ -544,7 +566,7 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   if (e == cudaSuccess) e = upload(&pl->d_twp, twp);
   if (e == cudaSuccess) e = upload(&pl->d_filt_hdr, fhdr);
   if (e == cudaSuccess) e = upload(&pl->d_filt_w, fw4);
-  if (e == cudaSuccess) e = upload(&pl->d_warp_filt, wfilt);
+  if (e == cudaSuccess) e = upload(&pl->d_warp_prog, wprog);
   if (e == cudaSuccess) e = upload(&pl->d_dct_t, dct_t);
   // opt in to the large dynamic shared memory of every kernel variant this plan can launch
   // (the attribute is per function, not per plan: opt in to the device maximum)
@@ -672,8 +694,8 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
   sa.win_off = p.center ? (p.n_fft - p.win_length) / 2 : 0; sa.win_len = p.win_length;
   sa.pre_emph = p.pre_emph;
   sa.window = pl->d_window; sa.tw1 = pl->d_tw1; sa.twp = pl->d_twp;
-  sa.filt_hdr = pl->d_filt_hdr; sa.filt_w = pl->d_filt_w; sa.n_w4 = pl->n_w4;
-  sa.warp_filt = pl->d_warp_filt; sa.tile_b0 = pa.tile_b0; sa.n_filt = p.n_filt;
+  sa.filt_hdr = pl->d_filt_hdr; sa.filt_w = pl->d_filt_w; sa.n_hdr = pl->n_hdr; sa.n_w4 = pl->n_w4;
+  sa.warp_prog = pl->d_warp_prog; sa.tile_b0 = pa.tile_b0; sa.n_filt = p.n_filt;
   sa.log_type = p.log_type; sa.amin = p.amin; sa.eps = 2.220446049250313e-16f;
   if (pl->need_ws_E) {
     sa.E = d_E; sa.e_stride_b = (long long)p.n_filt * w.t_ws; sa.e_stride_f = w.t_ws;

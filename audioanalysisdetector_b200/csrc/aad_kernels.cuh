@@ -144,12 +144,12 @@ struct StftCfg {
   static constexpr int N = 2 * M;         // n_fft
   static constexpr int K = M + 1;         // bins
   static constexpr int TILE = TILE_;      // frames per tile
-  static constexpr int NPAR = 32 / TILE;  // filterbank phase: lane = frame + TILE * (tap-group parity)
+  static constexpr int NPAR = 32 / TILE;  // filterbank phase: lane = frame + TILE * (segment parity)
   // power-row stride in floats.  The filterbank phase reads P[frame][4g .. 4g+3] as one LDS.128 per
   // lane: conflict-free iff SP/4 is odd.  Q rows double as the warp's 32x33 transpose scratch
   // (Q*SP >= 1056), and the row holds K bins plus zeroed padding (PAD words).
   static constexpr int SP = L == 4 ? 132 : (L == 8 ? 292 : (L == 16 ? 548 : 1060));
-  static constexpr int PAD = NPAR == 1 ? 3 : 7;
+  static constexpr int PAD = 3;
   static constexpr int ITERS = TILE / Q;  // warp-iterations per tile
   static constexpr int WARPS = ITERS >= 8 ? ITERS / 2 : 4;
   static constexpr int CTAS = L == 32 ? (TILE == 32 ? 1 : 2) : (L == 16 ? 2 : 4);
@@ -183,13 +183,15 @@ struct StftArgs {
   // filterbank program (copied to smem), two-tap banded form: the bins split into n_filt + 1
   // segments; inside segment s bin k feeds filter s with its rising weight wr[k] and filter s - 1
   // with its falling weight wf[k], so  energy[j] = R[j] + F[j + 1]  with (R, F)[s] the two
-  // weighted sums over segment s and every power value is read once.  Per segment a header
-  // {first bin (multiple of 4) | n_rounds << 16, weight offset in float4 units}; per round NPAR
-  // groups of 4 bins, each group two float4 {wr0, wf0, wr1, wf1}, {wr2, wf2, wr3, wf3} (zero padded).
-  const int2* filt_hdr;     // [n_filt + 1]
+  // weighted sums over segment s and every power value is read once.  Each warp owns a list of
+  // entries = the segments of its filter range; per entry a header {first bin (multiple of 4) |
+  // n_rounds << 16, weight offset in float4 units}; per round 4 bins as two float4
+  // {wr0, wf0, wr1, wf1}, {wr2, wf2, wr3, wf3} (zero padded).  With NPAR = 2 the two half-warps
+  // walk alternate entries of the list (rounds equalised per pair, list padded to an even length).
+  const int2* filt_hdr;     // [n_hdr]
   const float4* filt_w;     // [n_w4]
-  int n_w4;
-  const int32_t* warp_filt; // [WARPS + 1] filter range per warp (segments wf0 .. wf1 inclusive)
+  int n_hdr, n_w4;
+  const int4* warp_prog;    // [WARPS] {first filter, first entry, n_entries, n_filters}
   const int32_t* tile_b0;   // [n_tiles] from k_prepare
   int n_filt;
   int log_type;             // 0 dB, 1 ln
@@ -251,7 +253,7 @@ k_stft_fb(const StftArgs a) {
   float2* sTwp = reinterpret_cast<float2*>(smem + C::OFF_TWP);
   int* sMeta = reinterpret_cast<int*>(smem + C::OFF_META);
   int2* sHdr = reinterpret_cast<int2*>(smem + C::OFF_PROG);
-  float4* sW4 = reinterpret_cast<float4*>(smem + C::OFF_PROG + ((2 * (a.n_filt + 1) + 3) & ~3));
+  float4* sW4 = reinterpret_cast<float4*>(smem + C::OFF_PROG + ((2 * a.n_hdr + 3) & ~3));
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -261,9 +263,9 @@ k_stft_fb(const StftArgs a) {
   for (int i = tid; i < N; i += nthr) sWin[i] = a.window[i];
   for (int i = tid; i < 32 * L; i += nthr) sTw1[i] = a.tw1[i];
   for (int i = tid; i < M / 2; i += nthr) sTwp[i] = a.twp[i];
-  for (int i = tid; i <= a.n_filt; i += nthr) sHdr[i] = a.filt_hdr[i];
+  for (int i = tid; i < a.n_hdr; i += nthr) sHdr[i] = a.filt_hdr[i];
   for (int i = tid; i < a.n_w4; i += nthr) sW4[i] = a.filt_w[i];
-  const int wf0 = a.warp_filt[warp], wf1 = a.warp_filt[warp + 1];
+  const int4 wprog = a.warp_prog[warp];
   const int total = a.frame_off[a.B];
   const int n_tiles = (total + C::TILE - 1) / C::TILE;
   const float2* sWin2 = reinterpret_cast<const float2*>(sWin);
@@ -458,50 +460,57 @@ k_stft_fb(const StftArgs a) {
     }
     __syncthreads();
 
-    // ---- filterbank + log phase: lane = frame (+ group parity), warps split the filters ----
-    // Per segment: 4 bins per step (powers: one conflict-free LDS.128 per lane; weights: two
+    // ---- filterbank + log phase: lane = frame (+ segment parity), warps split the filters ----
+    // Per entry: 4 bins per round (powers: one conflict-free LDS.128 per lane; weights: two
     // LDS.128 broadcasts; four FFMA2 accumulate (rising, falling) sums with the power broadcast to
     // both halves), then filter s-1 = R[s-1] + F[s]: log, store, running max.
-    if (wf0 < wf1) {
+    if (wprog.w > 0) {
       const int fr = lane % C::TILE, par = lane / C::TILE;
       const int b = sMetaB[fr], t = sMetaT[fr];
       const bool valid = b >= 0;
-      const float* pbase = sP + fr * SP + 4 * par;
-      float* eptr = a.E + (valid ? (long long)b * a.e_stride_b + (long long)wf0 * a.e_stride_f + t : 0);
+      const float* pbase = sP + fr * SP;
+      // half-warp `par` emits filters wf0 - par, wf0 - par + NPAR, ...
+      float* eptr = a.E + (valid ? (long long)b * a.e_stride_b + (long long)(wprog.x - par) * a.e_stride_f + t : 0);
+      const long long estep = (long long)NPAR * a.e_stride_f;
       const float lscale = a.log_type == 0 ? 3.01029995663981195f : 0.69314718055994531f;
       float vmax = -INFINITY, chk = 0.f, rprev = 0.f;
-      for (int sg = wf0; sg <= wf1; ++sg) {
-        const int2 hd = sHdr[sg];
+      for (int i = 0; i < wprog.z; i += NPAR) {
+        const int2 hd = sHdr[wprog.y + i + par];
         const float4* pp = reinterpret_cast<const float4*>(pbase + (hd.x & 0xffff));
-        const float4* wp = sW4 + hd.y + 2 * par;
+        const float4* wp = sW4 + hd.y;
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll 2
         for (int gq = hd.x >> 16; gq > 0; --gq) {
-          const float4 p = *pp;
+          const float4 p = *pp++;
           const float4 wa = wp[0], wb = wp[1];
-          pp += NPAR;
-          wp += 2 * NPAR;
+          wp += 2;
           acc0 = __ffma2_rn(make_float2(p.x, p.x), make_float2(wa.x, wa.y), acc0);
           acc1 = __ffma2_rn(make_float2(p.y, p.y), make_float2(wa.z, wa.w), acc1);
           acc0 = __ffma2_rn(make_float2(p.z, p.z), make_float2(wb.x, wb.y), acc0);
           acc1 = __ffma2_rn(make_float2(p.w, p.w), make_float2(wb.z, wb.w), acc1);
         }
-        float2 rf = __fadd2_rn(acc0, acc1);  // (R[sg], F[sg])
+        const float2 rf = __fadd2_rn(acc0, acc1);  // (R, F) of this half-warp's segment
+        float en;
+        bool emit;
         if constexpr (NPAR == 2) {
-          rf.x += __shfl_xor_sync(0xffffffffu, rf.x, 16);
-          rf.y += __shfl_xor_sync(0xffffffffu, rf.y, 16);
+          // half 0 holds segment s = wf0 + i, half 1 segment s + 1: swap the falling sums
+          const float f_other = __shfl_xor_sync(0xffffffffu, rf.y, 16);
+          en = (par ? rprev : rf.x) + f_other;     // half 1: filter s - 1 = R[s-1] + F[s]; half 0: filter s = R[s] + F[s+1]
+          emit = par ? i > 0 : i < wprog.w;
+        } else {
+          en = rprev + rf.y;                       // filter s - 1
+          emit = i > 0;
         }
-        if (sg > wf0) {
-          const float en = rprev + rf.y;
+        if (emit) {
           // 10*log10(x) = 3.0103*log2(x), ln(x) = 0.6931*log2(x); MUFU.LG2 is accurate to 2 ulp,
           // i.e. <= 3e-5 dB / 4e-6 nepers here, far inside the 1e-3 parity tolerance
           const float arg = a.log_type == 0 ? fmaxf(a.amin, en) : (en == 0.f ? a.eps : en);
           const float val = lscale * __log2f(arg);
-          if (valid && par == 0) *eptr = val;
-          eptr += a.e_stride_f;
+          if (valid) *eptr = val;
           vmax = fmaxf(vmax, val);
           chk = __fmaf_rn(val, 0.f, chk);  // NaN/Inf poison
         }
+        if (NPAR == 1 ? i > 0 : true) eptr += estep;
         rprev = rf.x;
       }
       if (valid) {
