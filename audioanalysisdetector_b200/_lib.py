@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libaad_b200.so")
+LIB_PATH = os.environ.get("AAD_LIB_PATH") or os.path.join(_PKG_DIR, "libaad_b200.so")  # override: dev builds only
 
 # enums (mirror include/aad.h)
 KIND_LOGMEL, KIND_MFCC, KIND_LFCC = 0, 1, 2

@@ -249,27 +249,29 @@ static stft_kernel_t pick_stft_LT(int mode, bool pre) {
   }
 }
 static stft_kernel_t pick_stft(int L, int tile, int mode, bool pre) {
+#if AAD_ABLATE || defined(AAD_DEV_BUILD)
+  return L == 32 && tile == 32 && mode == 0 && !pre ? k_stft_fb<32, IN_F32, false, 32> : nullptr;  // dev builds: one variant
+#else
   switch (L) {
     case 4: return pick_stft_LT<4, 32>(mode, pre);
     case 8: return pick_stft_LT<8, 32>(mode, pre);
     case 16: return pick_stft_LT<16, 32>(mode, pre);
-    case 32: return tile == 16 ? pick_stft_LT<32, 16>(mode, pre) : pick_stft_LT<32, 32>(mode, pre);
+    case 32: return pick_stft_LT<32, 32>(mode, pre);
   }
   return nullptr;
+#endif
 }
 template <int L, int TILE>
-static void stft_cfg_LT(int* warps, int* ctas, size_t* fixed, int* npar) {
+static void stft_cfg_LT(int* warps, int* ctas, size_t* fixed, int* fbu) {
   using C = StftCfg<L, TILE>;
-  *warps = C::WARPS; *ctas = C::CTAS; *fixed = C::FIXED_BYTES; *npar = C::NPAR;
+  *warps = C::WARPS; *ctas = C::CTAS; *fixed = C::FIXED_BYTES; *fbu = C::FBU;
 }
-static void stft_cfg(int L, int tile, int* warps, int* ctas, size_t* fixed, int* npar) {
+static void stft_cfg(int L, int* warps, int* ctas, size_t* fixed, int* fbu) {
   switch (L) {
-    case 4: stft_cfg_LT<4, 32>(warps, ctas, fixed, npar); break;
-    case 8: stft_cfg_LT<8, 32>(warps, ctas, fixed, npar); break;
-    case 16: stft_cfg_LT<16, 32>(warps, ctas, fixed, npar); break;
-    default:
-      if (tile == 16) stft_cfg_LT<32, 16>(warps, ctas, fixed, npar);
-      else stft_cfg_LT<32, 32>(warps, ctas, fixed, npar);
+    case 4: stft_cfg_LT<4, 32>(warps, ctas, fixed, fbu); break;
+    case 8: stft_cfg_LT<8, 32>(warps, ctas, fixed, fbu); break;
+    case 16: stft_cfg_LT<16, 32>(warps, ctas, fixed, fbu); break;
+    default: stft_cfg_LT<32, 32>(warps, ctas, fixed, fbu);
   }
 }
 
@@ -416,16 +418,10 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, device);
   pl->L = p.n_fft / 64;
   pl->K = p.n_fft / 2 + 1;
-  // frames per K1 tile.  n_fft 2048: 32 (one 16-warp CTA per SM) or, with AAD_TILE=16 in the
-  // environment, 16 (two 8-warp CTAs per SM whose FFT and filterbank phases interleave).
-  pl->tile = 32;
-  if (pl->L == 32) {
-    const char* env = getenv("AAD_TILE");
-    if (env && atoi(env) == 16) pl->tile = 16;
-  }
+  pl->tile = 32;  // frames per K1 tile (n_fft 2048: one 16-warp CTA per SM)
   size_t k1_fixed = 0;
-  int npar = 1;
-  stft_cfg(pl->L, pl->tile, &pl->warps, &pl->ctas, &k1_fixed, &npar);
+  int fbu = 1;
+  stft_cfg(pl->L, &pl->warps, &pl->ctas, &k1_fixed, &fbu);
   pl->c_feat = p.n_ceps > 0 ? p.n_ceps : p.n_filt;
   pl->c_out = pl->c_feat * (1 + p.n_delta);
   // K2: four thread groups split the coefficient chunks of kc (even, <= 12) coefficients each
@@ -449,8 +445,8 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
     pl->h_window[win_off + n] = (float)w[n];
     win_half[win_off + n] = 0.5f * (float)w[n];
   }
-  std::vector<float2> tw1((size_t)32 * L), twp(M / 2);
-  for (int ka = 0; ka < 32; ++ka)
+  std::vector<float2> tw1((size_t)33 * L), twp(M / 2);
+  for (int ka = 0; ka <= 32; ++ka)  // row 32: W_M^(32 b) = W_L^b, the rotation of the kA <-> 32 - kA symmetry
     for (int b = 0; b < L; ++b) {
       double ang = -2.0 * kPiD * (double)((long long)b * ka % M) / M;
       tw1[(size_t)ka * L + b] = make_float2((float)std::cos(ang), (float)std::sin(ang));
@@ -504,16 +500,14 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
       if (f1 <= f0) continue;
       std::vector<int> ents;
       for (int sgi = f0; sgi <= f1; ++sgi) ents.push_back(sgi);
-      if (npar == 2 && (ents.size() & 1)) ents.push_back(-1);  // empty entry
+      while (ents.size() % fbu) ents.push_back(-1);  // empty entries
       wprog[wi] = make_int4(f0, (int)fhdr.size(), (int)ents.size(), f1 - f0);
       for (size_t e = 0; e < ents.size(); ++e) {
         const int sgi = ents[e];
         int k0 = sgi >= 0 ? sk0[sgi] : 0, k1 = sgi >= 0 ? sk1[sgi] : 0;
         int rounds = sgi >= 0 ? srounds[sgi] : 0;
-        if (npar == 2) {  // both half-warps run the same number of rounds
-          const int mate = ents[e ^ 1];
-          rounds = std::max(rounds, mate >= 0 ? srounds[mate] : 0);
-        }
+        for (size_t m = e / fbu * fbu; m < e / fbu * fbu + fbu; ++m)  // one round count per bundle
+          rounds = std::max(rounds, ents[m] >= 0 ? srounds[ents[m]] : 0);
         int k0a = std::min(k0 & ~3, row_limit - 4 * rounds);
         if (k0a < 0 || k0a > 0xffff || rounds > 0x7fff) {
           delete pl;
@@ -577,9 +571,10 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
     return AAD_ERR_UNSUPPORTED;
   }
   for (int mode = 0; mode < 3 && e == cudaSuccess; ++mode)
-    for (int pre = 0; pre < 2 && e == cudaSuccess; ++pre)
-      e = cudaFuncSetAttribute((const void*)pick_stft(L, pl->tile, mode, pre != 0),
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    for (int pre = 0; pre < 2 && e == cudaSuccess; ++pre) {
+      const void* fn = (const void*)pick_stft(L, pl->tile, mode, pre != 0);
+      if (fn) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    }
   if (e == cudaSuccess && pl->need_ws_E) {
     if (cep_smem_bytes(pl) > (size_t)optin) {
       aad_plan_destroy(pl);
@@ -706,6 +701,7 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
   sa.status = status;
   const int mode = wav_dtype == AAD_I16 ? IN_I16 : (p.quantize_i16 ? IN_F32_Q16 : IN_F32);
   stft_kernel_t kern = pick_stft(pl->L, pl->tile, mode, p.pre_emph != 0.f);
+  if (!kern) return AAD_ERR_UNSUPPORTED;
   const long long max_tiles = w.max_tiles;
   const int grid1 = (int)std::min<long long>((long long)pl->sm_count * pl->ctas, std::max<long long>(max_tiles, 1));
   kern<<<grid1, pl->warps * 32, pl->k1_smem, stream>>>(sa);

@@ -103,6 +103,26 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 w) {
   return __ffma2_rn(a, make_float2(w.x, w.x), t);
 }
 
+// complex product a * conj(w)  (2 packed instructions)
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 w) {
+  // a*conj(w) = w.x * (a.x, a.y) + w.y * (a.y, -a.x)
+  const float2 t = __fmul2_rn(make_float2(a.y, -a.x), make_float2(w.y, w.y));
+  return __ffma2_rn(a, make_float2(w.x, w.x), t);
+}
+
+// complex product a * exp(-2*pi*i*J/M) with a compile-time twiddle (2 packed instructions, immediates)
+template <int J, int M>
+__device__ __forceinline__ float2 cmul_const(float2 a) {
+  if constexpr (J % M == 0) {
+    return a;
+  } else {
+    constexpr cx_cs cs = cx_cossin_2pi(J, M);
+    constexpr float wr = float(cs.c), wi = float(-cs.s);
+    const float2 t = __fmul2_rn(make_float2(-a.y, a.x), make_float2(wi, wi));
+    return __ffma2_rn(a, make_float2(wr, wr), t);
+  }
+}
+
 // ---------------------------------------------------------------- butterflies
 // W = exp(-2*pi*i*J/M) = (wr, wi) with wi = -sin.  (a, b) <- (a + W b, a - W b).
 // Packed cost: 2 for W in {1, -i}, 3 otherwise (general: t = a + wr*b; a' = t + wi*(-b.y, b.x);

@@ -21,6 +21,25 @@ namespace aad {
 
 enum InMode { IN_F32 = 0, IN_F32_Q16 = 1, IN_I16 = 2 };
 
+// Development only: -DAAD_ABLATE=<mask> removes parts of k_stft_fb (results become wrong) so that the
+// marginal cost of each part can be timed (tools/ablate_k1.sh).  0 in every shipped build.
+#ifndef AAD_ABLATE
+#define AAD_ABLATE 0
+#endif
+constexpr int ABL = AAD_ABLATE;
+// Shared-memory traffic is the binding resource of k_stft_fb (ncu: l1tex data pipe ~72 %), the FMA
+// pipe has headroom.  These switches trade table loads for packed arithmetic:
+//   AAD_TWPGEN  split twiddle W_N^k = W_N^(j + L q) [per-lane register] * W_N^(32 s) [immediate]
+//   AAD_TW1SYM  pass-1 twiddles for kA > 16 from those for 32 - kA: W_M^(b kA) = W_L^b * conj(W_M^(b (32-kA)))
+#ifndef AAD_TWPGEN
+#define AAD_TWPGEN 1
+#endif
+#ifndef AAD_TW1SYM
+#define AAD_TW1SYM 0
+#endif
+// 1 window table, 2 tw1 table, 4 transposes, 8 filterbank phase, 16 split exchange + twp table,
+// 32 power stores, 64 butterflies, 128 global sample loads, 256 log in the filterbank emit
+
 // ---------------------------------------------------------------------------
 // ordered-int encoding of floats (monotone), for atomicMax / redux on floats
 // ---------------------------------------------------------------------------
@@ -144,15 +163,22 @@ struct StftCfg {
   static constexpr int N = 2 * M;         // n_fft
   static constexpr int K = M + 1;         // bins
   static constexpr int TILE = TILE_;      // frames per tile
-  static constexpr int NPAR = 32 / TILE;  // filterbank phase: lane = frame + TILE * (segment parity)
+#ifndef AAD_FBU
+#define AAD_FBU 2
+#endif
+  static constexpr int FBU = AAD_FBU;     // filterbank phase: entries processed together (ILP)
   // power-row stride in floats.  The filterbank phase reads P[frame][4g .. 4g+3] as one LDS.128 per
   // lane: conflict-free iff SP/4 is odd.  Q rows double as the warp's 32x33 transpose scratch
   // (Q*SP >= 1056), and the row holds K bins plus zeroed padding (PAD words).
   static constexpr int SP = L == 4 ? 132 : (L == 8 ? 292 : (L == 16 ? 548 : 1060));
   static constexpr int PAD = 3;
   static constexpr int ITERS = TILE / Q;  // warp-iterations per tile
+#ifdef AAD_WARPS_DEV
+  static constexpr int WARPS = AAD_WARPS_DEV;
+#else
   static constexpr int WARPS = ITERS >= 8 ? ITERS / 2 : 4;
-  static constexpr int CTAS = L == 32 ? (TILE == 32 ? 1 : 2) : (L == 16 ? 2 : 4);
+#endif
+  static constexpr int CTAS = L == 32 ? 1 : (L == 16 ? 2 : 4);
   // shared memory carve-up, in floats (the filterbank program follows at OFF_PROG)
   static constexpr int OFF_P = 0;
   static constexpr int OFF_WIN = TILE * SP;
@@ -161,7 +187,7 @@ struct StftCfg {
   static constexpr int OFF_META = OFF_TWP + 2 * (M / 2);      // 2 x {b[TILE], t[TILE]} (double buffered)
   static constexpr int OFF_PROG = OFF_META + 4 * TILE;        // segment headers + tap weights follow
   static constexpr size_t FIXED_BYTES = size_t(OFF_PROG) * 4;
-  static_assert(NPAR == 1 || NPAR == 2, "tile must be 16 or 32 frames");
+  static_assert(TILE == 32, "filterbank phase runs with lane = frame");
   static_assert(SP % 8 == 4, "LDS.128 over lane = frame needs an odd number of 16-byte units per row");
   static_assert(Q * SP >= 32 * 33, "power rows must hold the transpose scratch");
   static_assert(SP >= K + PAD, "row must hold the bins and the zero padding");
@@ -178,7 +204,7 @@ struct StftArgs {
   int win_off, win_len;     // window support inside the n_fft buffer
   float pre_emph;
   const float* window;      // [N]   0.5 * window (zero outside support)
-  const float2* tw1;        // [32*L] exp(-2 pi i b kA / M) at [kA*L + b]
+  const float2* tw1;        // [33*L] exp(-2 pi i b kA / M) at [kA*L + b]; row 32: exp(-2 pi i b / L)
   const float2* twp;        // [M/2]  exp(-2 pi i k / N)
   // filterbank program (copied to smem), two-tap banded form: the bins split into n_filt + 1
   // segments; inside segment s bin k feeds filter s with its rising weight wr[k] and filter s - 1
@@ -186,8 +212,9 @@ struct StftArgs {
   // weighted sums over segment s and every power value is read once.  Each warp owns a list of
   // entries = the segments of its filter range; per entry a header {first bin (multiple of 4) |
   // n_rounds << 16, weight offset in float4 units}; per round 4 bins as two float4
-  // {wr0, wf0, wr1, wf1}, {wr2, wf2, wr3, wf3} (zero padded).  With NPAR = 2 the two half-warps
-  // walk alternate entries of the list (rounds equalised per pair, list padded to an even length).
+  // {wr0, wf0, wr1, wf1}, {wr2, wf2, wr3, wf3} (zero padded).  Entries are processed FBU at a time
+  // (independent accumulators and log chains): the list is padded to a multiple of FBU with empty
+  // entries and the rounds are equalised inside each bundle.
   const int2* filt_hdr;     // [n_hdr]
   const float4* filt_w;     // [n_w4]
   int n_hdr, n_w4;
@@ -244,7 +271,7 @@ template <int L, int MODE, bool PRE, int TILE>
 __global__ void __launch_bounds__(StftCfg<L, TILE>::WARPS * 32, StftCfg<L, TILE>::CTAS)
 k_stft_fb(const StftArgs a) {
   using C = StftCfg<L, TILE>;
-  constexpr int Q = C::Q, M = C::M, N = C::N, SP = C::SP, NPAR = C::NPAR;
+  constexpr int Q = C::Q, M = C::M, N = C::N, SP = C::SP, FBU = C::FBU;
   constexpr int LOG2L = ilog2(L);
   extern __shared__ __align__(16) float smem[];
   float* sP = smem + C::OFF_P;
@@ -269,12 +296,16 @@ k_stft_fb(const StftArgs a) {
   const int total = a.frame_off[a.B];
   const int n_tiles = (total + C::TILE - 1) / C::TILE;
   const float2* sWin2 = reinterpret_cast<const float2*>(sWin);
+  constexpr bool TWPGEN = AAD_TWPGEN && Q <= 4;
+  float2 twp_base[Q];   // W_N^(j + L q)
+#pragma unroll
+  for (int q = 0; q < Q; ++q) twp_base[q] = TWPGEN ? __ldg(a.twp + j + L * q) : make_float2(0.f, 0.f);
+  const float2 tw1_rot = __ldg(a.tw1 + 32 * L + j);  // W_L^j = W_M^(32 j)
 
   // tile meta: global frame index -> (utterance, frame); computed one tile ahead by warp 0 so the
   // dependent index loads never sit on the critical path, and used to prefetch the next tile's
   // new samples into L2 (bulk prefetch: one instruction per frame)
   auto tile_meta = [&](int tile, int buf) {
-    if (lane >= C::TILE) return;
     const int gf = tile * C::TILE + lane;
     int b = -1, t = 0;
     if (tile < n_tiles && gf < total) {
@@ -350,7 +381,8 @@ k_stft_fb(const StftArgs a) {
           const float2* p = reinterpret_cast<const float2*>(row + 4ll * s0) + j;
           static_for<0, 32>([&](auto a_) {
             constexpr int A = decltype(a_)::value;
-            v[bitrev(A, 5)] = __ldg(p + L * A);
+            if constexpr (ABL & 128) v[bitrev(A, 5)] = make_float2(a.amin * (lane + A), a.eps * (s0 + A));
+            else v[bitrev(A, 5)] = __ldg(p + L * A);
           });
           if constexpr (PRE) {
             const float* ps = reinterpret_cast<const float*>(row + 4ll * s0) + 2 * j - 1;
@@ -368,7 +400,8 @@ k_stft_fb(const StftArgs a) {
               constexpr int A = decltype(a_)::value;
               float2 x = v[bitrev(A, 5)];
               if constexpr (MODE == IN_F32_Q16) x = make_float2(cvt_sample<MODE>(x.x), cvt_sample<MODE>(x.y));
-              v[bitrev(A, 5)] = pk_mul(x, sWin2[L * A + j]);
+              if constexpr (ABL & 1) v[bitrev(A, 5)] = pk_mul(x, make_float2(a.amin, a.eps));
+              else v[bitrev(A, 5)] = pk_mul(x, sWin2[L * A + j]);
             });
           }
         }
@@ -384,16 +417,27 @@ k_stft_fb(const StftArgs a) {
       }
 
       // pass 1: 32-point DFT over a (stride L), then twiddle W_M^(b*kA)
-      fft_dit<32, 0>(v);
-      static_for<1, 32>([&](auto k_) {
-        constexpr int KA = decltype(k_)::value;
-        v[KA] = cmul(v[KA], sTw1[KA * L + j]);
-      });
+      if constexpr (!(ABL & 64)) fft_dit<32, 0>(v);
+      if constexpr (AAD_TW1SYM) {
+        static_for<1, 17>([&](auto k_) {
+          constexpr int KA = decltype(k_)::value;
+          const float2 tw = sTw1[KA * L + j];
+          v[KA] = cmul(v[KA], tw);
+          if constexpr (KA < 16) v[32 - KA] = cmul(cmul_conj(v[32 - KA], tw), tw1_rot);
+        });
+      } else {
+        static_for<1, 32>([&](auto k_) {
+          constexpr int KA = decltype(k_)::value;
+          if constexpr (ABL & 2) v[KA] = cmul(v[KA], make_float2(a.amin, a.eps));
+          else v[KA] = cmul(v[KA], sTw1[KA * L + j]);
+        });
+      }
 
       // transpose through the warp's scratch (= its own power rows), re then im
       float* scr = sP + (it * Q) * SP;
       float* scr_w = scr + lane;
       const float* scr_r = scr + j * 33 + g * L;
+      if constexpr (!(ABL & 4)) {
       static_for<0, 32>([&](auto k_) {
         constexpr int KA = decltype(k_)::value;
         scr_w[KA * 33] = v[KA].x;
@@ -420,11 +464,12 @@ k_stft_fb(const StftArgs a) {
         });
       });
       __syncwarp();
+      }
 
       // pass 2: Q DFTs of length L over b  ->  v[q*L + kB] = Z[(j + L q) + 32 kB]
       static_for<0, Q>([&](auto q_) {
         constexpr int QQ = decltype(q_)::value;
-        fft_dit<L, QQ * L>(v);
+        if constexpr (!(ABL & 64)) fft_dit<L, QQ * L>(v);
       });
 
       // real-input split + power:  X[k] = E - T,  X[M-k] = conj(E + T),  T = i*w*O
@@ -437,17 +482,26 @@ k_stft_fb(const StftArgs a) {
           constexpr int ALT = QQ == 0 ? ((L - S) % L) : (Q - QQ) * L + (L - 1 - S);
           const float2 snd = (j == 0) ? v[ALT] : v[GEN];
           float2 r;  // Z[M - k]
+          if constexpr (ABL & 16) r = snd;
+          else {
           r.x = __shfl_sync(0xffffffffu, snd.x, partner);
           r.y = __shfl_sync(0xffffffffu, snd.y, partner);
+          }
           const float2 A = v[QQ * L + S];
           const float2 E = __fadd2_rn(A, make_float2(r.x, -r.y));   // A + conj(r)
           const float2 O = __fadd2_rn(A, make_float2(-r.x, r.y));   // A - conj(r)
           const int k = j + L * QQ + 32 * S;
-          const float2 wO = cmul(O, sTwp[k]);
+          float2 wO;
+          if constexpr (TWPGEN) wO = cmul(cmul_const<32 * S, N>(O), twp_base[QQ]);
+          else wO = (ABL & 16) ? cmul(O, make_float2(a.amin, a.eps)) : cmul(O, sTwp[k]);
           const float2 x1 = __fadd2_rn(E, make_float2(wO.y, -wO.x));  // E - i*wO
           const float2 x2 = __fadd2_rn(E, make_float2(-wO.y, wO.x));  // E + i*wO
+          if constexpr (ABL & 32) {
+            if (x1.x * x2.y == 123.456f) prow[k] = x1.y;
+          } else {
           prow[k] = __fmaf_rn(x1.x, x1.x, x1.y * x1.y);
           prow[M - k] = __fmaf_rn(x2.x, x2.x, x2.y * x2.y);
+          }
         });
       });
       if (j == 0) {
@@ -460,58 +514,65 @@ k_stft_fb(const StftArgs a) {
     }
     __syncthreads();
 
-    // ---- filterbank + log phase: lane = frame (+ segment parity), warps split the filters ----
-    // Per entry: 4 bins per round (powers: one conflict-free LDS.128 per lane; weights: two
-    // LDS.128 broadcasts; four FFMA2 accumulate (rising, falling) sums with the power broadcast to
-    // both halves), then filter s-1 = R[s-1] + F[s]: log, store, running max.
-    if (wprog.w > 0) {
-      const int fr = lane % C::TILE, par = lane / C::TILE;
-      const int b = sMetaB[fr], t = sMetaT[fr];
+    // ---- filterbank + log phase: lane = frame, warps split the filters ----
+    // FBU entries at a time.  Per entry and round: 4 bins (powers: one conflict-free LDS.128 per
+    // lane; weights: two LDS.128 broadcasts; four FFMA2 accumulate (rising, falling) sums with the
+    // power broadcast to both halves), then filter s-1 = R[s-1] + F[s]: log, store, running max.
+    if (wprog.w > 0 && !(ABL & 8)) {
+      const int b = sMetaB[lane], t = sMetaT[lane];
       const bool valid = b >= 0;
-      const float* pbase = sP + fr * SP;
-      // half-warp `par` emits filters wf0 - par, wf0 - par + NPAR, ...
-      float* eptr = a.E + (valid ? (long long)b * a.e_stride_b + (long long)(wprog.x - par) * a.e_stride_f + t : 0);
-      const long long estep = (long long)NPAR * a.e_stride_f;
+      const float* pbase = sP + lane * SP;
+      // entry i of the list emits filter wf0 + i - 1
+      float* eptr = a.E + (valid ? (long long)b * a.e_stride_b + (long long)(wprog.x - 1) * a.e_stride_f + t : 0);
       const float lscale = a.log_type == 0 ? 3.01029995663981195f : 0.69314718055994531f;
       float vmax = -INFINITY, chk = 0.f, rprev = 0.f;
-      for (int i = 0; i < wprog.z; i += NPAR) {
-        const int2 hd = sHdr[wprog.y + i + par];
-        const float4* pp = reinterpret_cast<const float4*>(pbase + (hd.x & 0xffff));
-        const float4* wp = sW4 + hd.y;
-        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-#pragma unroll 2
-        for (int gq = hd.x >> 16; gq > 0; --gq) {
-          const float4 p = *pp++;
-          const float4 wa = wp[0], wb = wp[1];
-          wp += 2;
-          acc0 = __ffma2_rn(make_float2(p.x, p.x), make_float2(wa.x, wa.y), acc0);
-          acc1 = __ffma2_rn(make_float2(p.y, p.y), make_float2(wa.z, wa.w), acc1);
-          acc0 = __ffma2_rn(make_float2(p.z, p.z), make_float2(wb.x, wb.y), acc0);
-          acc1 = __ffma2_rn(make_float2(p.w, p.w), make_float2(wb.z, wb.w), acc1);
+      for (int i0 = 0; i0 < wprog.z; i0 += FBU) {
+        int2 hd[FBU];
+#pragma unroll
+        for (int u = 0; u < FBU; ++u) hd[u] = sHdr[wprog.y + i0 + u];
+        const float4* pp[FBU];
+        const float4* wp[FBU];
+        float2 acc0[FBU], acc1[FBU];
+#pragma unroll
+        for (int u = 0; u < FBU; ++u) {
+          pp[u] = reinterpret_cast<const float4*>(pbase + (hd[u].x & 0xffff));
+          wp[u] = sW4 + hd[u].y;
+          acc0[u] = make_float2(0.f, 0.f);
+          acc1[u] = make_float2(0.f, 0.f);
         }
-        const float2 rf = __fadd2_rn(acc0, acc1);  // (R, F) of this half-warp's segment
-        float en;
-        bool emit;
-        if constexpr (NPAR == 2) {
-          // half 0 holds segment s = wf0 + i, half 1 segment s + 1: swap the falling sums
-          const float f_other = __shfl_xor_sync(0xffffffffu, rf.y, 16);
-          en = (par ? rprev : rf.x) + f_other;     // half 1: filter s - 1 = R[s-1] + F[s]; half 0: filter s = R[s] + F[s+1]
-          emit = par ? i > 0 : i < wprog.w;
-        } else {
-          en = rprev + rf.y;                       // filter s - 1
-          emit = i > 0;
+        for (int gq = hd[0].x >> 16; gq > 0; --gq) {  // same round count for the whole bundle
+#pragma unroll
+          for (int u = 0; u < FBU; ++u) {
+            const float4 p = *pp[u]++;
+            const float4 wa = wp[u][0], wb = wp[u][1];
+            wp[u] += 2;
+            acc0[u] = __ffma2_rn(make_float2(p.x, p.x), make_float2(wa.x, wa.y), acc0[u]);
+            acc1[u] = __ffma2_rn(make_float2(p.y, p.y), make_float2(wa.z, wa.w), acc1[u]);
+            acc0[u] = __ffma2_rn(make_float2(p.z, p.z), make_float2(wb.x, wb.y), acc0[u]);
+            acc1[u] = __ffma2_rn(make_float2(p.w, p.w), make_float2(wb.z, wb.w), acc1[u]);
+          }
         }
-        if (emit) {
+        float val[FBU];
+#pragma unroll
+        for (int u = 0; u < FBU; ++u) {
+          const float2 rf = __fadd2_rn(acc0[u], acc1[u]);  // (R, F) of entry i0 + u
+          const float en = rprev + rf.y;                   // filter wf0 + i0 + u - 1
+          rprev = rf.x;
           // 10*log10(x) = 3.0103*log2(x), ln(x) = 0.6931*log2(x); MUFU.LG2 is accurate to 2 ulp,
           // i.e. <= 3e-5 dB / 4e-6 nepers here, far inside the 1e-3 parity tolerance
           const float arg = a.log_type == 0 ? fmaxf(a.amin, en) : (en == 0.f ? a.eps : en);
-          const float val = lscale * __log2f(arg);
-          if (valid) *eptr = val;
-          vmax = fmaxf(vmax, val);
-          chk = __fmaf_rn(val, 0.f, chk);  // NaN/Inf poison
+          if constexpr (ABL & 256) val[u] = arg;
+          else val[u] = lscale * __log2f(arg);
         }
-        if (NPAR == 1 ? i > 0 : true) eptr += estep;
-        rprev = rf.x;
+#pragma unroll
+        for (int u = 0; u < FBU; ++u) {
+          const int fi_ = i0 + u;  // emits filter wf0 + fi_ - 1 when 1 <= fi_ <= n_filters
+          if (fi_ >= 1 && fi_ <= wprog.w) {
+            if (valid) eptr[(long long)fi_ * a.e_stride_f] = val[u];
+            vmax = fmaxf(vmax, val[u]);
+            chk = __fmaf_rn(val[u], 0.f, chk);  // NaN/Inf poison
+          }
+        }
       }
       if (valid) {
         if (a.utt_max) {
