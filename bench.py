@@ -332,7 +332,10 @@ def run_b200(args):
                    "parallelism": f"utterance-sharded x{world}, no collective in the hot path"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * Ls * 4 + B * 4,
                 "d2h_bytes_per_step": B * c_out * t_max * 4 + 2 * B * 4, "steps": e2e_steps,
-                "api": "Frontend.extract_host -> aad_extract_host (pinned host in/out, chunked H2D/compute/D2H)",
+                "ms_per_step": e2e_s / e2e_steps * 1e3,
+                "h2d_gbs": (B * Ls * 4) / (e2e_s / e2e_steps) / 1e9,
+                "api": "Frontend.extract_host -> aad_extract_host (pinned host in/out, chunked H2D/compute/D2H on 3 streams)",
+                "note": "PCIe-bound: the box measures 55.6 GB/s H2D (profiles/r1_pcie_probe.log)",
                 "max_abs_diff_vs_device_path": e2e_err},
         "gpu_launches": fe.launches_per_call * args.steps,
         "clocks": clocks,
