@@ -39,6 +39,7 @@ struct aad_plan {
   float taps[2][CEP_MAXW];
   // device tables
   float* d_window = nullptr;
+  float* d_window_i16 = nullptr;  // window * i16_scale (int16 input)
   float2* d_tw1 = nullptr;
   float2* d_twp = nullptr;
   int2* d_filt_hdr = nullptr;
@@ -371,6 +372,7 @@ int aad_plan_destroy(aad_plan* pl) {
   if (!pl) return AAD_OK;
   cudaSetDevice(pl->device);
   cudaFree(pl->d_window);
+  cudaFree(pl->d_window_i16);
   cudaFree(pl->d_tw1);
   cudaFree(pl->d_twp);
   cudaFree(pl->d_filt_hdr);
@@ -556,6 +558,14 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
 
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = upload(&pl->d_window, win_half);
+  {
+    // int16 input: the sample scale is folded into the window (exact for the power-of-two default)
+    float sc = p.i16_scale != 0.f ? p.i16_scale : (p.kind == AAD_KIND_LFCC ? 1.0f : 1.0f / 32768.0f);
+    pl->p.i16_scale = sc;
+    std::vector<float> win_i16(win_half);
+    for (auto& x : win_i16) x *= sc;
+    if (e == cudaSuccess) e = upload(&pl->d_window_i16, win_i16);
+  }
   if (e == cudaSuccess) e = upload(&pl->d_tw1, tw1);
   if (e == cudaSuccess) e = upload(&pl->d_twp, twp);
   if (e == cudaSuccess) e = upload(&pl->d_filt_hdr, fhdr);
@@ -688,7 +698,7 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
   sa.hop = p.hop_length; sa.s_off = p.center ? p.n_fft / 2 : 0;
   sa.win_off = p.center ? (p.n_fft - p.win_length) / 2 : 0; sa.win_len = p.win_length;
   sa.pre_emph = p.pre_emph;
-  sa.window = pl->d_window; sa.tw1 = pl->d_tw1; sa.twp = pl->d_twp;
+  sa.window = wav_dtype == AAD_I16 ? pl->d_window_i16 : pl->d_window; sa.tw1 = pl->d_tw1; sa.twp = pl->d_twp;
   sa.filt_hdr = pl->d_filt_hdr; sa.filt_w = pl->d_filt_w; sa.n_hdr = pl->n_hdr; sa.n_w4 = pl->n_w4;
   sa.warp_prog = pl->d_warp_prog; sa.tile_b0 = pa.tile_b0; sa.n_filt = p.n_filt;
   sa.log_type = p.log_type; sa.amin = p.amin; sa.eps = 2.220446049250313e-16f;

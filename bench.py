@@ -276,6 +276,23 @@ def run_b200(args):
     e2e_value = world * hours_per_step * e2e_steps / e2e_s
     e2e_err = float(np.abs(ho[:8] - out[:8].cpu().numpy()).max())
 
+    # ---- same, 16-bit PCM over the bus (the native format of the corpus; pcm/32768 is what
+    #      librosa.load decodes): half the H2D bytes, features bit-identical to the float path
+    host_pcm = torch.empty((B, Ls), dtype=torch.int16, pin_memory=True)
+    host_pcm.copy_((wav * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
+    hp = host_pcm.numpy()
+    fe.extract_host(hp, hlen, out=ho)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        fe.extract_host(hp, hlen, out=ho)
+    torch.cuda.synchronize(dev)
+    pcm_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    ref8, _, _ = fe(host_pcm[:8].to(dev).to(torch.float32).div_(32768.0))
+    pcm_err = float(np.abs(ho[:8] - ref8.cpu().numpy()).max())
+    pcm_value = world * hours_per_step * e2e_steps / pcm_s
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -337,6 +354,12 @@ def run_b200(args):
                 "api": "Frontend.extract_host -> aad_extract_host (pinned host in/out, chunked H2D/compute/D2H on 3 streams)",
                 "note": "PCIe-bound: the box measures 55.6 GB/s H2D (profiles/r1_pcie_probe.log)",
                 "max_abs_diff_vs_device_path": e2e_err},
+        "e2e_pcm16": {"value": pcm_value, "unit": UNIT, "h2d_bytes_per_step": B * Ls * 2 + B * 4,
+                      "d2h_bytes_per_step": B * c_out * t_max * 4 + 2 * B * 4, "steps": e2e_steps,
+                      "ms_per_step": pcm_s / e2e_steps * 1e3,
+                      "note": "same call with int16 PCM host buffers (pcm * 2^-15 folded into the window); "
+                              "informational, the headline e2e above moves float32",
+                      "max_abs_diff_vs_float_path_on_pcm_over_32768": pcm_err},
         "gpu_launches": fe.launches_per_call * args.steps,
         "clocks": clocks,
         "roofline": roofline,

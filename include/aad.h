@@ -32,7 +32,7 @@ enum aad_kind {        /* which reference extractor the plan mirrors */
   AAD_KIND_MFCC = 1,   /* extract_mfcc             ASV_dl_func.py:404-420 */
   AAD_KIND_LFCC = 2    /* extract_lfcc             ASV_dl_func.py:423-439 */
 };
-enum aad_dtype { AAD_F32 = 0, AAD_I16 = 1 };
+enum aad_dtype { AAD_F32 = 0, AAD_I16 = 1 }; /* AAD_I16: see aad_params.i16_scale */
 enum aad_window {
   AAD_WIN_HANN_PERIODIC = 0,    /* scipy get_window('hann', fftbins=True): librosa.stft */
   AAD_WIN_HAMMING_SYMMETRIC = 1 /* np.hamming(win_length): spafe windowing */
@@ -104,7 +104,9 @@ typedef struct aad_params {
   int32_t delta_width; /* odd, 3..9 (9 = librosa default) */
   int32_t layout;      /* aad_layout */
   int32_t time_mean;   /* 1: out[b][c] = mean over frames (the reference's mean=True, axis=1 of (C,T)) */
-  int32_t reserved0;
+  float i16_scale;     /* int16 input only: sample value = int16 * i16_scale.  0 -> default: 1/32768 for
+                          LOGMEL / MFCC (16-bit PCM as librosa.load / soundfile decode it to float32),
+                          1 for LFCC (spafe receives the raw int16 array, ASV_dl_func.py:434-435) */
   const float* custom_fb; /* HOST pointer, row-major n_filt x (n_fft/2+1); AAD_FB_CUSTOM only */
 } aad_params;
 

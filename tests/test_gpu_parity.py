@@ -140,6 +140,26 @@ def test_int16_input_equals_float_quantised_input(dev):
     assert np.array_equal(nfa, nfb) and np.array_equal(a, b)      # bit-exact: same arithmetic after the cast
 
 
+def test_pcm16_input_is_bit_identical_to_decoded_float(dev):
+    """16-bit PCM over the bus (half the H2D bytes): int16 * 2^-15 is folded into the window, so the
+    features equal those of the float32 waveform librosa.load / soundfile would decode (pcm / 32768)."""
+    from audioanalysisdetector_b200.frontend import Frontend
+    rng = np.random.default_rng(77)
+    pcm = np.clip(np.round(3000 * rng.standard_normal((3, 40000))), -32768, 32767).astype(np.int16)
+    pcm[1, 30000:] = 0
+    lens = torch.tensor([40000, 30000, 40000], dtype=torch.int32, device=dev)
+    for params in (FP().mfcc(16000, n_mfcc=20, n_delta=2), FP().logmel(16000, n_mels=80, n_fft=512, hop_length=160)):
+        fe = Frontend(params, dev)
+        a, nfa, sta = fe(torch.from_numpy(pcm).to(dev), lens)
+        b, nfb, stb = fe(torch.from_numpy(pcm.astype(np.float32) / 32768.0).to(dev), lens)
+        torch.cuda.synchronize()
+        assert torch.equal(nfa, nfb) and int(sta.sum()) == 0 and int(stb.sum()) == 0
+        assert torch.equal(a, b)
+        want = (oracle.mfcc_with_deltas_ref(pcm[0].astype(np.float32) / 32768.0, 16000, n_mfcc=20, n_delta=2)
+                if params.n_ceps else LR.logmel_db(pcm[0].astype(np.float32) / 32768.0, 16000, n_mels=80, n_fft=512, hop_length=160))
+        assert np.abs(a[0, :, :int(nfa[0])].cpu().numpy() - want).max() <= TOL_LOG
+
+
 def test_non_banded_custom_filterbank_is_rejected(dev):
     from audioanalysisdetector_b200 import AadError, Frontend
     L = LIB()
