@@ -178,7 +178,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _OUT.emit(json.dumps(line))
     return 0
 
 
@@ -365,13 +365,40 @@ def run_b200(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    _OUT.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+class _StdoutToStderr:
+    """Everything written to fd 1 while the bench runs (NCCL prints its version banner there) goes to
+    stderr, so that stdout carries exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+_OUT = None
+
+
 def main():
+    global _OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -384,9 +411,10 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_b200(args)
+    with _StdoutToStderr() as _OUT:
+        if args.impl == "reference":
+            return run_reference(args)
+        return run_b200(args)
 
 
 if __name__ == "__main__":
