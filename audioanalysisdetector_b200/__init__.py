@@ -9,10 +9,10 @@ from ._lib import AadError
 from .frontend import Frontend, FrontendParams, delta, fp32_peak_tflops
 from .extractors import (extract_features, extract_lfcc, extract_mel_spectrogram, extract_mfcc,
                          get_frontend)
-from .sharding import contiguous_shard, gather_features, partition_by_frames
+from .sharding import bind_to_gpu_numa, contiguous_shard, gather_features, partition_by_frames
 
 __all__ = [
     "AadError", "Frontend", "FrontendParams", "delta", "fp32_peak_tflops",
     "extract_features", "extract_lfcc", "extract_mel_spectrogram", "extract_mfcc", "get_frontend",
-    "contiguous_shard", "gather_features", "partition_by_frames",
+    "bind_to_gpu_numa", "contiguous_shard", "gather_features", "partition_by_frames",
 ]

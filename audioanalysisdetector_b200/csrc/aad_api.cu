@@ -868,6 +868,17 @@ int aad_fp32_peak(int device, int iters, double* tflops_out) {
   return cudaGetLastError() == cudaSuccess ? AAD_OK : AAD_ERR_CUDA;
 }
 
+#ifdef AAD_PHASE_TIMING
+// dev only: read and reset the phase counters of k_stft_fb
+int aad_dev_phase_cycles(unsigned long long* out4) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyFromSymbol(out4, g_phase_cycles, 4 * sizeof(unsigned long long)));
+  unsigned long long z[4] = {0, 0, 0, 0};
+  CUDA_TRY(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)));
+  return AAD_OK;
+}
+#endif
+
 // ---- host-buffer path: chunked H2D -> kernels -> D2H on three internal streams ----
 static int ensure(void** p, size_t* cap, size_t need) {
   if (*cap >= need) return AAD_OK;

@@ -267,6 +267,19 @@ __device__ __forceinline__ float2 i16pair_to_float2(unsigned p) {
   return __fadd2_rn(m, make_float2(-8421376.0f, -8421376.0f));
 }
 
+#ifdef AAD_PHASE_TIMING
+// dev only: warp-cycles spent in {FFT phase, barrier after it, filterbank phase, barrier after it}
+__device__ unsigned long long g_phase_cycles[4];
+#define AAD_PHASE_MARK(i)                                                         \
+  do {                                                                            \
+    long long now__ = clock64();                                                  \
+    if (lane == 0) atomicAdd(&g_phase_cycles[i], (unsigned long long)(now__ - tmark)); \
+    tmark = now__;                                                                \
+  } while (0)
+#else
+#define AAD_PHASE_MARK(i)
+#endif
+
 template <int L, int MODE, bool PRE, int TILE>
 __global__ void __launch_bounds__(StftCfg<L, TILE>::WARPS * 32, StftCfg<L, TILE>::CTAS)
 k_stft_fb(const StftArgs a) {
@@ -333,6 +346,9 @@ k_stft_fb(const StftArgs a) {
   if (warp == 0) tile_meta(blockIdx.x, 0);
   __syncthreads();
 
+#ifdef AAD_PHASE_TIMING
+  long long tmark = clock64();
+#endif
   int buf = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
     const int* sMetaB = sMeta + buf * 2 * C::TILE;
@@ -512,6 +528,7 @@ k_stft_fb(const StftArgs a) {
         for (int i = 1; i <= C::PAD; ++i) prow[M + i] = 0.f;
       }
     }
+    AAD_PHASE_MARK(0);
     __syncthreads();
 
     // ---- filterbank + log phase: lane = frame, warps split the filters ----
@@ -520,6 +537,10 @@ k_stft_fb(const StftArgs a) {
     // power broadcast to both halves), then filter s-1 = R[s-1] + F[s]: log, store, running max.
     if (wprog.w > 0 && !(ABL & 8)) {
       const int b = sMetaB[lane], t = sMetaT[lane];
+#ifdef AAD_PHASE_TIMING
+      if (b == 0x7fffffff) return;  // forces the first post-barrier load to complete: the barrier wait ends here
+      AAD_PHASE_MARK(1);
+#endif
       const bool valid = b >= 0;
       const float* pbase = sP + lane * SP;
       // entry i of the list emits filter wf0 + i - 1
@@ -583,7 +604,12 @@ k_stft_fb(const StftArgs a) {
         if (chk != chk) a.status[b] = 5;
       }
     }
+    AAD_PHASE_MARK(2);
     __syncthreads();  // sP free for the next tile's FFTs; next tile's meta (written above) visible
+#ifdef AAD_PHASE_TIMING
+    if (sMeta[(buf ^ 1) * 2 * C::TILE] == 0x7fffffff) return;
+    AAD_PHASE_MARK(3);
+#endif
   }
 }
 

@@ -66,3 +66,25 @@ def gather_features(local: torch.Tensor, local_index: torch.Tensor, n_total: int
         m = i >= 0
         out[i[m]] = f[m]
     return out
+
+
+def bind_to_gpu_numa(physical_gpu_index: int) -> Optional[List[int]]:
+    """Pin the calling process to the CPUs NVML reports as local to the GPU (same NUMA node / PCIe
+    root), so that pinned host buffers allocated afterwards are first-touched next to it.  With one
+    process per GPU this keeps every rank's H2D/D2H traffic off the inter-socket link.  Returns the
+    CPU list, or None when NVML / sched_setaffinity are unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(physical_gpu_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None

@@ -197,6 +197,8 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one process per GPU: run (and first-touch the pinned host buffers) on the GPU's own NUMA node
+    numa_cpus = aad.bind_to_gpu_numa(physical_gpu_index(local_rank)) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -346,7 +348,8 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "clips_per_gpu": B, "frames_per_gpu": frames,
                    "l2": "inputs larger than L2 (%.2f GB waveforms per GPU per step, no flush needed)" % (B * Ls * 4 / 1e9),
-                   "parallelism": f"utterance-sharded x{world}, no collective in the hot path"},
+                   "parallelism": f"utterance-sharded x{world}, no collective in the hot path",
+                   "host_affinity": (f"rank bound to {len(numa_cpus)} GPU-local CPUs (NVML)" if numa_cpus else "unbound")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * Ls * 4 + B * 4,
                 "d2h_bytes_per_step": B * c_out * t_max * 4 + 2 * B * 4, "steps": e2e_steps,
                 "ms_per_step": e2e_s / e2e_steps * 1e3,
