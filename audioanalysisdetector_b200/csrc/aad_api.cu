@@ -504,28 +504,32 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
       for (int sgi = f0; sgi <= f1; ++sgi) ents.push_back(sgi);
       while (ents.size() % fbu) ents.push_back(-1);  // empty entries
       wprog[wi] = make_int4(f0, (int)fhdr.size(), (int)ents.size(), f1 - f0);
-      for (size_t e = 0; e < ents.size(); ++e) {
-        const int sgi = ents[e];
-        int k0 = sgi >= 0 ? sk0[sgi] : 0, k1 = sgi >= 0 ? sk1[sgi] : 0;
-        int rounds = sgi >= 0 ? srounds[sgi] : 0;
-        for (size_t m = e / fbu * fbu; m < e / fbu * fbu + fbu; ++m)  // one round count per bundle
-          rounds = std::max(rounds, ents[m] >= 0 ? srounds[ents[m]] : 0);
-        int k0a = std::min(k0 & ~3, row_limit - 4 * rounds);
-        if (k0a < 0 || k0a > 0xffff || rounds > 0x7fff) {
-          delete pl;
-          return AAD_ERR_UNSUPPORTED;
-        }
-        fhdr.push_back(make_int2(k0a | (rounds << 16), (int)fw4.size()));
-        for (int g = 0; g < rounds; ++g) {
-          float w[8];
-          for (int i = 0; i < 4; ++i) {
-            const int k = k0a + g * 4 + i;
-            const bool in = k >= k0 && k < k1;
-            w[2 * i] = in ? fbw[k].x : 0.f;
-            w[2 * i + 1] = in ? fbw[k].y : 0.f;
+      for (size_t e0 = 0; e0 < ents.size(); e0 += fbu) {  // one bundle
+        int rounds = 0;
+        for (int u = 0; u < fbu; ++u)
+          rounds = std::max(rounds, ents[e0 + u] >= 0 ? srounds[ents[e0 + u]] : 0);
+        const size_t w_off = fw4.size();
+        fw4.resize(w_off + (size_t)rounds * fbu * 2, make_float4(0.f, 0.f, 0.f, 0.f));
+        for (int u = 0; u < fbu; ++u) {
+          const int sgi = ents[e0 + u];
+          const int k0 = sgi >= 0 ? sk0[sgi] : 0, k1 = sgi >= 0 ? sk1[sgi] : 0;
+          const int k0a = std::min(k0 & ~3, row_limit - 4 * rounds);
+          if (k0a < 0 || 4 * k0a > 0xffff || rounds > 0x7fff) {
+            delete pl;
+            return AAD_ERR_UNSUPPORTED;
           }
-          fw4.push_back(make_float4(w[0], w[1], w[2], w[3]));
-          fw4.push_back(make_float4(w[4], w[5], w[6], w[7]));
+          fhdr.push_back(make_int2((4 * k0a) | (rounds << 16), (int)(w_off * sizeof(float4))));
+          for (int g = 0; g < rounds; ++g) {
+            float w[8];
+            for (int i = 0; i < 4; ++i) {
+              const int k = k0a + g * 4 + i;
+              const bool in = k >= k0 && k < k1;
+              w[2 * i] = in ? fbw[k].x : 0.f;
+              w[2 * i + 1] = in ? fbw[k].y : 0.f;
+            }
+            fw4[w_off + ((size_t)g * fbu + u) * 2] = make_float4(w[0], w[1], w[2], w[3]);
+            fw4[w_off + ((size_t)g * fbu + u) * 2 + 1] = make_float4(w[4], w[5], w[6], w[7]);
+          }
         }
       }
     }

@@ -211,10 +211,11 @@ struct StftArgs {
   // with its falling weight wf[k], so  energy[j] = R[j] + F[j + 1]  with (R, F)[s] the two
   // weighted sums over segment s and every power value is read once.  Each warp owns a list of
   // entries = the segments of its filter range; per entry a header {first bin (multiple of 4) |
-  // n_rounds << 16, weight offset in float4 units}; per round 4 bins as two float4
-  // {wr0, wf0, wr1, wf1}, {wr2, wf2, wr3, wf3} (zero padded).  Entries are processed FBU at a time
-  // (independent accumulators and log chains): the list is padded to a multiple of FBU with empty
-  // entries and the rounds are equalised inside each bundle.
+  // n_rounds << 16 with the bin as a BYTE offset into the power row, weight BYTE offset}; per round 4
+  // bins as two float4 {wr0, wf0, wr1, wf1}, {wr2, wf2, wr3, wf3} (zero padded).  Entries are processed
+  // FBU at a time (a bundle: independent accumulators and log chains): the list is padded to a multiple
+  // of FBU with empty entries, the rounds are equalised inside each bundle and the bundle's weights are
+  // interleaved [round][entry][2 x float4] at the offset of its first entry.
   const int2* filt_hdr;     // [n_hdr]
   const float4* filt_w;     // [n_w4]
   int n_hdr, n_w4;
@@ -532,9 +533,10 @@ k_stft_fb(const StftArgs a) {
     __syncthreads();
 
     // ---- filterbank + log phase: lane = frame, warps split the filters ----
-    // FBU entries at a time.  Per entry and round: 4 bins (powers: one conflict-free LDS.128 per
-    // lane; weights: two LDS.128 broadcasts; four FFMA2 accumulate (rising, falling) sums with the
-    // power broadcast to both halves), then filter s-1 = R[s-1] + F[s]: log, store, running max.
+    // Entries are walked FBU at a time (one bundle).  Per round and entry: 4 bins (powers: one
+    // conflict-free LDS.128 per lane; weights: two LDS.128 broadcasts; four FFMA2 accumulate the
+    // (rising, falling) sums with the power broadcast to both halves), then filter s-1 = R[s-1] + F[s]:
+    // log, store, running max.  Headers carry byte offsets so that a bundle starts with two adds.
     if (wprog.w > 0 && !(ABL & 8)) {
       const int b = sMetaB[lane], t = sMetaT[lane];
 #ifdef AAD_PHASE_TIMING
@@ -542,57 +544,72 @@ k_stft_fb(const StftArgs a) {
       AAD_PHASE_MARK(1);
 #endif
       const bool valid = b >= 0;
-      const float* pbase = sP + lane * SP;
+      const char* pbase = reinterpret_cast<const char*>(sP + lane * SP);
+      const char* wbase = reinterpret_cast<const char*>(sW4);
       // entry i of the list emits filter wf0 + i - 1
       float* eptr = a.E + (valid ? (long long)b * a.e_stride_b + (long long)(wprog.x - 1) * a.e_stride_f + t : 0);
-      const float lscale = a.log_type == 0 ? 3.01029995663981195f : 0.69314718055994531f;
+      const long long estep = a.e_stride_f;
+      const bool is_db = a.log_type == 0;
+      const float lscale = is_db ? 3.01029995663981195f : 0.69314718055994531f;
+      const float amin_n = fmaxf(a.amin, 1.17549435e-38f);  // keeps MUFU.LG2 off the denormal path
       float vmax = -INFINITY, chk = 0.f, rprev = 0.f;
-      for (int i0 = 0; i0 < wprog.z; i0 += FBU) {
+      const int2* hp = sHdr + wprog.y;
+      for (int i0 = 0; i0 < wprog.z; i0 += FBU, hp += FBU) {
         int2 hd[FBU];
 #pragma unroll
-        for (int u = 0; u < FBU; ++u) hd[u] = sHdr[wprog.y + i0 + u];
-        const float4* pp[FBU];
-        const float4* wp[FBU];
+        for (int u = 0; u < FBU; ++u) hd[u] = hp[u];
+        const char* pp[FBU];
         float2 acc0[FBU], acc1[FBU];
 #pragma unroll
         for (int u = 0; u < FBU; ++u) {
-          pp[u] = reinterpret_cast<const float4*>(pbase + (hd[u].x & 0xffff));
-          wp[u] = sW4 + hd[u].y;
+          pp[u] = pbase + (hd[u].x & 0xffff);
           acc0[u] = make_float2(0.f, 0.f);
           acc1[u] = make_float2(0.f, 0.f);
         }
+        const char* wp = wbase + hd[0].y;  // the bundle's weights are interleaved: [round][entry][2 x float4]
         for (int gq = hd[0].x >> 16; gq > 0; --gq) {  // same round count for the whole bundle
 #pragma unroll
           for (int u = 0; u < FBU; ++u) {
-            const float4 p = *pp[u]++;
-            const float4 wa = wp[u][0], wb = wp[u][1];
-            wp[u] += 2;
+            const float4 p = *reinterpret_cast<const float4*>(pp[u]);
+            const float4 wa = *reinterpret_cast<const float4*>(wp + 32 * u);
+            const float4 wb = *reinterpret_cast<const float4*>(wp + 32 * u + 16);
+            pp[u] += 16;
             acc0[u] = __ffma2_rn(make_float2(p.x, p.x), make_float2(wa.x, wa.y), acc0[u]);
             acc1[u] = __ffma2_rn(make_float2(p.y, p.y), make_float2(wa.z, wa.w), acc1[u]);
             acc0[u] = __ffma2_rn(make_float2(p.z, p.z), make_float2(wb.x, wb.y), acc0[u]);
             acc1[u] = __ffma2_rn(make_float2(p.w, p.w), make_float2(wb.z, wb.w), acc1[u]);
           }
+          wp += 32 * FBU;
         }
-        float val[FBU];
+        float val[FBU], bad[FBU];
 #pragma unroll
         for (int u = 0; u < FBU; ++u) {
           const float2 rf = __fadd2_rn(acc0[u], acc1[u]);  // (R, F) of entry i0 + u
           const float en = rprev + rf.y;                   // filter wf0 + i0 + u - 1
           rprev = rf.x;
+          bad[u] = en;  // dB: max(amin, NaN) hides a NaN energy, so the energy itself is the poison source
           // 10*log10(x) = 3.0103*log2(x), ln(x) = 0.6931*log2(x); MUFU.LG2 is accurate to 2 ulp,
           // i.e. <= 3e-5 dB / 4e-6 nepers here, far inside the 1e-3 parity tolerance
-          const float arg = a.log_type == 0 ? fmaxf(a.amin, en) : (en == 0.f ? a.eps : en);
-          if constexpr (ABL & 256) val[u] = arg;
-          else val[u] = lscale * __log2f(arg);
+          if constexpr (ABL & 256) {
+            val[u] = en;
+          } else if (is_db) {
+            float l2;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(amin_n, en)));
+            val[u] = lscale * l2;
+          } else {
+            val[u] = lscale * __log2f(en == 0.f ? a.eps : en);
+            bad[u] = val[u];  // ln: also catches the log of a negative energy (custom filter banks)
+          }
         }
 #pragma unroll
         for (int u = 0; u < FBU; ++u) {
           const int fi_ = i0 + u;  // emits filter wf0 + fi_ - 1 when 1 <= fi_ <= n_filters
           if (fi_ >= 1 && fi_ <= wprog.w) {
-            if (valid) eptr[(long long)fi_ * a.e_stride_f] = val[u];
+            if (valid) *eptr = val[u];
             vmax = fmaxf(vmax, val[u]);
-            chk = __fmaf_rn(val[u], 0.f, chk);  // NaN/Inf poison
+            chk = __fmaf_rn(bad[u], 0.f, chk);  // NaN/Inf poison
           }
+          eptr += estep;
         }
       }
       if (valid) {

@@ -237,6 +237,25 @@ def test_length_edge_cases_and_status(dev):
     assert list(st) == [2, 0, 0, 0] and list(nf) == [0, 1, 1, 2]
 
 
+@pytest.mark.parametrize("kind", ["mfcc", "logmel512", "lfcc_noquant"])
+@pytest.mark.parametrize("poison", [np.nan, np.inf])
+def test_non_finite_audio_is_flagged_and_contained(dev, kind, poison):
+    """librosa.util.valid_audio raises on NaN/Inf (the reference then returns None for that row):
+    status NONFINITE for that utterance only; utterances sharing its tiles are bit-identical to a clean run.
+    (The reference's LFCC path casts to int16 first, which maps NaN to an integer without raising, so
+    only the un-quantised variant of that plan can see a non-finite sample.)"""
+    params = {"mfcc": FP().mfcc(16000, n_mfcc=13, n_delta=2),
+              "logmel512": FP().logmel(16000, n_mels=80, n_fft=512, hop_length=160),
+              "lfcc_noquant": FP().lfcc(16000, n_ceps=13, quantize_i16=False)}[kind]
+    clips = [noise(40, 6000), noise(41, 5000), noise(42, 7000)]
+    clean, nf0, st0, _ = run(params, clips, dev)
+    bad = [c.copy() for c in clips]
+    bad[1][2500] = poison
+    out, nf, st, _ = run(params, bad, dev)
+    assert list(st0) == [0, 0, 0] and list(st) == [0, 5, 0]
+    assert np.array_equal(out[0], clean[0]) and np.array_equal(out[2], clean[2])
+
+
 def test_padding_content_is_ignored_and_batch_invariant(dev):
     from audioanalysisdetector_b200.frontend import Frontend
     p = FP().mfcc(16000, n_mfcc=20, n_delta=2)
