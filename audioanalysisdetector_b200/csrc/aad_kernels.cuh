@@ -154,6 +154,62 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// Tensor memory (TMEM) as a per-lane table store.  The window and the pass-1 twiddles of k_stft_fb
+// are lane x register tables read once per frame; from shared memory they cost 126 wavefronts per
+// frame on the L1/shared data pipe, the kernel's most loaded unit.  TMEM (256 KB per SM, 128 lanes x
+// 512 columns x 32 bit) is read through its own datapath (tcgen05.ld, SASS LDTM): with the 32x32b
+// shape thread i of warp w reads lane 32*(w%4) + i, i.e. exactly "its own row".
+// ---------------------------------------------------------------------------
+#ifndef AAD_TMEM_TABLES
+#define AAD_TMEM_TABLES 1
+#endif
+#ifndef AAD_TWP_TMEM
+#define AAD_TWP_TMEM 1
+#endif
+// columns: [0, 64) window pairs, [64, 128) pass-1 twiddles, [128, 160) split twiddles (only when at
+// most two CTAs share the SM's 512 columns: allocations are powers of two)
+template <int CTAS>
+struct TmemCfg {
+  static constexpr bool TWP = AAD_TMEM_TABLES && AAD_TWP_TMEM && CTAS <= 2;
+  static constexpr int COLS = TWP ? 256 : 128;
+};
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float2 (&w)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      :: "r"(taddr), "r"(__float_as_uint(w[0].x)), "r"(__float_as_uint(w[0].y)), "r"(__float_as_uint(w[1].x)),
+         "r"(__float_as_uint(w[1].y)), "r"(__float_as_uint(w[2].x)), "r"(__float_as_uint(w[2].y)),
+         "r"(__float_as_uint(w[3].x)), "r"(__float_as_uint(w[3].y)), "r"(__float_as_uint(w[4].x)),
+         "r"(__float_as_uint(w[4].y)), "r"(__float_as_uint(w[5].x)), "r"(__float_as_uint(w[5].y)),
+         "r"(__float_as_uint(w[6].x)), "r"(__float_as_uint(w[6].y)), "r"(__float_as_uint(w[7].x)),
+         "r"(__float_as_uint(w[7].y))
+      : "memory");
+}
+// 8 float2 of this thread's TMEM row, starting at column (taddr & 0xffff): issue, then wait.  The
+// registers are operands of the wait so that no use can be scheduled ahead of it; the wait covers every
+// load issued before it, so a second chunk issued right after the wait stays in flight while the first
+// one is consumed.
+struct TmemChunk {
+  uint32_t r[16];
+  __device__ __forceinline__ void issue(uint32_t taddr) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+  }
+  __device__ __forceinline__ void wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+  }
+  __device__ __forceinline__ float2 get(int i) const {
+    return make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+  }
+};
+
+// ---------------------------------------------------------------------------
 // K1: fused STFT + power + filterbank + log
 // ---------------------------------------------------------------------------
 template <int L, int TILE_>
@@ -185,7 +241,8 @@ struct StftCfg {
   static constexpr int OFF_TW1 = OFF_WIN + N;
   static constexpr int OFF_TWP = OFF_TW1 + 2 * 32 * L;
   static constexpr int OFF_META = OFF_TWP + 2 * (M / 2);      // 2 x {b[TILE], t[TILE]} (double buffered)
-  static constexpr int OFF_PROG = OFF_META + 4 * TILE;        // segment headers + tap weights follow
+  static constexpr int OFF_TMEM = OFF_META + 4 * TILE;        // TMEM base address written by tcgen05.alloc
+  static constexpr int OFF_PROG = OFF_TMEM + 4;               // segment headers + tap weights follow
   static constexpr size_t FIXED_BYTES = size_t(OFF_PROG) * 4;
   static_assert(TILE == 32, "filterbank phase runs with lane = frame");
   static_assert(SP % 8 == 4, "LDS.128 over lane = frame needs an odd number of 16-byte units per row");
@@ -306,11 +363,56 @@ k_stft_fb(const StftArgs a) {
   for (int i = tid; i < M / 2; i += nthr) sTwp[i] = a.twp[i];
   for (int i = tid; i < a.n_hdr; i += nthr) sHdr[i] = a.filt_hdr[i];
   for (int i = tid; i < a.n_w4; i += nthr) sW4[i] = a.filt_w[i];
+#if AAD_TMEM_TABLES
+  // allocate 128 TMEM columns, fill this CTA's four lane quarters with the per-lane rows
+  //   columns [0, 64): window pairs 0.5*w[2(L A + j)], 0.5*w[2(L A + j) + 1], A = 0..31
+  //   columns [64, 128): pass-1 twiddles W_M^(j kA), kA = 0..31
+  volatile uint32_t& s_tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(smem + C::OFF_TMEM)), "r"((uint32_t)TmemCfg<C::CTAS>::COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_row = s_tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);
+  if (warp < 4) {
+    const float2* gwin2 = reinterpret_cast<const float2*>(a.window);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float2 w8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w8[i] = __ldg(gwin2 + L * (8 * c + i) + j);
+      tmem_st16(tmem_row + 16 * c, w8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w8[i] = __ldg(a.tw1 + (8 * c + i) * L + j);
+      tmem_st16(tmem_row + 64 + 16 * c, w8);
+    }
+    if constexpr (TmemCfg<C::CTAS>::TWP) {  // entry q*(L/2) + s = W_N^(j + L q + 32 s)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float2 w8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int e = 8 * c + i, q = e / (L / 2), sidx = e % (L / 2);
+          w8[i] = __ldg(a.twp + j + L * q + 32 * sidx);
+        }
+        tmem_st16(tmem_row + 128 + 16 * c, w8);
+      }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#endif
   const int4 wprog = a.warp_prog[warp];
   const int total = a.frame_off[a.B];
   const int n_tiles = (total + C::TILE - 1) / C::TILE;
   const float2* sWin2 = reinterpret_cast<const float2*>(sWin);
-  constexpr bool TWPGEN = AAD_TWPGEN && Q <= 4;
+  constexpr bool TWPTM = TmemCfg<C::CTAS>::TWP;
+  constexpr bool TWPGEN = !TWPTM && AAD_TWPGEN && Q <= 4;
   float2 twp_base[Q];   // W_N^(j + L q)
 #pragma unroll
   for (int q = 0; q < Q; ++q) twp_base[q] = TWPGEN ? __ldg(a.twp + j + L * q) : make_float2(0.f, 0.f);
@@ -386,12 +488,12 @@ k_stft_fb(const StftArgs a) {
               float xp = (float)__ldg(ps + 2 * L * A);
               float2 x = i16pair_to_float2(raw[A]);
               float2 e = make_float2(__fmaf_rn(-a.pre_emph, xp, x.x), __fmaf_rn(-a.pre_emph, x.x, x.y));
-              v[bitrev(A, 5)] = pk_mul(e, sWin2[L * A + j]);
+              v[bitrev(A, 5)] = e;
             });
           } else {
             static_for<0, 32>([&](auto a_) {
               constexpr int A = decltype(a_)::value;
-              v[bitrev(A, 5)] = pk_mul(i16pair_to_float2(raw[A]), sWin2[L * A + j]);
+              v[bitrev(A, 5)] = i16pair_to_float2(raw[A]);
             });
           }
         } else {
@@ -410,15 +512,13 @@ k_stft_fb(const StftArgs a) {
               x.x = cvt_sample<MODE>(x.x);
               x.y = cvt_sample<MODE>(x.y);
               float2 e = make_float2(__fmaf_rn(-a.pre_emph, xp, x.x), __fmaf_rn(-a.pre_emph, x.x, x.y));
-              v[bitrev(A, 5)] = pk_mul(e, sWin2[L * A + j]);
+              v[bitrev(A, 5)] = e;
             });
-          } else {
+          } else if constexpr (MODE == IN_F32_Q16) {
             static_for<0, 32>([&](auto a_) {
               constexpr int A = decltype(a_)::value;
-              float2 x = v[bitrev(A, 5)];
-              if constexpr (MODE == IN_F32_Q16) x = make_float2(cvt_sample<MODE>(x.x), cvt_sample<MODE>(x.y));
-              if constexpr (ABL & 1) v[bitrev(A, 5)] = pk_mul(x, make_float2(a.amin, a.eps));
-              else v[bitrev(A, 5)] = pk_mul(x, sWin2[L * A + j]);
+              const float2 x = v[bitrev(A, 5)];
+              v[bitrev(A, 5)] = make_float2(cvt_sample<MODE>(x.x), cvt_sample<MODE>(x.y));
             });
           }
         }
@@ -444,7 +544,7 @@ k_stft_fb(const StftArgs a) {
             x.x = (n0 >= n_lo && n0 < n_hi) ? load_masked<MODE, false>(row, s0 + n0, n0, len, a.win_off, a.win_len, 0.f) : 0.f;
             x.y = (n0 + 1 >= n_lo && n0 + 1 < n_hi) ? load_masked<MODE, false>(row, s0 + n0 + 1, n0 + 1, len, a.win_off, a.win_len, 0.f) : 0.f;
           }
-          v[bitrev(A, 5)] = pk_mul(x, sWin2[L * A + j]);
+          v[bitrev(A, 5)] = x;
         });
       } else {
         // pre-emphasis or unaligned rows on an edge frame: every sample with all masks
@@ -453,9 +553,32 @@ k_stft_fb(const StftArgs a) {
           const int n0 = 2 * (L * A + j);
           float x0 = load_masked<MODE, PRE>(row, s0 + n0, n0, len, a.win_off, a.win_len, a.pre_emph);
           float x1 = load_masked<MODE, PRE>(row, s0 + n0 + 1, n0 + 1, len, a.win_off, a.win_len, a.pre_emph);
-          v[bitrev(A, 5)] = pk_mul(make_float2(x0, x1), sWin2[L * A + j]);
+          v[bitrev(A, 5)] = make_float2(x0, x1);
         });
       }
+
+      // window: 0.5*w (zero outside its support) from this lane's TMEM row, next chunk in flight
+#if AAD_TMEM_TABLES
+      {
+        TmemChunk wc[2];
+        wc[0].issue(tmem_row);
+        static_for<0, 4>([&](auto c_) {
+          constexpr int CH = decltype(c_)::value;
+          wc[CH & 1].wait();
+          if constexpr (CH < 3) wc[(CH + 1) & 1].issue(tmem_row + 16 * (CH + 1));
+          static_for<0, 8>([&](auto i_) {
+            constexpr int A = 8 * CH + decltype(i_)::value;
+            v[bitrev(A, 5)] = pk_mul(v[bitrev(A, 5)], wc[CH & 1].get(A % 8));
+          });
+        });
+      }
+#else
+      static_for<0, 32>([&](auto a_) {
+        constexpr int A = decltype(a_)::value;
+        if constexpr (ABL & 1) v[bitrev(A, 5)] = pk_mul(v[bitrev(A, 5)], make_float2(a.amin, a.eps));
+        else v[bitrev(A, 5)] = pk_mul(v[bitrev(A, 5)], sWin2[L * A + j]);
+      });
+#endif
 
       // pass 1: 32-point DFT over a (stride L), then twiddle W_M^(b*kA)
       if constexpr (!(ABL & 64)) fft_dit<32, 0>(v);
@@ -467,11 +590,25 @@ k_stft_fb(const StftArgs a) {
           if constexpr (KA < 16) v[32 - KA] = cmul(cmul_conj(v[32 - KA], tw), tw1_rot);
         });
       } else {
+#if AAD_TMEM_TABLES
+        TmemChunk tc[2];
+        tc[0].issue(tmem_row + 64);
+        static_for<0, 4>([&](auto c_) {
+          constexpr int CH = decltype(c_)::value;
+          tc[CH & 1].wait();
+          if constexpr (CH < 3) tc[(CH + 1) & 1].issue(tmem_row + 64 + 16 * (CH + 1));
+          static_for<0, 8>([&](auto i_) {
+            constexpr int KA = 8 * CH + decltype(i_)::value;
+            if constexpr (KA > 0) v[KA] = cmul(v[KA], tc[CH & 1].get(KA % 8));
+          });
+        });
+#else
         static_for<1, 32>([&](auto k_) {
           constexpr int KA = decltype(k_)::value;
           if constexpr (ABL & 2) v[KA] = cmul(v[KA], make_float2(a.amin, a.eps));
           else v[KA] = cmul(v[KA], sTw1[KA * L + j]);
         });
+#endif
       }
 
       // transpose through the warp's scratch (= its own power rows), re then im
@@ -515,6 +652,15 @@ k_stft_fb(const StftArgs a) {
 
       // real-input split + power:  X[k] = E - T,  X[M-k] = conj(E + T),  T = i*w*O
       float* prow = sP + fi * SP;
+#if AAD_TMEM_TABLES
+      TmemChunk pc[2];
+      if constexpr (TWPTM) {
+        pc[0].issue(tmem_row + 128);
+        pc[1].issue(tmem_row + 144);
+        pc[0].wait();  // covers both
+        pc[1].wait();
+      }
+#endif
       static_for<0, Q>([&](auto q_) {
         constexpr int QQ = decltype(q_)::value;
         static_for<0, L / 2>([&](auto s_) {
@@ -533,6 +679,12 @@ k_stft_fb(const StftArgs a) {
           const float2 O = __fadd2_rn(A, make_float2(-r.x, r.y));   // A - conj(r)
           const int k = j + L * QQ + 32 * S;
           float2 wO;
+#if AAD_TMEM_TABLES
+          if constexpr (TWPTM) {
+            constexpr int EI = QQ * (L / 2) + S;
+            wO = cmul(O, pc[EI / 8].get(EI % 8));
+          } else
+#endif
           if constexpr (TWPGEN) wO = cmul(cmul_const<32 * S, N>(O), twp_base[QQ]);
           else wO = (ABL & 16) ? cmul(O, make_float2(a.amin, a.eps)) : cmul(O, sTwp[k]);
           const float2 x1 = __fadd2_rn(E, make_float2(wO.y, -wO.x));  // E - i*wO
@@ -652,6 +804,14 @@ k_stft_fb(const StftArgs a) {
     AAD_PHASE_MARK(3);
 #endif
   }
+#if AAD_TMEM_TABLES
+  // every warp is past its last tcgen05.ld (the loop ends with a CTA barrier; CTAs without tiles
+  // come straight from the set-up barrier)
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"((uint32_t)s_tmem_base), "r"((uint32_t)TmemCfg<C::CTAS>::COLS) : "memory");
+#endif
 }
 
 // ---------------------------------------------------------------------------
