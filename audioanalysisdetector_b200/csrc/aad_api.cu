@@ -741,12 +741,13 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
     }
     ca.tile_out = CEP_TS - (p.n_delta > 0 ? 2 * (p.delta_width / 2) : 0);
     const int gx = t_max <= CEP_TS ? 1 : (t_max + ca.tile_out - 1) / ca.tile_out;
-    dim3 grid(gx, B);
-    pick_cep(pl->kc)<<<grid, CEP_THREADS, cep_smem_bytes(pl), stream>>>(ca);
+    if ((long long)B * gx > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
+    ca.tiles_per_utt = gx;
+    pick_cep(pl->kc)<<<(unsigned)((long long)B * gx), CEP_THREADS, cep_smem_bytes(pl), stream>>>(ca);
     LAUNCH_CHECK("k_cepstra launch");
     if (prof) cudaEventRecord(pl->ev[3], stream);
     if (p.time_mean) {
-      dim3 gm((pl->c_out + 3) / 4, B);
+      dim3 gm(B, (pl->c_out + 3) / 4);
       k_time_mean<<<gm, 128, 0, stream>>>(d_feat, ca.out_stride_b, w.t_ws, d_nf, pl->c_out, out, out_stride_b);
     }
   } else {
@@ -754,9 +755,11 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
     fa.out = out; fa.stride_b = out_stride_b; fa.stride_f = t_alloc; fa.nf_eff = d_nf; fa.utt_max = d_max;
     fa.n_filt = p.n_filt; fa.ref_type = p.ref_type; fa.top_db = p.top_db;
     if (p.log_type == AAD_LOG_DB10) {
-      const int gx = std::max(1, std::min(64, (p.n_filt * std::max(t_max, 1) + 255) / 256));
-      dim3 grid(gx, B);
-      k_db_finalize<<<grid, 256, 0, stream>>>(fa);
+      const int n_row_blocks = (p.n_filt + FIN_ROWS - 1) / FIN_ROWS;
+      const int n_chunks = (std::max(t_max, 1) + FIN_CHUNK - 1) / FIN_CHUNK;
+      const long long nblk = (long long)B * n_row_blocks * n_chunks;
+      if (nblk > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
+      k_db_finalize<<<(unsigned)nblk, 256, 0, stream>>>(fa, n_row_blocks, n_chunks);
     }
     if (prof) cudaEventRecord(pl->ev[3], stream);
   }
@@ -782,13 +785,13 @@ int aad_delta(const float* x, const int32_t* n_frames, int B, int C, int32_t t_s
               int order, float* out, void* stream) {
   if (!x || !n_frames || !out || B <= 0 || C <= 0 || t_stride <= 0) return AAD_ERR_INVALID_ARG;
   if (width < 3 || width > CEP_MAXW || width % 2 == 0 || order < 1 || order > 2) return AAD_ERR_INVALID_ARG;
-  if (B > 65535 || C > 65535) return AAD_ERR_UNSUPPORTED;
+  if (C > 65535) return AAD_ERR_UNSUPPORTED;
   DeltaArgs da;
   float t1[CEP_MAXW], t2[CEP_MAXW];
   savgol_taps(width, t1, t2);
   std::memcpy(da.taps, order == 1 ? t1 : t2, sizeof(da.taps));
   da.x = x; da.out = out; da.n_frames = n_frames; da.C = C; da.t_stride = t_stride; da.width = width;
-  dim3 grid(std::max(1, std::min(64, (t_stride + 255) / 256)), C, B);
+  dim3 grid(B, C, std::max(1, std::min(64, (t_stride + 255) / 256)));
   (void)cudaGetLastError();
   k_delta<<<grid, 256, 0, (cudaStream_t)stream>>>(da);
   LAUNCH_CHECK("k_delta launch");

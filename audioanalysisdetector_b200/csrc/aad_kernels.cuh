@@ -839,6 +839,7 @@ struct CepArgs {
   long long out_stride_b;
   int out_stride_c, out_stride_t;  // CT: (t_alloc, 1); TC: (1, c_out)
   int tile_out;           // output frames per tile when T > CEP_TS
+  int tiles_per_utt;      // grid.x = B * tiles_per_utt
 };
 
 // One CTA = (utterance, tile of <= 128 frames).  Three phases:
@@ -853,16 +854,17 @@ template <int KC>
 __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
   constexpr int KCP = (KC + 3) & ~3;  // chunk stride in the table: 16-byte aligned rows
   extern __shared__ __align__(16) float smem[];
-  const int b = blockIdx.y;
+  // grid.x = B * tiles_per_utt, utterance-major: consecutive CTAs read neighbouring tiles of one utterance
+  const int b = blockIdx.x / a.tiles_per_utt, tile = blockIdx.x - b * a.tiles_per_utt;
   const int T = a.nf_eff[b];
   if (T == 0) return;
   int o0, o1;
   if (T <= CEP_TS) {
-    if (blockIdx.x > 0) return;
+    if (tile > 0) return;
     o0 = 0;
     o1 = T;
   } else {
-    o0 = blockIdx.x * a.tile_out;
+    o0 = tile * a.tile_out;
     if (o0 >= T) return;
     o1 = min(T, o0 + a.tile_out);
   }
@@ -1023,28 +1025,38 @@ struct FinArgs {
   int n_filt, ref_type;
   float top_db;
 };
-__global__ void __launch_bounds__(256) k_db_finalize(const FinArgs a) {
-  const int b = blockIdx.y;
+constexpr int FIN_ROWS = 8;      // filter rows per CTA (one per warp)
+constexpr int FIN_CHUNK = 1024;  // frames per CTA
+// grid.x = B * n_row_blocks * n_chunks (flattened, utterance-major)
+__global__ void __launch_bounds__(256) k_db_finalize(const FinArgs a, int n_row_blocks, int n_chunks) {
+  const int per_b = n_row_blocks * n_chunks;
+  const int b = blockIdx.x / per_b, r = blockIdx.x - b * per_b;
+  const int f = (r / n_chunks) * FIN_ROWS + (threadIdx.x >> 5);
+  const int t0 = (r % n_chunks) * FIN_CHUNK;
   const int T = a.nf_eff[b];
-  if (T == 0) return;
+  if (f >= a.n_filt || t0 >= T) return;
   const float m = dec_ordered(a.utt_max[b]);
   const float ref = a.ref_type == 1 ? m : 0.f;
   const float floorv = a.top_db >= 0.f ? (m - ref) - a.top_db : -INFINITY;
-  float* ob = a.out + (long long)b * a.stride_b;
-  const int total = a.n_filt * T;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int f = i / T, t = i - f * T;
-    float* p = ob + (long long)f * a.stride_f + t;
-    *p = fmaxf(*p - ref, floorv);
+  float* row = a.out + (long long)b * a.stride_b + (long long)f * a.stride_f;
+  const int t1 = min(T, t0 + FIN_CHUNK);
+  int t = t0 + (threadIdx.x & 31);
+  for (; t + 96 < t1; t += 128) {  // four independent coalesced accesses in flight per lane
+    float v0 = row[t], v1 = row[t + 32], v2 = row[t + 64], v3 = row[t + 96];
+    row[t] = fmaxf(v0 - ref, floorv);
+    row[t + 32] = fmaxf(v1 - ref, floorv);
+    row[t + 64] = fmaxf(v2 - ref, floorv);
+    row[t + 96] = fmaxf(v3 - ref, floorv);
   }
+  for (; t < t1; t += 32) row[t] = fmaxf(row[t] - ref, floorv);
 }
 
 // mean over frames of feat[b][c][0..T_b): one warp per (b, c)
 __global__ void __launch_bounds__(128) k_time_mean(const float* feat, long long stride_b, int stride_c,
                                                    const int32_t* nf_eff, int C, float* out,
                                                    long long out_stride_b) {
-  const int b = blockIdx.y;
-  const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int b = blockIdx.x;
+  const int c = blockIdx.y * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int T = nf_eff[b];
   if (c >= C || T == 0) return;
@@ -1065,12 +1077,12 @@ struct DeltaArgs {
   float taps[CEP_MAXW];
 };
 __global__ void __launch_bounds__(256) k_delta(const DeltaArgs a) {
-  const int b = blockIdx.z, c = blockIdx.y;
+  const int b = blockIdx.x, c = blockIdx.y;
   const int T = a.n_frames[b];
   const int h = a.width >> 1;
   if (T < a.width) return;
   const long long base = ((long long)b * a.C + c) * a.t_stride;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+  for (int t = blockIdx.z * blockDim.x + threadIdx.x; t < T; t += gridDim.z * blockDim.x) {
     int te = min(max(t, h), T - 1 - h);
     float d = 0.f;
     for (int i = 0; i < a.width; ++i) d = __fmaf_rn(a.taps[i], __ldg(a.x + base + te - h + i), d);
