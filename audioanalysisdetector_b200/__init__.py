@@ -7,12 +7,12 @@ arithmetic in hand-written sm_100a CUDA kernels behind the C ABI of include/aad.
 from . import _lib
 from ._lib import AadError
 from .frontend import Frontend, FrontendParams, delta, fp32_peak_tflops
-from .extractors import (extract_features, extract_lfcc, extract_mel_spectrogram, extract_mfcc,
-                         get_frontend)
+from .extractors import (compute_melspec, extract_features, extract_lfcc, extract_mel_spectrogram,
+                         extract_mfcc, get_frontend)
 from .sharding import bind_to_gpu_numa, contiguous_shard, gather_features, partition_by_frames
 
 __all__ = [
     "AadError", "Frontend", "FrontendParams", "delta", "fp32_peak_tflops",
-    "extract_features", "extract_lfcc", "extract_mel_spectrogram", "extract_mfcc", "get_frontend",
+    "compute_melspec", "extract_features", "extract_lfcc", "extract_mel_spectrogram", "extract_mfcc", "get_frontend",
     "bind_to_gpu_numa", "contiguous_shard", "gather_features", "partition_by_frames",
 ]

@@ -38,7 +38,7 @@ class AadParams(C.Structure):
         ("log_type", C.c_int32), ("ref_type", C.c_int32), ("amin", C.c_float),
         ("top_db", C.c_float), ("n_ceps", C.c_int32), ("n_delta", C.c_int32),
         ("delta_width", C.c_int32), ("layout", C.c_int32), ("time_mean", C.c_int32),
-        ("i16_scale", C.c_float), ("custom_fb", C.POINTER(C.c_float)),
+        ("i16_scale", C.c_float), ("znorm", C.c_int32), ("custom_fb", C.POINTER(C.c_float)),
     ]
 
 

@@ -410,6 +410,7 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   if (p.log_type != AAD_LOG_DB10 && p.log_type != AAD_LOG_LN) return AAD_ERR_INVALID_ARG;
   if (p.layout != AAD_LAYOUT_CT && p.layout != AAD_LAYOUT_TC) return AAD_ERR_INVALID_ARG;
   if (p.fmax > 0 && p.fmax > p.sample_rate / 2.0f + 1e-3f) return AAD_ERR_INVALID_ARG;
+  if (p.znorm && p.time_mean) return AAD_ERR_INVALID_ARG;
 
   CUDA_TRY(cudaSetDevice(device));
   aad_plan* pl = new (std::nothrow) aad_plan();
@@ -611,7 +612,7 @@ static int frames_for(const aad_params& p, int64_t len) {
 }
 
 struct WsLayout {
-  size_t off_frame_off, off_len, off_nf, off_max, off_tile, off_E, off_feat, total;
+  size_t off_frame_off, off_len, off_nf, off_max, off_zn, off_tile, off_E, off_feat, total;
   int t_ws;
   int max_tiles;
 };
@@ -622,6 +623,7 @@ static WsLayout ws_layout(const aad_plan* pl, int B, int t_max) {
   w.off_len = o;       o = align_up(o + (size_t)B * 4, 256);
   w.off_nf = o;        o = align_up(o + (size_t)B * 4, 256);
   w.off_max = o;       o = align_up(o + (size_t)B * 4, 256);
+  w.off_zn = o;        if (pl->p.znorm) o = align_up(o + (size_t)B * 2 * sizeof(double), 256);
   w.max_tiles = (int)(((long long)B * t_max + pl->tile - 1) / pl->tile);
   w.off_tile = o;      o = align_up(o + (size_t)(w.max_tiles + 1) * 4, 256);
   w.t_ws = (t_max + 31) / 32 * 32;
@@ -647,7 +649,8 @@ int aad_query(const aad_plan* pl, int B, int64_t max_len, int32_t* t_max, int32_
 
 int aad_plan_launches(const aad_plan* pl) {
   if (!pl) return AAD_ERR_INVALID_ARG;
-  return 2 + 1 + (pl->need_ws_feat ? 1 : 0);  // prepare, stft_fb, cepstra|finalize, [time_mean]
+  // prepare, stft_fb, cepstra|finalize, [time_mean], [znorm stats + apply]
+  return 2 + 1 + (pl->need_ws_feat ? 1 : 0) + (pl->p.znorm ? 2 : 0);
 }
 
 int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_stride,
@@ -689,6 +692,7 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
   pa.n_frames = n_frames; pa.status = status; pa.len_c = d_len; pa.nf_eff = d_nf;
   pa.frame_off = d_frame_off; pa.utt_max = d_max;
   pa.tile_b0 = (int32_t*)(ws + w.off_tile); pa.tile = pl->tile; pa.max_tiles = w.max_tiles;
+  pa.zn_stats = p.znorm ? (double*)(ws + w.off_zn) : nullptr;
   const bool prof = pl->profile;
   if (prof) cudaEventRecord(pl->ev[0], stream);
   (void)cudaGetLastError();  // clear stale non-sticky state left by earlier calls in this thread
@@ -762,6 +766,18 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
       k_db_finalize<<<(unsigned)nblk, 256, 0, stream>>>(fa, n_row_blocks, n_chunks);
     }
     if (prof) cudaEventRecord(pl->ev[3], stream);
+  }
+  if (p.znorm) {
+    ZnArgs za;
+    za.out = out; za.stride_b = out_stride_b; za.nf_eff = d_nf; za.C = pl->c_out;
+    if (p.layout == AAD_LAYOUT_CT) { za.stride_c = t_alloc; za.stride_t = 1; }
+    else { za.stride_c = 1; za.stride_t = pl->c_out; }
+    za.n_chunks = (int)(((long long)pl->c_out * std::max(t_max, 1) + ZN_CHUNK - 1) / ZN_CHUNK);
+    za.stats = pa.zn_stats;
+    const long long nblk = (long long)B * za.n_chunks;
+    if (nblk > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
+    k_znorm<false><<<(unsigned)nblk, 256, 0, stream>>>(za);
+    k_znorm<true><<<(unsigned)nblk, 256, 0, stream>>>(za);
   }
   if (prof) cudaEventRecord(pl->ev[4], stream);
   LAUNCH_CHECK("epilogue launch");

@@ -73,6 +73,7 @@ struct PrepArgs {
   int32_t* utt_max;    // ws: ordered-int encoded running max, init -inf
   int32_t* tile_b0;    // ws: [max_tiles] utterance holding the first frame of each K1 tile
   int tile, max_tiles;
+  double* zn_stats;    // ws: [B][2] z-norm accumulators (null when unused)
 };
 
 __global__ void __launch_bounds__(1024) k_prepare(PrepArgs a) {
@@ -104,6 +105,10 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepArgs a) {
       a.len_c[b] = (int)len;
       a.nf_eff[b] = nf;
       a.utt_max[b] = AAD_ENC_NEG_INF;
+      if (a.zn_stats) {
+        a.zn_stats[2 * b] = 0.0;
+        a.zn_stats[2 * b + 1] = 0.0;
+      }
     }
     // block exclusive scan of nf
     int x = nf;
@@ -1049,6 +1054,71 @@ __global__ void __launch_bounds__(256) k_db_finalize(const FinArgs a, int n_row_
     row[t + 96] = fmaxf(v3 - ref, floorv);
   }
   for (; t < t1; t += 32) row[t] = fmaxf(row[t] - ref, floorv);
+}
+
+// z-normalisation of an utterance's whole feature matrix (compute_melspec, ASV_dataset.ipynb:1151):
+// pass 1 accumulates sum and sum of squares in double (one atomicAdd pair per CTA), pass 2 applies
+// (x - mean) * rsqrt(var).  grid.x = B * n_chunks, a chunk = ZN_CHUNK consecutive elements of the
+// row-major (c, t) enumeration of the valid part.
+constexpr int ZN_CHUNK = 8192;
+struct ZnArgs {
+  float* out;
+  long long stride_b;
+  int stride_c, stride_t;
+  const int32_t* nf_eff;
+  int C, n_chunks;
+  double* stats;  // [B][2]
+};
+template <bool APPLY>
+__global__ void __launch_bounds__(256) k_znorm(const ZnArgs a) {
+  const int b = blockIdx.x / a.n_chunks, ch = blockIdx.x - b * a.n_chunks;
+  const int T = a.nf_eff[b];
+  const long long total = (long long)a.C * T;
+  const long long i0 = (long long)ch * ZN_CHUNK;
+  if (i0 >= total) return;
+  const long long i1 = min(total, i0 + ZN_CHUNK);
+  float* ob = a.out + (long long)b * a.stride_b;
+  float mean = 0.f, rstd = 0.f;
+  if (APPLY) {
+    const double n = (double)total, m = a.stats[2 * b] / n;
+    const double var = fmax(a.stats[2 * b + 1] / n - m * m, 0.0);
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(var));  // std == 0 -> inf/nan, as numpy's division by zero gives
+  }
+  double s1 = 0.0, s2 = 0.0;
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+    const int c = (int)(i / T), t = (int)(i - (long long)c * T);
+    float* p = ob + (long long)c * a.stride_c + (long long)t * a.stride_t;
+    if (APPLY) {
+      *p = (*p - mean) * rstd;
+    } else {
+      const double v = (double)*p;
+      s1 += v;
+      s2 += v * v;
+    }
+  }
+  if (!APPLY) {
+    __shared__ double red[2][8];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      red[0][threadIdx.x >> 5] = s1;
+      red[1][threadIdx.x >> 5] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t1 = 0, t2 = 0;
+      for (int w = 0; w < 8; ++w) {
+        t1 += red[0][w];
+        t2 += red[1][w];
+      }
+      atomicAdd(a.stats + 2 * b, t1);
+      atomicAdd(a.stats + 2 * b + 1, t2);
+    }
+  }
 }
 
 // mean over frames of feat[b][c][0..T_b): one warp per (b, c)

@@ -122,6 +122,17 @@ def extract_mel_spectrogram(filepath, chunk_start=None, chunk_end=None, sr=None,
         return None
 
 
+def compute_melspec(row, n_mels=128, hop_length=512, n_fft=2048):
+    """ASV_dataset.ipynb:1151 (cell [27]): z-normalised log-mel of a whole file -> (n_mels, T) float32.
+    Unlike the extractors above the notebook function has no try/except: errors propagate."""
+    y, sr = _prepare_clip(row, None, None, None, None)
+    params = FrontendParams.logmel(sr, n_mels=n_mels, n_fft=n_fft, hop_length=hop_length, znorm=True)
+    out, status = _run_batch(params, [y])
+    if out[0] is None:
+        raise ValueError(L.ITEM_STATUS_NAMES.get(int(status[0]), "item failed"))
+    return out[0]
+
+
 def extract_mfcc(filepath, chunk_start=None, chunk_end=None, sr=None, n_mfcc=13, mean=False, augment=None):
     try:
         y, sr = _prepare_clip(filepath, chunk_start, chunk_end, sr, augment)

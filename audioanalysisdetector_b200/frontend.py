@@ -48,6 +48,7 @@ class FrontendParams:
     delta_width: int = 9
     layout: int = L.LAYOUT_CT
     time_mean: bool = False
+    znorm: bool = False          # (x - mean) / std over the utterance's feature matrix (ASV_dataset.ipynb compute_melspec)
     i16_scale: float = 0.0       # int16 input: sample = int16 * i16_scale; 0 -> 1/32768 (log-mel / MFCC), 1 (LFCC)
     custom_fb: Optional[np.ndarray] = None   # (n_filt, n_fft//2+1) float32, FB_CUSTOM only
 
@@ -93,6 +94,7 @@ class FrontendParams:
         p.center = int(bool(self.center))
         p.quantize_i16 = int(bool(self.quantize_i16))
         p.time_mean = int(bool(self.time_mean))
+        p.znorm = int(bool(self.znorm))
         for f in ("pre_emph", "fmin", "fmax", "power_scale", "amin", "top_db", "i16_scale"):
             setattr(p, f, float(getattr(self, f)))
         keep = None

@@ -107,6 +107,9 @@ typedef struct aad_params {
   float i16_scale;     /* int16 input only: sample value = int16 * i16_scale.  0 -> default: 1/32768 for
                           LOGMEL / MFCC (16-bit PCM as librosa.load / soundfile decode it to float32),
                           1 for LFCC (spafe receives the raw int16 array, ASV_dl_func.py:434-435) */
+  int32_t znorm;       /* 1: out = (x - mean(x)) / std(x) over all valid elements of the utterance (population
+                          std), the compute_melspec variant of the reference (ASV_dataset.ipynb:1151,
+                          cell [27]); applied last; not combinable with time_mean */
   const float* custom_fb; /* HOST pointer, row-major n_filt x (n_fft/2+1); AAD_FB_CUSTOM only */
 } aad_params;
 

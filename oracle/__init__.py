@@ -25,6 +25,7 @@ reference legs may import this package.  The product package
 from . import librosa_ref, spafe_ref, delta_ref  # noqa: F401
 from .extractors_ref import (  # noqa: F401
     extract_mel_spectrogram_ref,
+    compute_melspec_ref,
     extract_mfcc_ref,
     extract_lfcc_ref,
     mfcc_with_deltas_ref,

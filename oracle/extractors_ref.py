@@ -33,6 +33,15 @@ def extract_mel_spectrogram_ref(y, sr, chunk_start=None, chunk_end=None, n_mels=
         return None
 
 
+def compute_melspec_ref(y, sr, n_mels=128, hop_length=512, n_fft=2048, dtype="ref"):
+    """ASV_dataset.ipynb:1151 (cell [27]) `compute_melspec` on a decoded waveform: log-mel
+    (melspectrogram(power=2.0) -> power_to_db(ref=np.max)) followed by a global z-normalisation
+    `(S - S.mean()) / S.std()` over the whole (n_mels, T) matrix (numpy: population std)."""
+    S_db = librosa_ref.logmel_db(np.asarray(y, dtype=np.float32), sr, n_mels=n_mels, n_fft=n_fft,
+                                 hop_length=hop_length, dtype=dtype)
+    return (S_db - S_db.mean()) / S_db.std()
+
+
 def extract_mfcc_ref(y, sr, chunk_start=None, chunk_end=None, n_mfcc=13, mean=False,
                      dtype="ref"):
     """ASV_dl_func.py:404-420 on a decoded float32 waveform -> (n_mfcc, T) float32."""

@@ -293,6 +293,25 @@ def test_layouts_and_time_mean(dev):
         np.testing.assert_allclose(lm_mean[i], oracle.extract_mel_spectrogram_ref(c, 16000, mean=True), atol=TOL_LOG)
 
 
+@pytest.mark.parametrize("layout", ["CT", "TC"])
+def test_znorm_compute_melspec_variant(dev, layout):
+    """ASV_dataset.ipynb compute_melspec: log-mel (128 mels, ref=np.max) then (S - S.mean()) / S.std()."""
+    L = LIB()
+    clips = [noise(50, 32000), speech(51, 47999), noise(52, 70000)]       # the last one spans several K2/znorm chunks
+    p = FP().logmel(16000, n_mels=128, znorm=True, layout=L.LAYOUT_CT if layout == "CT" else L.LAYOUT_TC)
+    out, nf, st, fe = run(p, clips, dev)
+    assert fe.launches_per_call == 5
+    for i, c in enumerate(clips):
+        want = oracle.compute_melspec_ref(c, 16000)
+        got = out[i, :, :nf[i]] if layout == "CT" else out[i, :nf[i], :].T
+        assert st[i] == 0 and np.abs(got - want).max() <= TOL_LOG
+        assert abs(float(got.mean())) <= 1e-4 and abs(float(got.std()) - 1.0) <= 1e-4
+    # also on cepstra (not a reference path, same epilogue)
+    out2, nf2, _, _ = run(FP().mfcc(16000, n_mfcc=13, n_delta=2, znorm=True), clips[:1], dev)
+    w = oracle.mfcc_with_deltas_ref(clips[0], 16000, n_mfcc=13, n_delta=2)
+    assert np.abs(out2[0, :, :nf2[0]] - (w - w.mean()) / w.std()).max() <= TOL_LOG
+
+
 def test_standalone_delta_matches_oracle(dev):
     import audioanalysisdetector_b200 as aad
     x = np.random.default_rng(5).standard_normal((3, 7, 50)).astype(np.float32)

@@ -130,3 +130,12 @@ def test_f32_chain_vs_f64_truth_within_tolerance():
     assert np.abs(a - b).max() <= 1e-3
     a, b = LR.mfcc(y, 16000, dtype="ref"), LR.mfcc(y, 16000, dtype="f64")
     assert np.abs(a - b).max() <= 1e-3
+
+
+def test_compute_melspec_ref_is_standardised():
+    """ASV_dataset.ipynb:1151: the z-normalised variant has zero mean / unit population std."""
+    import oracle
+    from helpers import noise
+    z = oracle.compute_melspec_ref(noise(3, 20000), 16000)
+    assert z.shape == (128, 1 + 20000 // 512) and z.dtype == np.float32
+    assert abs(float(z.mean())) < 1e-5 and abs(float(z.std()) - 1) < 1e-5
