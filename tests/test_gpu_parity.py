@@ -312,6 +312,63 @@ def test_znorm_compute_melspec_variant(dev, layout):
     assert np.abs(out2[0, :, :nf2[0]] - (w - w.mean()) / w.std()).max() <= TOL_LOG
 
 
+def test_seeded_parameter_sweep_matches_oracle(dev):
+    """Random (seeded) plans across every kernel variant: n_fft, hop, filters, cepstra, deltas, layout,
+    log-mel / MFCC / LFCC, float / int16 input, ragged lengths including very short clips."""
+    L = LIB()
+    rng = np.random.default_rng(2026)
+    for trial in range(14):
+        n_fft = int(rng.choice([256, 512, 1024, 2048]))
+        sr = int(rng.choice([8000, 16000, 22050, 48000]))
+        lens = [int(rng.integers(n_fft // 2, 6 * n_fft)) for _ in range(3)] + [int(rng.integers(1, n_fft // 2))]
+        clips = [noise(1000 + 10 * trial + i, n) if i % 2 == 0 else speech(1000 + 10 * trial + i, n, sr)
+                 for i, n in enumerate(lens)]
+        kind = trial % 3
+        if kind == 0:      # log-mel
+            hop = int(rng.integers(n_fft // 8, n_fft // 2 + 1))
+            n_mels = int(rng.integers(8, min(129, n_fft // 4)))
+            out, nf, st, _ = run(FP().logmel(sr, n_mels=n_mels, n_fft=n_fft, hop_length=hop), clips, dev)
+            for i, c in enumerate(clips):
+                want = LR.logmel_db(c, sr, n_mels=n_mels, n_fft=n_fft, hop_length=hop)
+                assert st[i] == 0 and nf[i] == want.shape[1], (trial, i)
+                assert np.abs(out[i, :, :nf[i]] - want).max() <= TOL_LOG, (trial, i, n_fft, hop, n_mels, sr)
+        elif kind == 1:    # MFCC + deltas
+            hop = int(rng.integers(n_fft // 8, n_fft // 2 + 1))
+            n_mels = int(rng.integers(16, min(129, n_fft // 4)))
+            n_mfcc = int(rng.integers(1, n_mels + 1))
+            n_delta = int(rng.integers(0, 3))
+            layout = L.LAYOUT_TC if trial % 2 else L.LAYOUT_CT
+            out, nf, st, _ = run(FP().mfcc(sr, n_mfcc=n_mfcc, n_mels=n_mels, n_fft=n_fft, hop_length=hop,
+                                           n_delta=n_delta, layout=layout), clips, dev)
+            for i, c in enumerate(clips):
+                T = 1 + len(c) // hop
+                if n_delta and T < 9:
+                    assert st[i] == 3, (trial, i)
+                    continue
+                want = oracle.mfcc_with_deltas_ref(c, sr, n_mfcc=n_mfcc, n_fft=n_fft, hop_length=hop, n_mels=n_mels,
+                                                   n_delta=n_delta)
+                got = out[i, :nf[i], :].T if layout == L.LAYOUT_TC else out[i, :, :nf[i]]
+                assert st[i] == 0 and nf[i] == want.shape[1], (trial, i)
+                assert np.abs(got - want).max() <= TOL_LOG, (trial, i, n_fft, hop, n_mels, n_mfcc, n_delta, sr)
+        else:              # LFCC on int16 PCM
+            win = int(rng.integers(n_fft // 2, n_fft + 1))
+            hop = int(rng.integers(win // 4, win // 2 + 1))
+            nfilts = int(rng.integers(8, 41))
+            n_ceps = int(rng.integers(1, nfilts + 1))
+            pcm = [SR.quantize_int16(c) for c in clips]
+            p = FP().lfcc(sr, n_ceps=n_ceps, nfilts=nfilts, nfft=n_fft, win_len=win / sr + 1e-9, win_hop=hop / sr + 1e-9)
+            assert p.win_length == win and p.hop_length == hop
+            out, nf, st, _ = run(p, pcm, dev, dtype=np.int16)
+            for i, c in enumerate(pcm):
+                if len(c) < win:
+                    assert st[i] == 2, (trial, i)
+                    continue
+                want = SR.lfcc(sig=c, fs=sr, num_ceps=n_ceps, nfilts=nfilts, nfft=n_fft, win_len=win / sr + 1e-9,
+                               win_hop=hop / sr + 1e-9)
+                assert st[i] == 0 and nf[i] == want.shape[0], (trial, i)
+                assert np.abs(out[i, :nf[i], :] - want).max() <= TOL_LOG, (trial, i, n_fft, win, hop, nfilts, n_ceps, sr)
+
+
 def test_standalone_delta_matches_oracle(dev):
     import audioanalysisdetector_b200 as aad
     x = np.random.default_rng(5).standard_normal((3, 7, 50)).astype(np.float32)
