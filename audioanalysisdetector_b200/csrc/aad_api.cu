@@ -28,10 +28,9 @@ struct aad_plan {
   int warps = 0, ctas = 0;
   size_t k1_smem = 0;
   int n_w4 = 0, n_hdr = 0;
-  int kc = 10;
+  int n_ksteps = 0, n_tiles = 0, cep_nt = 1;  // K2: DCT as a GEMM (K steps of 8 filters, N tiles of 8 coefficients)
   int c_feat = 0;     // rows before deltas
   int c_out = 0;
-  int ncp = 0;
   bool need_ws_E = false;     // filterbank energies go to workspace (cepstra / layout / mean follows)
   bool need_ws_feat = false;  // features go to workspace (time_mean follows)
   // host copies (introspection)
@@ -45,7 +44,8 @@ struct aad_plan {
   int2* d_filt_hdr = nullptr;
   float4* d_filt_w = nullptr;
   int4* d_warp_prog = nullptr;
-  float* d_dct_t = nullptr;
+  float4* d_dct_frag = nullptr;
+  float* d_dct_colsum = nullptr;
   // optional per-kernel timing (bench roofline): events recorded around each launch
   bool profile = false;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -277,22 +277,26 @@ static void stft_cfg(int L, int* warps, int* ctas, size_t* fixed, int* fbu) {
 }
 
 typedef void (*cep_kernel_t)(const CepArgs);
-static cep_kernel_t pick_cep(int kc) {
-  switch (kc) {
+static cep_kernel_t pick_cep(int nt) {  // coefficient n-tiles per pass
+  switch (nt) {
+    case 1: return k_cepstra<1>;
     case 2: return k_cepstra<2>;
+    case 3: return k_cepstra<3>;
     case 4: return k_cepstra<4>;
+    case 5: return k_cepstra<5>;
     case 6: return k_cepstra<6>;
-    case 8: return k_cepstra<8>;
-    case 10: return k_cepstra<10>;
-    default: return k_cepstra<12>;
+    case 7: return k_cepstra<7>;
+    default: return k_cepstra<8>;
   }
 }
 
 static size_t cep_smem_bytes(const aad_plan* pl) {
-  const int kcp = (pl->kc + 3) & ~3;
-  size_t f = 4 + (size_t)pl->p.n_filt * CEP_TS + 8 * CEP_TS;
-  if (pl->p.n_ceps > 0)
-    f += (size_t)(pl->ncp / pl->kc) * (pl->p.n_filt + 1) * kcp + (size_t)pl->p.n_ceps * CEP_TS;
+  const int kf = pl->p.n_ceps > 0 ? 8 * pl->n_ksteps : pl->p.n_filt;
+  size_t f = 4 + (size_t)kf * CEP_SE + 8 * CEP_TS;
+  if (pl->p.n_ceps > 0) {
+    f += (size_t)pl->n_ksteps * pl->n_tiles * 32 * 4 + (size_t)pl->n_tiles * 8;
+    if (pl->n_tiles > CEP_MAXNT) f += (size_t)pl->p.n_ceps * CEP_SC;  // no aliasing with several passes
+  }
   return f * 4;
 }
 
@@ -378,7 +382,8 @@ int aad_plan_destroy(aad_plan* pl) {
   cudaFree(pl->d_filt_hdr);
   cudaFree(pl->d_filt_w);
   cudaFree(pl->d_warp_prog);
-  cudaFree(pl->d_dct_t);
+  cudaFree(pl->d_dct_frag);
+  cudaFree(pl->d_dct_colsum);
   for (auto& e : pl->ev)
     if (e) cudaEventDestroy(e);
   if (pl->h_stage) cudaFreeHost(pl->h_stage);
@@ -427,9 +432,9 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   stft_cfg(pl->L, &pl->warps, &pl->ctas, &k1_fixed, &fbu);
   pl->c_feat = p.n_ceps > 0 ? p.n_ceps : p.n_filt;
   pl->c_out = pl->c_feat * (1 + p.n_delta);
-  // K2: four thread groups split the coefficient chunks of kc (even, <= 12) coefficients each
-  pl->kc = std::min(12, std::max(2, ((p.n_ceps + 3) / 4 + 1) & ~1));
-  pl->ncp = p.n_ceps > 0 ? (p.n_ceps + pl->kc - 1) / pl->kc * pl->kc : 0;
+  pl->n_ksteps = (p.n_filt + 7) / 8;
+  pl->n_tiles = (p.n_ceps + 7) / 8;
+  pl->cep_nt = std::max(1, std::min(pl->n_tiles, CEP_MAXNT));
   const bool direct = (p.n_ceps == 0 && p.n_delta == 0 && p.layout == AAD_LAYOUT_CT && !p.time_mean);
   pl->need_ws_E = !direct;
   pl->need_ws_feat = p.time_mean != 0;
@@ -538,26 +543,44 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   pl->n_hdr = (int)fhdr.size();
   pl->n_w4 = (int)fw4.size();
   pl->k1_smem = k1_fixed + (size_t)((2 * fhdr.size() + 3) & ~3) * 4 + fw4.size() * sizeof(float4);
-  // DCT-II ortho (scipy.fftpack.dct type 2 norm='ortho'), first n_ceps rows.  Device layout for K2:
-  // [chunk][m = 0..n_filt][kcp] with chunk = kc consecutive coefficients padded to kcp (16-byte rows);
-  // row n_filt of every chunk holds the column sums.
-  std::vector<float> dct_t;
+  // DCT-II ortho (scipy.fftpack.dct type 2 norm='ortho'), first n_ceps rows.  Device layout for K2: the
+  // transposed table D^T[filter][coef] as mma.m16n8k8 B fragments, split into tf32 hi + lo parts:
+  // [k-step][n-tile][lane = 4 g + t] = {b0 hi, b1 hi, b0 lo, b1 lo}, b0 = D^T[8 ks + t][8 nt + g],
+  // b1 = D^T[8 ks + t + 4][8 nt + g]; plus the column sums (per-frame mean re-addition).
+  std::vector<float4> dct_frag;
+  std::vector<float> dct_colsum;
   if (p.n_ceps > 0) {
-    const int Mf = p.n_filt, kc = pl->kc, kcp = (kc + 3) & ~3, n_chunks = pl->ncp / kc;
+    const int Mf = p.n_filt;
     pl->h_dct.assign((size_t)p.n_ceps * Mf, 0.f);
-    dct_t.assign((size_t)n_chunks * (Mf + 1) * kcp, 0.f);
+    dct_colsum.assign((size_t)pl->n_tiles * 8, 0.f);
     for (int k = 0; k < p.n_ceps; ++k) {
       const double fk = k == 0 ? std::sqrt(1.0 / (4.0 * Mf)) : std::sqrt(1.0 / (2.0 * Mf));
-      const size_t base = (size_t)(k / kc) * (Mf + 1) * kcp + (k % kc);
       double colsum = 0.0;
       for (int m = 0; m < Mf; ++m) {
         float v = (float)(2.0 * fk * std::cos(kPiD * k * (2.0 * m + 1.0) / (2.0 * Mf)));
         pl->h_dct[(size_t)k * Mf + m] = v;
-        dct_t[base + (size_t)m * kcp] = v;
         colsum += (double)v;
       }
-      dct_t[base + (size_t)Mf * kcp] = (float)colsum;  // exact re-addition of the per-frame mean
+      dct_colsum[k] = (float)colsum;  // exact re-addition of the per-frame mean
     }
+    auto dt = [&](int filt, int coef) { return filt < Mf && coef < p.n_ceps ? pl->h_dct[(size_t)coef * Mf + filt] : 0.f; };
+    auto tf32_hi = [](float x) {  // cvt.rna.tf32.f32: round to nearest (ties away) on the low 13 mantissa bits
+      uint32_t u;
+      std::memcpy(&u, &x, 4);
+      u = (u + 0x1000u) & 0xffffe000u;
+      float r;
+      std::memcpy(&r, &u, 4);
+      return r;
+    };
+    dct_frag.resize((size_t)pl->n_ksteps * pl->n_tiles * 32);
+    for (int ks = 0; ks < pl->n_ksteps; ++ks)
+      for (int nt = 0; nt < pl->n_tiles; ++nt)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int g = lane >> 2, t = lane & 3;
+          const float b0 = dt(8 * ks + t, 8 * nt + g), b1 = dt(8 * ks + t + 4, 8 * nt + g);
+          const float h0 = tf32_hi(b0), h1 = tf32_hi(b1);
+          dct_frag[((size_t)ks * pl->n_tiles + nt) * 32 + lane] = make_float4(h0, h1, b0 - h0, b1 - h1);
+        }
   }
   savgol_taps(p.n_delta > 0 ? p.delta_width : 9, pl->taps[0], pl->taps[1]);
 
@@ -576,7 +599,8 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   if (e == cudaSuccess) e = upload(&pl->d_filt_hdr, fhdr);
   if (e == cudaSuccess) e = upload(&pl->d_filt_w, fw4);
   if (e == cudaSuccess) e = upload(&pl->d_warp_prog, wprog);
-  if (e == cudaSuccess) e = upload(&pl->d_dct_t, dct_t);
+  if (e == cudaSuccess) e = upload(&pl->d_dct_frag, dct_frag);
+  if (e == cudaSuccess) e = upload(&pl->d_dct_colsum, dct_colsum);
   // opt in to the large dynamic shared memory of every kernel variant this plan can launch
   // (the attribute is per function, not per plan: opt in to the device maximum)
   int optin = 0;
@@ -595,7 +619,7 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
       aad_plan_destroy(pl);
       return AAD_ERR_UNSUPPORTED;
     }
-    e = cudaFuncSetAttribute((const void*)pick_cep(pl->kc), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    e = cudaFuncSetAttribute((const void*)pick_cep(pl->cep_nt), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   }
   if (e != cudaSuccess) {
     aad_plan_destroy(pl);
@@ -732,7 +756,8 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
     ca.E = d_E; ca.e_stride_b = sa.e_stride_b; ca.e_stride_f = sa.e_stride_f;
     ca.nf_eff = d_nf; ca.utt_max = d_max; ca.n_filt = p.n_filt;
     ca.log_type = p.log_type; ca.ref_type = p.ref_type; ca.top_db = p.top_db;
-    ca.n_ceps = p.n_ceps; ca.ncp = pl->ncp; ca.dct_t = pl->d_dct_t;
+    ca.n_ceps = p.n_ceps; ca.n_ksteps = pl->n_ksteps; ca.n_tiles = pl->n_tiles;
+    ca.dct_frag = pl->d_dct_frag; ca.dct_colsum = pl->d_dct_colsum;
     ca.n_delta = p.n_delta; ca.width = p.n_delta > 0 ? p.delta_width : 1;
     std::memcpy(ca.taps, pl->taps, sizeof(ca.taps));
     if (p.time_mean) {
@@ -747,7 +772,7 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
     const int gx = t_max <= CEP_TS ? 1 : (t_max + ca.tile_out - 1) / ca.tile_out;
     if ((long long)B * gx > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
     ca.tiles_per_utt = gx;
-    pick_cep(pl->kc)<<<(unsigned)((long long)B * gx), CEP_THREADS, cep_smem_bytes(pl), stream>>>(ca);
+    pick_cep(pl->cep_nt)<<<(unsigned)((long long)B * gx), CEP_THREADS, cep_smem_bytes(pl), stream>>>(ca);
     LAUNCH_CHECK("k_cepstra launch");
     if (prof) cudaEventRecord(pl->ev[3], stream);
     if (p.time_mean) {

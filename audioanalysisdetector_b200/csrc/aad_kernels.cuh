@@ -4,7 +4,7 @@
 //   k_stft_fb   : fused framing + window + real FFT + |X|^2 + banded filterbank + log
 //                 (persistent; one warp-iteration = 32/L frames, FFT entirely in registers,
 //                 packed FP32: FFMA2 / FADD2 / FMUL2 on float2 = one complex number)
-//   k_cepstra   : dB reference/floor + DCT-II + delta/delta-delta stencil + layout
+//   k_cepstra   : dB reference/floor + DCT-II (3xTF32 mma.sync) + delta/delta-delta stencil + layout
 //   k_db_finalize, k_time_mean, k_delta : small epilogues
 //
 // Replaces (reference call chain): librosa.stft / np.abs()**2 / filters.mel einsum /
@@ -823,8 +823,11 @@ k_stft_fb(const StftArgs a) {
 // K2: dB reference / floor + DCT-II + deltas + layout
 // ---------------------------------------------------------------------------
 constexpr int CEP_TS = 128;       // frames per tile held in smem
+constexpr int CEP_SE = CEP_TS + 8;  // row stride of the energy tile: A fragments (filter t, frame g) hit 32 banks
+constexpr int CEP_SC = CEP_TS + 4;  // row stride of the coefficient tile: C fragments (coef 2t, frame g) hit 32 banks
 constexpr int CEP_MAXW = 9;
-constexpr int CEP_THREADS = 256;  // 8 warps: 4 coefficient groups x 64 frame pairs
+constexpr int CEP_THREADS = 256;  // 8 warps = 8 m-tiles of 16 frames
+constexpr int CEP_MAXNT = 8;      // coefficient n-tiles (of 8) whose accumulators a warp holds at once
 
 struct CepArgs {
   const float* E;         // [B][n_filt][e_stride_f]
@@ -836,8 +839,9 @@ struct CepArgs {
   int log_type, ref_type;
   float top_db;           // < 0: none
   int n_ceps;             // 0: identity
-  int ncp;                // padded n_ceps (multiple of the chunk size KC)
-  const float* dct_t;     // [n_filt + 1][ncp]  (transposed DCT matrix, zero padded; last row = column sums)
+  int n_ksteps, n_tiles;  // DCT as GEMM: K = n_filt in steps of 8, N = n_ceps in tiles of 8
+  const float4* dct_frag; // [n_ksteps][n_tiles][32] B fragments {b0 hi, b1 hi, b0 lo, b1 lo} (tf32 split)
+  const float* dct_colsum; // [n_tiles * 8] column sums of the table (mean re-addition)
   int n_delta, width;
   float taps[2][CEP_MAXW];
   float* out;
@@ -847,17 +851,25 @@ struct CepArgs {
   int tiles_per_utt;      // grid.x = B * tiles_per_utt
 };
 
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 // One CTA = (utterance, tile of <= 128 frames).  Three phases:
 //  load : E tile -> sE[m][t] with the dB reference / floor applied (float4 along t, warp w owns the
 //         filterbank rows m = w (mod 8)), per-warp partial column sums for the per-frame mean
-//  DCT  : thread (p, grp) owns the frame PAIR (2p, 2p+1) and the coefficient chunks grp, grp+4, ..:
-//         acc[k] (float2 = the two frames) += (e - mean) * D[m][k] as one FFMA2 per (m, k) with the
-//         table value broadcast to both halves; the mean is added back through the column sums
+//  DCT  : C[frame][coef] = (E - mean)[frame][filter] . D^T[filter][coef] as a warp-level GEMM on the
+//         tensor cores, mma.sync.m16n8k8 TF32 with the 3-term split (hi*hi + lo*hi + hi*lo, fp32
+//         accumulate: ~2^-21 relative per product, inside the 1e-3 tolerance by three orders).  Warp w
+//         owns the 16 frames [16w, 16w+16) and all coefficient tiles; the table comes pre-split and
+//         pre-arranged as B fragments, the energies are centred (per-frame mean, re-added through the
+//         column sums) and split in registers.  The result overwrites the energy tile.
 //  out  : thread = frame column; static rows and the delta / delta-delta stencils as one FFMA2 per
 //         tap ((d1, d2) accumulated together), coalesced stores along t (CT) or along c (TC)
-template <int KC>
+template <int NT>
 __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
-  constexpr int KCP = (KC + 3) & ~3;  // chunk stride in the table: 16-byte aligned rows
   extern __shared__ __align__(16) float smem[];
   // grid.x = B * tiles_per_utt, utterance-major: consecutive CTAs read neighbouring tiles of one utterance
   const int b = blockIdx.x / a.tiles_per_utt, tile = blockIdx.x - b * a.tiles_per_utt;
@@ -883,14 +895,17 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
   const int nload = hi - lo;  // <= CEP_TS by construction
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = a.n_ceps > 0 ? a.n_ceps : a.n_filt;
-  const int n_chunks = a.ncp / KC;
+  const int kf = a.n_ceps > 0 ? 8 * a.n_ksteps : a.n_filt;  // energy rows incl. zero padding of K
+  const bool alias = a.n_tiles <= CEP_MAXNT;                 // coefficients overwrite the energy tile
 
   // 4 floats of slack in front: the fixed 9-tap stencil of a narrower delta window may read up to 3
   // columns before a row (with a zero tap)
-  float* sE = smem + 4;                               // [n_filt][CEP_TS]
-  float* sPart = sE + a.n_filt * CEP_TS;              // [8][CEP_TS] per-warp partial column sums
-  float* sD = sPart + 8 * CEP_TS;                     // [n_chunks][n_filt + 1][KCP] (last row: column sums)
-  float* sC = a.n_ceps > 0 ? sD + n_chunks * (a.n_filt + 1) * KCP : sE;  // [C][CEP_TS]
+  float* sE = smem + 4;                               // [kf][CEP_SE]
+  float* sPart = sE + kf * CEP_SE;                    // [8][CEP_TS] per-warp partial column sums
+  float4* sB = reinterpret_cast<float4*>(sPart + 8 * CEP_TS);  // [n_ksteps][n_tiles][32]
+  float* sCs = reinterpret_cast<float*>(sB + a.n_ksteps * a.n_tiles * 32);  // [n_tiles * 8]
+  float* sC = a.n_ceps == 0 ? sE : (alias ? sE : sCs + a.n_tiles * 8);      // [C][sc_stride]
+  const int sc_stride = a.n_ceps == 0 ? CEP_SE : CEP_SC;
 
   // reference / floor (librosa.power_to_db):  ls = E - ref ; ls = max(ls, max(ls) - top_db)
   float ref = 0.f, floorv = -INFINITY;
@@ -918,7 +933,7 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           float4 r = make_float4(xf(v[u].x, t4), xf(v[u].y, t4 + 1), xf(v[u].z, t4 + 2), xf(v[u].w, t4 + 3));
-          *reinterpret_cast<float4*>(sE + (m + 8 * u) * CEP_TS + t4) = r;
+          *reinterpret_cast<float4*>(sE + (m + 8 * u) * CEP_SE + t4) = r;
           ps.x += r.x; ps.y += r.y; ps.z += r.z; ps.w += r.w;
         }
       }
@@ -926,7 +941,7 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
         float4 v = t4 < nload ? __ldg(reinterpret_cast<const float4*>(Eb + (long long)m * a.e_stride_f + t4))
                               : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 r = make_float4(xf(v.x, t4), xf(v.y, t4 + 1), xf(v.z, t4 + 2), xf(v.w, t4 + 3));
-        *reinterpret_cast<float4*>(sE + m * CEP_TS + t4) = r;
+        *reinterpret_cast<float4*>(sE + m * CEP_SE + t4) = r;
         ps.x += r.x; ps.y += r.y; ps.z += r.z; ps.w += r.w;
       }
     } else {
@@ -937,56 +952,80 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
           const int t = t4 + u;
           r[u] = t < nload ? fmaxf(__ldg(Eb + (long long)m * a.e_stride_f + t) - ref, floorv) : 0.f;
         }
-        *reinterpret_cast<float4*>(sE + m * CEP_TS + t4) = make_float4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<float4*>(sE + m * CEP_SE + t4) = make_float4(r[0], r[1], r[2], r[3]);
         ps.x += r[0]; ps.y += r[1]; ps.z += r[2]; ps.w += r[3];
       }
     }
+    for (int m = a.n_filt + warp; m < kf; m += 8)  // zero rows that pad K to a multiple of 8
+      *reinterpret_cast<float4*>(sE + m * CEP_SE + t4) = make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(sPart + warp * CEP_TS + t4) = ps;
     if (a.n_ceps > 0) {
-      const int nd = n_chunks * (a.n_filt + 1) * KCP;  // multiple of 4 floats, cudaMalloc-aligned source
-      for (int i = tid * 4; i < nd; i += CEP_THREADS * 4)
-        *reinterpret_cast<float4*>(sD + i) = __ldg(reinterpret_cast<const float4*>(a.dct_t + i));
+      const int nb = a.n_ksteps * a.n_tiles * 32;
+      for (int i = tid; i < nb; i += CEP_THREADS) sB[i] = __ldg(a.dct_frag + i);
+      for (int i = tid; i < a.n_tiles * 8; i += CEP_THREADS) sCs[i] = __ldg(a.dct_colsum + i);
     }
   }
   __syncthreads();
 
-  // ---- DCT ----------------------------------------------------------------------------
+  // ---- DCT on the tensor cores ------------------------------------------------------------
   if (a.n_ceps > 0) {
-    // The DCT is linear: accumulate on the per-frame-centred energies (small partial sums,
-    // so float32 accumulation of ~100 same-sign dB values loses nothing) and add the mean
-    // back through the table's column sums (row n_filt of each chunk).
-    const int p = tid & 63, grp = tid >> 6;
-    const float2* sE2 = reinterpret_cast<const float2*>(sE) + p;
-    float2 mean2 = make_float2(0.f, 0.f);
+    const int g = lane >> 2, t = lane & 3;
+    const int f0 = 16 * warp + g, f1 = f0 + 8;  // the two frame rows of this thread's fragments
+    float mean0 = 0.f, mean1 = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) mean2 = __fadd2_rn(mean2, *reinterpret_cast<const float2*>(sPart + w * CEP_TS + 2 * p));
+    for (int w = 0; w < 8; ++w) {
+      mean0 += sPart[w * CEP_TS + f0];
+      mean1 += sPart[w * CEP_TS + f1];
+    }
     const float inv = 1.0f / (float)a.n_filt;
-    mean2 = __fmul2_rn(mean2, make_float2(inv, inv));
-    const float2 nmean2 = make_float2(-mean2.x, -mean2.y);
-    for (int ch = grp; ch < n_chunks; ch += 4) {
-      float2 acc[KC];
+    mean0 *= inv;
+    mean1 *= inv;
+    const float* ea = sE + t * CEP_SE + f0;  // A fragment (row g / g+8 = frame, col t / t+4 = filter)
+    for (int nt0 = 0; nt0 < a.n_tiles; nt0 += NT) {
+      float acc[NT][4];
 #pragma unroll
-      for (int i = 0; i < KC; ++i) acc[i] = make_float2(0.f, 0.f);
-      const float4* dch = reinterpret_cast<const float4*>(sD + ch * (a.n_filt + 1) * KCP);
-#pragma unroll 4
-      for (int m = 0; m < a.n_filt; ++m) {
-        const float2 e = __fadd2_rn(sE2[m * (CEP_TS / 2)], nmean2);
-        float d[KCP];
+      for (int n = 0; n < NT; ++n)
 #pragma unroll
-        for (int i = 0; i < KCP / 4; ++i) {
-          const float4 q = dch[m * (KCP / 4) + i];
-          d[4 * i] = q.x; d[4 * i + 1] = q.y; d[4 * i + 2] = q.z; d[4 * i + 3] = q.w;
+        for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+      const float4* bp = sB + nt0 * 32 + lane;
+#pragma unroll 2
+      for (int ks = 0; ks < a.n_ksteps; ++ks) {
+        const float* e = ea + ks * 8 * CEP_SE;
+        // centred energies (small magnitudes: the tf32 split and the fp32 accumulation lose nothing)
+        const float av[4] = {e[0] - mean0, e[8] - mean1, e[4 * CEP_SE] - mean0, e[4 * CEP_SE + 8] - mean1};
+        unsigned ahi[4], alo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ahi[i]) : "f"(av[i]));
+          alo[i] = __float_as_uint(av[i] - __uint_as_float(ahi[i]));
         }
 #pragma unroll
-        for (int i = 0; i < KC; ++i) acc[i] = __ffma2_rn(e, make_float2(d[i], d[i]), acc[i]);
+        for (int n = 0; n < NT; ++n) {
+          if (nt0 + n < a.n_tiles) {
+            const float4 q = bp[(ks * a.n_tiles + n) * 32];
+            mma_tf32(acc[n], ahi, __float_as_uint(q.x), __float_as_uint(q.y));
+            mma_tf32(acc[n], alo, __float_as_uint(q.x), __float_as_uint(q.y));
+            mma_tf32(acc[n], ahi, __float_as_uint(q.z), __float_as_uint(q.w));
+          }
+        }
       }
-      const float* colsum = reinterpret_cast<const float*>(dch) + a.n_filt * KCP;
+      if (alias) __syncthreads();  // single pass (n_tiles <= NT): every warp is done reading the energies
+      // C fragment: rows g / g+8 = frames f0 / f1, cols 2t, 2t+1 = coefficients
 #pragma unroll
-      for (int i = 0; i < KC; ++i)
-        if (ch * KC + i < a.n_ceps) {
-          const float cs = colsum[i];
-          *reinterpret_cast<float2*>(sC + (ch * KC + i) * CEP_TS + 2 * p) = __ffma2_rn(mean2, make_float2(cs, cs), acc[i]);
+      for (int n = 0; n < NT; ++n) {
+        const int c = (nt0 + n) * 8 + 2 * t;
+        if (nt0 + n < a.n_tiles) {
+          const float cs0 = sCs[c], cs1 = sCs[c + 1];
+          if (c < a.n_ceps) {
+            sC[c * CEP_SC + f0] = __fmaf_rn(mean0, cs0, acc[n][0]);
+            sC[c * CEP_SC + f1] = __fmaf_rn(mean1, cs0, acc[n][2]);
+          }
+          if (c + 1 < a.n_ceps) {
+            sC[(c + 1) * CEP_SC + f0] = __fmaf_rn(mean0, cs1, acc[n][1]);
+            sC[(c + 1) * CEP_SC + f1] = __fmaf_rn(mean1, cs1, acc[n][3]);
+          }
         }
+      }
     }
     __syncthreads();
   }
@@ -1005,8 +1044,8 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
       const int src = i - (CEP_MAXW / 2) + h;
       tp[i] = (src >= 0 && src < a.width) ? make_float2(a.taps[0][src], a.taps[1][src]) : make_float2(0.f, 0.f);
     }
-    const float* row = sC + half * CEP_TS;
-    for (int k = half; k < C; k += 2, row += 2 * CEP_TS, ob += cstep) {
+    const float* row = sC + half * sc_stride;
+    for (int k = half; k < C; k += 2, row += 2 * sc_stride, ob += cstep) {
       ob[0] = row[col];
       if (a.n_delta > 0) {
         const float* rc = row + te - CEP_MAXW / 2;
