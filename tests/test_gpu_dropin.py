@@ -4,6 +4,7 @@ import wave
 
 import numpy as np
 import pytest
+import torch
 
 import oracle
 from helpers import noise, speech
@@ -107,3 +108,27 @@ def test_extract_features_dispatcher(files, tmp_path):
     y, sr = cache[rows[0]["filepath"]]
     want = oracle.extract_mfcc_ref(y, sr, chunk_start=0.0, chunk_end=2.0, mean=True)
     assert df2["mfcc"].iloc[0].shape == (13,) and np.abs(df2["mfcc"].iloc[0] - want).max() <= 1e-3
+
+
+def test_features_drive_the_reference_consumer_to_the_same_scores():
+    """the path drops in ahead of cnn_bilstm_hybrid.AudioDeepfakeDetector.  Features
+    stay on the device in the (B, F, 63) layout the model consumes; scores must equal those the REAL
+    reference model gave on the oracle's features (tests/golden/consumer.npz)."""
+    from audioanalysisdetector_b200 import Frontend, FrontendParams
+    from oracle import consumer_ref
+    from test_oracle_consumer import consumer_clip, load_fixture
+    g, weights = load_fixture()
+    dev = torch.device("cuda:0")
+    wav = torch.from_numpy(np.stack([consumer_clip(int(s)) for s in g["seeds"]])).to(dev)
+    fe = Frontend(FrontendParams.mfcc(16000, n_mfcc=13), dev)
+    feats, nf, st = fe(wav)
+    assert feats.shape == (8, 13, 63) and int(st.sum()) == 0 and int(nf.min()) == 63
+    assert float((feats.cpu() - torch.from_numpy(g["features"])).abs().max()) <= 1e-3
+    with torch.no_grad():
+        scores = consumer_ref.forward(weights, feats)          # no host round trip, no transpose
+    assert scores.is_cuda
+    np.testing.assert_allclose(scores.cpu().numpy(), g["scores"], rtol=0, atol=2e-5)
+    # the comparison has teeth: shuffled features move the scores by far more than the tolerance
+    with torch.no_grad():
+        wrong = consumer_ref.forward(weights, feats.flip(0)).cpu().numpy()
+    assert np.abs(wrong - g["scores"]).max() > 2e-4
