@@ -241,11 +241,14 @@ struct StftCfg {
 #endif
   static constexpr int CTAS = L == 32 ? 1 : (L == 16 ? 2 : 4);
   // shared memory carve-up, in floats (the filterbank program follows at OFF_PROG)
+  // the window / twiddle tables live in tensor memory (or are generated) and take no shared memory then
+  static constexpr bool SMEM_WIN_TW1 = !AAD_TMEM_TABLES;
+  static constexpr bool SMEM_TWP = !(TmemCfg<CTAS>::TWP || (AAD_TWPGEN && Q <= 4));
   static constexpr int OFF_P = 0;
   static constexpr int OFF_WIN = TILE * SP;
-  static constexpr int OFF_TW1 = OFF_WIN + N;
-  static constexpr int OFF_TWP = OFF_TW1 + 2 * 32 * L;
-  static constexpr int OFF_META = OFF_TWP + 2 * (M / 2);      // 2 x {b[TILE], t[TILE]} (double buffered)
+  static constexpr int OFF_TW1 = OFF_WIN + (SMEM_WIN_TW1 ? N : 0);
+  static constexpr int OFF_TWP = OFF_TW1 + (SMEM_WIN_TW1 ? 2 * 32 * L : 0);
+  static constexpr int OFF_META = OFF_TWP + (SMEM_TWP ? 2 * (M / 2) : 0);  // 2 x {b[TILE], t[TILE]} (double buffered)
   static constexpr int OFF_TMEM = OFF_META + 4 * TILE;        // TMEM base address written by tcgen05.alloc
   static constexpr int OFF_PROG = OFF_TMEM + 4;               // segment headers + tap weights follow
   static constexpr size_t FIXED_BYTES = size_t(OFF_PROG) * 4;
@@ -363,9 +366,12 @@ k_stft_fb(const StftArgs a) {
   const int g = lane / L, j = lane % L;  // frame-in-iteration, lane within the frame's group
   const int partner = g * L + ((L - j) & (L - 1));
 
-  for (int i = tid; i < N; i += nthr) sWin[i] = a.window[i];
-  for (int i = tid; i < 32 * L; i += nthr) sTw1[i] = a.tw1[i];
-  for (int i = tid; i < M / 2; i += nthr) sTwp[i] = a.twp[i];
+  if constexpr (C::SMEM_WIN_TW1) {
+    for (int i = tid; i < N; i += nthr) sWin[i] = a.window[i];
+    for (int i = tid; i < 32 * L; i += nthr) sTw1[i] = a.tw1[i];
+  }
+  if constexpr (C::SMEM_TWP)
+    for (int i = tid; i < M / 2; i += nthr) sTwp[i] = a.twp[i];
   for (int i = tid; i < a.n_hdr; i += nthr) sHdr[i] = a.filt_hdr[i];
   for (int i = tid; i < a.n_w4; i += nthr) sW4[i] = a.filt_w[i];
 #if AAD_TMEM_TABLES
