@@ -96,3 +96,28 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_integration_md_struct_matches_binding():
+    """The ctypes stub shown to the reference's maintainers must mirror the real aad_params."""
+    import os
+    import re
+    from audioanalysisdetector_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = text[text.index("class AadParams(C.Structure)"):text.index("_aad.aad_params_default.argtypes")]
+    doc_fields = re.findall(r'\("(\w+)", C\.(?:c_\w+|POINTER\(C\.c_float\))\)', block)
+    assert doc_fields == [name for name, _ in _lib.AadParams._fields_]
+    header = open(os.path.join(root, "include", "aad.h")).read()
+    struct = header[header.index("typedef struct aad_params {"):header.index("} aad_params;")]
+    hdr_fields = re.findall(r"^\s*(?:const\s+)?(?:int32_t|float)\s*\*?\s*(\w+);", struct, flags=re.M)
+    assert hdr_fields == doc_fields
+
+
+def test_bind_to_gpu_numa_is_harmless_without_nvml():
+    import os
+    from audioanalysisdetector_b200 import sharding
+    before = os.sched_getaffinity(0)
+    cpus = sharding.bind_to_gpu_numa(0)
+    assert cpus is None or set(cpus) <= set(before)
+    os.sched_setaffinity(0, before)
