@@ -453,8 +453,8 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
     pl->h_window[win_off + n] = (float)w[n];
     win_half[win_off + n] = 0.5f * (float)w[n];
   }
-  std::vector<float2> tw1((size_t)33 * L), twp(M / 2);
-  for (int ka = 0; ka <= 32; ++ka)  // row 32: W_M^(32 b) = W_L^b, the rotation of the kA <-> 32 - kA symmetry
+  std::vector<float2> tw1((size_t)32 * L), twp(M / 2);
+  for (int ka = 0; ka < 32; ++ka)
     for (int b = 0; b < L; ++b) {
       double ang = -2.0 * kPiD * (double)((long long)b * ka % M) / M;
       tw1[(size_t)ka * L + b] = make_float2((float)std::cos(ang), (float)std::sin(ang));

@@ -103,13 +103,6 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 w) {
   return __ffma2_rn(a, make_float2(w.x, w.x), t);
 }
 
-// complex product a * conj(w)  (2 packed instructions)
-__device__ __forceinline__ float2 cmul_conj(float2 a, float2 w) {
-  // a*conj(w) = w.x * (a.x, a.y) + w.y * (a.y, -a.x)
-  const float2 t = __fmul2_rn(make_float2(a.y, -a.x), make_float2(w.y, w.y));
-  return __ffma2_rn(a, make_float2(w.x, w.x), t);
-}
-
 // complex product a * exp(-2*pi*i*J/M) with a compile-time twiddle (2 packed instructions, immediates)
 template <int J, int M>
 __device__ __forceinline__ float2 cmul_const(float2 a) {

@@ -30,12 +30,9 @@ constexpr int ABL = AAD_ABLATE;
 // Shared-memory traffic is the binding resource of k_stft_fb (ncu: l1tex data pipe ~72 %), the FMA
 // pipe has headroom.  These switches trade table loads for packed arithmetic:
 //   AAD_TWPGEN  split twiddle W_N^k = W_N^(j + L q) [per-lane register] * W_N^(32 s) [immediate]
-//   AAD_TW1SYM  pass-1 twiddles for kA > 16 from those for 32 - kA: W_M^(b kA) = W_L^b * conj(W_M^(b (32-kA)))
+// (regenerating the pass-1 twiddles for kA > 16 from their mirror images was tried and bought nothing)
 #ifndef AAD_TWPGEN
 #define AAD_TWPGEN 1
-#endif
-#ifndef AAD_TW1SYM
-#define AAD_TW1SYM 0
 #endif
 // 1 window table, 2 tw1 table, 4 transposes, 8 filterbank phase, 16 split exchange + twp table,
 // 32 power stores, 64 butterflies, 128 global sample loads, 256 log in the filterbank emit
@@ -269,7 +266,7 @@ struct StftArgs {
   int win_off, win_len;     // window support inside the n_fft buffer
   float pre_emph;
   const float* window;      // [N]   0.5 * window (zero outside support)
-  const float2* tw1;        // [33*L] exp(-2 pi i b kA / M) at [kA*L + b]; row 32: exp(-2 pi i b / L)
+  const float2* tw1;        // [32*L] exp(-2 pi i b kA / M) at [kA*L + b]
   const float2* twp;        // [M/2]  exp(-2 pi i k / N)
   // filterbank program (copied to smem), two-tap banded form: the bins split into n_filt + 1
   // segments; inside segment s bin k feeds filter s with its rising weight wr[k] and filter s - 1
@@ -427,7 +424,6 @@ k_stft_fb(const StftArgs a) {
   float2 twp_base[Q];   // W_N^(j + L q)
 #pragma unroll
   for (int q = 0; q < Q; ++q) twp_base[q] = TWPGEN ? __ldg(a.twp + j + L * q) : make_float2(0.f, 0.f);
-  const float2 tw1_rot = __ldg(a.tw1 + 32 * L + j);  // W_L^j = W_M^(32 j)
 
   // tile meta: global frame index -> (utterance, frame); computed one tile ahead by warp 0 so the
   // dependent index loads never sit on the critical path, and used to prefetch the next tile's
@@ -593,14 +589,7 @@ k_stft_fb(const StftArgs a) {
 
       // pass 1: 32-point DFT over a (stride L), then twiddle W_M^(b*kA)
       if constexpr (!(ABL & 64)) fft_dit<32, 0>(v);
-      if constexpr (AAD_TW1SYM) {
-        static_for<1, 17>([&](auto k_) {
-          constexpr int KA = decltype(k_)::value;
-          const float2 tw = sTw1[KA * L + j];
-          v[KA] = cmul(v[KA], tw);
-          if constexpr (KA < 16) v[32 - KA] = cmul(cmul_conj(v[32 - KA], tw), tw1_rot);
-        });
-      } else {
+      {
 #if AAD_TMEM_TABLES
         TmemChunk tc[2];
         tc[0].issue(tmem_row + 64);
