@@ -3,9 +3,10 @@
 //   k_prepare   : per-utterance frame counts, status, exclusive scan of frames, max init
 //   k_stft_fb   : fused framing + window + real FFT + |X|^2 + banded filterbank + log
 //                 (persistent; one warp-iteration = 32/L frames, FFT entirely in registers,
-//                 packed FP32: FFMA2 / FADD2 / FMUL2 on float2 = one complex number)
+//                 packed FP32: FFMA2 / FADD2 / FMUL2 on float2 = one complex number; window and
+//                 twiddle tables in tensor memory, read with tcgen05.ld)
 //   k_cepstra   : dB reference/floor + DCT-II (3xTF32 mma.sync) + delta/delta-delta stencil + layout
-//   k_db_finalize, k_time_mean, k_delta : small epilogues
+//   k_db_finalize, k_znorm, k_time_mean, k_delta : small epilogues
 //
 // Replaces (reference call chain): librosa.stft / np.abs()**2 / filters.mel einsum /
 // power_to_db / scipy dct inside librosa.feature.{melspectrogram,mfcc}
@@ -27,15 +28,17 @@ enum InMode { IN_F32 = 0, IN_F32_Q16 = 1, IN_I16 = 2 };
 #define AAD_ABLATE 0
 #endif
 constexpr int ABL = AAD_ABLATE;
-// Shared-memory traffic is the binding resource of k_stft_fb (ncu: l1tex data pipe ~72 %), the FMA
-// pipe has headroom.  These switches trade table loads for packed arithmetic:
-//   AAD_TWPGEN  split twiddle W_N^k = W_N^(j + L q) [per-lane register] * W_N^(32 s) [immediate]
-// (regenerating the pass-1 twiddles for kA > 16 from their mirror images was tried and bought nothing)
+// mask bits: 1 window table, 2 tw1 table (both only without AAD_TMEM_TABLES), 4 transposes, 8 filterbank
+// phase, 16 split exchange + twp table, 32 power stores, 64 butterflies, 128 global sample loads, 256 log
+// in the filterbank emit
+//
+// The shared-memory / L1 data pipe is the most loaded unit of k_stft_fb, the FMA pipe has headroom, so
+// table look-ups are kept off it: AAD_TMEM_TABLES (below) holds the lane x register tables in tensor
+// memory; on variants without TMEM room for the split twiddle, AAD_TWPGEN forms it as
+// W_N^k = W_N^(j + L q) [per-lane register] * W_N^(32 s) [immediate] instead of loading it.
 #ifndef AAD_TWPGEN
 #define AAD_TWPGEN 1
 #endif
-// 1 window table, 2 tw1 table, 4 transposes, 8 filterbank phase, 16 split exchange + twp table,
-// 32 power stores, 64 butterflies, 128 global sample loads, 256 log in the filterbank emit
 
 // ---------------------------------------------------------------------------
 // ordered-int encoding of floats (monotone), for atomicMax / redux on floats
