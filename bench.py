@@ -317,7 +317,11 @@ def run_b200(args):
         except Exception:
             traffic = None
     roofline = {
-        "bound": "fp32", "kernel": "k_stft_fb<32,f32>", "achieved": k1_tflops, "peak": fp32_peak,
+        "bound": "fp32",
+        "bound_note": "north_star: the slower of the FP32 compute peak and the HBM roofline; K1 does %.1f flop per byte, "
+                      "the ridge is %.1f, so the FP32 (CUDA-core) peak bounds it, not HBM and not the tensor pipe"
+                      % (work["flops_stft_fb"] / (4 * HOP + 4 * N_MELS), fp32_peak * 1e3 / peaks.get("hbm_gbs", 6650.0)),
+        "kernel": "k_stft_fb<32,f32>", "achieved": k1_tflops, "peak": fp32_peak,
         "unit": "TFLOP/s", "frac": k1_tflops / fp32_peak if fp32_peak else None, "traffic": traffic,
         "peak_source": "FFMA micro-benchmark measured in this run (aad_fp32_peak); nominal 148x128x2x1.965 GHz = %.1f" % fp32_nominal,
         "algorithmic_flops_per_frame": work["flops_stft_fb"], "frames_per_launch": frames,
