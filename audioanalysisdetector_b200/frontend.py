@@ -222,6 +222,17 @@ class Frontend:
             else:
                 shape = (B, t_alloc, c_out)
             out = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        else:
+            # the C ABI takes a raw pointer and one batch stride: everything else must be dense
+            if p.time_mean:
+                shape = (B, c_out)
+            elif p.layout == L.LAYOUT_CT:
+                shape = (B, c_out, t_alloc)
+            else:
+                shape = (B, t_alloc, c_out)
+            if (out.dtype != torch.float32 or out.device != self.device or tuple(out.shape) != shape
+                    or not out[0].is_contiguous() or (B > 1 and out.stride(0) < out[0].numel())):
+                raise L.AadError(f"out must be a float32 tensor of shape {shape} on {self.device} with dense rows")
         n_frames = torch.empty(B, dtype=torch.int32, device=self.device)
         status = torch.empty(B, dtype=torch.int32, device=self.device)
         ws = self._workspace(ws_bytes)

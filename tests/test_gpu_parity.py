@@ -369,6 +369,26 @@ def test_seeded_parameter_sweep_matches_oracle(dev):
                 assert np.abs(out[i, :nf[i], :] - want).max() <= TOL_LOG, (trial, i, n_fft, win, hop, nfilts, n_ceps, sr)
 
 
+def test_out_buffer_is_validated(dev):
+    from audioanalysisdetector_b200.frontend import Frontend
+    from audioanalysisdetector_b200 import AadError
+    fe = Frontend(FP().mfcc(16000, n_mfcc=13), dev)
+    wav = torch.zeros((2, 8000), device=dev)
+    t, c, _ = fe.query(2, 8000)
+    good = torch.zeros((2, c, t), device=dev)
+    fe(wav, out=good)
+    padded = torch.zeros((2, c + 3, t), device=dev)[:, :c, :]       # dense rows, larger batch stride: fine
+    fe(wav, out=padded)
+    for bad in (torch.zeros((2, c, t + 1), device=dev), torch.zeros((2, c, t), device=dev, dtype=torch.float64),
+                torch.zeros((2, c, t)), torch.zeros((2, t, c), device=dev).transpose(1, 2)):
+        with pytest.raises(AadError):
+            fe(wav, out=bad)
+    with pytest.raises(AadError):
+        fe(wav.double())
+    with pytest.raises(AadError):
+        fe(wav.cpu())
+
+
 def test_standalone_delta_matches_oracle(dev):
     import audioanalysisdetector_b200 as aad
     x = np.random.default_rng(5).standard_normal((3, 7, 50)).astype(np.float32)
