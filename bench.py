@@ -86,7 +86,7 @@ def calibrate_cpu_sample(target_cpu_s: float, cores: int) -> int:
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.004):
+    def __init__(self, index: int, period_s: float = 0.001):
         super().__init__(daemon=True)
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
