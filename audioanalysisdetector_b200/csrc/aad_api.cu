@@ -839,6 +839,30 @@ int aad_delta(const float* x, const int32_t* n_frames, int B, int C, int32_t t_s
   return AAD_OK;
 }
 
+int aad_scaler_accumulate(const float* x, int64_t n_rows, int32_t W, int64_t row_stride, double* stats,
+                          void* stream) {
+  if (!x || !stats || n_rows < 0 || W <= 0 || row_stride < W) return AAD_ERR_INVALID_ARG;
+  if (n_rows == 0) return AAD_OK;
+  const long long nblk = (n_rows + SC_ROWS - 1) / SC_ROWS;
+  if (nblk > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
+  (void)cudaGetLastError();
+  k_col_stats<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(x, n_rows, W, row_stride, stats);
+  LAUNCH_CHECK("k_col_stats launch");
+  return AAD_OK;
+}
+
+int aad_scaler_apply(float* x, int64_t n_rows, int32_t W, int64_t row_stride, const float* mean,
+                     const float* inv_scale, void* stream) {
+  if (!x || !mean || !inv_scale || n_rows < 0 || W <= 0 || row_stride < W) return AAD_ERR_INVALID_ARG;
+  if (n_rows == 0) return AAD_OK;
+  const long long nblk = (n_rows + SC_ROWS - 1) / SC_ROWS;
+  if (nblk > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
+  (void)cudaGetLastError();
+  k_col_apply<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(x, n_rows, W, row_stride, mean, inv_scale);
+  LAUNCH_CHECK("k_col_apply launch");
+  return AAD_OK;
+}
+
 int64_t aad_plan_table(const aad_plan* pl, int which, float* host_out, int64_t capacity) {
   if (!pl) return AAD_ERR_INVALID_ARG;
   const float* src = nullptr;

@@ -1158,6 +1158,48 @@ __global__ void __launch_bounds__(256) k_znorm(const ZnArgs a) {
   }
 }
 
+// Column statistics / standardisation over stacked feature rows: sklearn StandardScaler fitted on
+// np.vstack(per-utterance arrays) (ASV_dl_func.py:1113-1129, :963-973).  x is [n_rows][row_stride] with
+// W valid columns; stats = {sum[W], sumsq[W]} in double (atomicAdd per CTA; all-reduced across ranks by
+// the host before the apply pass).  Thread (col = tid % 64, lane row = tid / 64): coalesced row reads.
+constexpr int SC_ROWS = 256;  // rows per CTA
+__global__ void __launch_bounds__(256) k_col_stats(const float* x, long long n_rows, int W, long long row_stride,
+                                                   double* stats) {
+  __shared__ double red[2][4][64];
+  const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const long long r0 = (long long)blockIdx.x * SC_ROWS, r1 = min(n_rows, r0 + SC_ROWS);
+  for (int c0 = 0; c0 < W; c0 += 64) {
+    const int c = c0 + cl;
+    double s1 = 0.0, s2 = 0.0;
+    if (c < W)
+      for (long long r = r0 + rl; r < r1; r += 4) {
+        const double v = (double)__ldg(x + r * row_stride + c);
+        s1 += v;
+        s2 += v * v;
+      }
+    red[0][rl][cl] = s1;
+    red[1][rl][cl] = s2;
+    __syncthreads();
+    if (rl == 0 && c < W) {
+      atomicAdd(stats + c, red[0][0][cl] + red[0][1][cl] + red[0][2][cl] + red[0][3][cl]);
+      atomicAdd(stats + W + c, red[1][0][cl] + red[1][1][cl] + red[1][2][cl] + red[1][3][cl]);
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_col_apply(float* x, long long n_rows, int W, long long row_stride,
+                                                   const float* mean, const float* inv_scale) {
+  const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const long long r0 = (long long)blockIdx.x * SC_ROWS, r1 = min(n_rows, r0 + SC_ROWS);
+  for (int c = cl; c < W; c += 64) {
+    const float m = __ldg(mean + c), is = __ldg(inv_scale + c);
+    for (long long r = r0 + rl; r < r1; r += 4) {
+      float* p = x + r * row_stride + c;
+      *p = (*p - m) * is;
+    }
+  }
+}
+
 // mean over frames of feat[b][c][0..T_b): one warp per (b, c)
 __global__ void __launch_bounds__(128) k_time_mean(const float* feat, long long stride_b, int stride_c,
                                                    const int32_t* nf_eff, int C, float* out,

@@ -171,6 +171,18 @@ int aad_lfcc(const aad_plan* plan, const void* wav, int wav_dtype, int64_t wav_s
 int aad_delta(const float* x, const int32_t* n_frames, int B, int C, int32_t t_stride,
               int width, int order, float* out, void* stream);
 
+/* Feature standardisation, the step right after the path in the reference: sklearn StandardScaler
+ * fitted on np.vstack(per-utterance feature arrays) and applied per utterance
+ * (prepare_train_test_data ASV_dl_func.py:1113-1129, train_all_features :963-973).
+ *   aad_scaler_accumulate: stats[2*W] (device, double; zero it first) += {column sums, column sums of
+ *       squares} of x[n_rows][row_stride] (W valid columns).  Ranks all-reduce stats (SUM) before the
+ *       host turns them into mean / 1/scale (population variance; scale 1 where the variance is 0).
+ *   aad_scaler_apply: x = (x - mean[c]) * inv_scale[c] in place. */
+int aad_scaler_accumulate(const float* x, int64_t n_rows, int32_t W, int64_t row_stride, double* stats,
+                          void* stream);
+int aad_scaler_apply(float* x, int64_t n_rows, int32_t W, int64_t row_stride, const float* mean,
+                     const float* inv_scale, void* stream);
+
 /* Host-buffer convenience path (what the reference-facing Python drop-ins use for
  * host arrays): pinned-or-pageable HOST wav/lengths in, HOST out/n_frames/status back,
  * chunked H2D -> kernels -> D2H pipelined on internal streams.  Synchronous. */

@@ -132,3 +132,31 @@ def test_features_drive_the_reference_consumer_to_the_same_scores():
     with torch.no_grad():
         wrong = consumer_ref.forward(weights, feats.flip(0)).cpu().numpy()
     assert np.abs(wrong - g["scores"]).max() > 2e-4
+
+
+def test_device_standard_scaler_matches_sklearn():
+    """prepare_train_test_data (ASV_dl_func.py:1113-1129): StandardScaler.fit(np.vstack(features)) then
+    transform per utterance -- on the device, on the features the CUDA path just produced."""
+    from sklearn.preprocessing import StandardScaler
+    from audioanalysisdetector_b200 import DeviceStandardScaler, Frontend, FrontendParams
+    dev = torch.device("cuda:0")
+    clips = np.stack([noise(60 + i, 32000) if i % 2 else speech(60 + i, 32000) for i in range(24)])
+    fe = Frontend(FrontendParams.logmel(16000, n_mels=64), dev)
+    feats, nf, st = fe(torch.from_numpy(clips).to(dev))                    # (24, 64, 63)
+    assert int(st.sum()) == 0 and int(nf.min()) == 63
+    host = feats.cpu().numpy()
+    ref = StandardScaler().fit(np.vstack(list(host)))
+    sc = DeviceStandardScaler().fit(feats)
+    assert sc.n_samples_seen_ == 24 * 64
+    np.testing.assert_allclose(sc.mean_, ref.mean_, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(sc.scale_, ref.scale_, rtol=1e-6, atol=1e-6)
+    got = sc.transform(feats).cpu().numpy()
+    want = np.stack([ref.transform(x) for x in host])
+    assert np.abs(got - want).max() <= 1e-4
+    assert torch.equal(feats.cpu(), torch.from_numpy(host))                # transform(inplace=False) left the input alone
+    # time-major features (T, C), e.g. LFCC for the BiLSTM: columns = coefficients
+    fl = Frontend(FrontendParams.lfcc(16000, n_ceps=13), dev)
+    lf, _, _ = fl(torch.from_numpy(clips).to(dev))                         # (24, 198, 13)
+    ref2 = StandardScaler().fit(np.vstack(list(lf.cpu().numpy())))
+    got2 = DeviceStandardScaler().fit_transform(lf).cpu().numpy()
+    assert np.abs(got2 - np.stack([ref2.transform(x) for x in lf.cpu().numpy()])).max() <= 1e-4

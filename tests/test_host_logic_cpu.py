@@ -93,3 +93,53 @@ def test_sharded_gather_world_size_2_gloo():
     assert all(ok for _, ok, _ in res)
     loads = [l for _, _, l in res]
     assert abs(loads[0] - loads[1]) <= 509
+
+
+def test_scaler_merge_matches_sklearn():
+    """merge_stats == sklearn StandardScaler on np.vstack(...) (ASV_dl_func.py:1113-1129), including a
+    constant column (scale 1) -- the host half of DeviceStandardScaler.fit."""
+    from sklearn.preprocessing import StandardScaler
+    from audioanalysisdetector_b200.scaler import merge_stats
+    rng = np.random.default_rng(5)
+    utts = [(-60 + 15 * rng.standard_normal((64, 63))).astype(np.float32) for _ in range(7)]
+    for u in utts:
+        u[:, 10] = -80.0
+    X = np.vstack(utts).astype(np.float64)
+    ref = StandardScaler().fit(X)
+    mean, var, scale = merge_stats(X.shape[0], X.sum(0), (X * X).sum(0))
+    np.testing.assert_allclose(mean, ref.mean_, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(var, ref.var_, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(scale, ref.scale_, rtol=1e-9, atol=1e-9)
+    assert scale[10] == 1.0
+
+
+def _gloo_scaler_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)
+    X = rng.standard_normal((1000, 13))
+    part = X[sharding.contiguous_shard(1000, rank, world)]
+    stats = torch.from_numpy(np.concatenate([part.sum(0), (part * part).sum(0), [float(len(part))]]))
+    dist.all_reduce(stats, op=dist.ReduceOp.SUM)         # the exchange step of DeviceStandardScaler.fit
+    from audioanalysisdetector_b200.scaler import merge_stats
+    h = stats.numpy()
+    mean, var, scale = merge_stats(int(round(h[26])), h[:13], h[13:26])
+    q.put((rank, float(np.abs(mean - X.mean(0)).max()), float(np.abs(var - X.var(0)).max())))
+    dist.destroy_process_group()
+
+
+def test_scaler_statistics_all_reduce_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 200
+    procs = [ctx.Process(target=_gloo_scaler_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] < 1e-12 and r[2] < 1e-12 for r in res)
