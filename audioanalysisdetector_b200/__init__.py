@@ -9,11 +9,12 @@ from ._lib import AadError
 from .frontend import Frontend, FrontendParams, delta, fp32_peak_tflops
 from .extractors import (compute_melspec, extract_features, extract_lfcc, extract_mel_spectrogram,
                          extract_mfcc, get_frontend)
+from .corpus import DeviceCorpus, chunk_bounds, layout_files, two_second_chunks
 from .scaler import DeviceStandardScaler, merge_stats
 from .sharding import bind_to_gpu_numa, contiguous_shard, gather_features, partition_by_frames
 
 __all__ = [
     "AadError", "Frontend", "FrontendParams", "delta", "fp32_peak_tflops",
     "compute_melspec", "extract_features", "extract_lfcc", "extract_mel_spectrogram", "extract_mfcc", "get_frontend",
-    "DeviceStandardScaler", "merge_stats", "bind_to_gpu_numa", "contiguous_shard", "gather_features", "partition_by_frames",
+    "DeviceCorpus", "chunk_bounds", "layout_files", "two_second_chunks", "DeviceStandardScaler", "merge_stats", "bind_to_gpu_numa", "contiguous_shard", "gather_features", "partition_by_frames",
 ]

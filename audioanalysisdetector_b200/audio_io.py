@@ -21,10 +21,12 @@ def set_loader(fn: Optional[Callable[[str], Tuple[np.ndarray, int]]]):
     _loader = fn
 
 
-def _load_wav(path: str) -> Tuple[np.ndarray, int]:
+def _load_wav(path: str, keep_pcm16: bool = False) -> Tuple[np.ndarray, int]:
     with wave.open(path, "rb") as w:
         sr, nch, sw, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
         raw = w.readframes(n)
+    if sw == 2 and nch == 1 and keep_pcm16:
+        return np.frombuffer(raw, dtype="<i2").copy(), sr    # sample value = int16 / 32768 (as decoded below)
     if sw == 2:
         y = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
     elif sw == 4:
@@ -36,6 +38,14 @@ def _load_wav(path: str) -> Tuple[np.ndarray, int]:
     if nch > 1:
         y = y.reshape(-1, nch).mean(axis=1).astype(np.float32)   # librosa.to_mono
     return y, sr
+
+
+def load_pcm(source) -> Tuple[np.ndarray, int]:
+    """Like `load` at the native rate, but mono 16-bit PCM WAV files come back as the raw int16 samples
+    (value = int16 / 32768, exactly what `load` would return as float32): half the bytes to upload."""
+    if _loader is None and not isinstance(source, tuple) and str(source).lower().endswith(".wav"):
+        return _load_wav(str(source), keep_pcm16=True)
+    return load(source)
 
 
 def load(source, sr: Optional[int] = None) -> Tuple[np.ndarray, int]:

@@ -1,0 +1,172 @@
+"""Decode once, upload once, slice on the device: the input side of the extractors.
+
+In the reference every 2-second chunk row (`prepare_dataframe`, ASV_dl_func.py:287-293) calls
+`librosa.load(filepath)` on its whole file and then slices `y[start_sample:end_sample]`
+(ASV_dl_func.py:406-411, 425-429, 524-528), once per feature -- file decode dominates its wall time
+(SURVEY.md section 6).  `DeviceCorpus` decodes each distinct file once (16-bit PCM stays int16: half the
+PCIe bytes), puts all files back to back in ONE pinned buffer, uploads it with one copy, and hands the
+kernels a chunk table (element offset + length per row) instead of padded copies: `aad_extract_indexed`
+(include/aad.h).  Noise augmentation (`augment_audio(mode="noise")`, ASV_dl_func.py:78-93) is applied on
+the device to the rows that ask for it.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import audio_io
+from .frontend import Frontend, FrontendParams
+
+FILE_ALIGN = 8          # elements: every file starts on a 16-byte (int16) / 32-byte (float32) boundary
+NOISE_FACTOR = 1.022    # augment_audio's default factor for mode="noise" (ASV_dl_func.py:85-86)
+
+
+def _isnan(v) -> bool:
+    return isinstance(v, float) and math.isnan(v)
+
+
+def chunk_bounds(n_samples: int, sr: int, chunk_start, chunk_end) -> Tuple[int, int]:
+    """[start, end) of `y[start_sample:end_sample]` exactly as the extractors compute it
+    (ASV_dl_func.py:407-410): start = int(chunk_start * sr), end = min(int(chunk_end * sr), len(y)),
+    then Python slice semantics (a start past the end gives an empty clip).  No chunk -> whole file."""
+    if chunk_start is None or chunk_end is None or _isnan(chunk_start) or _isnan(chunk_end):
+        return 0, n_samples
+    start = int(chunk_start * sr)
+    end = min(int(chunk_end * sr), n_samples)
+    start, end, _ = slice(start, end).indices(n_samples)
+    return start, max(end, start)
+
+
+def two_second_chunks(n_samples: int, sr: int, chunk_s: float = 2.0) -> List[Tuple[float, float]]:
+    """The chunk rows `prepare_dataframe` makes for one file (ASV_dl_func.py:281-293): files shorter
+    than one chunk are dropped, the tail past the last full chunk is ignored."""
+    duration = n_samples / sr
+    if duration < chunk_s:
+        return []
+    return [(i * chunk_s, (i + 1) * chunk_s) for i in range(int(duration // chunk_s))]
+
+
+class DeviceCorpus:
+    """Decoded files in device memory + chunk tables over them."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise L.AadError("DeviceCorpus needs a CUDA device (there is no CPU path)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._index: Dict[object, int] = {}
+        self._host: List[np.ndarray] = []
+        self._keep: list = []
+        self.sample_rates: List[int] = []
+        self.n_samples: List[int] = []
+        self.base: List[int] = []            # element offset of every file inside the device buffer
+        self.pcm: Optional[torch.Tensor] = None
+        self._pcm_f32: Optional[torch.Tensor] = None
+        self.h2d_bytes = 0
+
+    # ---- building -----------------------------------------------------------------
+    def add(self, source) -> int:
+        """Decode `source` (path, or an in-memory (waveform, sr) pair) unless it is already here."""
+        if isinstance(source, tuple) and len(source) == 2:
+            key = (id(source[0]), int(source[1]))     # the waveform object identifies an in-memory clip
+        else:
+            key = str(source)
+        idx = self._index.get(key)
+        if idx is None:
+            self._keep.append(source)                 # ids stay unique while the corpus lives
+            y, sr = audio_io.load_pcm(source)
+            if y.dtype != np.int16:
+                y = np.ascontiguousarray(y, dtype=np.float32)
+            idx = self._index[key] = len(self._host)
+            self._host.append(y)
+            self.sample_rates.append(int(sr))
+            self.n_samples.append(int(len(y)))
+            self.pcm = None
+        return idx
+
+    def upload(self) -> torch.Tensor:
+        """One pinned staging buffer, one H2D copy.  int16 when every file is 16-bit PCM, else float32."""
+        if self.pcm is not None:
+            return self.pcm
+        if not self._host:
+            raise L.AadError("empty corpus")
+        all_i16 = all(y.dtype == np.int16 for y in self._host)
+        self.base, total = layout_files(self.n_samples)
+        stage = torch.zeros(total, dtype=torch.int16 if all_i16 else torch.float32, pin_memory=True)
+        sv = stage.numpy()
+        for y, b in zip(self._host, self.base):
+            sv[b:b + len(y)] = y if all_i16 or y.dtype != np.int16 else y.astype(np.float32) / 32768.0
+        self.pcm = stage.to(self.device, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()   # the staging buffer is released below
+        self.h2d_bytes = stage.numel() * stage.element_size()
+        self._pcm_f32 = None
+        return self.pcm
+
+    def as_float32(self) -> torch.Tensor:
+        """The corpus as librosa.load would return it (int16 / 32768 is exact in float32)."""
+        pcm = self.upload()
+        if pcm.dtype == torch.float32:
+            return pcm
+        if self._pcm_f32 is None:
+            self._pcm_f32 = pcm.to(torch.float32) * (1.0 / 32768.0)
+        return self._pcm_f32
+
+    # ---- chunk tables ---------------------------------------------------------------
+    def table(self, rows: Sequence[Tuple[int, object, object]]) -> Tuple[np.ndarray, np.ndarray]:
+        """rows of (file index, chunk_start s, chunk_end s) -> (element offsets int64, lengths int32)."""
+        if not self.base:
+            self.base, _ = layout_files(self.n_samples)
+        off = np.empty(len(rows), dtype=np.int64)
+        ln = np.empty(len(rows), dtype=np.int32)
+        for i, (f, cs, ce) in enumerate(rows):
+            s, e = chunk_bounds(self.n_samples[f], self.sample_rates[f], cs, ce)
+            off[i], ln[i] = self.base[f] + s, e - s
+        return off, ln
+
+    # ---- extraction -----------------------------------------------------------------
+    def extract(self, fe: Frontend, offsets: np.ndarray, lengths: np.ndarray,
+                noise_rows: Optional[Sequence[int]] = None, generator: Optional[torch.Generator] = None):
+        """Features of every chunk of the table, on the device: (features, n_frames, status).
+
+        `noise_rows`: indices of rows with augmentationType == "noise": they become
+        `y + 1.022 * randn(len(y))` in float32 (ASV_dl_func.py:84-89; the reference draws the noise from
+        numpy's unseeded global generator, so only its distribution can be reproduced)."""
+        pcm = self.upload()
+        if fe.params.quantize_i16 or (noise_rows is not None and len(noise_rows)):
+            pcm = self.as_float32()   # LFCC re-quantises the decoded float (y*32767 -> int16) itself
+        off = torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64)).to(self.device)
+        ln = torch.from_numpy(np.ascontiguousarray(lengths, dtype=np.int32)).to(self.device)
+        if noise_rows is not None and len(noise_rows):
+            pcm, off = self._with_noise(pcm, off, ln, np.asarray(noise_rows, dtype=np.int64), generator)
+        return fe.extract_indexed(pcm, off, ln, max_len=max(int(np.max(lengths)), 1))
+
+    def _with_noise(self, pcm, off, ln, rows, generator):
+        """Append noisy copies of the chosen chunks behind the corpus and point their rows at them."""
+        r = torch.from_numpy(rows).to(self.device)
+        rl = ln[r].to(torch.int64)
+        padded = (rl + FILE_ALIGN - 1) // FILE_ALIGN * FILE_ALIGN
+        dst0 = torch.cumsum(padded, 0) - padded                       # start of every copy in the appendix
+        total = int(padded.sum())
+        ext = torch.zeros(pcm.numel() + total, dtype=torch.float32, device=self.device)
+        ext[:pcm.numel()] = pcm
+        if int(rl.sum()) > 0:
+            which = torch.repeat_interleave(torch.arange(len(rows), device=self.device), rl)
+            within = torch.arange(int(rl.sum()), device=self.device) - torch.repeat_interleave(torch.cumsum(rl, 0) - rl, rl)
+            src = off[r][which] + within
+            noise = torch.randn(src.numel(), dtype=torch.float32, device=self.device, generator=generator)
+            ext[pcm.numel() + dst0[which] + within] = pcm[src] + NOISE_FACTOR * noise
+        off = off.clone()
+        off[r] = pcm.numel() + dst0
+        return ext, off
+
+
+def layout_files(n_samples: Sequence[int]) -> Tuple[List[int], int]:
+    """Element offset of every file (aligned to FILE_ALIGN) and the total buffer size."""
+    base, pos = [], 0
+    for n in n_samples:
+        base.append(pos)
+        pos += (int(n) + FILE_ALIGN - 1) // FILE_ALIGN * FILE_ALIGN
+    return base, max(pos, FILE_ALIGN)

@@ -677,12 +677,12 @@ int aad_plan_launches(const aad_plan* pl) {
   return 2 + 1 + (pl->need_ws_feat ? 1 : 0) + (pl->p.znorm ? 2 : 0);
 }
 
-int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_stride,
-                const int32_t* lengths, int B, int64_t max_len, float* out, int64_t out_stride_b,
-                int32_t t_alloc, int32_t* n_frames, int32_t* status, void* workspace,
-                size_t workspace_bytes, void* stream_) {
+static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_stride,
+                        const int64_t* row_off, const int32_t* lengths, int B, int64_t max_len, float* out,
+                        int64_t out_stride_b, int32_t t_alloc, int32_t* n_frames, int32_t* status,
+                        void* workspace, size_t workspace_bytes, void* stream_) {
   if (!pl || !wav || !lengths || !out || !n_frames || !status || !workspace) return AAD_ERR_INVALID_ARG;
-  if (B <= 0 || max_len <= 0 || max_len > wav_stride || t_alloc <= 0) return AAD_ERR_INVALID_ARG;
+  if (B <= 0 || max_len <= 0 || (!row_off && max_len > wav_stride) || t_alloc <= 0) return AAD_ERR_INVALID_ARG;
   if (wav_dtype != AAD_F32 && wav_dtype != AAD_I16) return AAD_ERR_INVALID_ARG;
   const aad_params& p = pl->p;
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -726,7 +726,7 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
 
   // K1
   StftArgs sa;
-  sa.wav = wav; sa.wav_stride = wav_stride; sa.len_c = d_len; sa.frame_off = d_frame_off; sa.B = B;
+  sa.wav = wav; sa.wav_stride = wav_stride; sa.row_off = reinterpret_cast<const long long*>(row_off); sa.len_c = d_len; sa.frame_off = d_frame_off; sa.B = B;
   sa.hop = p.hop_length; sa.s_off = p.center ? p.n_fft / 2 : 0;
   sa.win_off = p.center ? (p.n_fft - p.win_length) / 2 : 0; sa.win_len = p.win_length;
   sa.pre_emph = p.pre_emph;
@@ -807,6 +807,23 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
   if (prof) cudaEventRecord(pl->ev[4], stream);
   LAUNCH_CHECK("epilogue launch");
   return AAD_OK;
+}
+
+int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_stride,
+                const int32_t* lengths, int B, int64_t max_len, float* out, int64_t out_stride_b,
+                int32_t t_alloc, int32_t* n_frames, int32_t* status, void* workspace,
+                size_t workspace_bytes, void* stream) {
+  return extract_impl(pl, wav, wav_dtype, wav_stride, nullptr, lengths, B, max_len, out, out_stride_b, t_alloc,
+                      n_frames, status, workspace, workspace_bytes, stream);
+}
+
+int aad_extract_indexed(const aad_plan* pl, const void* wav, int wav_dtype, const int64_t* row_off,
+                        const int32_t* lengths, int B, int64_t max_len, float* out, int64_t out_stride_b,
+                        int32_t t_alloc, int32_t* n_frames, int32_t* status, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (!row_off) return AAD_ERR_INVALID_ARG;
+  return extract_impl(pl, wav, wav_dtype, 0, row_off, lengths, B, max_len, out, out_stride_b, t_alloc,
+                      n_frames, status, workspace, workspace_bytes, stream);
 }
 
 #define AAD_KIND_ALIAS(NAME, KIND)                                                                        \

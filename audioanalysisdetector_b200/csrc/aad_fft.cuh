@@ -152,10 +152,11 @@ __device__ __forceinline__ void butterfly(float2& a, float2& b) {
 
 // In-place DIT FFT of size N on v[OFF .. OFF+N).  Input must be stored in
 // bit-reversed order (element n at OFF + bitrev(n)); output is in natural order.
-template <int N, int OFF, int NV>
+// FIRST > 1 skips the leading stages (the caller has fused them with something else).
+template <int N, int OFF, int NV, int FIRST = 1>
 __device__ __forceinline__ void fft_dit(float2 (&v)[NV]) {
   constexpr int LOG2N = ilog2(N);
-  static_for<1, LOG2N + 1>([&](auto s_) {
+  static_for<FIRST, LOG2N + 1>([&](auto s_) {
     constexpr int S = decltype(s_)::value;
     constexpr int M = 1 << S;
     constexpr int H = M / 2;

@@ -39,6 +39,9 @@ constexpr int ABL = AAD_ABLATE;
 #ifndef AAD_TWPGEN
 #define AAD_TWPGEN 1
 #endif
+#ifndef AAD_WINFOLD
+#define AAD_WINFOLD 1
+#endif
 
 // ---------------------------------------------------------------------------
 // ordered-int encoding of floats (monotone), for atomicMax / redux on floats
@@ -262,6 +265,8 @@ struct StftCfg {
 struct StftArgs {
   const void* wav;
   long long wav_stride;     // elements
+  const long long* row_off; // [B] element offset of every utterance inside wav (chunks of decoded files,
+                            // may overlap), or null: utterance b starts at b * wav_stride
   const int32_t* len_c;     // [B] clamped lengths
   const int32_t* frame_off; // [B+1]
   int B;
@@ -394,7 +399,14 @@ k_stft_fb(const StftArgs a) {
     for (int c = 0; c < 4; ++c) {
       float2 w8[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) w8[i] = __ldg(gwin2 + L * (8 * c + i) + j);
+      for (int i = 0; i < 8; ++i) {
+#if AAD_WINFOLD
+        const int A = 4 * c + (i >> 1) + 16 * (i & 1);  // {w[A], w[A + 16]} side by side (see the window step)
+#else
+        const int A = 8 * c + i;
+#endif
+        w8[i] = __ldg(gwin2 + L * A + j);
+      }
       tmem_st16(tmem_row + 16 * c, w8);
 #pragma unroll
       for (int i = 0; i < 8; ++i) w8[i] = __ldg(a.tw1 + (8 * c + i) * L + j);
@@ -449,7 +461,8 @@ k_stft_fb(const StftArgs a) {
       long long s_hi = (long long)t * a.hop - a.s_off + N;
       if (s_lo < 0) s_lo = 0;
       if (s_hi > len) s_hi = len;
-      const char* row = static_cast<const char*>(a.wav) + (long long)b * a.wav_stride * ES;
+      const char* row = static_cast<const char*>(a.wav) +
+                        (a.row_off ? __ldg(a.row_off + b) : (long long)b * a.wav_stride) * ES;
       uintptr_t p0 = ((uintptr_t)(row + s_lo * ES) + 15) & ~(uintptr_t)15;
       uintptr_t p1 = (uintptr_t)(row + s_hi * ES) & ~(uintptr_t)15;
       if (p1 > p0)
@@ -477,7 +490,7 @@ k_stft_fb(const StftArgs a) {
       const int len = valid ? __ldg(a.len_c + b) : 0;
       const int s0 = t * a.hop - a.s_off;
       const char* row = static_cast<const char*>(a.wav) +
-                        (valid ? (long long)b * a.wav_stride * (MODE == IN_I16 ? 2 : 4) : 0);
+                        (valid ? (a.row_off ? __ldg(a.row_off + b) : (long long)b * a.wav_stride) * (MODE == IN_I16 ? 2 : 4) : 0);
       bool fast = valid && s0 >= (PRE ? 1 : 0) && (s0 + N) <= len;
       if constexpr (MODE == IN_I16) fast = fast && (((uintptr_t)(row + 2ll * s0)) & 3) == 0;
       else fast = fast && (((uintptr_t)(row + 4ll * s0)) & 7) == 0;
@@ -569,6 +582,28 @@ k_stft_fb(const StftArgs a) {
 
       // window: 0.5*w (zero outside its support) from this lane's TMEM row, next chunk in flight
 #if AAD_TMEM_TABLES
+#if AAD_WINFOLD
+      // window folded into the first butterfly stage of pass 1: samples A and A + 16 meet in stage 1
+      // (registers bitrev(A) = 2m and 2m + 1), so a' = xa*wa + xb*wb, b' = xa*wa - xb*wb is one FMUL2
+      // and two FFMA2 instead of two FMUL2 and two FADD2.  Chunk c holds {w[A], w[A + 16]}, A = 4c .. 4c + 3.
+      {
+        TmemChunk wc[2];
+        wc[0].issue(tmem_row);
+        static_for<0, 4>([&](auto c_) {
+          constexpr int CH = decltype(c_)::value;
+          wc[CH & 1].wait();
+          if constexpr (CH < 3) wc[(CH + 1) & 1].issue(tmem_row + 16 * (CH + 1));
+          static_for<0, 4>([&](auto i_) {
+            constexpr int I = decltype(i_)::value;
+            constexpr int RA = bitrev(4 * CH + I, 5);            // even register; RA + 1 = bitrev(A + 16)
+            const float2 t = pk_mul(v[RA], wc[CH & 1].get(2 * I));
+            const float2 xb = v[RA + 1], wb = wc[CH & 1].get(2 * I + 1);
+            v[RA] = pk_fma(xb, wb, t);
+            v[RA + 1] = pk_fma(make_float2(-xb.x, -xb.y), wb, t);
+          });
+        });
+      }
+#else
       {
         TmemChunk wc[2];
         wc[0].issue(tmem_row);
@@ -582,6 +617,7 @@ k_stft_fb(const StftArgs a) {
           });
         });
       }
+#endif
 #else
       static_for<0, 32>([&](auto a_) {
         constexpr int A = decltype(a_)::value;
@@ -591,7 +627,7 @@ k_stft_fb(const StftArgs a) {
 #endif
 
       // pass 1: 32-point DFT over a (stride L), then twiddle W_M^(b*kA)
-      if constexpr (!(ABL & 64)) fft_dit<32, 0>(v);
+      if constexpr (!(ABL & 64)) fft_dit<32, 0, 32, (AAD_WINFOLD && AAD_TMEM_TABLES) ? 2 : 1>(v);
       {
 #if AAD_TMEM_TABLES
         TmemChunk tc[2];

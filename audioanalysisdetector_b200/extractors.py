@@ -175,13 +175,32 @@ def _row_get(row, key, default=None):
     return v
 
 
+def _split_rows(feats, n_frames, status, params, post, mean, rows_idx, results, tag):
+    feats, n_frames, status = feats.cpu().numpy(), n_frames.cpu().numpy(), status.cpu().numpy()
+    for k, i in enumerate(rows_idx):
+        if status[k] != 0:
+            print(f"[BŁĄD {tag}] row {i}: {L.ITEM_STATUS_NAMES.get(int(status[k]), 'item failed')}")
+        elif params.time_mean:
+            results[i] = post(feats[k].copy(), mean)
+        elif params.layout == L.LAYOUT_CT:
+            results[i] = post(feats[k, :, :n_frames[k]].copy(), mean)
+        else:
+            results[i] = post(feats[k, :n_frames[k], :].copy(), mean)
+
+
 def extract_features(final_df, feature_extractors_map: Dict[str, Callable], col_name="filepath",
                      mean=False, aug_col="augmentationType", max_batch_samples: int = 1 << 28):
     """Reference dispatcher (ASV_dl_func.py:1031-1049): adds one object column per map key.
 
-    Recognised extractors (the three above) run as batched GPU calls; every file is
-    decoded once per feature and sliced into its chunks on the host."""
+    Recognised extractors (the three above) run as batched GPU calls over a `DeviceCorpus`: every
+    distinct file is decoded ONCE for all features and uploaded once (16-bit PCM as int16); the chunk
+    rows become a table of offsets into that buffer (`aad_extract_indexed`), so no chunk is copied or
+    padded on the host; "noise" rows are augmented on the device.  Any other callable in the map is
+    called per row, as the reference does."""
+    from .corpus import DeviceCorpus
     rows = [row for _, row in final_df.iterrows()]
+    corpus: Optional[DeviceCorpus] = None
+    file_of: List[Optional[int]] = [None] * len(rows)
     for name, func in feature_extractors_map.items():
         print(f"   - Ekstrahuję: {name}")
         if func not in _BATCHED:
@@ -192,37 +211,41 @@ def extract_features(final_df, feature_extractors_map: Dict[str, Callable], col_
             continue
         tag, mk_params, post = _BATCHED[func]
         results: List[Optional[np.ndarray]] = [None] * len(rows)
-        decoded: Dict[object, tuple] = {}
-        by_sr: Dict[int, List[tuple]] = {}
+        if corpus is None:                      # decode each distinct file once, for every feature
+            corpus = DeviceCorpus()
+            for i, r in enumerate(rows):
+                src = _row_get(r, col_name)
+                try:
+                    file_of[i] = corpus.add(src)
+                except Exception as e:
+                    print(f"[BŁĄD {tag}] {src if isinstance(src, str) else '<array>'}: {e}")
+        by_sr: Dict[int, List[int]] = {}
         for i, r in enumerate(rows):
-            src = _row_get(r, col_name)
-            try:
-                key = src if isinstance(src, str) else id(src)
-                if key not in decoded:
-                    decoded[key] = audio_io.load(src)
-                y, sr = _prepare_clip(decoded[key], _row_get(r, "chunk_start"), _row_get(r, "chunk_end"),
-                                      None, _row_get(r, aug_col))
-                by_sr.setdefault(sr, []).append((i, y))
-            except Exception as e:
-                print(f"[BŁĄD {tag}] {src if isinstance(src, str) else '<array>'}: {e}")
-        for sr, items in by_sr.items():
+            if file_of[i] is None:
+                continue
+            aug = _row_get(r, aug_col)
+            if aug == "change pitch":
+                print(f"[BŁĄD {tag}] row {i}: pitch-shift augmentation is outside the spectral front-end")
+                continue
+            by_sr.setdefault(corpus.sample_rates[file_of[i]], []).append(i)
+        for sr, idxs in by_sr.items():
             params = mk_params(sr, mean)
+            fe = get_frontend(params)
+            off, ln = corpus.table([(file_of[i], _row_get(rows[i], "chunk_start"), _row_get(rows[i], "chunk_end"))
+                                    for i in idxs])
             start = 0
-            while start < len(items):        # bound the padded batch (samples) per GPU call
+            while start < len(idxs):            # bound the output (rows x longest chunk) per GPU call
                 end, lmax = start, 0
-                while end < len(items):
-                    lm = max(lmax, len(items[end][1]))
+                while end < len(idxs):
+                    lm = max(lmax, int(ln[end]))
                     if end > start and lm * (end - start + 1) > max_batch_samples:
                         break
                     lmax, end = lm, end + 1
-                chunk = items[start:end]
+                part = idxs[start:end]
                 try:
-                    outs, status = _run_batch(params, [y for _, y in chunk])
-                    for (i, _), o, st in zip(chunk, outs, status):
-                        if o is None:
-                            print(f"[BŁĄD {tag}] row {i}: {L.ITEM_STATUS_NAMES.get(int(st), 'item failed')}")
-                        else:
-                            results[i] = post(o, mean)
+                    noise = [k for k, i in enumerate(part) if _row_get(rows[i], aug_col) == "noise"]
+                    feats, nf, st = corpus.extract(fe, off[start:end], ln[start:end], noise_rows=noise)
+                    _split_rows(feats, nf, st, params, post, mean, part, results, tag)
                 except Exception as e:
                     print(f"[BŁĄD {tag}] batch {start}:{end}: {e}")
                 start = end

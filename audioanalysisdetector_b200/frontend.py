@@ -244,6 +244,53 @@ class Frontend:
         L.check(rc, "aad_extract")
         return out, n_frames, status
 
+    # ---- chunks of decoded files that already sit in device memory ------------------
+    def extract_indexed(self, pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor,
+                        max_len: Optional[int] = None):
+        """pcm: 1-D float32|int16 on this device (decoded files back to back); utterance b is
+        pcm[offsets[b] : offsets[b] + lengths[b]] (offsets int64, lengths int32; chunks may overlap).
+        Same returns as __call__.  The reference slices `y[start_sample:end_sample]` after decoding the
+        whole file once per chunk (ASV_dl_func.py:406-411); here the slice is an offset in a table.
+        `max_len` (default lengths.max(), which costs a device->host read) bounds the output width."""
+        if pcm.dim() != 1 or not pcm.is_cuda or pcm.device != self.device or not pcm.is_contiguous():
+            raise L.AadError(f"pcm must be a contiguous 1-D tensor on {self.device}")
+        if pcm.dtype == torch.float32:
+            dt = L.F32
+        elif pcm.dtype == torch.int16:
+            dt = L.I16
+        else:
+            raise L.AadError("pcm must be float32 or int16")
+        offsets = offsets.to(device=self.device, dtype=torch.int64).contiguous()
+        lengths = lengths.to(device=self.device, dtype=torch.int32).contiguous()
+        B = int(offsets.numel())
+        if B == 0 or lengths.numel() != B:
+            raise L.AadError("offsets and lengths must be non-empty and of equal size")
+        # one fused check (a device->host read): every chunk inside the buffer
+        lo, hi = int(offsets.min()), int((offsets + lengths.clamp(min=0).to(torch.int64)).max())
+        if lo < 0 or hi > pcm.numel():
+            raise L.AadError(f"chunk table reaches outside the pcm buffer ([{lo}, {hi}) vs {pcm.numel()} samples)")
+        Lmax = int(max_len) if max_len is not None else max(int(lengths.max()), 1)
+        t_max, c_out, ws_bytes = self.query(B, Lmax)
+        t_alloc = max(t_max, 1)
+        p = self.params
+        if p.time_mean:
+            shape = (B, c_out)
+        elif p.layout == L.LAYOUT_CT:
+            shape = (B, c_out, t_alloc)
+        else:
+            shape = (B, t_alloc, c_out)
+        out = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        n_frames = torch.empty(B, dtype=torch.int32, device=self.device)
+        status = torch.empty(B, dtype=torch.int32, device=self.device)
+        ws = self._workspace(ws_bytes)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = self.lib.aad_extract_indexed(self._h, _ptr(pcm), dt, _ptr(offsets), _ptr(lengths), B, Lmax,
+                                              _ptr(out), out.stride(0), t_alloc, _ptr(n_frames), _ptr(status),
+                                              _ptr(ws), ws.numel(), C.c_void_p(stream))
+        L.check(rc, "aad_extract_indexed")
+        return out, n_frames, status
+
     # ---- host buffers in / out (pipelined H2D -> kernels -> D2H inside the library) ----
     def extract_host(self, wav: np.ndarray, lengths: Optional[np.ndarray] = None,
                      out: Optional[np.ndarray] = None, chunk_utts: int = 0):

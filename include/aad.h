@@ -151,6 +151,19 @@ int aad_extract(const aad_plan* plan, const void* wav, int wav_dtype, int64_t wa
                 int32_t t_alloc, int32_t* n_frames, int32_t* status, void* workspace,
                 size_t workspace_bytes, void* stream);
 
+/* The same call over CHUNKS of decoded files that already sit in device memory: utterance b is the
+ * lengths[b] samples starting at element row_off[b] of wav (int64, device); chunks may overlap and need
+ * no padding.  Replaces the reference's per-chunk `librosa.load(filepath)` + `y[start_sample:end_sample]`
+ * (ASV_dl_func.py:406-411, 425-429, 524-528: every 2-second chunk of prepare_dataframe :287-293 decodes
+ * its whole file again) by one decode + one upload per file and a chunk table.  The caller guarantees
+ * 0 <= row_off[b] and row_off[b] + lengths[b] <= elements of wav; chunk starts on even element offsets
+ * (8-byte aligned float32 / 4-byte aligned int16 addresses) take the vector-load path, others the
+ * per-sample path with identical results. */
+int aad_extract_indexed(const aad_plan* plan, const void* wav, int wav_dtype, const int64_t* row_off,
+                        const int32_t* lengths, int B, int64_t max_len, float* out, int64_t out_stride_b,
+                        int32_t t_alloc, int32_t* n_frames, int32_t* status, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* Kind-checked aliases of aad_extract (return AAD_ERR_KIND on mismatch). */
 int aad_logmel(const aad_plan* plan, const void* wav, int wav_dtype, int64_t wav_stride,
                const int32_t* lengths, int B, int64_t max_len, float* out, int64_t out_stride_b,

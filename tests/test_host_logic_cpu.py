@@ -143,3 +143,44 @@ def test_scaler_statistics_all_reduce_world_size_2_gloo():
         p.join(timeout=60)
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] < 1e-12 and r[2] < 1e-12 for r in res)
+
+
+def test_chunk_table_follows_the_reference_slicing():
+    """chunk_bounds == y[int(cs*sr):min(int(ce*sr), len(y))] (ASV_dl_func.py:407-410) for every case,
+    two_second_chunks == prepare_dataframe's rows (:281-293), layout_files keeps files aligned."""
+    from audioanalysisdetector_b200.corpus import FILE_ALIGN, chunk_bounds, layout_files, two_second_chunks
+    y = np.arange(70001)
+    for sr in (16000, 22050, 44100):
+        for cs, ce in [(0.0, 2.0), (2.0, 4.0), (1.3, 2.9), (4.0, 6.0), (100.0, 102.0), (0.0, 0.0), (3.0, 2.0),
+                       (-1.0, 1.0), (None, None), (float("nan"), float("nan"))]:
+            if cs is None or cs != cs:
+                want = y
+            else:
+                want = y[int(cs * sr):min(int(ce * sr), len(y))]
+            s, e = chunk_bounds(len(y), sr, cs, ce)
+            assert e - s == len(want) and (len(want) == 0 or (y[s] == want[0] and y[e - 1] == want[-1]))
+    assert two_second_chunks(5 * 16000 + 900, 16000) == [(0.0, 2.0), (2.0, 4.0)]
+    assert two_second_chunks(2 * 16000, 16000) == [(0.0, 2.0)]
+    assert two_second_chunks(2 * 16000 - 1, 16000) == []
+    base, total = layout_files([5, 16, 0, 17])
+    assert base == [0, 8, 24, 24] and total == 48 and all(b % FILE_ALIGN == 0 for b in base)
+    assert layout_files([])[1] == FILE_ALIGN
+
+
+def test_load_pcm_keeps_int16_and_equals_the_float_decode(tmp_path):
+    import wave
+    from audioanalysisdetector_b200 import audio_io
+    rng = np.random.default_rng(3)
+    pcm = rng.integers(-32768, 32767, size=5000, dtype=np.int16)
+    p = tmp_path / "a.wav"
+    with wave.open(str(p), "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(22050)
+        w.writeframes(pcm.astype("<i2").tobytes())
+    raw, sr = audio_io.load_pcm(str(p))
+    y, sr2 = audio_io.load(str(p))
+    assert raw.dtype == np.int16 and sr == sr2 == 22050 and np.array_equal(raw, pcm)
+    assert y.dtype == np.float32 and np.array_equal(raw.astype(np.float32) / 32768.0, y)
+    arr, sr3 = audio_io.load_pcm((y, 22050))                              # in-memory clips stay float32
+    assert arr.dtype == np.float32 and sr3 == 22050
