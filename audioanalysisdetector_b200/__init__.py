@@ -11,10 +11,11 @@ from .extractors import (compute_melspec, extract_features, extract_lfcc, extrac
                          extract_mfcc, get_frontend)
 from .corpus import DeviceCorpus, chunk_bounds, layout_files, two_second_chunks
 from .scaler import DeviceStandardScaler, merge_stats
-from .sharding import bind_to_gpu_numa, contiguous_shard, gather_features, partition_by_frames
+from .sharding import (bind_to_gpu_numa, contiguous_shard, gather_features, long_form_logmel, partition_by_frames,
+                       time_split)
 
 __all__ = [
     "AadError", "Frontend", "FrontendParams", "delta", "fp32_peak_tflops",
     "compute_melspec", "extract_features", "extract_lfcc", "extract_mel_spectrogram", "extract_mfcc", "get_frontend",
-    "DeviceCorpus", "chunk_bounds", "layout_files", "two_second_chunks", "DeviceStandardScaler", "merge_stats", "bind_to_gpu_numa", "contiguous_shard", "gather_features", "partition_by_frames",
+    "DeviceCorpus", "chunk_bounds", "layout_files", "two_second_chunks", "DeviceStandardScaler", "merge_stats", "bind_to_gpu_numa", "contiguous_shard", "gather_features", "long_form_logmel", "partition_by_frames", "time_split",
 ]

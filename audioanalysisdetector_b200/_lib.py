@@ -64,6 +64,8 @@ SYMBOLS = {
     "aad_lfcc": (C.c_int, _EXTRACT_ARGS),
     "aad_delta": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int32, C.c_int, C.c_int,
                             C.c_void_p, C.c_void_p]),
+    "aad_db_reference": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int32,
+                                   C.c_int, C.c_float, C.c_void_p]),
     "aad_scaler_accumulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "aad_scaler_apply": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),

@@ -781,7 +781,7 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
     }
   } else {
     FinArgs fa;
-    fa.out = out; fa.stride_b = out_stride_b; fa.stride_f = t_alloc; fa.nf_eff = d_nf; fa.utt_max = d_max;
+    fa.out = out; fa.stride_b = out_stride_b; fa.stride_f = t_alloc; fa.nf_eff = d_nf; fa.utt_max = d_max; fa.utt_max_f = nullptr;
     fa.n_filt = p.n_filt; fa.ref_type = p.ref_type; fa.top_db = p.top_db;
     if (p.log_type == AAD_LOG_DB10) {
       const int n_row_blocks = (p.n_filt + FIN_ROWS - 1) / FIN_ROWS;
@@ -853,6 +853,24 @@ int aad_delta(const float* x, const int32_t* n_frames, int B, int C, int32_t t_s
   (void)cudaGetLastError();
   k_delta<<<grid, 256, 0, (cudaStream_t)stream>>>(da);
   LAUNCH_CHECK("k_delta launch");
+  return AAD_OK;
+}
+
+int aad_db_reference(float* x, int64_t stride_b, int32_t stride_f, const int32_t* n_frames, const float* utt_max,
+                     int B, int n_filt, int32_t t_max, int ref_type, float top_db, void* stream) {
+  if (!x || !n_frames || !utt_max || B <= 0 || n_filt <= 0 || t_max <= 0 || stride_f < t_max) return AAD_ERR_INVALID_ARG;
+  if (ref_type != AAD_REF_ONE && ref_type != AAD_REF_UTT_MAX) return AAD_ERR_INVALID_ARG;
+  if (stride_b == 0) stride_b = (int64_t)n_filt * stride_f;
+  FinArgs fa;
+  fa.out = x; fa.stride_b = stride_b; fa.stride_f = stride_f; fa.nf_eff = n_frames; fa.utt_max = nullptr;
+  fa.utt_max_f = utt_max; fa.n_filt = n_filt; fa.ref_type = ref_type; fa.top_db = top_db;
+  const int n_row_blocks = (n_filt + FIN_ROWS - 1) / FIN_ROWS;
+  const int n_chunks = (t_max + FIN_CHUNK - 1) / FIN_CHUNK;
+  const long long nblk = (long long)B * n_row_blocks * n_chunks;
+  if (nblk > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
+  (void)cudaGetLastError();
+  k_db_finalize<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(fa, n_row_blocks, n_chunks);
+  LAUNCH_CHECK("k_db_finalize launch");
   return AAD_OK;
 }
 

@@ -227,10 +227,14 @@ struct StftCfg {
   static constexpr int N = 2 * M;         // n_fft
   static constexpr int K = M + 1;         // bins
   static constexpr int TILE = TILE_;      // frames per tile
-#ifndef AAD_FBU
-#define AAD_FBU 2
+  // filterbank phase: entries processed together (ILP).  Measured (profiles/r1_experiments.md): bundles of 2
+  // are best for n_fft 2048 (1 / 2 / 3 / 4: 1.48 / 1.21 / 1.25 / 1.26 ms), bundles of 3 for n_fft 512 with its
+  // short segments (2 / 3 / 4: 1.143 / 1.120 / 1.116 ms on 80 mels; LFCC 1.239 / 1.235 / 1.288)
+#ifdef AAD_FBU
+  static constexpr int FBU = AAD_FBU;
+#else
+  static constexpr int FBU = L == 8 ? 3 : 2;
 #endif
-  static constexpr int FBU = AAD_FBU;     // filterbank phase: entries processed together (ILP)
   // power-row stride in floats.  The filterbank phase reads P[frame][4g .. 4g+3] as one LDS.128 per
   // lane: conflict-free iff SP/4 is odd.  Q rows double as the warp's 32x33 transpose scratch
   // (Q*SP >= 1056), and the row holds K bins plus zeroed padding (PAD words).
@@ -1099,7 +1103,8 @@ struct FinArgs {
   long long stride_b;
   int stride_f;
   const int32_t* nf_eff;
-  const int32_t* utt_max;
+  const int32_t* utt_max;   // ordered-int encoded (written by k_stft_fb) ...
+  const float* utt_max_f;   // ... or plain floats from the caller (aad_db_reference); one of the two
   int n_filt, ref_type;
   float top_db;
 };
@@ -1113,7 +1118,7 @@ __global__ void __launch_bounds__(256) k_db_finalize(const FinArgs a, int n_row_
   const int t0 = (r % n_chunks) * FIN_CHUNK;
   const int T = a.nf_eff[b];
   if (f >= a.n_filt || t0 >= T) return;
-  const float m = dec_ordered(a.utt_max[b]);
+  const float m = a.utt_max_f ? a.utt_max_f[b] : dec_ordered(a.utt_max[b]);
   const float ref = a.ref_type == 1 ? m : 0.f;
   const float floorv = a.top_db >= 0.f ? (m - ref) - a.top_db : -INFINITY;
   float* row = a.out + (long long)b * a.stride_b + (long long)f * a.stride_f;

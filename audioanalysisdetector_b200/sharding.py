@@ -68,6 +68,79 @@ def gather_features(local: torch.Tensor, local_index: torch.Tensor, n_total: int
     return out
 
 
+# --------------------------------------------------------------------------------------------------
+# Long-form audio with fewer utterances than GPUs (BASELINE config 5): split ONE utterance
+# along time.  Frames are independent except for power_to_db's per-utterance maximum (ref=np.max and
+# the top_db floor, ASV_dl_func.py:534), so the only exchange step is one MAX all-reduce of a float.
+# --------------------------------------------------------------------------------------------------
+def time_split(length: int, n_fft: int, hop: int, rank: int, world_size: int) -> dict:
+    """Rank's share of the frames of one centred STFT (T = 1 + length // hop frames).
+
+    Returns the frame range [t0, t1) it owns, the sample range [s0, s1) it has to read so that each of
+    those frames sees exactly the samples it sees in the unsplit signal, and `skip`: local frame
+    `skip + i` of the slice (extracted with the usual centre padding) IS global frame `t0 + i`.
+    The slice starts `ceil((n_fft/2) / hop)` hops early (s0 is a multiple of hop, so aligned loads stay
+    aligned) and ends n_fft/2 samples after the centre of the last owned frame; local frames before
+    `skip` or after `skip + (t1 - t0)` touch the slice's artificial zero padding and are dropped."""
+    T = 1 + length // hop
+    fr = contiguous_shard(T, rank, world_size)
+    t0, t1 = fr.start, fr.stop
+    if t1 <= t0:
+        return {"t0": t0, "t1": t0, "s0": 0, "s1": 0, "skip": 0}
+    k = -(-(n_fft // 2) // hop)
+    skip = min(k, t0)
+    s0 = (t0 - skip) * hop
+    s1 = min(length, (t1 - 1) * hop + n_fft // 2)
+    return {"t0": t0, "t1": t1, "s0": s0, "s1": max(s1, s0), "skip": skip}
+
+
+def long_form_logmel(params, wav: torch.Tensor, rank: int, world_size: int, group=None,
+                     local_max_hook=None):
+    """Log-mel (dB) of ONE long utterance `wav` [L] (on this rank's GPU) split along time over the ranks.
+
+    Every rank extracts its frames with the reference disabled (raw 10 log10(max(amin, S))), the
+    utterance maximum is MAX-all-reduced (the one exchange step), then `aad_db_reference` applies
+    `ref=np.max` / `top_db` exactly as power_to_db does.  Returns (features [n_mels, t1 - t0], (t0, t1)):
+    the concatenation over ranks equals the unsplit extraction bit for bit.
+    `local_max_hook(local_max) -> global_max` replaces the all-reduce (tests on one GPU)."""
+    import ctypes as C
+    import torch.distributed as dist
+    from . import _lib as L
+    from .frontend import Frontend, _ptr
+    if params.kind != L.KIND_LOGMEL or not params.center or params.time_mean or params.znorm or params.layout != L.LAYOUT_CT:
+        raise L.AadError("long_form_logmel needs a centred log-mel plan in CT layout")
+    part = time_split(int(wav.numel()), params.n_fft, params.hop_length, rank, world_size)
+    n = part["t1"] - part["t0"]
+    dev = wav.device
+    raw = params.replace(ref_type=L.REF_ONE, top_db=-1.0)
+    fe = Frontend(raw, dev)
+    if n > 0:
+        off = torch.tensor([part["s0"]], dtype=torch.int64, device=dev)
+        ln = torch.tensor([part["s1"] - part["s0"]], dtype=torch.int32, device=dev)
+        feats, nf, st = fe.extract_indexed(wav, off, ln, max_len=part["s1"] - part["s0"])
+        if int(st[0]) != 0:
+            raise L.AadError(f"piece {rank}: {L.ITEM_STATUS_NAMES.get(int(st[0]), 'item failed')}")
+        mine = feats[0, :, part["skip"]:part["skip"] + n].contiguous()
+        local_max = mine.max().reshape(1)
+    else:
+        mine = torch.zeros((params.n_filt, 0), dtype=torch.float32, device=dev)
+        local_max = torch.full((1,), float("-inf"), dtype=torch.float32, device=dev)
+    if local_max_hook is not None:
+        gmax = local_max_hook(local_max)
+    else:
+        gmax = local_max.clone()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
+    if n > 0:
+        nfr = torch.tensor([n], dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            L.check(fe.lib.aad_db_reference(_ptr(mine), 0, n, _ptr(nfr), _ptr(gmax.contiguous()), 1, params.n_filt, n,
+                                            int(params.ref_type), float(params.top_db), C.c_void_p(stream)),
+                    "aad_db_reference")
+    return mine, (part["t0"], part["t1"])
+
+
 def bind_to_gpu_numa(physical_gpu_index: int) -> Optional[List[int]]:
     """Pin the calling process to the CPUs NVML reports as local to the GPU (same NUMA node / PCIe
     root), so that pinned host buffers allocated afterwards are first-touched next to it.  With one

@@ -184,6 +184,15 @@ int aad_lfcc(const aad_plan* plan, const void* wav, int wav_dtype, int64_t wav_s
 int aad_delta(const float* x, const int32_t* n_frames, int B, int C, int32_t t_stride,
               int width, int order, float* out, void* stream);
 
+/* librosa.power_to_db's reference / floor (ASV_dl_func.py:534) as a separate step, for an utterance whose
+ * frames were computed in several pieces (time-axis split of long-form audio across GPUs):
+ * every piece is extracted with ref_type = AAD_REF_ONE and top_db < 0 (raw 10 log10(max(amin, S))), the
+ * caller reduces the per-utterance maximum over the pieces (one MAX all-reduce of B floats), then
+ *   x[b][f][t] = max(x - ref, (utt_max[b] - ref) - top_db),  ref = utt_max[b] (AAD_REF_UTT_MAX) or 0,
+ * in place on x[B][n_filt][stride_f] (CT layout), frames t < n_frames[b].  top_db < 0: no floor. */
+int aad_db_reference(float* x, int64_t stride_b, int32_t stride_f, const int32_t* n_frames, const float* utt_max,
+                     int B, int n_filt, int32_t t_max, int ref_type, float top_db, void* stream);
+
 /* Feature standardisation, the step right after the path in the reference: sklearn StandardScaler
  * fitted on np.vstack(per-utterance feature arrays) and applied per utterance
  * (prepare_train_test_data ASV_dl_func.py:1113-1129, train_all_features :963-973).

@@ -140,3 +140,33 @@ def test_noise_augmentation_on_device_is_y_plus_factor_times_randn():
     # the added noise has the reference's variance: mean power rises by ~ 1.022^2
     y_aug = np.concatenate(noisy)
     assert abs(np.var(y_aug - np.concatenate([clips[0][2 * SR:4 * SR], clips[1]])) / 1.022 ** 2 - 1) < 0.05
+
+
+def test_long_form_time_split_equals_the_unsplit_extraction():
+    """BASELINE config 5 with fewer utterances than GPUs: one utterance split along time over `world`
+    ranks (here run one after the other on one GPU, the MAX all-reduce replaced by a hook); the
+    concatenated pieces equal the single-pass log-mel (ref=np.max, top_db=80) bit for bit."""
+    from audioanalysisdetector_b200 import FrontendParams, long_form_logmel
+    dev = torch.device("cuda:0")
+    sr, L = 48000, 48000 * 20 + 333
+    y = speech(31, L, sr)
+    y[: sr] *= 1e-4                                                        # a quiet stretch: the floor bites
+    wav = torch.from_numpy(y).to(dev)
+    params = FrontendParams.logmel(sr, n_mels=128, n_fft=2048, hop_length=480)
+    want, nf, st = _fe(params)(wav[None, :])
+    T = int(nf[0])
+    assert int(st[0]) == 0 and float(want[0].min()) == -80.0               # top_db active
+    for world in (2, 3, 8):
+        raws = []
+        for r in range(world):                                             # pass 1: local maxima
+            raws.append(long_form_logmel(params.replace(ref_type=0, top_db=-1.0), wav, r, world,
+                                         local_max_hook=lambda m: m)[0])
+        gmax = torch.stack([x.max() for x in raws if x.numel()]).max().reshape(1)
+        pieces, covered = [], []
+        for r in range(world):
+            f, (t0, t1) = long_form_logmel(params, wav, r, world, local_max_hook=lambda m: gmax)
+            pieces.append(f)
+            covered.append((t0, t1))
+        assert covered[0][0] == 0 and covered[-1][1] == T
+        got = torch.cat(pieces, dim=1)
+        assert got.shape == (128, T) and torch.equal(got, want[0, :, :T])

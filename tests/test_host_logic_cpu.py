@@ -184,3 +184,29 @@ def test_load_pcm_keeps_int16_and_equals_the_float_decode(tmp_path):
     assert y.dtype == np.float32 and np.array_equal(raw.astype(np.float32) / 32768.0, y)
     arr, sr3 = audio_io.load_pcm((y, 22050))                              # in-memory clips stay float32
     assert arr.dtype == np.float32 and sr3 == 22050
+
+
+def test_time_split_covers_every_frame_with_its_own_samples():
+    """sharding.time_split (long-form audio over several GPUs): the pieces own disjoint frame
+    ranges that cover the utterance, and local frame skip + i of a piece reads exactly the samples global
+    frame t0 + i reads (windows clipped at the true signal ends only)."""
+    for length, n_fft, hop in [(28_800_000, 2048, 480), (64000, 2048, 512), (64000, 512, 160), (5000, 2048, 512),
+                               (479, 2048, 480), (100_001, 1024, 256)]:
+        T = 1 + length // hop
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                p = sharding.time_split(length, n_fft, hop, r, world)
+                seen += list(range(p["t0"], p["t1"]))
+                if p["t1"] == p["t0"]:
+                    continue
+                assert 0 <= p["s0"] <= p["s1"] <= length and p["s0"] % hop == 0
+                T_local = 1 + (p["s1"] - p["s0"]) // hop
+                assert p["skip"] + (p["t1"] - p["t0"]) <= T_local
+                for i in (0, p["t1"] - p["t0"] - 1):
+                    g_lo, g_hi = (p["t0"] + i) * hop - n_fft // 2, (p["t0"] + i) * hop + n_fft // 2
+                    l_lo = p["s0"] + (p["skip"] + i) * hop - n_fft // 2
+                    assert l_lo == g_lo                                       # same window position
+                    # the part of the window inside the true signal is inside the slice
+                    assert max(g_lo, 0) >= p["s0"] and min(g_hi, length) <= p["s1"]
+            assert seen == list(range(T))
