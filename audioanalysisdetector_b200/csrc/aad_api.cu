@@ -673,8 +673,11 @@ int aad_query(const aad_plan* pl, int B, int64_t max_len, int32_t* t_max, int32_
 
 int aad_plan_launches(const aad_plan* pl) {
   if (!pl) return AAD_ERR_INVALID_ARG;
-  // prepare, stft_fb, cepstra|finalize, [time_mean], [znorm stats + apply]
-  return 2 + 1 + (pl->need_ws_feat ? 1 : 0) + (pl->p.znorm ? 2 : 0);
+  // prepare, stft_fb, cepstra | finalize (only when there is a reference or a floor to apply), [time_mean],
+  // [znorm stats + apply]
+  const aad_params& p = pl->p;
+  const bool fin = pl->need_ws_E || (p.log_type == AAD_LOG_DB10 && (p.ref_type == AAD_REF_UTT_MAX || p.top_db >= 0.f));
+  return 2 + (fin ? 1 : 0) + (pl->need_ws_feat ? 1 : 0) + (p.znorm ? 2 : 0);
 }
 
 static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_stride,
@@ -783,7 +786,7 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
     FinArgs fa;
     fa.out = out; fa.stride_b = out_stride_b; fa.stride_f = t_alloc; fa.nf_eff = d_nf; fa.utt_max = d_max; fa.utt_max_f = nullptr;
     fa.n_filt = p.n_filt; fa.ref_type = p.ref_type; fa.top_db = p.top_db;
-    if (p.log_type == AAD_LOG_DB10) {
+    if (p.log_type == AAD_LOG_DB10 && (p.ref_type == AAD_REF_UTT_MAX || p.top_db >= 0.f)) {  // else: identity
       const int n_row_blocks = (p.n_filt + FIN_ROWS - 1) / FIN_ROWS;
       const int n_chunks = (std::max(t_max, 1) + FIN_CHUNK - 1) / FIN_CHUNK;
       const long long nblk = (long long)B * n_row_blocks * n_chunks;

@@ -246,12 +246,13 @@ class Frontend:
 
     # ---- chunks of decoded files that already sit in device memory ------------------
     def extract_indexed(self, pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor,
-                        max_len: Optional[int] = None):
+                        max_len: Optional[int] = None, validate: bool = True):
         """pcm: 1-D float32|int16 on this device (decoded files back to back); utterance b is
         pcm[offsets[b] : offsets[b] + lengths[b]] (offsets int64, lengths int32; chunks may overlap).
         Same returns as __call__.  The reference slices `y[start_sample:end_sample]` after decoding the
         whole file once per chunk (ASV_dl_func.py:406-411); here the slice is an offset in a table.
-        `max_len` (default lengths.max(), which costs a device->host read) bounds the output width."""
+        `max_len` (default lengths.max(), which costs a device->host read) bounds the output width;
+        `validate=False` skips the bounds check of the table (another device->host read)."""
         if pcm.dim() != 1 or not pcm.is_cuda or pcm.device != self.device or not pcm.is_contiguous():
             raise L.AadError(f"pcm must be a contiguous 1-D tensor on {self.device}")
         if pcm.dtype == torch.float32:
@@ -265,10 +266,10 @@ class Frontend:
         B = int(offsets.numel())
         if B == 0 or lengths.numel() != B:
             raise L.AadError("offsets and lengths must be non-empty and of equal size")
-        # one fused check (a device->host read): every chunk inside the buffer
-        lo, hi = int(offsets.min()), int((offsets + lengths.clamp(min=0).to(torch.int64)).max())
-        if lo < 0 or hi > pcm.numel():
-            raise L.AadError(f"chunk table reaches outside the pcm buffer ([{lo}, {hi}) vs {pcm.numel()} samples)")
+        if validate:   # a device->host read: every chunk inside the buffer (skip it for tables built on the host)
+            lo, hi = int(offsets.min()), int((offsets + lengths.clamp(min=0).to(torch.int64)).max())
+            if lo < 0 or hi > pcm.numel():
+                raise L.AadError(f"chunk table reaches outside the pcm buffer ([{lo}, {hi}) vs {pcm.numel()} samples)")
         Lmax = int(max_len) if max_len is not None else max(int(lengths.max()), 1)
         t_max, c_out, ws_bytes = self.query(B, Lmax)
         t_alloc = max(t_max, 1)

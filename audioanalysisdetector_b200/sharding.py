@@ -94,50 +94,61 @@ def time_split(length: int, n_fft: int, hop: int, rank: int, world_size: int) ->
     return {"t0": t0, "t1": t1, "s0": s0, "s1": max(s1, s0), "skip": skip}
 
 
+_split_tables: dict = {}
+
+
 def long_form_logmel(params, wav: torch.Tensor, rank: int, world_size: int, group=None,
-                     local_max_hook=None):
+                     local_max_hook=None, check_status: bool = True):
     """Log-mel (dB) of ONE long utterance `wav` [L] (on this rank's GPU) split along time over the ranks.
 
     Every rank extracts its frames with the reference disabled (raw 10 log10(max(amin, S))), the
     utterance maximum is MAX-all-reduced (the one exchange step), then `aad_db_reference` applies
     `ref=np.max` / `top_db` exactly as power_to_db does.  Returns (features [n_mels, t1 - t0], (t0, t1)):
     the concatenation over ranks equals the unsplit extraction bit for bit.
+    The features are a view into the piece's output (row stride = frames of the piece).  Nothing in the
+    call waits for the GPU unless `check_status` (a device->host read of the piece's status word).
     `local_max_hook(local_max) -> global_max` replaces the all-reduce (tests on one GPU)."""
     import ctypes as C
     import torch.distributed as dist
     from . import _lib as L
-    from .frontend import Frontend, _ptr
+    from .extractors import get_frontend
+    from .frontend import _ptr
     if params.kind != L.KIND_LOGMEL or not params.center or params.time_mean or params.znorm or params.layout != L.LAYOUT_CT:
         raise L.AadError("long_form_logmel needs a centred log-mel plan in CT layout")
     part = time_split(int(wav.numel()), params.n_fft, params.hop_length, rank, world_size)
     n = part["t1"] - part["t0"]
     dev = wav.device
     raw = params.replace(ref_type=L.REF_ONE, top_db=-1.0)
-    fe = Frontend(raw, dev)
+    fe = get_frontend(raw, dev)          # cached plan: repeated calls build no tables
+    key = (int(wav.numel()), params.n_fft, params.hop_length, rank, world_size, str(dev))
+    tabs = _split_tables.get(key)
+    if tabs is None:                     # the one-row chunk table of this piece, built once (no per-call H2D)
+        tabs = _split_tables[key] = (torch.tensor([part["s0"]], dtype=torch.int64, device=dev),
+                                     torch.tensor([max(part["s1"] - part["s0"], 0)], dtype=torch.int32, device=dev),
+                                     torch.tensor([n], dtype=torch.int32, device=dev))
+    off, ln, nfr = tabs
+    status = None
     if n > 0:
-        off = torch.tensor([part["s0"]], dtype=torch.int64, device=dev)
-        ln = torch.tensor([part["s1"] - part["s0"]], dtype=torch.int32, device=dev)
-        feats, nf, st = fe.extract_indexed(wav, off, ln, max_len=part["s1"] - part["s0"])
-        if int(st[0]) != 0:
-            raise L.AadError(f"piece {rank}: {L.ITEM_STATUS_NAMES.get(int(st[0]), 'item failed')}")
-        mine = feats[0, :, part["skip"]:part["skip"] + n].contiguous()
-        local_max = mine.max().reshape(1)
+        feats, _, status = fe.extract_indexed(wav, off, ln, max_len=part["s1"] - part["s0"], validate=False)
+        mine = feats[0, :, part["skip"]:part["skip"] + n]          # a view: rows keep the stride of the piece
+        local_max = mine.amax().reshape(1)
     else:
         mine = torch.zeros((params.n_filt, 0), dtype=torch.float32, device=dev)
         local_max = torch.full((1,), float("-inf"), dtype=torch.float32, device=dev)
     if local_max_hook is not None:
         gmax = local_max_hook(local_max)
     else:
-        gmax = local_max.clone()
+        gmax = local_max
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
     if n > 0:
-        nfr = torch.tensor([n], dtype=torch.int32, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
-            L.check(fe.lib.aad_db_reference(_ptr(mine), 0, n, _ptr(nfr), _ptr(gmax.contiguous()), 1, params.n_filt, n,
-                                            int(params.ref_type), float(params.top_db), C.c_void_p(stream)),
-                    "aad_db_reference")
+            L.check(fe.lib.aad_db_reference(_ptr(mine), 0, mine.stride(0), _ptr(nfr), _ptr(gmax.contiguous()), 1,
+                                            params.n_filt, n, int(params.ref_type), float(params.top_db),
+                                            C.c_void_p(stream)), "aad_db_reference")
+    if check_status and status is not None and int(status[0]) != 0:
+        raise L.AadError(f"piece {rank}: {L.ITEM_STATUS_NAMES.get(int(status[0]), 'item failed')}")
     return mine, (part["t0"], part["t1"])
 
 
