@@ -39,6 +39,9 @@ constexpr int ABL = AAD_ABLATE;
 #ifndef AAD_TWPGEN
 #define AAD_TWPGEN 1
 #endif
+#ifndef AAD_ROW_SKEW
+#define AAD_ROW_SKEW 1
+#endif
 #ifndef AAD_WINFOLD
 #define AAD_WINFOLD 1
 #endif
@@ -238,7 +241,17 @@ struct StftCfg {
   // power-row stride in floats.  The filterbank phase reads P[frame][4g .. 4g+3] as one LDS.128 per
   // lane: conflict-free iff SP/4 is odd.  Q rows double as the warp's 32x33 transpose scratch
   // (Q*SP >= 1056), and the row holds K bins plus zeroed padding (PAD words).
-  static constexpr int SP = L == 4 ? 132 : (L == 8 ? 292 : (L == 16 ? 548 : 1060));
+  // For L = 8 / 16 (4 / 2 frames per warp-iteration) no single stride serves both access patterns: the
+  // power stores of a warp-iteration (Q rows x L consecutive bins) need stride = L (mod 32), the
+  // filterbank reads stride/4 odd.  There the stride is a multiple of 32 and row r is skewed by
+  // skew(r) = L (r mod Q) + 4 ((r / Q) mod (8 / Q)) words: the Q rows of an iteration tile the 32 banks
+  // and 8 consecutive rows start in 8 different 16-byte bank groups (measured before: 2-way conflicts on
+  // every power store of the n_fft 512 shape, 9 % of its shared-memory wavefronts).
+  static constexpr bool SKEW = AAD_ROW_SKEW && (L == 8 || L == 16);
+  static constexpr int SP = L == 4 ? 132 : (L == 8 ? (SKEW ? 288 : 292) : (L == 16 ? (SKEW ? 544 : 548) : 1060));
+  __host__ __device__ static constexpr int skew(int r) {
+    return SKEW ? L * (r & (Q - 1)) + 4 * ((r / Q) & (8 / Q - 1)) : 0;
+  }
   static constexpr int PAD = 3;
   static constexpr int ITERS = TILE / Q;  // warp-iterations per tile
 #ifdef AAD_WARPS_DEV
@@ -260,9 +273,9 @@ struct StftCfg {
   static constexpr int OFF_PROG = OFF_TMEM + 4;               // segment headers + tap weights follow
   static constexpr size_t FIXED_BYTES = size_t(OFF_PROG) * 4;
   static_assert(TILE == 32, "filterbank phase runs with lane = frame");
-  static_assert(SP % 8 == 4, "LDS.128 over lane = frame needs an odd number of 16-byte units per row");
+  static_assert(SKEW ? SP % 32 == 0 : SP % 8 == 4, "LDS.128 over lane = frame needs 8 rows in 8 different 16-byte bank groups");
   static_assert(Q * SP >= 32 * 33, "power rows must hold the transpose scratch");
-  static_assert(SP >= K + PAD, "row must hold the bins and the zero padding");
+  static_assert(SP >= K + PAD + (SKEW ? 28 : 0), "row must hold the bins, the zero padding and the skew");
   static_assert(OFF_PROG % 4 == 0 && OFF_WIN % 4 == 0, "tables must be 16-byte aligned");
 };
 
@@ -694,7 +707,7 @@ k_stft_fb(const StftArgs a) {
       });
 
       // real-input split + power:  X[k] = E - T,  X[M-k] = conj(E + T),  T = i*w*O
-      float* prow = sP + fi * SP;
+      float* prow = sP + fi * SP + C::skew(fi);
 #if AAD_TMEM_TABLES
       TmemChunk pc[2];
       if constexpr (TWPTM) {
@@ -763,7 +776,7 @@ k_stft_fb(const StftArgs a) {
       AAD_PHASE_MARK(1);
 #endif
       const bool valid = b >= 0;
-      const char* pbase = reinterpret_cast<const char*>(sP + lane * SP);
+      const char* pbase = reinterpret_cast<const char*>(sP + lane * SP + C::skew(lane));
       const char* wbase = reinterpret_cast<const char*>(sW4);
       // entry i of the list emits filter wf0 + i - 1
       float* eptr = a.E + (valid ? (long long)b * a.e_stride_b + (long long)(wprog.x - 1) * a.e_stride_f + t : 0);
