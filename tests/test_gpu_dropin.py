@@ -160,3 +160,45 @@ def test_device_standard_scaler_matches_sklearn():
     ref2 = StandardScaler().fit(np.vstack(list(lf.cpu().numpy())))
     got2 = DeviceStandardScaler().fit_transform(lf).cpu().numpy()
     assert np.abs(got2 - np.stack([ref2.transform(x) for x in lf.cpu().numpy()])).max() <= 1e-4
+
+
+def test_train_fun_extractors_and_dispatcher(files, tmp_path):
+    """train_fun.py:69-88 (one averaged vector per file; LFCC averaged over TIME, unlike ASV_dl_func) and the
+    `func(path)` loop at :339-344."""
+    pd = pytest.importorskip("pandas")
+    from audioanalysisdetector_b200 import train_fun as tf
+    for p in files:
+        y, sr = _decoded(p)
+        mf = tf.extract_mfcc(p)
+        want = oracle.extract_mfcc_ref(y, sr, mean=True)
+        assert mf.shape == (13,) and mf.dtype == np.float32 and np.abs(mf - want).max() <= 1e-3
+        lf = tf.extract_lfcc(p)
+        want = oracle.extract_lfcc_ref(y, sr, mean=True, mean_axis=0)
+        assert lf.shape == (13,) and lf.dtype == np.float64 and np.abs(lf - want).max() <= 1e-3
+    assert tf.extract_mfcc(str(tmp_path / "missing.wav")) is None and tf.extract_lfcc(str(tmp_path / "missing.wav")) is None
+    df = pd.DataFrame({"file_path": files + [str(tmp_path / "missing.wav")], "label": ["a", "b", "a", "b"]})
+    df = tf.run_feature_extractors(df, {"MFCC": tf.extract_mfcc, "LFCC": tf.extract_lfcc, "len": lambda p: len(p)})
+    assert df["MFCC"].iloc[-1] is None and df["LFCC"].iloc[-1] is None and df["len"].iloc[0] == len(files[0])
+    for i, p in enumerate(files):
+        y, sr = _decoded(p)
+        assert np.abs(df["MFCC"].iloc[i] - oracle.extract_mfcc_ref(y, sr, mean=True)).max() <= 1e-3
+        assert np.abs(df["LFCC"].iloc[i] - oracle.extract_lfcc_ref(y, sr, mean=True, mean_axis=0)).max() <= 1e-3
+    assert len(df.dropna(subset=["MFCC", "LFCC"])) == len(files)               # train_fun.py:347
+
+
+def test_asv_func_signatures_default_to_the_time_mean(files):
+    """ASV_func.py:43-73,142-156: mean=True by default, LFCC averaged over time (axis 0)."""
+    from audioanalysisdetector_b200 import asv_func as af
+    y, sr = _decoded(files[0])
+    kw = dict(chunk_start=1.0, chunk_end=3.0)
+    got = af.extract_mfcc(files[0], **kw)
+    assert got.shape == (13,) and np.abs(got - oracle.extract_mfcc_ref(y, sr, mean=True, **kw)).max() <= 1e-3
+    got = af.extract_mel_spectrogram(files[0], **kw)
+    assert got.shape == (64,) and np.abs(got - oracle.extract_mel_spectrogram_ref(y, sr, mean=True, **kw)).max() <= 1e-3
+    got = af.extract_lfcc(files[0], **kw)
+    want = oracle.extract_lfcc_ref(y, sr, mean=True, mean_axis=0, **kw)
+    assert got.shape == want.shape == (13,) and got.dtype == np.float64 and np.abs(got - want).max() <= 1e-3
+    got = af.extract_lfcc(files[0], mean=False, **kw)
+    want = oracle.extract_lfcc_ref(y, sr, **kw)
+    assert got.shape == want.shape == (198, 13) and np.abs(got - want).max() <= 1e-3
+    assert af.extract_lfcc(files[0], chunk_start=100.0, chunk_end=102.0) is None
