@@ -9,6 +9,7 @@ from ._lib import AadError
 from .frontend import Frontend, FrontendParams, delta, fp32_peak_tflops
 from .extractors import (compute_melspec, extract_features, extract_lfcc, extract_mel_spectrogram,
                          extract_mfcc, get_frontend)
+from .detector import DetectorEngine
 from .corpus import DeviceCorpus, chunk_bounds, layout_files, two_second_chunks
 from . import asv_func, train_fun  # noqa: F401  (drop-ins for the older ASV_func.py / train_fun.py signatures)
 from .scaler import DeviceStandardScaler, merge_stats
@@ -18,5 +19,5 @@ from .sharding import (bind_to_gpu_numa, contiguous_shard, gather_features, long
 __all__ = [
     "AadError", "Frontend", "FrontendParams", "delta", "fp32_peak_tflops",
     "compute_melspec", "extract_features", "extract_lfcc", "extract_mel_spectrogram", "extract_mfcc", "get_frontend",
-    "DeviceCorpus", "chunk_bounds", "layout_files", "two_second_chunks", "DeviceStandardScaler", "merge_stats", "bind_to_gpu_numa", "contiguous_shard", "gather_features", "long_form_logmel", "partition_by_frames", "time_split",
+    "DetectorEngine", "DeviceCorpus", "chunk_bounds", "layout_files", "two_second_chunks", "DeviceStandardScaler", "merge_stats", "bind_to_gpu_numa", "contiguous_shard", "gather_features", "long_form_logmel", "partition_by_frames", "time_split",
 ]

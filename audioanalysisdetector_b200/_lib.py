@@ -42,6 +42,18 @@ class AadParams(C.Structure):
     ]
 
 
+class AadDetectorWeights(C.Structure):
+    """mirrors `struct aad_detector_weights` (include/aad.h)"""
+    _FP = C.POINTER(C.c_float)
+    _fields_ = [("struct_size", C.c_int32), ("feature_dim", C.c_int32),
+                ("conv_w", _FP), ("conv_b", _FP), ("bn_w", _FP), ("bn_b", _FP), ("bn_mean", _FP), ("bn_var", _FP),
+                ("bn_eps", C.c_float),
+                ("w_ih", _FP), ("w_hh", _FP), ("b_ih", _FP), ("b_hh", _FP),
+                ("w_ih_r", _FP), ("w_hh_r", _FP), ("b_ih_r", _FP), ("b_hh_r", _FP),
+                ("attn_w", _FP), ("attn_b", _FP), ("ln_w", _FP), ("ln_b", _FP),
+                ("fc1_w", _FP), ("fc1_b", _FP), ("fc2_w", _FP), ("fc2_b", _FP)]
+
+
 # every symbol include/aad.h declares: name -> (restype, argtypes)
 _EXTRACT_ARGS = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64,
                  C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
@@ -66,6 +78,11 @@ SYMBOLS = {
                             C.c_void_p, C.c_void_p]),
     "aad_db_reference": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int32,
                                    C.c_int, C.c_float, C.c_void_p]),
+    "aad_detector_create": (C.c_int, [C.POINTER(AadDetectorWeights), C.c_int, C.POINTER(C.c_void_p)]),
+    "aad_detector_destroy": (C.c_int, [C.c_void_p]),
+    "aad_detector_query": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]),
+    "aad_detector_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_size_t, C.c_void_p]),
     "aad_scaler_accumulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "aad_scaler_apply": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),

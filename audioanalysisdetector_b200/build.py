@@ -14,7 +14,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libaad_b200.so")
-SOURCES = [os.path.join(CSRC, "aad_api.cu")]
+SOURCES = [os.path.join(CSRC, "aad_api.cu"), os.path.join(CSRC, "aad_detector.cu")]
 HEADERS = [os.path.join(CSRC, "aad_kernels.cuh"), os.path.join(CSRC, "aad_fft.cuh"),
            os.path.join(os.path.dirname(PKG_DIR), "include", "aad.h")]
 

@@ -213,6 +213,34 @@ int aad_extract_host(aad_plan* plan, const void* wav_host, int wav_dtype, int64_
                      int64_t out_stride_b, int32_t t_alloc, int32_t* n_frames_host,
                      int32_t* status_host, int chunk_utts);
 
+/* ---- the consumer of the features ------------------------------------------------------
+ * Inference of the reference's AudioDeepfakeDetector (cnn_bilstm_hybrid.py:20-68, eval mode: dropout off,
+ * BatchNorm on running statistics) on the front-end's output where it lies in device memory:
+ * Conv1d(63 -> 64, k 3) over the F feature rows with the 63 frames as channels + BatchNorm + ReLU +
+ * MaxPool(2) -> BiLSTM(64 -> 2 x 32) -> LayerNorm(1)-weighted max over time -> Linear(64, 64) + ReLU ->
+ * Linear(64, 1) + Sigmoid.  Replaces `model(x)` at cnn_bilstm_hybrid.py:54-68 and the per-item
+ * torch.tensor(...) collation of CQCCDataset (:4-15).  Weights: HOST pointers in the layouts of the
+ * reference's state dict (conv_w [64][63][3]; w_ih [128][64], w_hh [128][32], gate order i, f, g, o; *_r the
+ * reverse direction; fc1_w [64][64], fc2_w [1][64]).  attn_w / attn_b / ln_w are accepted for completeness:
+ * LayerNorm over one element returns ln_b for every finite input, so they cannot influence the output. */
+typedef struct aad_detector aad_detector;
+typedef struct aad_detector_weights {
+  int32_t struct_size;   /* sizeof(aad_detector_weights) */
+  int32_t feature_dim;   /* F: 13 (MFCC), 19 (CQCC), 64 (log-mel) ...; pooled sequence length F / 2 */
+  const float *conv_w, *conv_b, *bn_w, *bn_b, *bn_mean, *bn_var;
+  float bn_eps;          /* 1e-5 */
+  const float *w_ih, *w_hh, *b_ih, *b_hh, *w_ih_r, *w_hh_r, *b_ih_r, *b_hh_r;
+  const float *attn_w, *attn_b, *ln_w, *ln_b;
+  const float *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+} aad_detector_weights;
+int aad_detector_create(const aad_detector_weights* w, int device, aad_detector** out);
+int aad_detector_destroy(aad_detector* det);
+int aad_detector_query(const aad_detector* det, int B, size_t* workspace_bytes);
+/* feats [B][F][stride_f >= 63] float32 (CT layout, frames 0..62 of every row are read), stride_b in elements
+ * (0 = dense); scores [B] float32 out; enqueued on `stream`, never synchronised. */
+int aad_detector_forward(const aad_detector* det, const float* feats, int64_t stride_b, int32_t stride_f, int B,
+                         float* scores, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- introspection (tests / parity) ---------------------------------------- */
 enum aad_table { AAD_TABLE_WINDOW = 0, AAD_TABLE_FILTERBANK = 1, AAD_TABLE_DCT = 2, AAD_TABLE_DELTA_TAPS = 3 };
 /* Copies a plan table to HOST memory as float32: WINDOW [n_fft] (unscaled, zero-extended),

@@ -1,0 +1,76 @@
+"""GPU: the CNN-BiLSTM consumer as hand-written kernels (DetectorEngine, csrc/aad_detector.cu) against the scores
+of the REAL reference class (tests/golden/consumer.npz, made by tests/golden/make_consumer_golden.py from
+/root/reference/cnn_bilstm_hybrid.py) and against its functional restatement (oracle/consumer_ref.py) on
+seeded random weights and inputs.  Tolerance on the sigmoid scores: 2e-5."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import consumer_ref
+from test_oracle_consumer import consumer_clip, load_fixture
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-5
+
+
+def random_state(seed, ln_bias=0.7):
+    from audioanalysisdetector_b200.detector import _NAMES, _SHAPES
+    rng = np.random.default_rng(seed)
+    st = {}
+    for field, name in _NAMES.items():
+        shape = _SHAPES[field]
+        fan = max(int(np.prod(shape[1:])) if len(shape) > 1 else 8, 1)
+        st[name] = torch.from_numpy((rng.standard_normal(shape) / np.sqrt(fan)).astype(np.float32))
+    st["feature_extractor.1.running_var"] = torch.from_numpy(rng.uniform(0.3, 2.0, 64).astype(np.float32))
+    st["feature_extractor.1.weight"] = torch.from_numpy(rng.uniform(0.5, 1.5, 64).astype(np.float32))
+    st["layer_norm.bias"] = torch.tensor([ln_bias], dtype=torch.float32)
+    return st
+
+
+def test_scores_equal_the_real_reference_model_on_the_golden_fixture():
+    from audioanalysisdetector_b200 import DetectorEngine, Frontend, FrontendParams
+    g, weights = load_fixture()
+    dev = torch.device("cuda:0")
+    eng = DetectorEngine(weights, feature_dim=13, device=dev)
+    got = eng(torch.from_numpy(g["features"]).to(dev))
+    assert got.shape == (8, 1) and got.dtype == torch.float32
+    np.testing.assert_allclose(got.cpu().numpy(), g["scores"], rtol=0, atol=TOL)
+    # the whole hand-off on the device: waveform -> CUDA front-end -> CUDA detector, no host round trip
+    wav = torch.from_numpy(np.stack([consumer_clip(int(s)) for s in g["seeds"]])).to(dev)
+    feats, nf, st = Frontend(FrontendParams.mfcc(16000, n_mfcc=13), dev)(wav)
+    np.testing.assert_allclose(eng(feats).cpu().numpy(), g["scores"], rtol=0, atol=TOL)
+    assert np.abs(eng(feats.flip(0)).cpu().numpy() - g["scores"]).max() > 2e-4      # the comparison has teeth
+
+
+@pytest.mark.parametrize("F,B,ln_bias", [(13, 1, 1.0), (13, 1000, 0.7), (19, 333, -0.5), (64, 257, 1.3), (12, 65, 1.0)])
+def test_matches_the_functional_restatement_on_random_weights(F, B, ln_bias):
+    from audioanalysisdetector_b200 import DetectorEngine
+    dev = torch.device("cuda:0")
+    state = random_state(100 + F, ln_bias)
+    g = torch.Generator(device=dev).manual_seed(F * 1000 + B)
+    x = 5.0 * torch.randn((B, F, 63), generator=g, device=dev) - 2.0
+    with torch.no_grad():
+        want = consumer_ref.forward(state, x.cpu())     # on the CPU: cuDNN's convolution would run in TF32
+    got = DetectorEngine(state, feature_dim=F, device=dev)(x).cpu()
+    assert got.shape == want.shape == (B, 1)
+    assert float((got - want).abs().max()) <= TOL
+    assert B == 1 or float(want.std()) > 1e-3                                      # scores are not saturated
+
+
+def test_strided_input_reads_the_first_63_frames():
+    """Features of longer clips ((B, F, T > 63) with a row stride) go in as they are: frames 0..62, like x[:, :, :63]."""
+    from audioanalysisdetector_b200 import AadError, DetectorEngine
+    dev = torch.device("cuda:0")
+    state = random_state(7)
+    g = torch.Generator(device=dev).manual_seed(3)
+    big = torch.randn((50, 13, 126), generator=g, device=dev)
+    eng = DetectorEngine(state, feature_dim=13, device=dev)
+    with torch.no_grad():
+        want = consumer_ref.forward(state, big[:, :, :63].contiguous().cpu())
+    assert float((eng(big).cpu() - want).abs().max()) <= TOL
+    assert float((eng(big[10:40]).cpu() - want[10:40]).abs().max()) <= TOL          # a batch slice (offset base pointer)
+    with pytest.raises(AadError):
+        eng(big[:, :, :40])                                                        # fewer than 63 frames
+    with pytest.raises(AadError):
+        eng(big[:, :12, :])                                                        # wrong feature count
+    assert eng(big[:0]).shape == (0, 1)

@@ -210,3 +210,26 @@ def test_time_split_covers_every_frame_with_its_own_samples():
                     # the part of the window inside the true signal is inside the slice
                     assert max(g_lo, 0) >= p["s0"] and min(g_hi, length) <= p["s1"]
             assert seen == list(range(T))
+
+
+def test_detector_weight_packing_validates_the_state_dict():
+    """DetectorEngine's host half: the reference's parameter names and default shapes (cnn_bilstm_hybrid.py:20-52),
+    pointers into float32 host copies that stay alive; anything else is rejected before the C ABI sees it."""
+    import ctypes as C
+    from audioanalysisdetector_b200 import AadError
+    from audioanalysisdetector_b200.detector import _NAMES, _SHAPES, pack_weights
+    from test_oracle_consumer import load_fixture
+    _, weights = load_fixture()
+    w, keep = pack_weights(weights, 13)
+    assert w.struct_size == C.sizeof(type(w)) and w.feature_dim == 13 and len(keep) == len(_NAMES)
+    assert all(a.dtype == np.float32 and a.flags["C_CONTIGUOUS"] for a in keep)
+    assert w.conv_w[5] == np.float32(np.asarray(weights["feature_extractor.0.weight"]).reshape(-1)[5])
+    bad = dict(weights)
+    del bad["bilstm.weight_hh_l0_reverse"]
+    with pytest.raises(AadError):
+        pack_weights(bad, 13)
+    bad = dict(weights)
+    bad["classifier.0.weight"] = np.zeros((32, 64), np.float32)                    # dense_units != 64
+    with pytest.raises(AadError):
+        pack_weights(bad, 13)
+    assert set(_SHAPES) == set(_NAMES)

@@ -6,9 +6,10 @@ across the GPUs of one box (no collective in the extraction; one all-gather of t
     python tools/c4_pipeline.py                          # one GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/c4_pipeline.py
 
-The consumer is the reference's AudioDeepfakeDetector (cnn_bilstm_hybrid.py:20-68) restated in
-oracle/consumer_ref.py with the committed fixture weights (stock PyTorch ops; it is not part of the hot
-path).  This script is an example / measurement tool, not a product entry point.
+The consumer is the reference's AudioDeepfakeDetector (cnn_bilstm_hybrid.py:20-68) with the committed
+fixture weights, run by the hand-written kernels of DetectorEngine (csrc/aad_detector.cu); the same model as
+stock PyTorch ops (oracle/consumer_ref.py, the restatement the tests pin to the real reference class) is timed
+beside it and checks the scores.  This script is an example / measurement tool, not a product entry point.
 """
 import json
 import os
@@ -48,32 +49,37 @@ def main():
     weights = {k[3:]: torch.from_numpy(g[k]).to(dev) for k in g.files if k.startswith("w::")}
     fe_mfcc = Frontend(FrontendParams.mfcc(SR, n_mfcc=13), dev)
     fe_mel = Frontend(FrontendParams.logmel(SR, n_mels=64), dev)
+    engine = aad.DetectorEngine(weights, feature_dim=13, device=dev)
 
     def step():
         feats, nf, st = fe_mfcc(wav)                 # (n_local, 13, 63) on device
         mel, _, _ = fe_mel(wav)                      # (n_local, 64, 63): the second feature of the map
+        scores = engine(feats)                       # hand-written CNN-BiLSTM inference, features stay where they are
         with torch.no_grad():
-            scores = torch.cat([consumer_ref.forward(weights, feats[i:i + 4096]) for i in range(0, n_local, 4096)])
-        return feats, mel, scores, st
+            ref = torch.cat([consumer_ref.forward(weights, feats[i:i + 4096]) for i in range(0, n_local, 4096)])
+        return feats, mel, scores, st, ref
 
     for _ in range(2):
         step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
     e0.record()
     feats, nf, st = fe_mfcc(wav)
     mel, _, _ = fe_mel(wav)
     e1.record()
-    with torch.no_grad():
-        scores = torch.cat([consumer_ref.forward(weights, feats[i:i + 4096]) for i in range(0, n_local, 4096)])
+    scores = engine(feats)
     e2.record()
+    with torch.no_grad():
+        ref = torch.cat([consumer_ref.forward(weights, feats[i:i + 4096]) for i in range(0, n_local, 4096)])
+    e3.record()
     torch.cuda.synchronize(dev)
-    t_feat, t_model = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    t_feat, t_model, t_torch = e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3)
+    max_diff = float((scores - ref).abs().max().item())
     idx = torch.arange(sl.start, sl.stop, device=dev)
     all_scores = aad.gather_features(scores, idx, N_CHUNKS)          # one all-gather, outside the extraction
-    t = torch.tensor([t_feat, t_model], device=dev, dtype=torch.float64)
+    t = torch.tensor([t_feat, t_model, t_torch, max_diff], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
@@ -81,7 +87,8 @@ def main():
         print(json.dumps({
             "config": "configs[3]: 25 380 x 2 s @16 kHz -> MFCC-13 + log-mel-64 -> CNN-BiLSTM scores",
             "n_gpus": world, "chunks_per_gpu": n_local, "status_nonzero": int(st.ne(0).sum().item()),
-            "features_ms": float(t[0]), "model_ms": float(t[1]),
+            "features_ms": float(t[0]), "model_ms": float(t[1]), "model_stock_pytorch_ms": float(t[2]),
+            "scores_max_abs_diff_vs_stock_pytorch": float(t[3]),
             "features_audio_hours_per_s": hours / (float(t[0]) * 1e-3),
             "pipeline_audio_hours_per_s": hours / ((float(t[0]) + float(t[1])) * 1e-3),
             "scores_shape": list(all_scores.shape), "scores_mean": float(all_scores.mean().item()),
