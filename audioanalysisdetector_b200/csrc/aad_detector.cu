@@ -53,9 +53,10 @@ __global__ void __launch_bounds__(256) k_det_transpose(const float* __restrict__
 
 // ---------------------------------------------------------------- conv + BN + ReLU, lane = sample
 // smem: Wt[KCONV][64] (k = tap * 63 + ci), scale[64], shift[64] (BatchNorm folded around the conv bias)
-__global__ void __launch_bounds__(64) k_det_conv(const float* __restrict__ X0, int F, int Bp, int n_pos,
-                                                 const float* __restrict__ Wt, const float* __restrict__ scale_shift,
-                                                 float* __restrict__ H0) {
+constexpr int CONV_WARPS = 4;  // a CTA = 32 samples; warp w takes positions w, w + 4, ... (the batch is small: more warps per SM)
+__global__ void __launch_bounds__(32 * CONV_WARPS) k_det_conv(const float* __restrict__ X0, int F, int Bp, int n_pos,
+                                                             const float* __restrict__ Wt, const float* __restrict__ scale_shift,
+                                                             float* __restrict__ H0) {
   extern __shared__ __align__(16) float sm[];
   float* sW = sm;
   float* sSS = sm + KCONV * C1;
@@ -63,8 +64,8 @@ __global__ void __launch_bounds__(64) k_det_conv(const float* __restrict__ X0, i
     reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(Wt) + i);
   for (int i = threadIdx.x; i < 2 * C1; i += blockDim.x) sSS[i] = __ldg(scale_shift + i);
   __syncthreads();
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;  // Bp is a multiple of the block size
-  for (int p = 0; p < n_pos; ++p) {
+  const int b = blockIdx.x * 32 + (threadIdx.x & 31);  // Bp is a multiple of 32
+  for (int p = threadIdx.x >> 5; p < n_pos; p += CONV_WARPS) {
     float2 acc[C1 / 2];
 #pragma unroll
     for (int i = 0; i < C1 / 2; ++i) acc[i] = make_float2(0.f, 0.f);
@@ -73,15 +74,21 @@ __global__ void __launch_bounds__(64) k_det_conv(const float* __restrict__ X0, i
       if (q < 0 || q >= F) continue;  // zero padding
       const float* xp = X0 + (long long)q * T_IN * Bp + b;
       const float4* wp = reinterpret_cast<const float4*>(sW + tap * T_IN * C1);
-#pragma unroll 3
-      for (int ci = 0; ci < T_IN; ++ci) {
-        const float x = __ldg(xp + (long long)ci * Bp);
-        const float2 xx = make_float2(x, x);
+      // the inputs come from L2 (X0 does not fit L1): 21 loads in flight per lane, three batches per tap
+#pragma unroll 1
+      for (int c0 = 0; c0 < T_IN; c0 += 21) {
+        float xs[21];
 #pragma unroll
-        for (int i = 0; i < C1 / 4; ++i) {
-          const float4 w = wp[ci * (C1 / 4) + i];
-          acc[2 * i] = __ffma2_rn(xx, make_float2(w.x, w.y), acc[2 * i]);
-          acc[2 * i + 1] = __ffma2_rn(xx, make_float2(w.z, w.w), acc[2 * i + 1]);
+        for (int i = 0; i < 21; ++i) xs[i] = __ldg(xp + (long long)(c0 + i) * Bp);
+#pragma unroll
+        for (int ci = 0; ci < 21; ++ci) {
+          const float2 xx = make_float2(xs[ci], xs[ci]);
+#pragma unroll
+          for (int i = 0; i < C1 / 4; ++i) {
+            const float4 w = wp[(c0 + ci) * (C1 / 4) + i];
+            acc[2 * i] = __ffma2_rn(xx, make_float2(w.x, w.y), acc[2 * i]);
+            acc[2 * i + 1] = __ffma2_rn(xx, make_float2(w.z, w.w), acc[2 * i + 1]);
+          }
         }
       }
     }
@@ -99,9 +106,13 @@ __global__ void __launch_bounds__(64) k_det_conv(const float* __restrict__ X0, i
 //       W1t[64 in][64 out], b1[64], w2[64], misc[2] = {b2, ln_bias}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-__global__ void __launch_bounds__(256) k_det_lstm(const float* __restrict__ H0, int P, int B, int Bp,
-                                                  const float* __restrict__ blob, int blob_floats,
-                                                  float* __restrict__ scores) {
+// A tile of 32 samples is run by TWO warps, one per LSTM direction (the batch is small: this doubles the warps per
+// SM and halves the critical path); they meet once, at a named barrier, to hand the backward half of the pooled
+// vector to the forward warp, which runs the classifier.  sPool: [pairs per CTA][32 units][32 lanes].
+constexpr int LSTM_THREADS = 512;
+__global__ void __launch_bounds__(LSTM_THREADS) k_det_lstm(const float* __restrict__ H0, int P, int B, int Bp,
+                                                          const float* __restrict__ blob, int blob_floats,
+                                                          float* __restrict__ scores) {
   extern __shared__ __align__(16) float sm[];
   for (int i = threadIdx.x; i < blob_floats / 4; i += blockDim.x)
     reinterpret_cast<float4*>(sm)[i] = __ldg(reinterpret_cast<const float4*>(blob) + i);
@@ -112,70 +123,81 @@ __global__ void __launch_bounds__(256) k_det_lstm(const float* __restrict__ H0, 
   const float* sB1 = sW1 + 2 * HID * DENSE;
   const float* sW2 = sB1 + DENSE;
   const float b2 = sW2[DENSE], ln_b = sW2[DENSE + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pair = warp >> 1, dir = warp & 1, pairs_per_cta = LSTM_THREADS / 64;
+  float* sPool = sm + blob_floats + pair * HID * 32;
 
-  const int warps_per_cta = blockDim.x >> 5, lane = threadIdx.x & 31;
-  for (int tile = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); tile * 32 < B; tile += gridDim.x * warps_per_cta) {
+  // tile -> (CTA, warp pair) with the CTA index fastest: a small batch spreads over all SMs before it stacks up
+  for (int tile = pair * gridDim.x + blockIdx.x; tile * 32 < B; tile += gridDim.x * pairs_per_cta) {
     const int b = tile * 32 + lane;  // < Bp
-    float pm[2 * HID];               // running max over time of lstm_out * ln_bias (dynamic index: local memory)
-    for (int u = 0; u < 2 * HID; ++u) pm[u] = -INFINITY;
-    for (int dir = 0; dir < 2; ++dir) {
-      float v[C1 + HID];             // [x_t | h_{t-1}], static indices only: registers
-      float c[HID], hn[HID];         // dynamic index: local memory
+    float v[C1 + HID];               // [x_t | h_{t-1}], static indices only: registers
+    float c[HID], hn[HID], pm[HID];  // dynamic index: local memory
 #pragma unroll
-      for (int j = 0; j < HID; ++j) v[C1 + j] = 0.f;
-      for (int u = 0; u < HID; ++u) c[u] = 0.f;
-      const float4* Wd = sWq + dir * 96 * HID;
-      const float4* Bd = sBq + dir * HID;
-      for (int s = 0; s < P; ++s) {
-        const int t = dir ? P - 1 - s : s;
-        const float* h0 = H0 + (long long)(2 * t) * C1 * Bp + b;
+    for (int j = 0; j < HID; ++j) v[C1 + j] = 0.f;
+    for (int u = 0; u < HID; ++u) {
+      c[u] = 0.f;
+      pm[u] = -INFINITY;             // running max over time of lstm_out * ln_bias
+    }
+    const float4* Wd = sWq + dir * 96 * HID;
+    const float4* Bd = sBq + dir * HID;
+    for (int s = 0; s < P; ++s) {
+      const int t = dir ? P - 1 - s : s;
+      const float* h0 = H0 + (long long)(2 * t) * C1 * Bp + b;
 #pragma unroll
-        for (int j = 0; j < C1; ++j)   // MaxPool1d(2) of the conv output (already BN + ReLU)
-          v[j] = fmaxf(__ldg(h0 + (long long)j * Bp), __ldg(h0 + (long long)(C1 + j) * Bp));
+      for (int j = 0; j < C1; ++j)   // MaxPool1d(2) of the conv output (already BN + ReLU)
+        v[j] = fmaxf(__ldg(h0 + (long long)j * Bp), __ldg(h0 + (long long)(C1 + j) * Bp));
 #pragma unroll 1
-        for (int u = 0; u < HID; ++u) {
-          const float4 bq = Bd[u];
-          float2 g01 = make_float2(bq.x, bq.y), g23 = make_float2(bq.z, bq.w);
-          float2 h01 = make_float2(0.f, 0.f), h23 = make_float2(0.f, 0.f);  // second chain (ILP)
+      for (int u = 0; u < HID; ++u) {
+        const float4 bq = Bd[u];
+        float2 g01 = make_float2(bq.x, bq.y), g23 = make_float2(bq.z, bq.w);
+        float2 h01 = make_float2(0.f, 0.f), h23 = make_float2(0.f, 0.f);  // second chain (ILP)
 #pragma unroll
-          for (int j = 0; j < C1 + HID; j += 2) {
-            const float4 w0 = Wd[j * HID + u], w1 = Wd[(j + 1) * HID + u];
-            const float2 x0 = make_float2(v[j], v[j]), x1 = make_float2(v[j + 1], v[j + 1]);
-            g01 = __ffma2_rn(x0, make_float2(w0.x, w0.y), g01);
-            g23 = __ffma2_rn(x0, make_float2(w0.z, w0.w), g23);
-            h01 = __ffma2_rn(x1, make_float2(w1.x, w1.y), h01);
-            h23 = __ffma2_rn(x1, make_float2(w1.z, w1.w), h23);
-          }
-          const float gi = sigmoidf_(g01.x + h01.x), gf = sigmoidf_(g01.y + h01.y);
-          const float gg = tanhf(g23.x + h23.x), go = sigmoidf_(g23.y + h23.y);
-          const float cn = fmaf(gf, c[u], gi * gg);
-          c[u] = cn;
-          const float h = go * tanhf(cn);
-          hn[u] = h;
-          pm[dir * HID + u] = fmaxf(pm[dir * HID + u], h * ln_b);
+        for (int j = 0; j < C1 + HID; j += 2) {
+          const float4 w0 = Wd[j * HID + u], w1 = Wd[(j + 1) * HID + u];
+          const float2 x0 = make_float2(v[j], v[j]), x1 = make_float2(v[j + 1], v[j + 1]);
+          g01 = __ffma2_rn(x0, make_float2(w0.x, w0.y), g01);
+          g23 = __ffma2_rn(x0, make_float2(w0.z, w0.w), g23);
+          h01 = __ffma2_rn(x1, make_float2(w1.x, w1.y), h01);
+          h23 = __ffma2_rn(x1, make_float2(w1.z, w1.w), h23);
         }
-#pragma unroll
-        for (int j = 0; j < HID; ++j) v[C1 + j] = hn[j];
+        const float gi = sigmoidf_(g01.x + h01.x), gf = sigmoidf_(g01.y + h01.y);
+        const float gg = tanhf(g23.x + h23.x), go = sigmoidf_(g23.y + h23.y);
+        const float cn = fmaf(gf, c[u], gi * gg);
+        c[u] = cn;
+        const float h = go * tanhf(cn);
+        hn[u] = h;
+        pm[u] = fmaxf(pm[u], h * ln_b);
       }
-    }
-    // classifier: Linear(64, 64) + ReLU + Linear(64, 1) + Sigmoid
-    float x[2 * HID];
 #pragma unroll
-    for (int j = 0; j < 2 * HID; ++j) x[j] = pm[j];
-    float z = b2;
+      for (int j = 0; j < HID; ++j) v[C1 + j] = hn[j];
+    }
+    // the backward warp hands its half of the pooled vector over; the forward warp runs the classifier
+    if (dir == 1)
+      for (int u = 0; u < HID; ++u) sPool[u * 32 + lane] = pm[u];
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+    if (dir == 0) {
+      float x[2 * HID];
+#pragma unroll
+      for (int j = 0; j < HID; ++j) {
+        x[j] = pm[j];
+        x[HID + j] = sPool[j * 32 + lane];
+      }
+      float z = b2;
 #pragma unroll 1
-    for (int n = 0; n < DENSE; n += 4) {
-      float4 a = *reinterpret_cast<const float4*>(sB1 + n);
+      for (int n = 0; n < DENSE; n += 4) {
+        float4 a = *reinterpret_cast<const float4*>(sB1 + n);
 #pragma unroll
-      for (int j = 0; j < 2 * HID; ++j) {
-        const float4 w = *reinterpret_cast<const float4*>(sW1 + j * DENSE + n);
-        a.x = fmaf(x[j], w.x, a.x); a.y = fmaf(x[j], w.y, a.y); a.z = fmaf(x[j], w.z, a.z); a.w = fmaf(x[j], w.w, a.w);
+        for (int j = 0; j < 2 * HID; ++j) {
+          const float4 w = *reinterpret_cast<const float4*>(sW1 + j * DENSE + n);
+          a.x = fmaf(x[j], w.x, a.x); a.y = fmaf(x[j], w.y, a.y); a.z = fmaf(x[j], w.z, a.z); a.w = fmaf(x[j], w.w, a.w);
+        }
+        const float4 w2 = *reinterpret_cast<const float4*>(sW2 + n);
+        z = fmaf(fmaxf(a.x, 0.f), w2.x, z); z = fmaf(fmaxf(a.y, 0.f), w2.y, z);
+        z = fmaf(fmaxf(a.z, 0.f), w2.z, z); z = fmaf(fmaxf(a.w, 0.f), w2.w, z);
       }
-      const float4 w2 = *reinterpret_cast<const float4*>(sW2 + n);
-      z = fmaf(fmaxf(a.x, 0.f), w2.x, z); z = fmaf(fmaxf(a.y, 0.f), w2.y, z);
-      z = fmaf(fmaxf(a.z, 0.f), w2.z, z); z = fmaf(fmaxf(a.w, 0.f), w2.w, z);
+      if (b < B) scores[b] = sigmoidf_(z);
     }
-    if (b < B) scores[b] = sigmoidf_(z);
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");  // sPool is free for the pair's next tile
   }
 }
 
@@ -193,9 +215,10 @@ struct aad_detector {
 using namespace aadd;
 
 static size_t det_conv_smem() { return (size_t)(KCONV * C1 + 2 * C1) * 4; }
+static size_t det_lstm_smem(int blob_floats) { return ((size_t)blob_floats + (LSTM_THREADS / 64) * HID * 32) * 4; }
 
 static void det_layout(const aad_detector* d, int B, int* Bp, size_t* off_x0, size_t* off_h0, size_t* total) {
-  *Bp = (B + 63) / 64 * 64;
+  *Bp = (B + 31) / 32 * 32;
   size_t o = 0;
   *off_x0 = o; o += (size_t)d->F * T_IN * *Bp * 4; o = (o + 255) & ~(size_t)255;
   *off_h0 = o; o += (size_t)2 * d->P * C1 * *Bp * 4; o = (o + 255) & ~(size_t)255;
@@ -259,7 +282,7 @@ int aad_detector_create(const aad_detector_weights* w, int device, aad_detector*
   if (e == cudaSuccess) e = cudaMemcpy(d->d_ss, ss.data(), ss.size() * 4, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(d->d_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)k_det_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)det_conv_smem());
-  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)k_det_lstm, cudaFuncAttributeMaxDynamicSharedMemorySize, d->blob_floats * 4);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)k_det_lstm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)det_lstm_smem(d->blob_floats));
   if (e != cudaSuccess) {
     aad_detector_destroy(d);
     return AAD_ERR_CUDA;
@@ -299,10 +322,11 @@ int aad_detector_forward(const aad_detector* d, const float* feats, int64_t stri
   float* H0 = (float*)((char*)workspace + off_h0);
   (void)cudaGetLastError();
   k_det_transpose<<<dim3(Bp / 32, 2, d->F), 256, 0, stream>>>(feats, stride_b, stride_f, B, Bp, X0);
-  k_det_conv<<<Bp / 64, 64, det_conv_smem(), stream>>>(X0, d->F, Bp, 2 * d->P, d->d_wt, d->d_ss, H0);
-  const int tiles = (B + 31) / 32;
-  const int grid = std::max(1, std::min(d->sm_count, (tiles + 7) / 8));
-  k_det_lstm<<<grid, 256, (size_t)d->blob_floats * 4, stream>>>(H0, d->P, B, Bp, d->d_blob, d->blob_floats, scores);
+  k_det_conv<<<Bp / 32, 32 * CONV_WARPS, det_conv_smem(), stream>>>(X0, d->F, Bp, 2 * d->P, d->d_wt, d->d_ss, H0);
+  const int tiles = (B + 31) / 32, per_cta = LSTM_THREADS / 64;
+  const int grid = std::max(1, std::min(d->sm_count, tiles));
+  (void)per_cta;
+  k_det_lstm<<<grid, LSTM_THREADS, det_lstm_smem(d->blob_floats), stream>>>(H0, d->P, B, Bp, d->d_blob, d->blob_floats, scores);
   return cudaGetLastError() == cudaSuccess ? AAD_OK : AAD_ERR_CUDA;
 }
 
