@@ -12,6 +12,7 @@ from .extractors import (compute_melspec, extract_features, extract_lfcc, extrac
 from .detector import DetectorEngine
 from .corpus import DeviceCorpus, chunk_bounds, layout_files, two_second_chunks
 from . import asv_func, train_fun  # noqa: F401  (drop-ins for the older ASV_func.py / train_fun.py signatures)
+from .pipeline import score_files
 from .scaler import DeviceStandardScaler, merge_stats
 from .sharding import (bind_to_gpu_numa, contiguous_shard, gather_features, long_form_logmel, partition_by_frames,
                        time_split)
@@ -19,5 +20,5 @@ from .sharding import (bind_to_gpu_numa, contiguous_shard, gather_features, long
 __all__ = [
     "AadError", "Frontend", "FrontendParams", "delta", "fp32_peak_tflops",
     "compute_melspec", "extract_features", "extract_lfcc", "extract_mel_spectrogram", "extract_mfcc", "get_frontend",
-    "DetectorEngine", "DeviceCorpus", "chunk_bounds", "layout_files", "two_second_chunks", "DeviceStandardScaler", "merge_stats", "bind_to_gpu_numa", "contiguous_shard", "gather_features", "long_form_logmel", "partition_by_frames", "time_split",
+    "DetectorEngine", "score_files", "DeviceCorpus", "chunk_bounds", "layout_files", "two_second_chunks", "DeviceStandardScaler", "merge_stats", "bind_to_gpu_numa", "contiguous_shard", "gather_features", "long_form_logmel", "partition_by_frames", "time_split",
 ]

@@ -74,3 +74,32 @@ def test_strided_input_reads_the_first_63_frames():
     with pytest.raises(AadError):
         eng(big[:, :12, :])                                                        # wrong feature count
     assert eng(big[:0]).shape == (0, 1)
+
+
+def test_score_files_equals_the_reference_flow_chunk_by_chunk(tmp_path):
+    """wav files -> 2-s chunk rows -> MFCC-13 -> model, all on the device, against the same flow done by hand with
+    the oracle: per-chunk slicing (ASV_dl_func.py:407-410), librosa MFCC restatement, the model's restatement."""
+    import wave
+    import oracle
+    from audioanalysisdetector_b200 import audio_io, score_files
+    from helpers import noise, speech
+    sr = 16000
+    paths = []
+    for i, n in enumerate((5 * sr + 100, 2 * sr, sr)):                     # 2 chunks, 1 chunk, none
+        p = tmp_path / f"s{i}.wav"
+        with wave.open(str(p), "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(sr)
+            y = speech(40 + i, n) if i % 2 else noise(40 + i, n)
+            w.writeframes(np.round(y * 32767).astype("<i2").tobytes())
+        paths.append(str(p))
+    _, weights = load_fixture()
+    scores, rows = score_files(paths, weights)
+    assert rows == [(0, 0.0, 2.0), (0, 2.0, 4.0), (1, 0.0, 2.0)] and scores.shape == (3,)
+    feats = []
+    for i, cs, ce in rows:
+        y, _ = audio_io.load(paths[i])
+        feats.append(oracle.extract_mfcc_ref(y, sr, chunk_start=cs, chunk_end=ce))
+    with torch.no_grad():
+        want = consumer_ref.forward(weights, torch.from_numpy(np.stack(feats)))[:, 0].numpy()
+    assert np.abs(scores - want).max() <= 5e-5       # 1e-3 feature tolerance through the model
+    assert score_files([paths[2]], weights)[0].shape == (0,)
