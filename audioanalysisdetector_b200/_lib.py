@@ -71,6 +71,9 @@ SYMBOLS = {
     "aad_extract_indexed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                       C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_size_t, C.c_void_p]),
+    "aad_extract_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "aad_logmel": (C.c_int, _EXTRACT_ARGS),
     "aad_mfcc": (C.c_int, _EXTRACT_ARGS),
     "aad_lfcc": (C.c_int, _EXTRACT_ARGS),

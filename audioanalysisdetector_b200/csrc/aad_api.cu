@@ -11,7 +11,7 @@
 #include <vector>
 
 #include "../../include/aad.h"
-#include "aad_kernels.cuh"
+#include "aad_stft_inst.h"
 
 using namespace aad;
 
@@ -28,6 +28,7 @@ struct aad_plan {
   int warps = 0, ctas = 0;
   size_t k1_smem = 0;
   int n_w4 = 0, n_hdr = 0;
+  int smem_optin = 0;  // device limit of dynamic shared memory per CTA
   int n_ksteps = 0, n_tiles = 0, cep_nt = 1;  // K2: DCT as a GEMM (K steps of 8 filters, N tiles of 8 coefficients)
   int c_feat = 0;     // rows before deltas
   int c_out = 0;
@@ -237,30 +238,15 @@ static cudaError_t upload(T** dptr, const std::vector<T>& h) {
 }
 
 // ---- kernel dispatch table --------------------------------------------------
-typedef void (*stft_kernel_t)(const StftArgs);
-template <int L, int TILE>
-static stft_kernel_t pick_stft_LT(int mode, bool pre) {
-  switch (mode * 2 + (pre ? 1 : 0)) {
-    case 0: return k_stft_fb<L, IN_F32, false, TILE>;
-    case 1: return k_stft_fb<L, IN_F32, true, TILE>;
-    case 2: return k_stft_fb<L, IN_F32_Q16, false, TILE>;
-    case 3: return k_stft_fb<L, IN_F32_Q16, true, TILE>;
-    case 4: return k_stft_fb<L, IN_I16, false, TILE>;
-    default: return k_stft_fb<L, IN_I16, true, TILE>;
-  }
-}
-static stft_kernel_t pick_stft(int L, int tile, int mode, bool pre) {
-#if AAD_ABLATE || defined(AAD_DEV_BUILD)
-  return L == 32 && tile == 32 && mode == 0 && !pre ? k_stft_fb<32, IN_F32, false, 32> : nullptr;  // dev builds: one variant
-#else
-  switch (L) {
-    case 4: return pick_stft_LT<4, 32>(mode, pre);
-    case 8: return pick_stft_LT<8, 32>(mode, pre);
-    case 16: return pick_stft_LT<16, 32>(mode, pre);
-    case 32: return pick_stft_LT<32, 32>(mode, pre);
+static stft_kernel_t pick_stft(int L, int tile, int mode, bool pre, bool pair = false) {
+  if (tile != 32) return nullptr;
+  switch (L) {  // instantiated per transform size in aad_stft_inst.cu
+    case 4: return pick_stft_L4(mode, pre, pair);
+    case 8: return pick_stft_L8(mode, pre, pair);
+    case 16: return pick_stft_L16(mode, pre, pair);
+    case 32: return pick_stft_L32(mode, pre, pair);
   }
   return nullptr;
-#endif
 }
 template <int L, int TILE>
 static void stft_cfg_LT(int* warps, int* ctas, size_t* fixed, int* fbu) {
@@ -315,6 +301,7 @@ const char* aad_strerror(int err) {
     case AAD_ERR_CUDA: return "CUDA runtime error";
     case AAD_ERR_WORKSPACE: return "workspace too small";
     case AAD_ERR_KIND: return "plan kind does not match entry point";
+    case AAD_ERR_PAIR: return "plans cannot be paired (different STFT, or the second is not a plain log filter bank)";
     case AAD_ERR_FILTERBANK: return "filterbank is not banded (at most two adjacent filters per bin)";
   }
   return "unknown error";
@@ -605,6 +592,7 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   // (the attribute is per function, not per plan: opt in to the device maximum)
   int optin = 0;
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  pl->smem_optin = optin;
   if (pl->k1_smem > (size_t)optin) {
     aad_plan_destroy(pl);
     return AAD_ERR_UNSUPPORTED;
@@ -613,6 +601,8 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
     for (int pre = 0; pre < 2 && e == cudaSuccess; ++pre) {
       const void* fn = (const void*)pick_stft(L, pl->tile, mode, pre != 0);
       if (fn) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+      const void* fp = (const void*)pick_stft(L, pl->tile, mode, pre != 0, true);
+      if (fp && e == cudaSuccess) e = cudaFuncSetAttribute(fp, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     }
   if (e == cudaSuccess && pl->need_ws_E) {
     if (cep_smem_bytes(pl) > (size_t)optin) {
@@ -680,10 +670,22 @@ int aad_plan_launches(const aad_plan* pl) {
   return 2 + (fin ? 1 : 0) + (pl->need_ws_feat ? 1 : 0) + (p.znorm ? 2 : 0);
 }
 
+// `pl2` (optional): a second plan over the SAME STFT whose filter bank runs in the same k_stft_fb launch (one
+// STFT, two features); it must be a plain log filter-bank plan (no DCT, deltas, time mean or z-norm; CT layout).
+struct PairArgs {
+  const aad_plan* pl2 = nullptr;
+  float* out2 = nullptr;
+  int64_t out2_stride_b = 0;
+  void* ws2 = nullptr;
+  size_t ws2_bytes = 0;
+};
+
+static size_t prog_smem_bytes(const aad_plan* pl) { return (size_t)((2 * pl->n_hdr + 3) & ~3) * 4 + (size_t)pl->n_w4 * sizeof(float4); }
+
 static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_stride,
                         const int64_t* row_off, const int32_t* lengths, int B, int64_t max_len, float* out,
                         int64_t out_stride_b, int32_t t_alloc, int32_t* n_frames, int32_t* status,
-                        void* workspace, size_t workspace_bytes, void* stream_) {
+                        void* workspace, size_t workspace_bytes, void* stream_, const PairArgs& pair = PairArgs()) {
   if (!pl || !wav || !lengths || !out || !n_frames || !status || !workspace) return AAD_ERR_INVALID_ARG;
   if (B <= 0 || max_len <= 0 || (!row_off && max_len > wav_stride) || t_alloc <= 0) return AAD_ERR_INVALID_ARG;
   if (wav_dtype != AAD_F32 && wav_dtype != AAD_I16) return AAD_ERR_INVALID_ARG;
@@ -718,6 +720,26 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
   pa.t_alloc = p.time_mean ? w.t_ws : t_cap;
   pa.n_frames = n_frames; pa.status = status; pa.len_c = d_len; pa.nf_eff = d_nf;
   pa.frame_off = d_frame_off; pa.utt_max = d_max;
+  // paired call: the second plan shares the STFT; its only state is its own per-utterance maximum
+  const aad_plan* pl2 = pair.pl2;
+  int32_t* d_max2 = nullptr;
+  int64_t out2_stride_b = pair.out2_stride_b;
+  if (pl2) {
+    const aad_params& q = pl2->p;
+    if (!pair.out2 || !pair.ws2) return AAD_ERR_INVALID_ARG;
+    if (q.n_fft != p.n_fft || q.hop_length != p.hop_length || q.win_length != p.win_length || q.window != p.window ||
+        q.center != p.center || q.pre_emph != p.pre_emph || q.quantize_i16 != p.quantize_i16 ||
+        q.sample_rate != p.sample_rate || q.i16_scale != p.i16_scale || pl2->warps != pl->warps || pl2->L != pl->L)
+      return AAD_ERR_PAIR;
+    if (pl2->need_ws_E || pl2->need_ws_feat || q.znorm || q.layout != AAD_LAYOUT_CT) return AAD_ERR_PAIR;
+    size_t need2 = 0;
+    if ((rc = aad_query(pl2, B, max_len, nullptr, nullptr, &need2)) != AAD_OK) return rc;
+    if (pair.ws2_bytes < need2) return AAD_ERR_WORKSPACE;
+    d_max2 = (int32_t*)((char*)pair.ws2 + ws_layout(pl2, B, std::max(t_max, 1)).off_max);
+    if (out2_stride_b == 0) out2_stride_b = (int64_t)pl2->c_out * t_alloc;
+    if (pl->k1_smem + prog_smem_bytes(pl2) > (size_t)pl->smem_optin) return AAD_ERR_UNSUPPORTED;
+  }
+  pa.utt_max2 = d_max2;
   pa.tile_b0 = (int32_t*)(ws + w.off_tile); pa.tile = pl->tile; pa.max_tiles = w.max_tiles;
   pa.zn_stats = p.znorm ? (double*)(ws + w.off_zn) : nullptr;
   const bool prof = pl->profile;
@@ -744,12 +766,21 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
   }
   sa.utt_max = p.log_type == AAD_LOG_DB10 ? d_max : nullptr;
   sa.status = status;
+  sa.filt_hdr2 = nullptr; sa.filt_w2 = nullptr; sa.n_hdr2 = 0; sa.n_w42 = 0; sa.warp_prog2 = nullptr;
+  sa.log_type2 = 0; sa.amin2 = 0.f; sa.E2 = nullptr; sa.e2_stride_b = 0; sa.e2_stride_f = 0; sa.utt_max2 = nullptr;
+  if (pl2) {
+    const aad_params& q = pl2->p;
+    sa.filt_hdr2 = pl2->d_filt_hdr; sa.filt_w2 = pl2->d_filt_w; sa.n_hdr2 = pl2->n_hdr; sa.n_w42 = pl2->n_w4;
+    sa.warp_prog2 = pl2->d_warp_prog; sa.log_type2 = q.log_type; sa.amin2 = q.amin;
+    sa.E2 = pair.out2; sa.e2_stride_b = out2_stride_b; sa.e2_stride_f = t_alloc;
+    sa.utt_max2 = q.log_type == AAD_LOG_DB10 ? d_max2 : nullptr;
+  }
   const int mode = wav_dtype == AAD_I16 ? IN_I16 : (p.quantize_i16 ? IN_F32_Q16 : IN_F32);
-  stft_kernel_t kern = pick_stft(pl->L, pl->tile, mode, p.pre_emph != 0.f);
-  if (!kern) return AAD_ERR_UNSUPPORTED;
+  stft_kernel_t kern = pick_stft(pl->L, pl->tile, mode, p.pre_emph != 0.f, pl2 != nullptr);
+  if (!kern) return pl2 ? AAD_ERR_PAIR : AAD_ERR_UNSUPPORTED;
   const long long max_tiles = w.max_tiles;
   const int grid1 = (int)std::min<long long>((long long)pl->sm_count * pl->ctas, std::max<long long>(max_tiles, 1));
-  kern<<<grid1, pl->warps * 32, pl->k1_smem, stream>>>(sa);
+  kern<<<grid1, pl->warps * 32, pl->k1_smem + (pl2 ? prog_smem_bytes(pl2) : 0), stream>>>(sa);
   LAUNCH_CHECK("k_stft_fb launch");
   if (prof) cudaEventRecord(pl->ev[2], stream);
 
@@ -795,6 +826,19 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
     }
     if (prof) cudaEventRecord(pl->ev[3], stream);
   }
+  if (pl2) {
+    const aad_params& q = pl2->p;
+    if (q.log_type == AAD_LOG_DB10 && (q.ref_type == AAD_REF_UTT_MAX || q.top_db >= 0.f)) {
+      FinArgs fb;
+      fb.out = pair.out2; fb.stride_b = out2_stride_b; fb.stride_f = t_alloc; fb.nf_eff = d_nf; fb.utt_max = d_max2;
+      fb.utt_max_f = nullptr; fb.n_filt = q.n_filt; fb.ref_type = q.ref_type; fb.top_db = q.top_db;
+      const int n_row_blocks = (q.n_filt + FIN_ROWS - 1) / FIN_ROWS;
+      const int n_chunks = (std::max(t_max, 1) + FIN_CHUNK - 1) / FIN_CHUNK;
+      const long long nblk = (long long)B * n_row_blocks * n_chunks;
+      if (nblk > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
+      k_db_finalize<<<(unsigned)nblk, 256, 0, stream>>>(fb, n_row_blocks, n_chunks);
+    }
+  }
   if (p.znorm) {
     ZnArgs za;
     za.out = out; za.stride_b = out_stride_b; za.nf_eff = d_nf; za.C = pl->c_out;
@@ -818,6 +862,18 @@ int aad_extract(const aad_plan* pl, const void* wav, int wav_dtype, int64_t wav_
                 size_t workspace_bytes, void* stream) {
   return extract_impl(pl, wav, wav_dtype, wav_stride, nullptr, lengths, B, max_len, out, out_stride_b, t_alloc,
                       n_frames, status, workspace, workspace_bytes, stream);
+}
+
+int aad_extract_pair(const aad_plan* pl, const aad_plan* pl2, const void* wav, int wav_dtype, int64_t wav_stride,
+                     const int64_t* row_off, const int32_t* lengths, int B, int64_t max_len, float* out,
+                     int64_t out_stride_b, float* out2, int64_t out2_stride_b, int32_t t_alloc, int32_t* n_frames,
+                     int32_t* status, void* workspace, size_t workspace_bytes, void* workspace2,
+                     size_t workspace2_bytes, void* stream) {
+  if (!pl2) return AAD_ERR_INVALID_ARG;
+  PairArgs pair;
+  pair.pl2 = pl2; pair.out2 = out2; pair.out2_stride_b = out2_stride_b; pair.ws2 = workspace2; pair.ws2_bytes = workspace2_bytes;
+  return extract_impl(pl, wav, wav_dtype, wav_stride, row_off, lengths, B, max_len, out, out_stride_b, t_alloc,
+                      n_frames, status, workspace, workspace_bytes, stream, pair);
 }
 
 int aad_extract_indexed(const aad_plan* pl, const void* wav, int wav_dtype, const int64_t* row_off,
@@ -978,16 +1034,6 @@ int aad_fp32_peak(int device, int iters, double* tflops_out) {
   return cudaGetLastError() == cudaSuccess ? AAD_OK : AAD_ERR_CUDA;
 }
 
-#ifdef AAD_PHASE_TIMING
-// dev only: read and reset the phase counters of k_stft_fb
-int aad_dev_phase_cycles(unsigned long long* out4) {
-  CUDA_TRY(cudaDeviceSynchronize());
-  CUDA_TRY(cudaMemcpyFromSymbol(out4, g_phase_cycles, 4 * sizeof(unsigned long long)));
-  unsigned long long z[4] = {0, 0, 0, 0};
-  CUDA_TRY(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)));
-  return AAD_OK;
-}
-#endif
 
 // ---- host-buffer path: chunked H2D -> kernels -> D2H on three internal streams ----
 static int ensure(void** p, size_t* cap, size_t need) {

@@ -77,11 +77,13 @@ struct PrepArgs {
   int32_t* nf_eff;     // ws: frames actually computed (0 when status != 0)
   int32_t* frame_off;  // ws: [B+1] exclusive scan of nf_eff
   int32_t* utt_max;    // ws: ordered-int encoded running max, init -inf
+  int32_t* utt_max2;   // the same for the second filter bank of a paired call (or null)
   int32_t* tile_b0;    // ws: [max_tiles] utterance holding the first frame of each K1 tile
   int tile, max_tiles;
   double* zn_stats;    // ws: [B][2] z-norm accumulators (null when unused)
 };
 
+#ifndef AAD_STFT_ONLY  // the translation units that only instantiate k_stft_fb (aad_stft_inst.cu) skip the other kernels
 __global__ void __launch_bounds__(1024) k_prepare(PrepArgs a) {
   __shared__ int warp_sums[32];
   __shared__ int carry_s;
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepArgs a) {
       a.len_c[b] = (int)len;
       a.nf_eff[b] = nf;
       a.utt_max[b] = AAD_ENC_NEG_INF;
+      if (a.utt_max2) a.utt_max2[b] = AAD_ENC_NEG_INF;
       if (a.zn_stats) {
         a.zn_stats[2 * b] = 0.0;
         a.zn_stats[2 * b + 1] = 0.0;
@@ -163,6 +166,8 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepArgs a) {
   }
   if (tid == 0) a.frame_off[a.B] = carry_s;
 }
+
+#endif  // AAD_STFT_ONLY
 
 // ---------------------------------------------------------------------------
 // Tensor memory (TMEM) as a per-lane table store.  The window and the pass-1 twiddles of k_stft_fb
@@ -316,6 +321,19 @@ struct StftArgs {
   int e_stride_f;
   int32_t* utt_max;         // ordered-int encoded, or null
   int32_t* status;          // for NONFINITE flagging
+  // Optional SECOND filter bank over the same power spectra: one STFT, two features (e.g. the 128-mel bank of
+  // the MFCC plan and the 64-mel bank of the log-mel plan, the extractor map of ASV_deep_learning.ipynb:152-160).
+  // Same program format, built for the same warp count and bundle size; read by the PAIR instantiations only.
+  const int2* filt_hdr2;
+  const float4* filt_w2;
+  int n_hdr2, n_w42;
+  const int4* warp_prog2;
+  int log_type2;
+  float amin2;
+  float* E2;
+  long long e2_stride_b;
+  int e2_stride_f;
+  int32_t* utt_max2;
 };
 
 template <int MODE>
@@ -368,7 +386,7 @@ __device__ unsigned long long g_phase_cycles[4];
 #define AAD_PHASE_MARK(i)
 #endif
 
-template <int L, int MODE, bool PRE, int TILE>
+template <int L, int MODE, bool PRE, int TILE, bool PAIR = false>
 __global__ void __launch_bounds__(StftCfg<L, TILE>::WARPS * 32, StftCfg<L, TILE>::CTAS)
 k_stft_fb(const StftArgs a) {
   using C = StftCfg<L, TILE>;
@@ -396,6 +414,12 @@ k_stft_fb(const StftArgs a) {
     for (int i = tid; i < M / 2; i += nthr) sTwp[i] = a.twp[i];
   for (int i = tid; i < a.n_hdr; i += nthr) sHdr[i] = a.filt_hdr[i];
   for (int i = tid; i < a.n_w4; i += nthr) sW4[i] = a.filt_w[i];
+  if constexpr (PAIR) {  // second program behind the first (pointers are re-derived where it runs: no live registers)
+    int2* sHdr2 = reinterpret_cast<int2*>(sW4 + a.n_w4);
+    float4* sW42 = reinterpret_cast<float4*>(reinterpret_cast<float*>(sHdr2) + ((2 * a.n_hdr2 + 3) & ~3));
+    for (int i = tid; i < a.n_hdr2; i += nthr) sHdr2[i] = a.filt_hdr2[i];
+    for (int i = tid; i < a.n_w42; i += nthr) sW42[i] = a.filt_w2[i];
+  }
 #if AAD_TMEM_TABLES
   // allocate 128 TMEM columns, fill this CTA's four lane quarters with the per-lane rows
   //   columns [0, 64): window pairs 0.5*w[2(L A + j)], 0.5*w[2(L A + j) + 1], A = 0..31
@@ -769,6 +793,8 @@ k_stft_fb(const StftArgs a) {
     // conflict-free LDS.128 per lane; weights: two LDS.128 broadcasts; four FFMA2 accumulate the
     // (rising, falling) sums with the power broadcast to both halves), then filter s-1 = R[s-1] + F[s]:
     // log, store, running max.  Headers carry byte offsets so that a bundle starts with two adds.
+    auto fb_phase = [&](const int4 wprog, const int2* sHdr, const float4* sW4, float* Eout, long long e_stride_b,
+                        int e_stride_f, int log_type, float amin, int32_t* utt_max) {
     if (wprog.w > 0 && !(ABL & 8)) {
       const int b = sMetaB[lane], t = sMetaT[lane];
 #ifdef AAD_PHASE_TIMING
@@ -779,11 +805,11 @@ k_stft_fb(const StftArgs a) {
       const char* pbase = reinterpret_cast<const char*>(sP + lane * SP + C::skew(lane));
       const char* wbase = reinterpret_cast<const char*>(sW4);
       // entry i of the list emits filter wf0 + i - 1
-      float* eptr = a.E + (valid ? (long long)b * a.e_stride_b + (long long)(wprog.x - 1) * a.e_stride_f + t : 0);
-      const long long estep = a.e_stride_f;
-      const bool is_db = a.log_type == 0;
+      float* eptr = Eout + (valid ? (long long)b * e_stride_b + (long long)(wprog.x - 1) * e_stride_f + t : 0);
+      const long long estep = e_stride_f;
+      const bool is_db = log_type == 0;
       const float lscale = is_db ? 3.01029995663981195f : 0.69314718055994531f;
-      const float amin_n = fmaxf(a.amin, 1.17549435e-38f);  // keeps MUFU.LG2 off the denormal path
+      const float amin_n = fmaxf(amin, 1.17549435e-38f);  // keeps MUFU.LG2 off the denormal path
       float vmax = -INFINITY, chk = 0.f, rprev = 0.f;
       const int2* hp = sHdr + wprog.y;
       for (int i0 = 0; i0 < wprog.z; i0 += FBU, hp += FBU) {
@@ -845,13 +871,20 @@ k_stft_fb(const StftArgs a) {
         }
       }
       if (valid) {
-        if (a.utt_max) {
+        if (utt_max) {
           unsigned peers = __match_any_sync(__activemask(), b);
           int enc = __reduce_max_sync(peers, enc_ordered(vmax));
-          if ((int)(__ffs(peers) - 1) == lane) atomicMax(a.utt_max + b, enc);
+          if ((int)(__ffs(peers) - 1) == lane) atomicMax(utt_max + b, enc);
         }
         if (chk != chk) a.status[b] = 5;
       }
+    }
+    };
+    fb_phase(wprog, sHdr, sW4, a.E, a.e_stride_b, a.e_stride_f, a.log_type, a.amin, a.utt_max);
+    if constexpr (PAIR) {
+      const int2* sHdr2 = reinterpret_cast<const int2*>(sW4 + a.n_w4);
+      const float4* sW42 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sHdr2) + ((2 * a.n_hdr2 + 3) & ~3));
+      fb_phase(__ldg(a.warp_prog2 + warp), sHdr2, sW42, a.E2, a.e2_stride_b, a.e2_stride_f, a.log_type2, a.amin2, a.utt_max2);
     }
     AAD_PHASE_MARK(2);
     __syncthreads();  // sP free for the next tile's FFTs; next tile's meta (written above) visible
@@ -870,6 +903,7 @@ k_stft_fb(const StftArgs a) {
 #endif
 }
 
+#ifndef AAD_STFT_ONLY
 // ---------------------------------------------------------------------------
 // K2: dB reference / floor + DCT-II + deltas + layout
 // ---------------------------------------------------------------------------
@@ -1308,5 +1342,7 @@ __global__ void __launch_bounds__(256) k_fma_peak(float* sink, int iters) {
   float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
   if (s == 123.456f) sink[0] = s;
 }
+
+#endif  // AAD_STFT_ONLY
 
 }  // namespace aad

@@ -244,6 +244,42 @@ class Frontend:
         L.check(rc, "aad_extract")
         return out, n_frames, status
 
+    # ---- one STFT, two features -------------------------------------------------------
+    def extract_pair(self, other: "Frontend", wav: torch.Tensor, lengths: Optional[torch.Tensor] = None):
+        """This plan's features AND `other`'s (a plain log filter-bank plan over the same STFT, e.g. the 64-mel
+        log-mel next to this MFCC plan) from ONE pass over the waveforms: `other`'s filter bank runs on the power
+        spectra this plan computes, in the same kernel launch (`aad_extract_pair`).
+        Returns ((features, other_features), n_frames, status); other_features is [B, n_filt, Tmax]."""
+        if wav.dim() != 2 or not wav.is_cuda or wav.device != self.device or other.device != self.device:
+            raise L.AadError(f"wav and both plans must be on {self.device}")
+        dt = L.F32 if wav.dtype == torch.float32 else (L.I16 if wav.dtype == torch.int16 else None)
+        if dt is None:
+            raise L.AadError("wav must be float32 or int16")
+        if wav.stride(1) != 1:
+            wav = wav.contiguous()
+        B, Lmax = wav.shape
+        if lengths is None:
+            lengths = torch.full((B,), Lmax, dtype=torch.int32, device=self.device)
+        else:
+            lengths = lengths.to(device=self.device, dtype=torch.int32).contiguous()
+        t_max, c_out, ws_bytes = self.query(B, Lmax)
+        _, c2, ws2_bytes = other.query(B, Lmax)
+        t_alloc = max(t_max, 1)
+        p = self.params
+        shape = (B, c_out) if p.time_mean else ((B, c_out, t_alloc) if p.layout == L.LAYOUT_CT else (B, t_alloc, c_out))
+        out = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        out2 = torch.zeros((B, c2, t_alloc), dtype=torch.float32, device=self.device)
+        n_frames = torch.empty(B, dtype=torch.int32, device=self.device)
+        status = torch.empty(B, dtype=torch.int32, device=self.device)
+        ws, ws2 = self._workspace(ws_bytes), other._workspace(ws2_bytes)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = self.lib.aad_extract_pair(self._h, other._h, _ptr(wav), dt, wav.stride(0), None, _ptr(lengths), B, Lmax,
+                                           _ptr(out), out.stride(0), _ptr(out2), out2.stride(0), t_alloc, _ptr(n_frames),
+                                           _ptr(status), _ptr(ws), ws.numel(), _ptr(ws2), ws2.numel(), C.c_void_p(stream))
+        L.check(rc, "aad_extract_pair")
+        return (out, out2), n_frames, status
+
     # ---- chunks of decoded files that already sit in device memory ------------------
     def extract_indexed(self, pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor,
                         max_len: Optional[int] = None, validate: bool = True):

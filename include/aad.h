@@ -63,7 +63,8 @@ enum aad_error {
   AAD_ERR_CUDA = -3,
   AAD_ERR_WORKSPACE = -4, /* workspace too small */
   AAD_ERR_KIND = -5,      /* plan kind does not match the entry point */
-  AAD_ERR_FILTERBANK = -6 /* custom filterbank is not two-adjacent-filters-per-bin */
+  AAD_ERR_FILTERBANK = -6, /* custom filterbank is not two-adjacent-filters-per-bin */
+  AAD_ERR_PAIR = -7        /* aad_extract_pair: the two plans do not share one STFT, or the second is not a plain log filter bank */
 };
 
 enum aad_item_status { /* status[b] */
@@ -163,6 +164,20 @@ int aad_extract_indexed(const aad_plan* plan, const void* wav, int wav_dtype, co
                         const int32_t* lengths, int B, int64_t max_len, float* out, int64_t out_stride_b,
                         int32_t t_alloc, int32_t* n_frames, int32_t* status, void* workspace,
                         size_t workspace_bytes, void* stream);
+
+/* One STFT, two features: `plan2` (a plain log filter-bank plan: no DCT, deltas, time mean or z-norm, CT layout,
+ * e.g. the 64-mel log-mel of extract_mel_spectrogram) runs its filter bank on the power spectra that `plan`
+ * (any plan over the same n_fft / hop / window / centring / input conversion, e.g. the MFCC of extract_mfcc)
+ * computes in the same kernel launch.  The reference's extractor map runs librosa.stft once per feature and
+ * chunk (ASV_deep_learning.ipynb:152-160 -> ASV_dl_func.py:416,533); here the second feature costs one more
+ * pass over the power tile in shared memory.  row_off: null (rows of wav_stride) or a chunk table as in
+ * aad_extract_indexed.  out2: [B][n_filt2][t_alloc]; workspace2: aad_query(plan2, ...) bytes; n_frames and
+ * status are shared.  Returns AAD_ERR_PAIR when the plans cannot be paired. */
+int aad_extract_pair(const aad_plan* plan, const aad_plan* plan2, const void* wav, int wav_dtype, int64_t wav_stride,
+                     const int64_t* row_off, const int32_t* lengths, int B, int64_t max_len, float* out,
+                     int64_t out_stride_b, float* out2, int64_t out2_stride_b, int32_t t_alloc, int32_t* n_frames,
+                     int32_t* status, void* workspace, size_t workspace_bytes, void* workspace2,
+                     size_t workspace2_bytes, void* stream);
 
 /* Kind-checked aliases of aad_extract (return AAD_ERR_KIND on mismatch). */
 int aad_logmel(const aad_plan* plan, const void* wav, int wav_dtype, int64_t wav_stride,

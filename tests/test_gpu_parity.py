@@ -456,3 +456,29 @@ def test_full_size_config2_properties(dev):
     d2 = aad.delta(static, order=2)
     assert (out[:64, 40:80] - d1).abs().max().item() <= 1e-5
     assert (out[:64, 80:120] - d2).abs().max().item() <= 1e-5
+
+
+def test_paired_extraction_equals_the_two_separate_calls(dev):
+    """One STFT, two features (aad_extract_pair): the second plan's filter bank runs on the first plan's power
+    spectra in the same launch; both outputs equal the separate calls bit for bit, ragged batch included."""
+    from audioanalysisdetector_b200 import AadError, Frontend
+    clips = [speech(70, 32000), noise(71, 20000), speech(72, 47001), noise(73, 3000), np.zeros(0, np.float32)]
+    w, lens = pad_batch(clips)
+    wav, ln = torch.from_numpy(w).to(dev), torch.from_numpy(lens).to(dev)
+    for pa, pb in [(FP().mfcc(16000, n_mfcc=13), FP().logmel(16000, n_mels=64)),
+                   (FP().mfcc(16000, n_mfcc=40, n_delta=2), FP().logmel(16000, n_mels=64)),
+                   (FP().logmel(16000, n_mels=128), FP().logmel(16000, n_mels=64, fmax=4000.0)),
+                   (FP().mfcc(16000, n_mfcc=20, n_mels=80, n_fft=512, hop_length=160),
+                    FP().logmel(16000, n_mels=40, n_fft=512, hop_length=160))]:
+        fa, fb = Frontend(pa, dev), Frontend(pb, dev)
+        a_alone, nf_a, st_a = fa(wav, ln)
+        b_alone, nf_b, st_b = fb(wav, ln)
+        (a_pair, b_pair), nf, st = fa.extract_pair(fb, wav, ln)
+        assert torch.equal(nf, nf_a) and torch.equal(st, st_a)
+        assert torch.equal(a_pair, a_alone)
+        ok = st == 0                                                # n_frames and status are the first plan's
+        assert torch.equal(b_pair[ok], b_alone[ok]) and float(b_pair[~ok].abs().max()) == 0.0
+    with pytest.raises(AadError):                                   # different STFT
+        Frontend(FP().mfcc(16000), dev).extract_pair(Frontend(FP().logmel(16000, n_fft=512, hop_length=160), dev), wav, ln)
+    with pytest.raises(AadError):                                   # the second plan must be a plain filter bank
+        Frontend(FP().logmel(16000), dev).extract_pair(Frontend(FP().mfcc(16000), dev), wav, ln)

@@ -52,8 +52,7 @@ def main():
     engine = aad.DetectorEngine(weights, feature_dim=13, device=dev)
 
     def step():
-        feats, nf, st = fe_mfcc(wav)                 # (n_local, 13, 63) on device
-        mel, _, _ = fe_mel(wav)                      # (n_local, 64, 63): the second feature of the map
+        (feats, mel), nf, st = fe_mfcc.extract_pair(fe_mel, wav)   # (n, 13, 63) and (n, 64, 63) from ONE STFT
         scores = engine(feats)                       # hand-written CNN-BiLSTM inference, features stay where they are
         with torch.no_grad():
             ref = torch.cat([consumer_ref.forward(weights, feats[i:i + 4096]) for i in range(0, n_local, 4096)])
@@ -65,9 +64,13 @@ def main():
         dist.barrier()
     torch.cuda.synchronize(dev)
     e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    f_sep, _, _ = fe_mfcc(wav)                       # the same two features as two separate extractions
+    m_sep, _, _ = fe_mel(wav)
+    eb.record()
     e0.record()
-    feats, nf, st = fe_mfcc(wav)
-    mel, _, _ = fe_mel(wav)
+    (feats, mel), nf, st = fe_mfcc.extract_pair(fe_mel, wav)
     e1.record()
     scores = engine(feats)
     e2.record()
@@ -76,10 +79,12 @@ def main():
     e3.record()
     torch.cuda.synchronize(dev)
     t_feat, t_model, t_torch = e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3)
+    t_sep = ea.elapsed_time(eb)
+    pair_equal = float(torch.equal(feats, f_sep) and torch.equal(mel, m_sep))
     max_diff = float((scores - ref).abs().max().item())
     idx = torch.arange(sl.start, sl.stop, device=dev)
     all_scores = aad.gather_features(scores, idx, N_CHUNKS)          # one all-gather, outside the extraction
-    t = torch.tensor([t_feat, t_model, t_torch, max_diff], device=dev, dtype=torch.float64)
+    t = torch.tensor([t_feat, t_model, t_torch, max_diff, t_sep, -pair_equal], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
@@ -87,7 +92,9 @@ def main():
         print(json.dumps({
             "config": "configs[3]: 25 380 x 2 s @16 kHz -> MFCC-13 + log-mel-64 -> CNN-BiLSTM scores",
             "n_gpus": world, "chunks_per_gpu": n_local, "status_nonzero": int(st.ne(0).sum().item()),
-            "features_ms": float(t[0]), "model_ms": float(t[1]), "model_stock_pytorch_ms": float(t[2]),
+            "features_ms": float(t[0]), "features_as_two_extractions_ms": float(t[4]),
+            "paired_features_equal_separate_bitwise": bool(float(t[5]) == -1.0),
+            "model_ms": float(t[1]), "model_stock_pytorch_ms": float(t[2]),
             "scores_max_abs_diff_vs_stock_pytorch": float(t[3]),
             "features_audio_hours_per_s": hours / (float(t[0]) * 1e-3),
             "pipeline_audio_hours_per_s": hours / ((float(t[0]) + float(t[1])) * 1e-3),
