@@ -143,6 +143,17 @@ class DeviceCorpus:
             pcm, off = self._with_noise(pcm, off, ln, np.asarray(noise_rows, dtype=np.int64), generator)
         return fe.extract_indexed(pcm, off, ln, max_len=max(int(np.max(lengths)), 1))
 
+    def extract_pair(self, fe: Frontend, fe2: Frontend, offsets: np.ndarray, lengths: np.ndarray):
+        """Two features of every chunk from ONE STFT (`Frontend.extract_pair` over the chunk table):
+        ((features, features2), n_frames, status).  Both plans must read the corpus the same way (no
+        re-quantising LFCC plan here) and no row may ask for augmentation."""
+        if fe.params.quantize_i16 or fe2.params.quantize_i16:
+            raise L.AadError("paired extraction is for plans over the same STFT (mel-type plans)")
+        pcm = self.upload()
+        off = torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64)).to(self.device)
+        ln = torch.from_numpy(np.ascontiguousarray(lengths, dtype=np.int32)).to(self.device)
+        return fe.extract_pair(fe2, pcm, ln, offsets=off, max_len=max(int(np.max(lengths)), 1))
+
     def _with_noise(self, pcm, off, ln, rows, generator):
         """Append noisy copies of the chosen chunks behind the corpus and point their rows at them."""
         r = torch.from_numpy(rows).to(self.device)

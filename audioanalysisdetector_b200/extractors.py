@@ -201,6 +201,12 @@ def extract_features(final_df, feature_extractors_map: Dict[str, Callable], col_
     rows = [row for _, row in final_df.iterrows()]
     corpus: Optional[DeviceCorpus] = None
     file_of: List[Optional[int]] = [None] * len(rows)
+    funcs = list(feature_extractors_map.values())
+    # MFCC and log-mel over the same rows share one STFT: the second one rides on the first one's kernel launch
+    pair_ok = (extract_mfcc in funcs and extract_mel_spectrogram in funcs and
+               funcs.index(extract_mfcc) < funcs.index(extract_mel_spectrogram) and
+               not any(_row_get(r, aug_col) == "noise" for r in rows))
+    paired_mel: Dict[tuple, tuple] = {}      # (sr, start, end) -> (features, n_frames, status) of the mel plan
     for name, func in feature_extractors_map.items():
         print(f"   - Ekstrahuję: {name}")
         if func not in _BATCHED:
@@ -243,6 +249,20 @@ def extract_features(final_df, feature_extractors_map: Dict[str, Callable], col_
                     lmax, end = lm, end + 1
                 part = idxs[start:end]
                 try:
+                    key = (sr, start, end)
+                    if pair_ok and func is extract_mfcc:
+                        mel_params = _BATCHED[extract_mel_spectrogram][1](sr, mean)
+                        if not mel_params.time_mean:        # the rider must be a plain filter-bank plan
+                            (feats, mfeats), nf, st = corpus.extract_pair(fe, get_frontend(mel_params), off[start:end], ln[start:end])
+                            paired_mel[key] = (mfeats, nf, st)
+                            _split_rows(feats, nf, st, params, post, mean, part, results, tag)
+                            start = end
+                            continue
+                    if func is extract_mel_spectrogram and key in paired_mel:
+                        feats, nf, st = paired_mel.pop(key)
+                        _split_rows(feats, nf, st, params, post, mean, part, results, tag)
+                        start = end
+                        continue
                     noise = [k for k, i in enumerate(part) if _row_get(rows[i], aug_col) == "noise"]
                     feats, nf, st = corpus.extract(fe, off[start:end], ln[start:end], noise_rows=noise)
                     _split_rows(feats, nf, st, params, post, mean, part, results, tag)

@@ -245,23 +245,37 @@ class Frontend:
         return out, n_frames, status
 
     # ---- one STFT, two features -------------------------------------------------------
-    def extract_pair(self, other: "Frontend", wav: torch.Tensor, lengths: Optional[torch.Tensor] = None):
+    def extract_pair(self, other: "Frontend", wav: torch.Tensor, lengths: Optional[torch.Tensor] = None,
+                     offsets: Optional[torch.Tensor] = None, max_len: Optional[int] = None):
         """This plan's features AND `other`'s (a plain log filter-bank plan over the same STFT, e.g. the 64-mel
         log-mel next to this MFCC plan) from ONE pass over the waveforms: `other`'s filter bank runs on the power
         spectra this plan computes, in the same kernel launch (`aad_extract_pair`).
+        `wav` is a padded batch [B, Lmax] (+ `lengths`), or -- with `offsets` -- a 1-D buffer of decoded files and a
+        chunk table (offsets int64, lengths int32, as in `extract_indexed`; the caller vouches for the table).
         Returns ((features, other_features), n_frames, status); other_features is [B, n_filt, Tmax]."""
-        if wav.dim() != 2 or not wav.is_cuda or wav.device != self.device or other.device != self.device:
+        if not wav.is_cuda or wav.device != self.device or other.device != self.device:
             raise L.AadError(f"wav and both plans must be on {self.device}")
         dt = L.F32 if wav.dtype == torch.float32 else (L.I16 if wav.dtype == torch.int16 else None)
         if dt is None:
             raise L.AadError("wav must be float32 or int16")
-        if wav.stride(1) != 1:
-            wav = wav.contiguous()
-        B, Lmax = wav.shape
-        if lengths is None:
-            lengths = torch.full((B,), Lmax, dtype=torch.int32, device=self.device)
+        if offsets is None:
+            if wav.dim() != 2:
+                raise L.AadError("wav must be [B, Lmax] (or 1-D with a chunk table)")
+            if wav.stride(1) != 1:
+                wav = wav.contiguous()
+            B, Lmax = wav.shape
+            stride = wav.stride(0)
+            if lengths is None:
+                lengths = torch.full((B,), Lmax, dtype=torch.int32, device=self.device)
+            off_ptr = None
         else:
-            lengths = lengths.to(device=self.device, dtype=torch.int32).contiguous()
+            if wav.dim() != 1 or not wav.is_contiguous() or lengths is None:
+                raise L.AadError("a chunk table needs a contiguous 1-D buffer, offsets and lengths")
+            offsets = offsets.to(device=self.device, dtype=torch.int64).contiguous()
+            B, stride = int(offsets.numel()), 0
+            Lmax = int(max_len) if max_len is not None else max(int(lengths.max()), 1)
+            off_ptr = _ptr(offsets)
+        lengths = lengths.to(device=self.device, dtype=torch.int32).contiguous()
         t_max, c_out, ws_bytes = self.query(B, Lmax)
         _, c2, ws2_bytes = other.query(B, Lmax)
         t_alloc = max(t_max, 1)
@@ -274,7 +288,7 @@ class Frontend:
         ws, ws2 = self._workspace(ws_bytes), other._workspace(ws2_bytes)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            rc = self.lib.aad_extract_pair(self._h, other._h, _ptr(wav), dt, wav.stride(0), None, _ptr(lengths), B, Lmax,
+            rc = self.lib.aad_extract_pair(self._h, other._h, _ptr(wav), dt, stride, off_ptr, _ptr(lengths), B, Lmax,
                                            _ptr(out), out.stride(0), _ptr(out2), out2.stride(0), t_alloc, _ptr(n_frames),
                                            _ptr(status), _ptr(ws), ws.numel(), _ptr(ws2), ws2.numel(), C.c_void_p(stream))
         L.check(rc, "aad_extract_pair")

@@ -103,6 +103,12 @@ def test_extract_features_dispatcher(files, tmp_path):
         assert np.abs(r["mfcc"] - oracle.extract_mfcc_ref(y, sr, **kw)).max() <= 1e-3
         assert np.abs(r["lfcc"] - oracle.extract_lfcc_ref(y, sr, **kw)).max() <= 1e-3
         assert list(r["custom"]) == [r["chunk_start"], r["chunk_end"]]
+    # 'mfcc' before 'mel-spect' in the map: both come from ONE STFT (aad_extract_pair); same values as above
+    df3 = aad.extract_features(pd.DataFrame(rows), {"mfcc": aad.extract_mfcc, "mel-spect": aad.extract_mel_spectrogram})
+    for i in range(len(rows) - 1):
+        assert np.array_equal(df3["mfcc"].iloc[i], df["mfcc"].iloc[i])
+        assert np.array_equal(df3["mel-spect"].iloc[i], df["mel-spect"].iloc[i])
+    assert df3["mfcc"].iloc[-1] is None and df3["mel-spect"].iloc[-1] is None
     # mean=True variant of the dispatcher (ASV_func.py defaults)
     df2 = aad.extract_features(pd.DataFrame(rows[:3]), {"mfcc": aad.extract_mfcc}, mean=True)
     y, sr = cache[rows[0]["filepath"]]
