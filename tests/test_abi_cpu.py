@@ -121,3 +121,25 @@ def test_bind_to_gpu_numa_is_harmless_without_nvml():
     cpus = sharding.bind_to_gpu_numa(0)
     assert cpus is None or set(cpus) <= set(before)
     os.sched_setaffinity(0, before)
+
+
+def test_new_entry_points_validate_their_arguments_before_touching_the_gpu(built_lib):
+    """Argument checks of the entry points added around the path (no device work is reached)."""
+    from audioanalysisdetector_b200 import _lib as L
+    INV = -1
+    assert built_lib.aad_extract_indexed(None, None, 0, None, None, 1, 10, None, 0, 1, None, None, None, 0, None) == INV
+    assert built_lib.aad_extract_pair(None, None, None, 0, 0, None, None, 1, 10, None, 0, None, 0, 1, None, None, None, 0,
+                                      None, 0, None) == INV
+    assert built_lib.aad_db_reference(None, 0, 64, None, None, 1, 64, 63, 1, 80.0, None) == INV
+    assert built_lib.aad_scaler_accumulate(None, 10, 13, 13, None, None) == INV
+    assert built_lib.aad_scaler_apply(None, 10, 13, 13, None, None, None) == INV
+    w = L.AadDetectorWeights()
+    h = C.c_void_p()
+    assert built_lib.aad_detector_create(C.byref(w), 0, C.byref(h)) == INV            # struct_size not set
+    w.struct_size = C.sizeof(L.AadDetectorWeights)
+    w.feature_dim = 13
+    assert built_lib.aad_detector_create(C.byref(w), 0, C.byref(h)) == INV            # null weight pointers
+    assert built_lib.aad_detector_query(None, 8, None) == INV
+    assert built_lib.aad_detector_forward(None, None, 0, 63, 8, None, None, 0, None) == INV
+    assert built_lib.aad_detector_destroy(None) == 0
+    assert b"paired" in built_lib.aad_strerror(-7)
