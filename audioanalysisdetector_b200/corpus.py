@@ -19,7 +19,7 @@ import torch
 
 from . import _lib as L
 from . import audio_io
-from .frontend import Frontend, FrontendParams
+from .frontend import Frontend
 
 FILE_ALIGN = 8          # elements: every file starts on a 16-byte (int16) / 32-byte (float32) boundary
 NOISE_FACTOR = 1.022    # augment_audio's default factor for mode="noise" (ASV_dl_func.py:85-86)
