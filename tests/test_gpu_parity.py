@@ -482,3 +482,25 @@ def test_paired_extraction_equals_the_two_separate_calls(dev):
         Frontend(FP().mfcc(16000), dev).extract_pair(Frontend(FP().logmel(16000, n_fft=512, hop_length=160), dev), wav, ln)
     with pytest.raises(AadError):                                   # the second plan must be a plain filter bank
         Frontend(FP().logmel(16000), dev).extract_pair(Frontend(FP().mfcc(16000), dev), wav, ln)
+
+
+def test_cuda_path_matches_torchaudio_directly(dev):
+    """Not through the oracle: the CUDA path against torchaudio's own MFCC / log-mel chain (an independent
+    implementation of the algorithm of librosa.feature.mfcc / power_to_db(ref=np.max)), 1e-3 on dB values."""
+    ta = pytest.importorskip("torchaudio")
+    sr = 16000
+    clips = [speech(81, 32000), noise(82, 40000), speech(83, 52345)]
+    mel_kw = dict(n_fft=2048, hop_length=512, center=True, pad_mode="constant", power=2.0, norm="slaney",
+                  mel_scale="slaney", f_min=0.0, f_max=sr / 2)
+    mfcc_t = ta.transforms.MFCC(sample_rate=sr, n_mfcc=20, dct_type=2, norm="ortho", log_mels=False,
+                                melkwargs=dict(n_mels=128, **mel_kw))
+    mel_t = ta.transforms.MelSpectrogram(sample_rate=sr, n_mels=64, **mel_kw)
+    out, nf, st, _ = run(FP().mfcc(sr, n_mfcc=20), clips, dev)
+    mel, _, _, _ = run(FP().logmel(sr, n_mels=64), clips, dev)
+    for i, y in enumerate(clips):
+        want = mfcc_t(torch.from_numpy(y)).numpy()
+        assert nf[i] == want.shape[1] and np.abs(out[i, :, :nf[i]] - want).max() <= 1e-3
+        S = mel_t(torch.from_numpy(y))
+        db = ta.functional.amplitude_to_DB(S[None], multiplier=10.0, amin=1e-10,
+                                           db_multiplier=float(torch.log10(torch.clamp(S.max(), min=1e-10))), top_db=80.0)[0]
+        assert np.abs(mel[i, :, :nf[i]] - db.numpy()).max() <= 1e-3

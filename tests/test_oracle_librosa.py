@@ -139,3 +139,28 @@ def test_compute_melspec_ref_is_standardised():
     z = oracle.compute_melspec_ref(noise(3, 20000), 16000)
     assert z.shape == (128, 1 + 20000 // 512) and z.dtype == np.float32
     assert abs(float(z.mean())) < 1e-5 and abs(float(z.std()) - 1) < 1e-5
+
+
+def test_full_chains_match_torchaudio_live():
+    """Independent implementation of the whole chain (the oracle is otherwise pinned stage by stage): torchaudio's
+    MFCC transform (MelSpectrogram with Slaney scale / norm -> AmplitudeToDB(power, top_db 80, ref 1) -> ortho DCT-II)
+    is the same algorithm as librosa.feature.mfcc (ASV_dl_func.py:416), and amplitude_to_DB with the utterance
+    maximum as reference is power_to_db(ref=np.max) (:534).  torchaudio runs its FFT in float32: 1e-3 on dB values."""
+    ta = pytest.importorskip("torchaudio")
+    import torch
+    import oracle
+    from helpers import noise, speech
+    sr = 16000
+    for y in (speech(1, 32000), noise(2, 40000), speech(3, 2 * sr) * np.float32(1e-3)):
+        mel_kw = dict(n_fft=2048, hop_length=512, center=True, pad_mode="constant", power=2.0, norm="slaney",
+                      mel_scale="slaney", f_min=0.0, f_max=sr / 2)
+        t = ta.transforms.MFCC(sample_rate=sr, n_mfcc=13, dct_type=2, norm="ortho", log_mels=False,
+                               melkwargs=dict(n_mels=128, **mel_kw))
+        got = t(torch.from_numpy(y)).numpy()
+        want = oracle.extract_mfcc_ref(y, sr)
+        assert got.shape == want.shape and np.abs(got - want).max() <= 1e-3
+        S = ta.transforms.MelSpectrogram(sample_rate=sr, n_mels=64, **mel_kw)(torch.from_numpy(y))
+        db = ta.functional.amplitude_to_DB(S[None], multiplier=10.0, amin=1e-10,
+                                           db_multiplier=float(torch.log10(torch.clamp(S.max(), min=1e-10))), top_db=80.0)[0]
+        want = oracle.extract_mel_spectrogram_ref(y, sr)
+        assert db.shape == want.shape and np.abs(db.numpy() - want).max() <= 1e-3
