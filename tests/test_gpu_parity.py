@@ -504,3 +504,24 @@ def test_cuda_path_matches_torchaudio_directly(dev):
         db = ta.functional.amplitude_to_DB(S[None], multiplier=10.0, amin=1e-10,
                                            db_multiplier=float(torch.log10(torch.clamp(S.max(), min=1e-10))), top_db=80.0)[0]
         assert np.abs(mel[i, :, :nf[i]] - db.numpy()).max() <= 1e-3
+
+
+def test_linear_filterbank_cepstra_match_torchaudio_lfcc(dev):
+    """The linear (continuous-frequency) filter bank + dB + DCT chain against torchaudio.transforms.LFCC, an
+    independent implementation (centred Hann STFT, unit-peak linear triangles, AmplitudeToDB(top_db 80), ortho
+    DCT-II): pins AAD_FB_LINEAR_CONT and the n_fft 512 kernels without going through the oracle."""
+    ta = pytest.importorskip("torchaudio")
+    from audioanalysisdetector_b200.frontend import FrontendParams
+    L = LIB()
+    sr = 16000
+    clips = [speech(91, 32000), noise(92, 24000)]
+    p = FrontendParams(kind=L.KIND_MFCC, sample_rate=sr, n_fft=512, win_length=512, hop_length=160,
+                       window=L.WIN_HANN_PERIODIC, center=True, n_filt=64, fb_type=L.FB_LINEAR_CONT, fmin=0.0, fmax=sr / 2,
+                       log_type=L.LOG_DB10, ref_type=L.REF_ONE, amin=1e-10, top_db=80.0, n_ceps=20, layout=L.LAYOUT_CT)
+    out, nf, st, _ = run(p, clips, dev)
+    t = ta.transforms.LFCC(sample_rate=sr, n_filter=64, f_min=0.0, f_max=sr / 2, n_lfcc=20, dct_type=2, norm="ortho",
+                           log_lf=False, speckwargs=dict(n_fft=512, hop_length=160, center=True, pad_mode="constant", power=2.0))
+    for i, y in enumerate(clips):
+        want = t(torch.from_numpy(y)).numpy()
+        assert st[i] == 0 and nf[i] == want.shape[1]
+        assert np.abs(out[i, :, :nf[i]] - want).max() <= 1e-3
