@@ -42,6 +42,9 @@ constexpr int ABL = AAD_ABLATE;
 #ifndef AAD_ROW_SKEW
 #define AAD_ROW_SKEW 1
 #endif
+#ifndef AAD_TWFOLD
+#define AAD_TWFOLD 1
+#endif
 #ifndef AAD_WINFOLD
 #define AAD_WINFOLD 1
 #endif
@@ -392,6 +395,9 @@ k_stft_fb(const StftArgs a) {
   using C = StftCfg<L, TILE>;
   constexpr int Q = C::Q, M = C::M, N = C::N, SP = C::SP, FBU = C::FBU;
   constexpr int LOG2L = ilog2(L);
+  // n_fft 2048: the inter-pass twiddle is applied AFTER the transpose (the table is symmetric in (b, kA)) and fused
+  // with the first butterfly stage of pass 2: 5 packed instructions per butterfly instead of 6
+  constexpr bool TWFOLD = AAD_TWFOLD && AAD_TMEM_TABLES && L == 32;
   extern __shared__ __align__(16) float smem[];
   float* sP = smem + C::OFF_P;
   float* sWin = smem + C::OFF_WIN;
@@ -450,7 +456,11 @@ k_stft_fb(const StftArgs a) {
       }
       tmem_st16(tmem_row + 16 * c, w8);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) w8[i] = __ldg(a.tw1 + (8 * c + i) * L + j);
+      for (int i = 0; i < 8; ++i) {
+        // TWFOLD: {W^(j b), W^(j (b + 16))} side by side, b = 4c .. 4c + 3 (the pairs of pass 2's first stage)
+        const int kA = TWFOLD ? 4 * c + (i >> 1) + 16 * (i & 1) : 8 * c + i;
+        w8[i] = __ldg(a.tw1 + kA * L + j);
+      }
       tmem_st16(tmem_row + 64 + 16 * c, w8);
     }
     if constexpr (TmemCfg<C::CTAS>::TWP) {  // entry q*(L/2) + s = W_N^(j + L q + 32 s)
@@ -671,6 +681,7 @@ k_stft_fb(const StftArgs a) {
       if constexpr (!(ABL & 64)) fft_dit<32, 0, 32, (AAD_WINFOLD && AAD_TMEM_TABLES) ? 2 : 1>(v);
       {
 #if AAD_TMEM_TABLES
+        if constexpr (!TWFOLD) {
         TmemChunk tc[2];
         tc[0].issue(tmem_row + 64);
         static_for<0, 4>([&](auto c_) {
@@ -682,6 +693,7 @@ k_stft_fb(const StftArgs a) {
             if constexpr (KA > 0) v[KA] = cmul(v[KA], tc[CH & 1].get(KA % 8));
           });
         });
+        }
 #else
         static_for<1, 32>([&](auto k_) {
           constexpr int KA = decltype(k_)::value;
@@ -725,6 +737,30 @@ k_stft_fb(const StftArgs a) {
       }
 
       // pass 2: Q DFTs of length L over b  ->  v[q*L + kB] = Z[(j + L q) + 32 kB]
+#if AAD_TMEM_TABLES
+      if constexpr (TWFOLD) {
+        // twiddle + first stage of pass 2: registers 2m, 2m + 1 hold b and b + 16;  a' = ta a + tb b,  b' = ta a - tb b
+        TmemChunk tc[2];
+        tc[0].issue(tmem_row + 64);
+        static_for<0, 4>([&](auto c_) {
+          constexpr int CH = decltype(c_)::value;
+          tc[CH & 1].wait();
+          if constexpr (CH < 3) tc[(CH + 1) & 1].issue(tmem_row + 64 + 16 * (CH + 1));
+          static_for<0, 4>([&](auto i_) {
+            constexpr int I = decltype(i_)::value;
+            constexpr int BA = 4 * CH + I, RA = bitrev(BA, 5);
+            const float2 tb = tc[CH & 1].get(2 * I + 1), b0 = v[RA + 1];
+            float2 u = v[RA];
+            if constexpr (BA > 0) u = cmul(u, tc[CH & 1].get(2 * I));
+            const float2 t1 = __ffma2_rn(b0, make_float2(tb.x, tb.x), u);
+            const float2 na = __ffma2_rn(make_float2(-b0.y, b0.x), make_float2(tb.y, tb.y), t1);
+            v[RA + 1] = __ffma2_rn(u, make_float2(2.0f, 2.0f), make_float2(-na.x, -na.y));
+            v[RA] = na;
+          });
+        });
+        if constexpr (!(ABL & 64)) fft_dit<32, 0, 32, 2>(v);
+      } else
+#endif
       static_for<0, Q>([&](auto q_) {
         constexpr int QQ = decltype(q_)::value;
         if constexpr (!(ABL & 64)) fft_dit<L, QQ * L>(v);
