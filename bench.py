@@ -346,6 +346,35 @@ def run_b200(args):
                "sample": f"{n_sample} of {B} clips, in memory, joblib loky n_jobs={cores}, oracle numpy/scipy "
                          f"restatement of librosa 0.11 (librosa not installed here)"}
 
+    # optional second CPU baseline: torchaudio's own MFCC chain on the host, all torch threads,
+    # batched (no per-clip process fan-out); same algorithm for the static rows, its own delta edge handling
+    cpu_ta = None
+    if world == 1 and not args.no_cpu:
+        try:
+            import torchaudio
+            n_ta = min(B, 512)
+            yb = torch.clamp(0.1 * torch.randn((n_ta, Ls), generator=torch.Generator().manual_seed(7)), -1, 1)
+            mfcc_t = torchaudio.transforms.MFCC(sample_rate=SR, n_mfcc=40, dct_type=2, norm="ortho", log_mels=False,
+                                                melkwargs=dict(n_fft=2048, hop_length=512, n_mels=128, center=True,
+                                                               pad_mode="constant", power=2.0, norm="slaney",
+                                                               mel_scale="slaney", f_min=0.0, f_max=SR / 2))
+
+            def ta_pass():
+                with torch.no_grad():
+                    m = mfcc_t(yb)
+                    d1 = torchaudio.functional.compute_deltas(m, win_length=9)
+                    return torch.cat([m, d1, torchaudio.functional.compute_deltas(d1, win_length=9)], dim=1)
+            ta_pass()
+            t0 = time.perf_counter()
+            ta_pass()
+            dt_ta = time.perf_counter() - t0
+            cpu_ta = {"value": n_ta * CLIP_S / 3600.0 / dt_ta, "unit": UNIT, "threads": torch.get_num_threads(),
+                      "kind": "torchaudio " + torchaudio.__version__,
+                      "sample": f"{n_ta} of {B} clips as one batch, transforms.MFCC(40) + compute_deltas x2 on the CPU "
+                                f"(f32 FFT; delta edges replicate instead of librosa's interp fit): informational"}
+        except Exception as e:  # torchaudio missing or a different API: the key stays null
+            cpu_ta = {"unavailable": str(e)[:120]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -371,6 +400,7 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "cpu_baseline_torchaudio": cpu_ta,
     }
     _OUT.emit(json.dumps(line))
     if world > 1:
