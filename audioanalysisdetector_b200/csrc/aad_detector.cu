@@ -53,7 +53,11 @@ __global__ void __launch_bounds__(256) k_det_transpose(const float* __restrict__
 
 // ---------------------------------------------------------------- conv + BN + ReLU, lane = sample
 // smem: Wt[KCONV][64] (k = tap * 63 + ci), scale[64], shift[64] (BatchNorm folded around the conv bias)
-constexpr int CONV_WARPS = 4;  // a CTA = 32 samples; warp w takes positions w, w + 4, ... (the batch is small: more warps per SM)
+// A CTA = 32 samples x 4 warps; warp w = (position-pair group w >> 1, channel half w & 1): it computes TWO adjacent
+// positions for 32 of the 64 channels, so that every broadcast LDS.128 of weights feeds four FFMA2 instead of two
+// (both compute kernels are co-bound by the shared-memory pipe and the FMA pipe) and the batch still spreads over
+// many warps per SM.  Pairs (2i, 2i + 1) are exactly what MaxPool1d(2) combines later.
+constexpr int CONV_WARPS = 4;
 __global__ void __launch_bounds__(32 * CONV_WARPS) k_det_conv(const float* __restrict__ X0, int F, int Bp, int n_pos,
                                                              const float* __restrict__ Wt, const float* __restrict__ scale_shift,
                                                              float* __restrict__ H0) {
@@ -65,38 +69,48 @@ __global__ void __launch_bounds__(32 * CONV_WARPS) k_det_conv(const float* __res
   for (int i = threadIdx.x; i < 2 * C1; i += blockDim.x) sSS[i] = __ldg(scale_shift + i);
   __syncthreads();
   const int b = blockIdx.x * 32 + (threadIdx.x & 31);  // Bp is a multiple of 32
-  for (int p = threadIdx.x >> 5; p < n_pos; p += CONV_WARPS) {
-    float2 acc[C1 / 2];
+  const int warp = threadIdx.x >> 5, half = warp & 1, c0 = half * (C1 / 2);
+  for (int p = 2 * (warp >> 1); p < n_pos; p += CONV_WARPS) {   // n_pos is even: positions p, p + 1
+    float2 acc0[C1 / 4], acc1[C1 / 4];
 #pragma unroll
-    for (int i = 0; i < C1 / 2; ++i) acc[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < C1 / 4; ++i) acc0[i] = acc1[i] = make_float2(0.f, 0.f);
     for (int tap = 0; tap < 3; ++tap) {
-      const int q = p + tap - 1;
-      if (q < 0 || q >= F) continue;  // zero padding
-      const float* xp = X0 + (long long)q * T_IN * Bp + b;
-      const float4* wp = reinterpret_cast<const float4*>(sW + tap * T_IN * C1);
-      // the inputs come from L2 (X0 does not fit L1): 21 loads in flight per lane, three batches per tap
+      const int q0 = p + tap - 1, q1 = q0 + 1;           // input rows of the two positions for this tap
+      const bool in0 = q0 >= 0 && q0 < F, in1 = q1 < F;  // zero padding (q1 >= 0 always)
+      const float* xp0 = X0 + (long long)(in0 ? q0 : 0) * T_IN * Bp + b;
+      const float* xp1 = X0 + (long long)(in1 ? q1 : 0) * T_IN * Bp + b;
+      const float4* wp = reinterpret_cast<const float4*>(sW + tap * T_IN * C1 + c0);
 #pragma unroll 1
-      for (int c0 = 0; c0 < T_IN; c0 += 21) {
-        float xs[21];
+      for (int cb = 0; cb < T_IN; cb += 9) {             // the inputs come from L2: 18 loads in flight per lane
+        float xa[9], xb[9];
 #pragma unroll
-        for (int i = 0; i < 21; ++i) xs[i] = __ldg(xp + (long long)(c0 + i) * Bp);
+        for (int i = 0; i < 9; ++i) {
+          xa[i] = in0 ? __ldg(xp0 + (long long)(cb + i) * Bp) : 0.f;
+          xb[i] = in1 ? __ldg(xp1 + (long long)(cb + i) * Bp) : 0.f;
+        }
 #pragma unroll
-        for (int ci = 0; ci < 21; ++ci) {
-          const float2 xx = make_float2(xs[ci], xs[ci]);
+        for (int ci = 0; ci < 9; ++ci) {
+          const float2 x0 = make_float2(xa[ci], xa[ci]), x1 = make_float2(xb[ci], xb[ci]);
 #pragma unroll
-          for (int i = 0; i < C1 / 4; ++i) {
-            const float4 w = wp[(c0 + ci) * (C1 / 4) + i];
-            acc[2 * i] = __ffma2_rn(xx, make_float2(w.x, w.y), acc[2 * i]);
-            acc[2 * i + 1] = __ffma2_rn(xx, make_float2(w.z, w.w), acc[2 * i + 1]);
+          for (int i = 0; i < C1 / 8; ++i) {
+            const float4 w = wp[(cb + ci) * (C1 / 4) + i];
+            acc0[2 * i] = __ffma2_rn(x0, make_float2(w.x, w.y), acc0[2 * i]);
+            acc0[2 * i + 1] = __ffma2_rn(x0, make_float2(w.z, w.w), acc0[2 * i + 1]);
+            acc1[2 * i] = __ffma2_rn(x1, make_float2(w.x, w.y), acc1[2 * i]);
+            acc1[2 * i + 1] = __ffma2_rn(x1, make_float2(w.z, w.w), acc1[2 * i + 1]);
           }
         }
       }
     }
-    float* hp = H0 + (long long)p * C1 * Bp + b;
+    float* hp0 = H0 + ((long long)p * C1 + c0) * Bp + b;
+    float* hp1 = hp0 + (long long)C1 * Bp;
 #pragma unroll
-    for (int i = 0; i < C1 / 2; ++i) {
-      hp[(long long)(2 * i) * Bp] = fmaxf(fmaf(acc[i].x, sSS[2 * i], sSS[C1 + 2 * i]), 0.f);
-      hp[(long long)(2 * i + 1) * Bp] = fmaxf(fmaf(acc[i].y, sSS[2 * i + 1], sSS[C1 + 2 * i + 1]), 0.f);
+    for (int i = 0; i < C1 / 4; ++i) {
+      const float s0 = sSS[c0 + 2 * i], s1 = sSS[c0 + 2 * i + 1], t0 = sSS[C1 + c0 + 2 * i], t1 = sSS[C1 + c0 + 2 * i + 1];
+      hp0[(long long)(2 * i) * Bp] = fmaxf(fmaf(acc0[i].x, s0, t0), 0.f);
+      hp0[(long long)(2 * i + 1) * Bp] = fmaxf(fmaf(acc0[i].y, s1, t1), 0.f);
+      hp1[(long long)(2 * i) * Bp] = fmaxf(fmaf(acc1[i].x, s0, t0), 0.f);
+      hp1[(long long)(2 * i + 1) * Bp] = fmaxf(fmaf(acc1[i].y, s1, t1), 0.f);
     }
   }
 }
