@@ -28,12 +28,12 @@ enum InMode { IN_F32 = 0, IN_F32_Q16 = 1, IN_I16 = 2 };
 #define AAD_ABLATE 0
 #endif
 constexpr int ABL = AAD_ABLATE;
-// mask bits: 1 window table, 2 tw1 table (both only without AAD_TMEM_TABLES), 4 transposes, 8 filterbank
+// mask bits: 4 transposes, 8 filterbank
 // phase, 16 split exchange + twp table, 32 power stores, 64 butterflies, 128 global sample loads, 256 log
 // in the filterbank emit
 //
 // The shared-memory / L1 data pipe is the most loaded unit of k_stft_fb, the FMA pipe has headroom, so
-// table look-ups are kept off it: AAD_TMEM_TABLES (below) holds the lane x register tables in tensor
+// table look-ups are kept off it: the lane x register tables (window, twiddles) live in tensor
 // memory; on variants without TMEM room for the split twiddle, AAD_TWPGEN forms it as
 // W_N^k = W_N^(j + L q) [per-lane register] * W_N^(32 s) [immediate] instead of loading it.
 #ifndef AAD_TWPGEN
@@ -44,9 +44,6 @@ constexpr int ABL = AAD_ABLATE;
 #endif
 #ifndef AAD_TWFOLD
 #define AAD_TWFOLD 1
-#endif
-#ifndef AAD_WINFOLD
-#define AAD_WINFOLD 1
 #endif
 
 // ---------------------------------------------------------------------------
@@ -179,9 +176,6 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepArgs a) {
 // 512 columns x 32 bit) is read through its own datapath (tcgen05.ld, SASS LDTM): with the 32x32b
 // shape thread i of warp w reads lane 32*(w%4) + i, i.e. exactly "its own row".
 // ---------------------------------------------------------------------------
-#ifndef AAD_TMEM_TABLES
-#define AAD_TMEM_TABLES 1
-#endif
 #ifndef AAD_TWP_TMEM
 #define AAD_TWP_TMEM 1
 #endif
@@ -189,7 +183,7 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepArgs a) {
 // most two CTAs share the SM's 512 columns: allocations are powers of two)
 template <int CTAS>
 struct TmemCfg {
-  static constexpr bool TWP = AAD_TMEM_TABLES && AAD_TWP_TMEM && CTAS <= 2;
+  static constexpr bool TWP = AAD_TWP_TMEM && CTAS <= 2;
   static constexpr int COLS = TWP ? 256 : 128;
 };
 
@@ -270,12 +264,9 @@ struct StftCfg {
   static constexpr int CTAS = L == 32 ? 1 : (L == 16 ? 2 : 4);
   // shared memory carve-up, in floats (the filterbank program follows at OFF_PROG)
   // the window / twiddle tables live in tensor memory (or are generated) and take no shared memory then
-  static constexpr bool SMEM_WIN_TW1 = !AAD_TMEM_TABLES;
   static constexpr bool SMEM_TWP = !(TmemCfg<CTAS>::TWP || (AAD_TWPGEN && Q <= 4));
   static constexpr int OFF_P = 0;
-  static constexpr int OFF_WIN = TILE * SP;
-  static constexpr int OFF_TW1 = OFF_WIN + (SMEM_WIN_TW1 ? N : 0);
-  static constexpr int OFF_TWP = OFF_TW1 + (SMEM_WIN_TW1 ? 2 * 32 * L : 0);
+  static constexpr int OFF_TWP = TILE * SP;
   static constexpr int OFF_META = OFF_TWP + (SMEM_TWP ? 2 * (M / 2) : 0);  // 2 x {b[TILE], t[TILE]} (double buffered)
   static constexpr int OFF_TMEM = OFF_META + 4 * TILE;        // TMEM base address written by tcgen05.alloc
   static constexpr int OFF_PROG = OFF_TMEM + 4;               // segment headers + tap weights follow
@@ -284,7 +275,7 @@ struct StftCfg {
   static_assert(SKEW ? SP % 32 == 0 : SP % 8 == 4, "LDS.128 over lane = frame needs 8 rows in 8 different 16-byte bank groups");
   static_assert(Q * SP >= 32 * 33, "power rows must hold the transpose scratch");
   static_assert(SP >= K + PAD + (SKEW ? 28 : 0), "row must hold the bins, the zero padding and the skew");
-  static_assert(OFF_PROG % 4 == 0 && OFF_WIN % 4 == 0, "tables must be 16-byte aligned");
+  static_assert(OFF_PROG % 4 == 0 && OFF_TWP % 4 == 0, "tables must be 16-byte aligned");
 };
 
 struct StftArgs {
@@ -337,6 +328,10 @@ struct StftArgs {
   long long e2_stride_b;
   int e2_stride_f;
   int32_t* utt_max2;
+  // k_stft_ws only: the filter bank as mma.sync B fragments, per filter-bank warp (see WsCfg)
+  const float4* ws_frag;              // [FB_WARPS][MAXG][32 lanes][4]
+  const int4* ws_ctl;                 // [FB_WARPS] {first 16-bin group, number of groups, first n-tile, 0}
+  const unsigned long long* ws_emit;  // [FB_WARPS] 2 bits per group: n-tiles completed by that group
 };
 
 template <int MODE>
@@ -389,69 +384,48 @@ __device__ unsigned long long g_phase_cycles[4];
 #define AAD_PHASE_MARK(i)
 #endif
 
-template <int L, int MODE, bool PRE, int TILE, bool PAIR = false>
-__global__ void __launch_bounds__(StftCfg<L, TILE>::WARPS * 32, StftCfg<L, TILE>::CTAS)
-k_stft_fb(const StftArgs a) {
+// ---------------------------------------------------------------------------
+// One warp-iteration of the STFT: Q = 32 / L frames (L lanes each) -> their power spectra in shared memory.
+// Shared by k_stft_fb (phase-structured) and k_stft_ws (warp-specialised).
+// ---------------------------------------------------------------------------
+template <int L, int MODE, bool PRE, int TILE>
+struct FrameFft {
   using C = StftCfg<L, TILE>;
-  constexpr int Q = C::Q, M = C::M, N = C::N, SP = C::SP, FBU = C::FBU;
-  constexpr int LOG2L = ilog2(L);
+  static constexpr int Q = C::Q, M = C::M, N = C::N, LOG2L = ilog2(L);
   // n_fft 2048: the inter-pass twiddle is applied AFTER the transpose (the table is symmetric in (b, kA)) and fused
   // with the first butterfly stage of pass 2: 5 packed instructions per butterfly instead of 6
-  constexpr bool TWFOLD = AAD_TWFOLD && AAD_TMEM_TABLES && L == 32;
-  extern __shared__ __align__(16) float smem[];
-  float* sP = smem + C::OFF_P;
-  float* sWin = smem + C::OFF_WIN;
-  float2* sTw1 = reinterpret_cast<float2*>(smem + C::OFF_TW1);
-  float2* sTwp = reinterpret_cast<float2*>(smem + C::OFF_TWP);
-  int* sMeta = reinterpret_cast<int*>(smem + C::OFF_META);
-  int2* sHdr = reinterpret_cast<int2*>(smem + C::OFF_PROG);
-  float4* sW4 = reinterpret_cast<float4*>(smem + C::OFF_PROG + ((2 * a.n_hdr + 3) & ~3));
+  static constexpr bool TWFOLD = AAD_TWFOLD && L == 32;
+  static constexpr bool TWPTM = TmemCfg<C::CTAS>::TWP;
+  static constexpr bool TWPGEN = !TWPTM && AAD_TWPGEN && Q <= 4;
 
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const int g = lane / L, j = lane % L;  // frame-in-iteration, lane within the frame's group
-  const int partner = g * L + ((L - j) & (L - 1));
+  int lane, j, g, partner;  // lane = g * L + j: frame-in-iteration g, lane j within the frame's group
+  uint32_t tmem_row;        // TMEM address of this thread's row (lane quarter of the warp, column 0 of the tables)
+  float2 twp_base[Q];       // W_N^(j + L q) (TWPGEN)
+  const float2* sTwp;       // split twiddles in shared memory (only the variants with neither TMEM room nor TWPGEN)
 
-  if constexpr (C::SMEM_WIN_TW1) {
-    for (int i = tid; i < N; i += nthr) sWin[i] = a.window[i];
-    for (int i = tid; i < 32 * L; i += nthr) sTw1[i] = a.tw1[i];
+  __device__ __forceinline__ void init(const StftArgs& a, int lane_, uint32_t tmem_row_, const float2* sTwp_) {
+    lane = lane_;
+    g = lane / L;
+    j = lane % L;
+    partner = g * L + ((L - j) & (L - 1));
+    tmem_row = tmem_row_;
+    sTwp = sTwp_;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) twp_base[q] = TWPGEN ? __ldg(a.twp + j + L * q) : make_float2(0.f, 0.f);
   }
-  if constexpr (C::SMEM_TWP)
-    for (int i = tid; i < M / 2; i += nthr) sTwp[i] = a.twp[i];
-  for (int i = tid; i < a.n_hdr; i += nthr) sHdr[i] = a.filt_hdr[i];
-  for (int i = tid; i < a.n_w4; i += nthr) sW4[i] = a.filt_w[i];
-  if constexpr (PAIR) {  // second program behind the first (pointers are re-derived where it runs: no live registers)
-    int2* sHdr2 = reinterpret_cast<int2*>(sW4 + a.n_w4);
-    float4* sW42 = reinterpret_cast<float4*>(reinterpret_cast<float*>(sHdr2) + ((2 * a.n_hdr2 + 3) & ~3));
-    for (int i = tid; i < a.n_hdr2; i += nthr) sHdr2[i] = a.filt_hdr2[i];
-    for (int i = tid; i < a.n_w42; i += nthr) sW42[i] = a.filt_w2[i];
-  }
-#if AAD_TMEM_TABLES
-  // allocate 128 TMEM columns, fill this CTA's four lane quarters with the per-lane rows
-  //   columns [0, 64): window pairs 0.5*w[2(L A + j)], 0.5*w[2(L A + j) + 1], A = 0..31
-  //   columns [64, 128): pass-1 twiddles W_M^(j kA), kA = 0..31
-  volatile uint32_t& s_tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM);
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 :: "r"((uint32_t)__cvta_generic_to_shared(smem + C::OFF_TMEM)), "r"((uint32_t)TmemCfg<C::CTAS>::COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_row = s_tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);
-  if (warp < 4) {
+
+  // Fill one TMEM lane quarter with the per-lane rows (executed by one warp per quarter):
+  //   columns [0, 64): window pairs {0.5 w[2(L A + j)], 0.5 w[2(L A + j) + 1]} ordered {w[A], w[A + 16]} (see the window step)
+  //   columns [64, 128): pass-1 twiddles W_M^(j kA)
+  //   columns [128, 160): split twiddles W_N^(j + L q + 32 s) (TWPTM only)
+  __device__ __forceinline__ static void fill_tables(const StftArgs& a, uint32_t tmem_row, int j) {
     const float2* gwin2 = reinterpret_cast<const float2*>(a.window);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       float2 w8[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-#if AAD_WINFOLD
-        const int A = 4 * c + (i >> 1) + 16 * (i & 1);  // {w[A], w[A + 16]} side by side (see the window step)
-#else
-        const int A = 8 * c + i;
-#endif
+        const int A = 4 * c + (i >> 1) + 16 * (i & 1);
         w8[i] = __ldg(gwin2 + L * A + j);
       }
       tmem_st16(tmem_row + 16 * c, w8);
@@ -463,7 +437,7 @@ k_stft_fb(const StftArgs a) {
       }
       tmem_st16(tmem_row + 64 + 16 * c, w8);
     }
-    if constexpr (TmemCfg<C::CTAS>::TWP) {  // entry q*(L/2) + s = W_N^(j + L q + 32 s)
+    if constexpr (TWPTM) {  // entry q*(L/2) + s = W_N^(j + L q + 32 s)
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         float2 w8[8];
@@ -477,19 +451,302 @@ k_stft_fb(const StftArgs a) {
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
+
+  // valid / t / len / row: this lane's frame (the L lanes of a frame agree): frame t of an utterance of len samples
+  // whose first sample is at `row`.  scr: warp-private scratch of >= 32 * 33 floats (may alias prow: the transposes
+  // are over before the powers are written).  prow: power row of this lane's frame, M + 1 + NPAD floats are written.
+  template <int NPAD>
+  __device__ __forceinline__ void run(const StftArgs& a, bool valid, int t, int len, const char* row, float* scr,
+                                      float* prow) const {
+    const int s0 = t * a.hop - a.s_off;
+    bool fast = valid && s0 >= (PRE ? 1 : 0) && (s0 + N) <= len;
+    if constexpr (MODE == IN_I16) fast = fast && (((uintptr_t)(row + 2ll * s0)) & 3) == 0;
+    else fast = fast && (((uintptr_t)(row + 4ll * s0)) & 7) == 0;
+
+    float2 v[32];
+    if (__all_sync(0xffffffffu, fast)) {
+      if constexpr (MODE == IN_I16) {
+        const unsigned* p = reinterpret_cast<const unsigned*>(row + 2ll * s0) + j;
+        unsigned raw[32];
+        static_for<0, 32>([&](auto a_) {
+          constexpr int A = decltype(a_)::value;
+          raw[A] = __ldg(p + L * A);
+        });
+        if constexpr (PRE) {
+          const short* ps = reinterpret_cast<const short*>(row + 2ll * s0) + 2 * j - 1;
+          static_for<0, 32>([&](auto a_) {
+            constexpr int A = decltype(a_)::value;
+            float xp = (float)__ldg(ps + 2 * L * A);
+            float2 x = i16pair_to_float2(raw[A]);
+            float2 e = make_float2(__fmaf_rn(-a.pre_emph, xp, x.x), __fmaf_rn(-a.pre_emph, x.x, x.y));
+            v[bitrev(A, 5)] = e;
+          });
+        } else {
+          static_for<0, 32>([&](auto a_) {
+            constexpr int A = decltype(a_)::value;
+            v[bitrev(A, 5)] = i16pair_to_float2(raw[A]);
+          });
+        }
+      } else {
+        const float2* p = reinterpret_cast<const float2*>(row + 4ll * s0) + j;
+        static_for<0, 32>([&](auto a_) {
+          constexpr int A = decltype(a_)::value;
+          if constexpr (ABL & 128) v[bitrev(A, 5)] = make_float2(a.amin * (lane + A), a.eps * (s0 + A));
+          else v[bitrev(A, 5)] = __ldg(p + L * A);
+        });
+        if constexpr (PRE) {
+          const float* ps = reinterpret_cast<const float*>(row + 4ll * s0) + 2 * j - 1;
+          static_for<0, 32>([&](auto a_) {
+            constexpr int A = decltype(a_)::value;
+            float xp = cvt_sample<MODE>(__ldg(ps + 2 * L * A));
+            float2 x = v[bitrev(A, 5)];
+            x.x = cvt_sample<MODE>(x.x);
+            x.y = cvt_sample<MODE>(x.y);
+            float2 e = make_float2(__fmaf_rn(-a.pre_emph, xp, x.x), __fmaf_rn(-a.pre_emph, x.x, x.y));
+            v[bitrev(A, 5)] = e;
+          });
+        } else if constexpr (MODE == IN_F32_Q16) {
+          static_for<0, 32>([&](auto a_) {
+            constexpr int A = decltype(a_)::value;
+            const float2 x = v[bitrev(A, 5)];
+            v[bitrev(A, 5)] = make_float2(cvt_sample<MODE>(x.x), cvt_sample<MODE>(x.y));
+          });
+        }
+      }
+    } else if (!PRE && __all_sync(0xffffffffu, !valid || (((uintptr_t)(row + (MODE == IN_I16 ? 2ll : 4ll) * s0)) & (MODE == IN_I16 ? 3 : 7)) == 0)) {
+      // edge frames on aligned rows (centre padding, utterance tail, zero-extended window): pairs
+      // fully inside [n_lo, n_hi) keep the vector load, the (at most two) straddling pairs and the
+      // pairs outside are handled per sample.  Keeps an edge frame within ~10 % of an interior one,
+      // which matters because the 16 warps of a tile meet at a barrier.
+      const int n_lo = max(a.win_off, -s0);
+      const int n_hi = valid ? min(a.win_off + a.win_len, len - s0) : 0;
+      static_for<0, 32>([&](auto a_) {
+        constexpr int A = decltype(a_)::value;
+        const int n0 = 2 * (L * A + j);
+        float2 x;
+        if (n0 >= n_lo && n0 + 2 <= n_hi) {
+          if constexpr (MODE == IN_I16) {
+            x = i16pair_to_float2(__ldg(reinterpret_cast<const unsigned*>(row + 2ll * (s0 + n0))));
+          } else {
+            x = __ldg(reinterpret_cast<const float2*>(row + 4ll * (s0 + n0)));
+            if constexpr (MODE == IN_F32_Q16) x = make_float2(cvt_sample<MODE>(x.x), cvt_sample<MODE>(x.y));
+          }
+        } else {
+          x.x = (n0 >= n_lo && n0 < n_hi) ? load_masked<MODE, false>(row, s0 + n0, n0, len, a.win_off, a.win_len, 0.f) : 0.f;
+          x.y = (n0 + 1 >= n_lo && n0 + 1 < n_hi) ? load_masked<MODE, false>(row, s0 + n0 + 1, n0 + 1, len, a.win_off, a.win_len, 0.f) : 0.f;
+        }
+        v[bitrev(A, 5)] = x;
+      });
+    } else {
+      // pre-emphasis or unaligned rows on an edge frame: every sample with all masks
+      static_for<0, 32>([&](auto a_) {
+        constexpr int A = decltype(a_)::value;
+        const int n0 = 2 * (L * A + j);
+        float x0 = load_masked<MODE, PRE>(row, s0 + n0, n0, len, a.win_off, a.win_len, a.pre_emph);
+        float x1 = load_masked<MODE, PRE>(row, s0 + n0 + 1, n0 + 1, len, a.win_off, a.win_len, a.pre_emph);
+        v[bitrev(A, 5)] = make_float2(x0, x1);
+      });
+    }
+
+    // window: 0.5*w (zero outside its support) from this lane's TMEM row, next chunk in flight
+    // window folded into the first butterfly stage of pass 1: samples A and A + 16 meet in stage 1
+    // (registers bitrev(A) = 2m and 2m + 1), so a' = xa*wa + xb*wb, b' = xa*wa - xb*wb is one FMUL2
+    // and two FFMA2 instead of two FMUL2 and two FADD2.  Chunk c holds {w[A], w[A + 16]}, A = 4c .. 4c + 3.
+    {
+      TmemChunk wc[2];
+      wc[0].issue(tmem_row);
+      static_for<0, 4>([&](auto c_) {
+        constexpr int CH = decltype(c_)::value;
+        wc[CH & 1].wait();
+        if constexpr (CH < 3) wc[(CH + 1) & 1].issue(tmem_row + 16 * (CH + 1));
+        static_for<0, 4>([&](auto i_) {
+          constexpr int I = decltype(i_)::value;
+          constexpr int RA = bitrev(4 * CH + I, 5);            // even register; RA + 1 = bitrev(A + 16)
+          const float2 t = pk_mul(v[RA], wc[CH & 1].get(2 * I));
+          const float2 xb = v[RA + 1], wb = wc[CH & 1].get(2 * I + 1);
+          v[RA] = pk_fma(xb, wb, t);
+          v[RA + 1] = pk_fma(make_float2(-xb.x, -xb.y), wb, t);
+        });
+      });
+    }
+
+    // pass 1: 32-point DFT over a (stride L), then twiddle W_M^(b*kA)
+    if constexpr (!(ABL & 64)) fft_dit<32, 0, 32, 2>(v);
+    {
+      if constexpr (!TWFOLD) {
+      TmemChunk tc[2];
+      tc[0].issue(tmem_row + 64);
+      static_for<0, 4>([&](auto c_) {
+        constexpr int CH = decltype(c_)::value;
+        tc[CH & 1].wait();
+        if constexpr (CH < 3) tc[(CH + 1) & 1].issue(tmem_row + 64 + 16 * (CH + 1));
+        static_for<0, 8>([&](auto i_) {
+          constexpr int KA = 8 * CH + decltype(i_)::value;
+          if constexpr (KA > 0) v[KA] = cmul(v[KA], tc[CH & 1].get(KA % 8));
+        });
+      });
+      }
+    }
+
+    // transpose through the warp's scratch (= its own power rows), re then im
+    float* scr_w = scr + lane;
+    const float* scr_r = scr + j * 33 + g * L;
+    if constexpr (!(ABL & 4)) {
+    static_for<0, 32>([&](auto k_) {
+      constexpr int KA = decltype(k_)::value;
+      scr_w[KA * 33] = v[KA].x;
+    });
+    __syncwarp();
+    static_for<0, Q>([&](auto q_) {
+      constexpr int QQ = decltype(q_)::value;
+      static_for<0, L>([&](auto b_) {
+        constexpr int BB = decltype(b_)::value;
+        v[QQ * L + bitrev(BB, LOG2L)].x = scr_r[QQ * L * 33 + BB];
+      });
+    });
+    __syncwarp();
+    static_for<0, 32>([&](auto k_) {
+      constexpr int KA = decltype(k_)::value;
+      scr_w[KA * 33] = v[KA].y;
+    });
+    __syncwarp();
+    static_for<0, Q>([&](auto q_) {
+      constexpr int QQ = decltype(q_)::value;
+      static_for<0, L>([&](auto b_) {
+        constexpr int BB = decltype(b_)::value;
+        v[QQ * L + bitrev(BB, LOG2L)].y = scr_r[QQ * L * 33 + BB];
+      });
+    });
+    __syncwarp();
+    }
+
+    // pass 2: Q DFTs of length L over b  ->  v[q*L + kB] = Z[(j + L q) + 32 kB]
+    if constexpr (TWFOLD) {
+      // twiddle + first stage of pass 2: registers 2m, 2m + 1 hold b and b + 16;  a' = ta a + tb b,  b' = ta a - tb b
+      TmemChunk tc[2];
+      tc[0].issue(tmem_row + 64);
+      static_for<0, 4>([&](auto c_) {
+        constexpr int CH = decltype(c_)::value;
+        tc[CH & 1].wait();
+        if constexpr (CH < 3) tc[(CH + 1) & 1].issue(tmem_row + 64 + 16 * (CH + 1));
+        static_for<0, 4>([&](auto i_) {
+          constexpr int I = decltype(i_)::value;
+          constexpr int BA = 4 * CH + I, RA = bitrev(BA, 5);
+          const float2 tb = tc[CH & 1].get(2 * I + 1), b0 = v[RA + 1];
+          float2 u = v[RA];
+          if constexpr (BA > 0) u = cmul(u, tc[CH & 1].get(2 * I));
+          const float2 t1 = __ffma2_rn(b0, make_float2(tb.x, tb.x), u);
+          const float2 na = __ffma2_rn(make_float2(-b0.y, b0.x), make_float2(tb.y, tb.y), t1);
+          v[RA + 1] = __ffma2_rn(u, make_float2(2.0f, 2.0f), make_float2(-na.x, -na.y));
+          v[RA] = na;
+        });
+      });
+      if constexpr (!(ABL & 64)) fft_dit<32, 0, 32, 2>(v);
+    } else
+    static_for<0, Q>([&](auto q_) {
+      constexpr int QQ = decltype(q_)::value;
+      if constexpr (!(ABL & 64)) fft_dit<L, QQ * L>(v);
+    });
+
+    // real-input split + power:  X[k] = E - T,  X[M-k] = conj(E + T),  T = i*w*O
+    TmemChunk pc[2];
+    if constexpr (TWPTM) {
+      pc[0].issue(tmem_row + 128);
+      pc[1].issue(tmem_row + 144);
+      pc[0].wait();  // covers both
+      pc[1].wait();
+    }
+    static_for<0, Q>([&](auto q_) {
+      constexpr int QQ = decltype(q_)::value;
+      static_for<0, L / 2>([&](auto s_) {
+        constexpr int S = decltype(s_)::value;
+        constexpr int GEN = (Q - 1 - QQ) * L + (L - 1 - S);
+        constexpr int ALT = QQ == 0 ? ((L - S) % L) : (Q - QQ) * L + (L - 1 - S);
+        const float2 snd = (j == 0) ? v[ALT] : v[GEN];
+        float2 r;  // Z[M - k]
+        if constexpr (ABL & 16) r = snd;
+        else {
+        r.x = __shfl_sync(0xffffffffu, snd.x, partner);
+        r.y = __shfl_sync(0xffffffffu, snd.y, partner);
+        }
+        const float2 A = v[QQ * L + S];
+        const float2 E = __fadd2_rn(A, make_float2(r.x, -r.y));   // A + conj(r)
+        const float2 O = __fadd2_rn(A, make_float2(-r.x, r.y));   // A - conj(r)
+        const int k = j + L * QQ + 32 * S;
+        float2 wO;
+        if constexpr (TWPTM) {
+          constexpr int EI = QQ * (L / 2) + S;
+          wO = cmul(O, pc[EI / 8].get(EI % 8));
+        } else
+        if constexpr (TWPGEN) wO = cmul(cmul_const<32 * S, N>(O), twp_base[QQ]);
+        else wO = (ABL & 16) ? cmul(O, make_float2(a.amin, a.eps)) : cmul(O, sTwp[k]);
+        const float2 x1 = __fadd2_rn(E, make_float2(wO.y, -wO.x));  // E - i*wO
+        const float2 x2 = __fadd2_rn(E, make_float2(-wO.y, wO.x));  // E + i*wO
+        if constexpr (ABL & 32) {
+          if (x1.x * x2.y == 123.456f) prow[k] = x1.y;
+        } else {
+        prow[k] = __fmaf_rn(x1.x, x1.x, x1.y * x1.y);
+        prow[M - k] = __fmaf_rn(x2.x, x2.x, x2.y * x2.y);
+        }
+      });
+    });
+    if (j == 0) {
+      float2 A = v[L / 2];
+      prow[M / 2] = 4.0f * __fmaf_rn(A.x, A.x, A.y * A.y);
+      // padding read by the last tap groups of a segment that reaches the Nyquist bin
+#pragma unroll
+      for (int i = 1; i <= NPAD; ++i) prow[M + i] = 0.f;
+    }
+  }
+};
+
+template <int L, int MODE, bool PRE, int TILE, bool PAIR = false>
+__global__ void __launch_bounds__(StftCfg<L, TILE>::WARPS * 32, StftCfg<L, TILE>::CTAS)
+k_stft_fb(const StftArgs a) {
+  using C = StftCfg<L, TILE>;
+  using FFT = FrameFft<L, MODE, PRE, TILE>;
+  constexpr int Q = C::Q, M = C::M, N = C::N, SP = C::SP, FBU = C::FBU;
+  extern __shared__ __align__(16) float smem[];
+  float* sP = smem + C::OFF_P;
+  float2* sTwp = reinterpret_cast<float2*>(smem + C::OFF_TWP);
+  int* sMeta = reinterpret_cast<int*>(smem + C::OFF_META);
+  int2* sHdr = reinterpret_cast<int2*>(smem + C::OFF_PROG);
+  float4* sW4 = reinterpret_cast<float4*>(smem + C::OFF_PROG + ((2 * a.n_hdr + 3) & ~3));
+
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane / L;
+
+  if constexpr (C::SMEM_TWP)
+    for (int i = tid; i < M / 2; i += nthr) sTwp[i] = a.twp[i];
+  for (int i = tid; i < a.n_hdr; i += nthr) sHdr[i] = a.filt_hdr[i];
+  for (int i = tid; i < a.n_w4; i += nthr) sW4[i] = a.filt_w[i];
+  if constexpr (PAIR) {  // second program behind the first (pointers are re-derived where it runs: no live registers)
+    int2* sHdr2 = reinterpret_cast<int2*>(sW4 + a.n_w4);
+    float4* sW42 = reinterpret_cast<float4*>(reinterpret_cast<float*>(sHdr2) + ((2 * a.n_hdr2 + 3) & ~3));
+    for (int i = tid; i < a.n_hdr2; i += nthr) sHdr2[i] = a.filt_hdr2[i];
+    for (int i = tid; i < a.n_w42; i += nthr) sW42[i] = a.filt_w2[i];
+  }
+  // allocate the TMEM columns, fill this CTA's four lane quarters with the per-lane tables
+  volatile uint32_t& s_tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(smem + C::OFF_TMEM)), "r"((uint32_t)TmemCfg<C::CTAS>::COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#endif
+  const uint32_t tmem_row = s_tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);
+  if (warp < 4) FFT::fill_tables(a, tmem_row, lane % L);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  FFT fft;
+  fft.init(a, lane, tmem_row, sTwp);
   const int4 wprog = a.warp_prog[warp];
   const int total = a.frame_off[a.B];
   const int n_tiles = (total + C::TILE - 1) / C::TILE;
-  const float2* sWin2 = reinterpret_cast<const float2*>(sWin);
-  constexpr bool TWPTM = TmemCfg<C::CTAS>::TWP;
-  constexpr bool TWPGEN = !TWPTM && AAD_TWPGEN && Q <= 4;
-  float2 twp_base[Q];   // W_N^(j + L q)
-#pragma unroll
-  for (int q = 0; q < Q; ++q) twp_base[q] = TWPGEN ? __ldg(a.twp + j + L * q) : make_float2(0.f, 0.f);
 
   // tile meta: global frame index -> (utterance, frame); computed one tile ahead by warp 0 so the
   // dependent index loads never sit on the critical path, and used to prefetch the next tile's
@@ -539,287 +796,10 @@ k_stft_fb(const StftArgs a) {
       const bool valid = b >= 0;
       if (!__any_sync(0xffffffffu, valid)) continue;
       const int len = valid ? __ldg(a.len_c + b) : 0;
-      const int s0 = t * a.hop - a.s_off;
       const char* row = static_cast<const char*>(a.wav) +
                         (valid ? (a.row_off ? __ldg(a.row_off + b) : (long long)b * a.wav_stride) * (MODE == IN_I16 ? 2 : 4) : 0);
-      bool fast = valid && s0 >= (PRE ? 1 : 0) && (s0 + N) <= len;
-      if constexpr (MODE == IN_I16) fast = fast && (((uintptr_t)(row + 2ll * s0)) & 3) == 0;
-      else fast = fast && (((uintptr_t)(row + 4ll * s0)) & 7) == 0;
-
-      float2 v[32];
-      if (__all_sync(0xffffffffu, fast)) {
-        if constexpr (MODE == IN_I16) {
-          const unsigned* p = reinterpret_cast<const unsigned*>(row + 2ll * s0) + j;
-          unsigned raw[32];
-          static_for<0, 32>([&](auto a_) {
-            constexpr int A = decltype(a_)::value;
-            raw[A] = __ldg(p + L * A);
-          });
-          if constexpr (PRE) {
-            const short* ps = reinterpret_cast<const short*>(row + 2ll * s0) + 2 * j - 1;
-            static_for<0, 32>([&](auto a_) {
-              constexpr int A = decltype(a_)::value;
-              float xp = (float)__ldg(ps + 2 * L * A);
-              float2 x = i16pair_to_float2(raw[A]);
-              float2 e = make_float2(__fmaf_rn(-a.pre_emph, xp, x.x), __fmaf_rn(-a.pre_emph, x.x, x.y));
-              v[bitrev(A, 5)] = e;
-            });
-          } else {
-            static_for<0, 32>([&](auto a_) {
-              constexpr int A = decltype(a_)::value;
-              v[bitrev(A, 5)] = i16pair_to_float2(raw[A]);
-            });
-          }
-        } else {
-          const float2* p = reinterpret_cast<const float2*>(row + 4ll * s0) + j;
-          static_for<0, 32>([&](auto a_) {
-            constexpr int A = decltype(a_)::value;
-            if constexpr (ABL & 128) v[bitrev(A, 5)] = make_float2(a.amin * (lane + A), a.eps * (s0 + A));
-            else v[bitrev(A, 5)] = __ldg(p + L * A);
-          });
-          if constexpr (PRE) {
-            const float* ps = reinterpret_cast<const float*>(row + 4ll * s0) + 2 * j - 1;
-            static_for<0, 32>([&](auto a_) {
-              constexpr int A = decltype(a_)::value;
-              float xp = cvt_sample<MODE>(__ldg(ps + 2 * L * A));
-              float2 x = v[bitrev(A, 5)];
-              x.x = cvt_sample<MODE>(x.x);
-              x.y = cvt_sample<MODE>(x.y);
-              float2 e = make_float2(__fmaf_rn(-a.pre_emph, xp, x.x), __fmaf_rn(-a.pre_emph, x.x, x.y));
-              v[bitrev(A, 5)] = e;
-            });
-          } else if constexpr (MODE == IN_F32_Q16) {
-            static_for<0, 32>([&](auto a_) {
-              constexpr int A = decltype(a_)::value;
-              const float2 x = v[bitrev(A, 5)];
-              v[bitrev(A, 5)] = make_float2(cvt_sample<MODE>(x.x), cvt_sample<MODE>(x.y));
-            });
-          }
-        }
-      } else if (!PRE && __all_sync(0xffffffffu, !valid || (((uintptr_t)(row + (MODE == IN_I16 ? 2ll : 4ll) * s0)) & (MODE == IN_I16 ? 3 : 7)) == 0)) {
-        // edge frames on aligned rows (centre padding, utterance tail, zero-extended window): pairs
-        // fully inside [n_lo, n_hi) keep the vector load, the (at most two) straddling pairs and the
-        // pairs outside are handled per sample.  Keeps an edge frame within ~10 % of an interior one,
-        // which matters because the 16 warps of a tile meet at a barrier.
-        const int n_lo = max(a.win_off, -s0);
-        const int n_hi = valid ? min(a.win_off + a.win_len, len - s0) : 0;
-        static_for<0, 32>([&](auto a_) {
-          constexpr int A = decltype(a_)::value;
-          const int n0 = 2 * (L * A + j);
-          float2 x;
-          if (n0 >= n_lo && n0 + 2 <= n_hi) {
-            if constexpr (MODE == IN_I16) {
-              x = i16pair_to_float2(__ldg(reinterpret_cast<const unsigned*>(row + 2ll * (s0 + n0))));
-            } else {
-              x = __ldg(reinterpret_cast<const float2*>(row + 4ll * (s0 + n0)));
-              if constexpr (MODE == IN_F32_Q16) x = make_float2(cvt_sample<MODE>(x.x), cvt_sample<MODE>(x.y));
-            }
-          } else {
-            x.x = (n0 >= n_lo && n0 < n_hi) ? load_masked<MODE, false>(row, s0 + n0, n0, len, a.win_off, a.win_len, 0.f) : 0.f;
-            x.y = (n0 + 1 >= n_lo && n0 + 1 < n_hi) ? load_masked<MODE, false>(row, s0 + n0 + 1, n0 + 1, len, a.win_off, a.win_len, 0.f) : 0.f;
-          }
-          v[bitrev(A, 5)] = x;
-        });
-      } else {
-        // pre-emphasis or unaligned rows on an edge frame: every sample with all masks
-        static_for<0, 32>([&](auto a_) {
-          constexpr int A = decltype(a_)::value;
-          const int n0 = 2 * (L * A + j);
-          float x0 = load_masked<MODE, PRE>(row, s0 + n0, n0, len, a.win_off, a.win_len, a.pre_emph);
-          float x1 = load_masked<MODE, PRE>(row, s0 + n0 + 1, n0 + 1, len, a.win_off, a.win_len, a.pre_emph);
-          v[bitrev(A, 5)] = make_float2(x0, x1);
-        });
-      }
-
-      // window: 0.5*w (zero outside its support) from this lane's TMEM row, next chunk in flight
-#if AAD_TMEM_TABLES
-#if AAD_WINFOLD
-      // window folded into the first butterfly stage of pass 1: samples A and A + 16 meet in stage 1
-      // (registers bitrev(A) = 2m and 2m + 1), so a' = xa*wa + xb*wb, b' = xa*wa - xb*wb is one FMUL2
-      // and two FFMA2 instead of two FMUL2 and two FADD2.  Chunk c holds {w[A], w[A + 16]}, A = 4c .. 4c + 3.
-      {
-        TmemChunk wc[2];
-        wc[0].issue(tmem_row);
-        static_for<0, 4>([&](auto c_) {
-          constexpr int CH = decltype(c_)::value;
-          wc[CH & 1].wait();
-          if constexpr (CH < 3) wc[(CH + 1) & 1].issue(tmem_row + 16 * (CH + 1));
-          static_for<0, 4>([&](auto i_) {
-            constexpr int I = decltype(i_)::value;
-            constexpr int RA = bitrev(4 * CH + I, 5);            // even register; RA + 1 = bitrev(A + 16)
-            const float2 t = pk_mul(v[RA], wc[CH & 1].get(2 * I));
-            const float2 xb = v[RA + 1], wb = wc[CH & 1].get(2 * I + 1);
-            v[RA] = pk_fma(xb, wb, t);
-            v[RA + 1] = pk_fma(make_float2(-xb.x, -xb.y), wb, t);
-          });
-        });
-      }
-#else
-      {
-        TmemChunk wc[2];
-        wc[0].issue(tmem_row);
-        static_for<0, 4>([&](auto c_) {
-          constexpr int CH = decltype(c_)::value;
-          wc[CH & 1].wait();
-          if constexpr (CH < 3) wc[(CH + 1) & 1].issue(tmem_row + 16 * (CH + 1));
-          static_for<0, 8>([&](auto i_) {
-            constexpr int A = 8 * CH + decltype(i_)::value;
-            v[bitrev(A, 5)] = pk_mul(v[bitrev(A, 5)], wc[CH & 1].get(A % 8));
-          });
-        });
-      }
-#endif
-#else
-      static_for<0, 32>([&](auto a_) {
-        constexpr int A = decltype(a_)::value;
-        if constexpr (ABL & 1) v[bitrev(A, 5)] = pk_mul(v[bitrev(A, 5)], make_float2(a.amin, a.eps));
-        else v[bitrev(A, 5)] = pk_mul(v[bitrev(A, 5)], sWin2[L * A + j]);
-      });
-#endif
-
-      // pass 1: 32-point DFT over a (stride L), then twiddle W_M^(b*kA)
-      if constexpr (!(ABL & 64)) fft_dit<32, 0, 32, (AAD_WINFOLD && AAD_TMEM_TABLES) ? 2 : 1>(v);
-      {
-#if AAD_TMEM_TABLES
-        if constexpr (!TWFOLD) {
-        TmemChunk tc[2];
-        tc[0].issue(tmem_row + 64);
-        static_for<0, 4>([&](auto c_) {
-          constexpr int CH = decltype(c_)::value;
-          tc[CH & 1].wait();
-          if constexpr (CH < 3) tc[(CH + 1) & 1].issue(tmem_row + 64 + 16 * (CH + 1));
-          static_for<0, 8>([&](auto i_) {
-            constexpr int KA = 8 * CH + decltype(i_)::value;
-            if constexpr (KA > 0) v[KA] = cmul(v[KA], tc[CH & 1].get(KA % 8));
-          });
-        });
-        }
-#else
-        static_for<1, 32>([&](auto k_) {
-          constexpr int KA = decltype(k_)::value;
-          if constexpr (ABL & 2) v[KA] = cmul(v[KA], make_float2(a.amin, a.eps));
-          else v[KA] = cmul(v[KA], sTw1[KA * L + j]);
-        });
-#endif
-      }
-
-      // transpose through the warp's scratch (= its own power rows), re then im
-      float* scr = sP + (it * Q) * SP;
-      float* scr_w = scr + lane;
-      const float* scr_r = scr + j * 33 + g * L;
-      if constexpr (!(ABL & 4)) {
-      static_for<0, 32>([&](auto k_) {
-        constexpr int KA = decltype(k_)::value;
-        scr_w[KA * 33] = v[KA].x;
-      });
-      __syncwarp();
-      static_for<0, Q>([&](auto q_) {
-        constexpr int QQ = decltype(q_)::value;
-        static_for<0, L>([&](auto b_) {
-          constexpr int BB = decltype(b_)::value;
-          v[QQ * L + bitrev(BB, LOG2L)].x = scr_r[QQ * L * 33 + BB];
-        });
-      });
-      __syncwarp();
-      static_for<0, 32>([&](auto k_) {
-        constexpr int KA = decltype(k_)::value;
-        scr_w[KA * 33] = v[KA].y;
-      });
-      __syncwarp();
-      static_for<0, Q>([&](auto q_) {
-        constexpr int QQ = decltype(q_)::value;
-        static_for<0, L>([&](auto b_) {
-          constexpr int BB = decltype(b_)::value;
-          v[QQ * L + bitrev(BB, LOG2L)].y = scr_r[QQ * L * 33 + BB];
-        });
-      });
-      __syncwarp();
-      }
-
-      // pass 2: Q DFTs of length L over b  ->  v[q*L + kB] = Z[(j + L q) + 32 kB]
-#if AAD_TMEM_TABLES
-      if constexpr (TWFOLD) {
-        // twiddle + first stage of pass 2: registers 2m, 2m + 1 hold b and b + 16;  a' = ta a + tb b,  b' = ta a - tb b
-        TmemChunk tc[2];
-        tc[0].issue(tmem_row + 64);
-        static_for<0, 4>([&](auto c_) {
-          constexpr int CH = decltype(c_)::value;
-          tc[CH & 1].wait();
-          if constexpr (CH < 3) tc[(CH + 1) & 1].issue(tmem_row + 64 + 16 * (CH + 1));
-          static_for<0, 4>([&](auto i_) {
-            constexpr int I = decltype(i_)::value;
-            constexpr int BA = 4 * CH + I, RA = bitrev(BA, 5);
-            const float2 tb = tc[CH & 1].get(2 * I + 1), b0 = v[RA + 1];
-            float2 u = v[RA];
-            if constexpr (BA > 0) u = cmul(u, tc[CH & 1].get(2 * I));
-            const float2 t1 = __ffma2_rn(b0, make_float2(tb.x, tb.x), u);
-            const float2 na = __ffma2_rn(make_float2(-b0.y, b0.x), make_float2(tb.y, tb.y), t1);
-            v[RA + 1] = __ffma2_rn(u, make_float2(2.0f, 2.0f), make_float2(-na.x, -na.y));
-            v[RA] = na;
-          });
-        });
-        if constexpr (!(ABL & 64)) fft_dit<32, 0, 32, 2>(v);
-      } else
-#endif
-      static_for<0, Q>([&](auto q_) {
-        constexpr int QQ = decltype(q_)::value;
-        if constexpr (!(ABL & 64)) fft_dit<L, QQ * L>(v);
-      });
-
-      // real-input split + power:  X[k] = E - T,  X[M-k] = conj(E + T),  T = i*w*O
-      float* prow = sP + fi * SP + C::skew(fi);
-#if AAD_TMEM_TABLES
-      TmemChunk pc[2];
-      if constexpr (TWPTM) {
-        pc[0].issue(tmem_row + 128);
-        pc[1].issue(tmem_row + 144);
-        pc[0].wait();  // covers both
-        pc[1].wait();
-      }
-#endif
-      static_for<0, Q>([&](auto q_) {
-        constexpr int QQ = decltype(q_)::value;
-        static_for<0, L / 2>([&](auto s_) {
-          constexpr int S = decltype(s_)::value;
-          constexpr int GEN = (Q - 1 - QQ) * L + (L - 1 - S);
-          constexpr int ALT = QQ == 0 ? ((L - S) % L) : (Q - QQ) * L + (L - 1 - S);
-          const float2 snd = (j == 0) ? v[ALT] : v[GEN];
-          float2 r;  // Z[M - k]
-          if constexpr (ABL & 16) r = snd;
-          else {
-          r.x = __shfl_sync(0xffffffffu, snd.x, partner);
-          r.y = __shfl_sync(0xffffffffu, snd.y, partner);
-          }
-          const float2 A = v[QQ * L + S];
-          const float2 E = __fadd2_rn(A, make_float2(r.x, -r.y));   // A + conj(r)
-          const float2 O = __fadd2_rn(A, make_float2(-r.x, r.y));   // A - conj(r)
-          const int k = j + L * QQ + 32 * S;
-          float2 wO;
-#if AAD_TMEM_TABLES
-          if constexpr (TWPTM) {
-            constexpr int EI = QQ * (L / 2) + S;
-            wO = cmul(O, pc[EI / 8].get(EI % 8));
-          } else
-#endif
-          if constexpr (TWPGEN) wO = cmul(cmul_const<32 * S, N>(O), twp_base[QQ]);
-          else wO = (ABL & 16) ? cmul(O, make_float2(a.amin, a.eps)) : cmul(O, sTwp[k]);
-          const float2 x1 = __fadd2_rn(E, make_float2(wO.y, -wO.x));  // E - i*wO
-          const float2 x2 = __fadd2_rn(E, make_float2(-wO.y, wO.x));  // E + i*wO
-          if constexpr (ABL & 32) {
-            if (x1.x * x2.y == 123.456f) prow[k] = x1.y;
-          } else {
-          prow[k] = __fmaf_rn(x1.x, x1.x, x1.y * x1.y);
-          prow[M - k] = __fmaf_rn(x2.x, x2.x, x2.y * x2.y);
-          }
-        });
-      });
-      if (j == 0) {
-        float2 A = v[L / 2];
-        prow[M / 2] = 4.0f * __fmaf_rn(A.x, A.x, A.y * A.y);
-        // padding read by the last tap groups of a segment that reaches the Nyquist bin
-#pragma unroll
-        for (int i = 1; i <= C::PAD; ++i) prow[M + i] = 0.f;
-      }
+      // transposes go through the warp's own power rows
+      fft.template run<C::PAD>(a, valid, t, len, row, sP + (it * Q) * SP, sP + fi * SP + C::skew(fi));
     }
     AAD_PHASE_MARK(0);
     __syncthreads();
@@ -929,14 +909,332 @@ k_stft_fb(const StftArgs a) {
     AAD_PHASE_MARK(3);
 #endif
   }
-#if AAD_TMEM_TABLES
   // every warp is past its last tcgen05.ld (the loop ends with a CTA barrier; CTAs without tiles
   // come straight from the set-up barrier)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"((uint32_t)s_tmem_base), "r"((uint32_t)TmemCfg<C::CTAS>::COLS) : "memory");
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// ---------------------------------------------------------------------------
+// K1 for n_fft 2048, warp-specialised (k_stft_ws).  Same arithmetic up to the power spectrum as k_stft_fb
+// (FrameFft), but the CTA is a pipeline instead of two phases separated by CTA-wide barriers:
+//
+//   12 FFT warps (producers): each takes frames round-robin, transforms one at a time and writes its power
+//       spectrum into a row of a 16-frame tile buffer (the row doubles as the warp's transpose scratch), then
+//       arrives on the buffer's `full` mbarrier.  The next frame's index look-ups are in flight during the
+//       transform, the frame after that is prefetched into L2.
+//   4 filter-bank warps (consumers, one per scheduler): wait for a full 16-frame tile and apply the filter
+//       bank on the TENSOR cores: E[frame][filter] = P[frame][bin] . W[bin][filter] with mma.sync.m16n8k8
+//       TF32 and the 3-term split hi*hi + lo*hi + hi*lo (fp32 accumulate, ~2^-21 per product).  The bank is
+//       banded, so a warp owns a contiguous range of n-tiles (8 filters) and walks only the 16-bin groups
+//       that touch them, with a rolling window of two n-tiles; its B fragments are per-lane constants held in
+//       tensor memory (columns [160, 512) of the warp's own lane quarter) and read with tcgen05.ld.  One
+//       LDS.128 per lane and row delivers the A values of two k-steps (the k index inside a group is
+//       permuted so that a lane's four bins are contiguous).  Then log, store, running maximum as in
+//       k_stft_fb, and the buffer is handed back through its `empty` mbarrier.
+//
+// Nothing in the steady state is a CTA-wide barrier: FFT warps drift apart instead of meeting twice per 32
+// frames, the filter bank costs no FMA-pipe slots, a third of the shared-memory wavefronts and half the
+// issue slots of the SIMT form, and runs next to the transforms instead of between them.
+// ---------------------------------------------------------------------------
+struct WsCfg {
+#ifdef AAD_WS_NBUF  // dev builds only
+  static constexpr int TILE = 16, NBUF = AAD_WS_NBUF;
+#else
+  static constexpr int TILE = 16, NBUF = 3;
 #endif
+#if defined(AAD_WS_FFTW) && defined(AAD_WS_FBW)  // dev builds only (warp split experiments)
+  static constexpr int FFT_WARPS = AAD_WS_FFTW, FB_WARPS = AAD_WS_FBW;
+#else
+  static constexpr int FFT_WARPS = 12, FB_WARPS = 4;
+#endif
+  static constexpr int WARPS = FFT_WARPS + FB_WARPS;
+  static constexpr int M = 1024;
+  static constexpr int GROUP = 16;                      // bins per filter-bank step (two mma k-steps)
+  static constexpr int NGROUPS = (M + 1 + GROUP - 1) / GROUP;  // 65
+  static constexpr int KPAD = NGROUPS * GROUP;          // bins incl. zeroed padding (1040)
+  // power-row stride in words: = 16 (mod 32) so that the A-fragment LDS.128 of 8 consecutive lanes
+  // (two rows x four 16-byte pieces) covers all 32 banks; holds the padded bins and the 32 x 33 scratch
+  static constexpr int SPW = 1072;
+  static constexpr int TMEM_FB0 = 160;                  // first TMEM column of the filter-bank fragments
+  static constexpr int MAXG = (512 - TMEM_FB0) / 16;    // groups per filter-bank warp (16 columns each)
+  static constexpr int OFF_META = NBUF * TILE * SPW;    // int b[NBUF][TILE], t[NBUF][TILE]
+  static constexpr int OFF_BAR = OFF_META + 2 * NBUF * TILE;  // full[NBUF], empty[NBUF] (8 bytes each)
+  static constexpr int OFF_TMEM = OFF_BAR + 4 * NBUF;
+  static constexpr size_t SMEM_BYTES = size_t(OFF_TMEM + 4) * 4;
+  static_assert(SPW % 32 == 16 && SPW >= KPAD && SPW >= 32 * 33, "power row stride");
+  static_assert(OFF_BAR % 2 == 0, "mbarriers are 8-byte aligned");
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(WsCfg::WARPS * 32, 1) k_stft_ws(const StftArgs a) {
+  using W = WsCfg;
+  using FFT = FrameFft<32, MODE, false, 32>;
+  constexpr int N = 2048;
+  extern __shared__ __align__(16) float smem[];
+  float* sP = smem;
+  int* sMeta = reinterpret_cast<int*>(smem + W::OFF_META);
+  const uint32_t bar0 = smem_u32(smem + W::OFF_BAR);
+  auto full_bar = [&](int buf) { return bar0 + 8u * (uint32_t)buf; };
+  auto empty_bar = [&](int buf) { return bar0 + 8u * (uint32_t)(W::NBUF + buf); };
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // set-up: tensor memory (all 512 columns: this kernel is alone on its SM), tables, mbarriers
+  volatile uint32_t& s_tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + W::OFF_TMEM);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(smem + W::OFF_TMEM)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (int i = 0; i < W::NBUF; ++i) {
+      mbar_init(full_bar(i), W::TILE);       // one arrival per frame row
+      mbar_init(empty_bar(i), W::FB_WARPS > 0 ? W::FB_WARPS : 1);  // one arrival per filter-bank warp
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_row = s_tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);
+  if (warp < 4) {
+    FFT::fill_tables(a, tmem_row, lane);
+  } else if (warp >= W::FFT_WARPS) {
+    const int q = warp - W::FFT_WARPS;
+    const int ng = __ldg(&a.ws_ctl[q].y);
+    const float4* src = a.ws_frag + ((size_t)q * W::MAXG * 32 + lane) * 4;
+    for (int i = 0; i < ng; ++i, src += 32 * 4) {
+      float2 w8[8];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 f = __ldg(src + c);
+        w8[2 * c] = make_float2(f.x, f.y);
+        w8[2 * c + 1] = make_float2(f.z, f.w);
+      }
+      tmem_st16(tmem_row + W::TMEM_FB0 + 16 * i, w8);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  const int total = __ldg(a.frame_off + a.B);
+  const int n_tiles = (total + W::TILE - 1) / W::TILE;
+  const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp < W::FFT_WARPS) {
+    // ---------------- producers: one frame at a time ----------------
+    FFT fft;
+    fft.init(a, lane, tmem_row, nullptr);
+    constexpr int ES = MODE == IN_I16 ? 2 : 4;
+    const int n_slots = my_tiles * W::TILE;  // slot s = (tile s / 16 of this CTA, row s % 16)
+    struct Slot {
+      int b, t, len;
+      const char* row;
+    };
+    auto slot_meta = [&](int s) {
+      Slot m;
+      m.b = -1; m.t = 0; m.len = 0; m.row = static_cast<const char*>(a.wav);
+      if (s < n_slots) {
+        const int tile = (int)blockIdx.x + (s >> 4) * (int)gridDim.x;
+        const int gf = tile * W::TILE + (s & 15);
+        if (gf < total) {
+          int b = __ldg(a.tile_b0 + tile);
+          int nxt = __ldg(a.frame_off + b + 1);
+          while (gf >= nxt) nxt = __ldg(a.frame_off + (++b) + 1);
+          m.t = gf - __ldg(a.frame_off + b);
+          m.b = b;
+          m.len = __ldg(a.len_c + b);
+          m.row += (a.row_off ? __ldg(a.row_off + b) : (long long)b * a.wav_stride) * ES;
+        }
+      }
+      return m;
+    };
+    auto l2_prefetch = [&](const Slot& m) {  // the samples this frame adds to its predecessor's
+      if (m.b >= 0 && lane == 0) {
+        long long s_lo = (long long)m.t * a.hop - a.s_off + (m.t == 0 ? 0 : N - a.hop);
+        long long s_hi = (long long)m.t * a.hop - a.s_off + N;
+        if (s_lo < 0) s_lo = 0;
+        if (s_hi > m.len) s_hi = m.len;
+        uintptr_t p0 = ((uintptr_t)(m.row + s_lo * ES) + 15) & ~(uintptr_t)15;
+        uintptr_t p1 = (uintptr_t)(m.row + s_hi * ES) & ~(uintptr_t)15;
+        if (p1 > p0)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"((unsigned)(p1 - p0)) : "memory");
+      }
+    };
+    Slot cur = slot_meta(warp), nx1 = slot_meta(warp + W::FFT_WARPS);
+    for (int s = warp; s < n_slots; s += W::FFT_WARPS) {
+      const Slot nx2 = slot_meta(s + 2 * W::FFT_WARPS);  // consumed two frames from now: never waited for
+      l2_prefetch(nx1);
+      const int tl = s >> 4, r = s & 15, buf = tl % W::NBUF, use = tl / W::NBUF;
+#ifndef AAD_WS_NOFB
+      if (use > 0) mbar_wait(empty_bar(buf), (uint32_t)(use - 1) & 1u);  // the consumers are done with the previous tile here
+#endif
+      float* prow = sP + (buf * W::TILE + r) * W::SPW;
+      if (cur.b >= 0) fft.template run<W::KPAD - W::M - 1>(a, true, cur.t, cur.len, cur.row, prow, prow);
+      if (lane == 0) {
+        sMeta[buf * 2 * W::TILE + r] = cur.b;
+        sMeta[buf * 2 * W::TILE + W::TILE + r] = cur.t;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(buf));
+      cur = nx1;
+      nx1 = nx2;
+    }
+  } else {
+#ifndef AAD_WS_NOFB
+    // ---------------- consumers: filter bank of one 16-frame tile on the tensor cores ----------------
+    const int q = warp - W::FFT_WARPS;
+    const int4 ctl = __ldg(a.ws_ctl + q);
+    const unsigned long long emit_bits = __ldg(a.ws_emit + q);
+    const int g = lane >> 2, tq = lane & 3;
+    const bool is_db = a.log_type == 0;
+    const float lscale = is_db ? 3.01029995663981195f : 0.69314718055994531f;
+    const float amin_n = fmaxf(a.amin, 1.17549435e-38f);  // keeps MUFU.LG2 off the denormal path
+    const long long estep = a.e_stride_f;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int buf = tl % W::NBUF, use = tl / W::NBUF;
+      mbar_wait(full_bar(buf), (uint32_t)use & 1u);
+      const int* mb = sMeta + buf * 2 * W::TILE;
+      const int b0 = mb[g], t0 = mb[W::TILE + g], b1 = mb[g + 8], t1 = mb[W::TILE + g + 8];
+      const float* r0 = sP + (buf * W::TILE + g) * W::SPW + W::GROUP * ctl.x + 4 * tq;
+      const float* r1 = r0 + 8 * W::SPW;
+      // filter f of the frames in rows g / g + 8 goes to e0[f * estep] / e1[f * estep]
+      float* e0 = a.E + (b0 >= 0 ? (long long)b0 * a.e_stride_b + t0 : 0);
+      float* e1 = a.E + (b1 >= 0 ? (long long)b1 * a.e_stride_b + t1 : 0);
+      float acc[2][2][4];  // [window slot][k-step of the group][fragment]
+#pragma unroll
+      for (int i = 0; i < 16; ++i) (&acc[0][0][0])[i] = 0.f;
+      int nt = ctl.z;      // n-tile in window slot 0
+      unsigned long long eb = emit_bits;
+      float vmax0 = -INFINITY, vmax1 = -INFINITY, chk0 = 0.f, chk1 = 0.f;
+      uint32_t wcol = tmem_row + W::TMEM_FB0;
+#pragma unroll 1
+      for (int i = 0; i < ctl.y; ++i, r0 += W::GROUP, r1 += W::GROUP, wcol += 16, eb >>= 2) {
+        TmemChunk wc;
+        wc.issue(wcol);
+        const float4 x0 = *reinterpret_cast<const float4*>(r0), x1 = *reinterpret_cast<const float4*>(r1);
+        // A fragments of the two k-steps: (row g, k tq), (row g + 8, k tq), (row g, k tq + 4), (row g + 8, k tq + 4)
+        // with k tq <-> bin 4 tq + 2 ks, k tq + 4 <-> bin 4 tq + 2 ks + 1 of the group
+        const float xs[8] = {x0.x, x1.x, x0.y, x1.y, x0.z, x1.z, x0.w, x1.w};
+        unsigned hi[2][4], lo[2][4];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const unsigned h = __float_as_uint(xs[u]) & 0xffffe000u;  // what the tensor core keeps of xs[u]
+          hi[u >> 2][u & 3] = h;
+          lo[u >> 2][u & 3] = __float_as_uint(xs[u] - __uint_as_float(h));
+        }
+        wc.wait();
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) {
+            const unsigned bh0 = wc.r[(ks * 2 + sl) * 4], bh1 = wc.r[(ks * 2 + sl) * 4 + 1];
+            const unsigned bl0 = wc.r[(ks * 2 + sl) * 4 + 2], bl1 = wc.r[(ks * 2 + sl) * 4 + 3];
+#ifdef AAD_WS_NOMMA  // dev only: timing without the tensor-core work (results wrong)
+            acc[sl][ks][0] += __uint_as_float(hi[ks][0] ^ bh0) + __uint_as_float(lo[ks][1] ^ bl1);
+            acc[sl][ks][2] += __uint_as_float(hi[ks][2] ^ bh1) + __uint_as_float(lo[ks][3] ^ bl0);
+#else
+            mma_tf32(acc[sl][ks], hi[ks], bh0, bh1);
+            mma_tf32(acc[sl][ks], lo[ks], bh0, bh1);
+            mma_tf32(acc[sl][ks], hi[ks], bl0, bl1);
+#endif
+          }
+        for (int ne = (int)(eb & 3ull); ne > 0; --ne) {  // n-tile nt is complete: log, store, slide the window
+          const int f = 8 * nt + 2 * tq;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float en = acc[0][0][e] + acc[0][1][e];
+            float val, bad = en;  // dB: max(amin, NaN) hides a NaN energy, so the energy itself is the poison source
+            if (is_db) {
+              float l2;
+              asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(amin_n, en)));
+              val = lscale * l2;
+            } else {
+              val = lscale * __log2f(en == 0.f ? a.eps : en);
+              bad = val;
+            }
+            const int ff = f + (e & 1);
+            if (ff < a.n_filt) {
+              if (e < 2) {
+                if (b0 >= 0) e0[ff * estep] = val;
+                vmax0 = fmaxf(vmax0, val);
+                chk0 = __fmaf_rn(bad, 0.f, chk0);
+              } else {
+                if (b1 >= 0) e1[ff * estep] = val;
+                vmax1 = fmaxf(vmax1, val);
+                chk1 = __fmaf_rn(bad, 0.f, chk1);
+              }
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc[0][0][e] = acc[1][0][e];
+            acc[0][1][e] = acc[1][1][e];
+            acc[1][0][e] = 0.f;
+            acc[1][1][e] = 0.f;
+          }
+          ++nt;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(buf));  // every power value of this tile has been consumed
+      // per-utterance running maximum (ref=np.max / top_db) and NaN / Inf poison: reduce over the quad,
+      // then one atomic per utterance among the eight quad leaders
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        vmax0 = fmaxf(vmax0, __shfl_xor_sync(0xffffffffu, vmax0, o));
+        vmax1 = fmaxf(vmax1, __shfl_xor_sync(0xffffffffu, vmax1, o));
+        chk0 += __shfl_xor_sync(0xffffffffu, chk0, o);
+        chk1 += __shfl_xor_sync(0xffffffffu, chk1, o);
+      }
+      if (tq == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int b = h ? b1 : b0;
+          const float vm = h ? vmax1 : vmax0, ck = h ? chk1 : chk0;
+          if (a.utt_max) {
+            const unsigned peers = __match_any_sync(0x11111111u, b);
+            const int enc = __reduce_max_sync(peers, enc_ordered(vm));
+            if (b >= 0 && (int)(__ffs(peers) - 1) == lane) atomicMax(a.utt_max + b, enc);
+          }
+          if (b >= 0 && ck != ck) a.status[b] = 5;
+        }
+      }
+    }
+#endif
+  }
+  // every warp is past its last tcgen05.ld
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"((uint32_t)s_tmem_base), "r"(512u) : "memory");
 }
 
 #ifndef AAD_STFT_ONLY
@@ -971,12 +1269,6 @@ struct CepArgs {
   int tile_out;           // output frames per tile when T > CEP_TS
   int tiles_per_utt;      // grid.x = B * tiles_per_utt
 };
-
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 // One CTA = (utterance, tile of <= 128 frames).  Three phases:
 //  load : E tile -> sE[m][t] with the dB reference / floor applied (float4 along t, warp w owns the
