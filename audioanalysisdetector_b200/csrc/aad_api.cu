@@ -45,11 +45,6 @@ struct aad_plan {
   int2* d_filt_hdr = nullptr;
   float4* d_filt_w = nullptr;
   int4* d_warp_prog = nullptr;
-  // k_stft_ws (n_fft 2048, filter bank on the tensor cores): usable when the bank fits its rolling window
-  bool ws_ok = false;
-  float4* d_ws_frag = nullptr;
-  int4* d_ws_ctl = nullptr;
-  unsigned long long* d_ws_emit = nullptr;
   float4* d_dct_frag = nullptr;
   float* d_dct_colsum = nullptr;
   // optional per-kernel timing (bench roofline): events recorded around each launch
@@ -217,117 +212,6 @@ static int band_filterbank(const std::vector<float>& fb, int nf, int K, std::vec
 }
 
 
-// ---- k_stft_ws: the filter bank as mma.sync.m16n8k8 B fragments --------------------------------------------
-// The dense bank W[filter][bin] is cut into n-tiles of 8 filters and groups of 16 bins.  Each of the FB_WARPS
-// consumer warps owns a contiguous range of n-tiles and walks the groups that touch them with a window of two
-// n-tiles (slots): group i of the warp contributes to n-tiles cur and cur + 1 only, and after it the n-tiles that
-// are complete are emitted (2 bits per group).  Returns false when the bank does not fit that scheme (a group
-// touching three n-tiles, too many groups for the warp's tensor-memory columns): the caller keeps k_stft_fb.
-// Fragment of (group G, k-step ks, n-tile n), lane = 4 g + t:  b0 = W[8 n + g][16 G + 4 t + 2 ks],
-// b1 = W[8 n + g][16 G + 4 t + 2 ks + 1], as tf32 hi / lo parts {b0 hi, b1 hi, b0 lo, b1 lo}.
-static bool build_ws_tables(const std::vector<float>& fb, int nf, int K, std::vector<float4>& frag,
-                            std::vector<int4>& ctl, std::vector<unsigned long long>& emit) {
-  using Wc = WsCfg;
-  if (K != Wc::M + 1) return false;
-  const int NT = (nf + 7) / 8;
-  auto wgt = [&](int f, int k) { return (f < nf && k < K) ? fb[(size_t)f * K + k] : 0.f; };
-  std::vector<int> firstG(NT, 1 << 30), lastG(NT, -1);
-  for (int n = 0; n < NT; ++n)
-    for (int f = 8 * n; f < std::min(nf, 8 * n + 8); ++f)
-      for (int k = 0; k < K; ++k)
-        if (fb[(size_t)f * K + k] != 0.f) {
-          firstG[n] = std::min(firstG[n], k / Wc::GROUP);
-          lastG[n] = std::max(lastG[n], k / Wc::GROUP);
-        }
-  auto range_groups = [&](int n0, int n1, int* g0, int* g1) {
-    int lo = 1 << 30, hi = -1;
-    for (int n = n0; n < n1; ++n) {
-      lo = std::min(lo, firstG[n]);
-      hi = std::max(hi, lastG[n]);
-    }
-    if (hi < 0) lo = hi = 0;
-    *g0 = lo;
-    *g1 = hi;
-  };
-  auto cost = [&](int n0, int n1) {
-    if (n1 <= n0) return 0.0;
-    int g0, g1;
-    range_groups(n0, n1, &g0, &g1);
-    return (double)(g1 - g0 + 1) + 1.5 * (n1 - n0);
-  };
-  // contiguous partition of the n-tiles over the warps minimising the largest cost
-  const int NW = Wc::FB_WARPS;
-  int cut[NW + 1] = {0};
-  {
-    double best = 1e30;
-    int c[3];
-    for (c[0] = 0; c[0] <= NT; ++c[0])
-      for (c[1] = c[0]; c[1] <= NT; ++c[1])
-        for (c[2] = c[1]; c[2] <= NT; ++c[2]) {
-          const double m = std::max(std::max(cost(0, c[0]), cost(c[0], c[1])), std::max(cost(c[1], c[2]), cost(c[2], NT)));
-          if (m < best) {
-            best = m;
-            cut[1] = c[0]; cut[2] = c[1]; cut[3] = c[2];
-          }
-        }
-    cut[0] = 0;
-    cut[NW] = NT;
-  }
-  auto tf32_hi = [](float x) {
-    uint32_t u;
-    std::memcpy(&u, &x, 4);
-    u = (u + 0x1000u) & 0xffffe000u;
-    float r;
-    std::memcpy(&r, &u, 4);
-    return r;
-  };
-  frag.assign((size_t)NW * Wc::MAXG * 32 * 4, make_float4(0.f, 0.f, 0.f, 0.f));
-  ctl.assign(NW, make_int4(0, 0, 0, 0));
-  emit.assign(NW, 0ull);
-  for (int q = 0; q < NW; ++q) {
-    const int n0 = cut[q], n1 = cut[q + 1];
-    if (n1 <= n0) continue;  // idle warp: zero groups, nothing to emit
-    int g0, g1;
-    range_groups(n0, n1, &g0, &g1);
-    const int ng = g1 - g0 + 1;
-    if (ng > Wc::MAXG || ng > 32) return false;
-    ctl[q] = make_int4(g0, ng, n0, 0);
-    int cur = n0;
-    for (int i = 0; i < ng; ++i) {
-      const int G = g0 + i;
-      for (int n = n0; n < n1; ++n) {  // every owned n-tile this group touches must sit in the window
-        bool touch = false;
-        for (int f = 8 * n; f < 8 * n + 8 && !touch; ++f)
-          for (int k = Wc::GROUP * G; k < Wc::GROUP * (G + 1); ++k)
-            if (wgt(f, k) != 0.f) {
-              touch = true;
-              break;
-            }
-        if (touch && (n < cur || n > cur + 1)) return false;
-      }
-      for (int lane = 0; lane < 32; ++lane) {
-        const int g = lane >> 2, t = lane & 3;
-        for (int ks = 0; ks < 2; ++ks)
-          for (int sl = 0; sl < 2; ++sl) {
-            const int n = cur + sl, k = Wc::GROUP * G + 4 * t + 2 * ks;
-            const float b0 = n < n1 ? wgt(8 * n + g, k) : 0.f, b1 = n < n1 ? wgt(8 * n + g, k + 1) : 0.f;
-            const float h0 = tf32_hi(b0), h1 = tf32_hi(b1);
-            frag[(((size_t)q * Wc::MAXG + i) * 32 + lane) * 4 + ks * 2 + sl] = make_float4(h0, h1, b0 - h0, b1 - h1);
-          }
-      }
-      int e = 0;
-      while (cur < n1 && lastG[cur] <= G) {
-        ++e;
-        ++cur;
-      }
-      if (e > 3) return false;
-      emit[q] |= (unsigned long long)e << (2 * i);
-    }
-    if (cur != n1) return false;
-  }
-  return true;
-}
-
 static void savgol_taps(int width, float t1[CEP_MAXW], float t2[CEP_MAXW]) {
   // least-squares polynomial fit of degree d, d-th derivative at the window centre
   // (scipy.signal.savgol_coeffs(width, polyorder=d, deriv=d), d = 1, 2)
@@ -486,9 +370,6 @@ int aad_plan_destroy(aad_plan* pl) {
   cudaFree(pl->d_filt_hdr);
   cudaFree(pl->d_filt_w);
   cudaFree(pl->d_warp_prog);
-  cudaFree(pl->d_ws_frag);
-  cudaFree(pl->d_ws_ctl);
-  cudaFree(pl->d_ws_emit);
   cudaFree(pl->d_dct_frag);
   cudaFree(pl->d_dct_colsum);
   for (auto& e : pl->ev)
@@ -647,17 +528,6 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
       }
     }
   }
-  // n_fft 2048: the warp-specialised kernel with the filter bank on the tensor cores, when the bank fits it
-  // (AAD_K1=fb in the environment keeps the phase-structured kernel: A/B timing and cross-checks)
-  std::vector<float4> ws_frag;
-  std::vector<int4> ws_ctl;
-  std::vector<unsigned long long> ws_emit;
-  {
-    const char* k1 = std::getenv("AAD_K1");
-    const bool want_ws = !(k1 && std::strcmp(k1, "fb") == 0);
-    pl->ws_ok = want_ws && L == 32 && pick_stft_ws(0) != nullptr && build_ws_tables(pl->h_fb, p.n_filt, K, ws_frag, ws_ctl, ws_emit);
-    if (pl->ws_ok) pl->tile = WsCfg::TILE;  // sizes the tile -> utterance index of the workspace
-  }
   pl->n_hdr = (int)fhdr.size();
   pl->n_w4 = (int)fw4.size();
   pl->k1_smem = k1_fixed + (size_t)((2 * fhdr.size() + 3) & ~3) * 4 + fw4.size() * sizeof(float4);
@@ -717,11 +587,6 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   if (e == cudaSuccess) e = upload(&pl->d_filt_hdr, fhdr);
   if (e == cudaSuccess) e = upload(&pl->d_filt_w, fw4);
   if (e == cudaSuccess) e = upload(&pl->d_warp_prog, wprog);
-  if (pl->ws_ok) {
-    if (e == cudaSuccess) e = upload(&pl->d_ws_frag, ws_frag);
-    if (e == cudaSuccess) e = upload(&pl->d_ws_ctl, ws_ctl);
-    if (e == cudaSuccess) e = upload(&pl->d_ws_emit, ws_emit);
-  }
   if (e == cudaSuccess) e = upload(&pl->d_dct_frag, dct_frag);
   if (e == cudaSuccess) e = upload(&pl->d_dct_colsum, dct_colsum);
   // opt in to the large dynamic shared memory of every kernel variant this plan can launch
@@ -732,11 +597,6 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   if (pl->k1_smem > (size_t)optin) {
     aad_plan_destroy(pl);
     return AAD_ERR_UNSUPPORTED;
-  }
-  if (pl->ws_ok && WsCfg::SMEM_BYTES > (size_t)optin) pl->ws_ok = false;
-  for (int mode = 0; mode < 3 && e == cudaSuccess && pl->ws_ok; ++mode) {
-    const void* fw = (const void*)pick_stft_ws(mode);
-    if (fw) e = cudaFuncSetAttribute(fw, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   }
   for (int mode = 0; mode < 3 && e == cudaSuccess; ++mode)
     for (int pre = 0; pre < 2 && e == cudaSuccess; ++pre) {
@@ -882,9 +742,7 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
   }
   pa.utt_max2 = d_max2;
   const int mode = wav_dtype == AAD_I16 ? IN_I16 : (p.quantize_i16 ? IN_F32_Q16 : IN_F32);
-  // n_fft 2048 without a second filter bank: warp-specialised kernel on 16-frame tiles
-  const bool use_ws = pl->ws_ok && !pl2 && p.pre_emph == 0.f && pick_stft_ws(mode) != nullptr;
-  const int k1_tile = use_ws ? WsCfg::TILE : 32;
+  const int k1_tile = pl->tile;
   pa.tile_b0 = (int32_t*)(ws + w.off_tile); pa.tile = k1_tile; pa.max_tiles = w.max_tiles;
   pa.zn_stats = p.znorm ? (double*)(ws + w.off_zn) : nullptr;
   const bool prof = pl->profile;
@@ -920,19 +778,12 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
     sa.E2 = pair.out2; sa.e2_stride_b = out2_stride_b; sa.e2_stride_f = t_alloc;
     sa.utt_max2 = q.log_type == AAD_LOG_DB10 ? d_max2 : nullptr;
   }
-  sa.ws_frag = pl->d_ws_frag; sa.ws_ctl = pl->d_ws_ctl; sa.ws_emit = pl->d_ws_emit;
-  const long long max_tiles = ((long long)B * std::max(t_max, 1) + k1_tile - 1) / k1_tile;
-  if (use_ws) {
-    const int grid1 = (int)std::min<long long>((long long)pl->sm_count, std::max<long long>(max_tiles, 1));
-    pick_stft_ws(mode)<<<grid1, WsCfg::WARPS * 32, WsCfg::SMEM_BYTES, stream>>>(sa);
-    LAUNCH_CHECK("k_stft_ws launch");
-  } else {
-    stft_kernel_t kern = pick_stft(pl->L, 32, mode, p.pre_emph != 0.f, pl2 != nullptr);
-    if (!kern) return pl2 ? AAD_ERR_PAIR : AAD_ERR_UNSUPPORTED;
-    const int grid1 = (int)std::min<long long>((long long)pl->sm_count * pl->ctas, std::max<long long>(max_tiles, 1));
-    kern<<<grid1, pl->warps * 32, pl->k1_smem + (pl2 ? prog_smem_bytes(pl2) : 0), stream>>>(sa);
-    LAUNCH_CHECK("k_stft_fb launch");
-  }
+  stft_kernel_t kern = pick_stft(pl->L, pl->tile, mode, p.pre_emph != 0.f, pl2 != nullptr);
+  if (!kern) return pl2 ? AAD_ERR_PAIR : AAD_ERR_UNSUPPORTED;
+  const long long max_tiles = w.max_tiles;
+  const int grid1 = (int)std::min<long long>((long long)pl->sm_count * pl->ctas, std::max<long long>(max_tiles, 1));
+  kern<<<grid1, pl->warps * 32, pl->k1_smem + (pl2 ? prog_smem_bytes(pl2) : 0), stream>>>(sa);
+  LAUNCH_CHECK("k_stft_fb launch");
   if (prof) cudaEventRecord(pl->ev[2], stream);
 
   // K2

@@ -328,10 +328,6 @@ struct StftArgs {
   long long e2_stride_b;
   int e2_stride_f;
   int32_t* utt_max2;
-  // k_stft_ws only: the filter bank as mma.sync B fragments, per filter-bank warp (see WsCfg)
-  const float4* ws_frag;              // [FB_WARPS][MAXG][32 lanes][4]
-  const int4* ws_ctl;                 // [FB_WARPS] {first 16-bin group, number of groups, first n-tile, 0}
-  const unsigned long long* ws_emit;  // [FB_WARPS] 2 bits per group: n-tiles completed by that group
 };
 
 template <int MODE>
@@ -386,7 +382,6 @@ __device__ unsigned long long g_phase_cycles[4];
 
 // ---------------------------------------------------------------------------
 // One warp-iteration of the STFT: Q = 32 / L frames (L lanes each) -> their power spectra in shared memory.
-// Shared by k_stft_fb (phase-structured) and k_stft_ws (warp-specialised).
 // ---------------------------------------------------------------------------
 template <int L, int MODE, bool PRE, int TILE>
 struct FrameFft {
@@ -452,18 +447,16 @@ struct FrameFft {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
 
+  // load: the samples of this lane's frame into v (bit-reversed register order), with pre-emphasis / quantisation.
   // valid / t / len / row: this lane's frame (the L lanes of a frame agree): frame t of an utterance of len samples
-  // whose first sample is at `row`.  scr: warp-private scratch of >= 32 * 33 floats (may alias prow: the transposes
-  // are over before the powers are written).  prow: power row of this lane's frame, M + 1 + NPAD floats are written.
-  template <int NPAD>
-  __device__ __forceinline__ void run(const StftArgs& a, bool valid, int t, int len, const char* row, float* scr,
-                                      float* prow) const {
+  // whose first sample is at `row`.
+  __device__ __forceinline__ void load(const StftArgs& a, bool valid, int t, int len, const char* row,
+                                       float2 (&v)[32]) const {
     const int s0 = t * a.hop - a.s_off;
     bool fast = valid && s0 >= (PRE ? 1 : 0) && (s0 + N) <= len;
     if constexpr (MODE == IN_I16) fast = fast && (((uintptr_t)(row + 2ll * s0)) & 3) == 0;
     else fast = fast && (((uintptr_t)(row + 4ll * s0)) & 7) == 0;
 
-    float2 v[32];
     if (__all_sync(0xffffffffu, fast)) {
       if constexpr (MODE == IN_I16) {
         const unsigned* p = reinterpret_cast<const unsigned*>(row + 2ll * s0) + j;
@@ -548,6 +541,26 @@ struct FrameFft {
       });
     }
 
+  }
+
+  // request the samples of warp-iteration `it` of the tile whose meta is (mB, mT); false: no valid frame in it
+  __device__ __forceinline__ bool load_iter(const StftArgs& a, const int* mB, const int* mT, int it, float2 (&v)[32]) const {
+    const int fi = it * Q + g;
+    const int b = mB[fi], t = mT[fi];
+    const bool valid = b >= 0;
+    if (!__any_sync(0xffffffffu, valid)) return false;
+    const int len = valid ? __ldg(a.len_c + b) : 0;
+    const char* row = static_cast<const char*>(a.wav) +
+                      (valid ? (a.row_off ? __ldg(a.row_off + b) : (long long)b * a.wav_stride) * (MODE == IN_I16 ? 2 : 4) : 0);
+    load(a, valid, t, len, row, v);
+    return true;
+  }
+
+  // transform: window, FFT, real-input split, power.  scr: warp-private scratch of >= 32 * 33 floats (may alias prow:
+  // the transposes are over before the powers are written).  prow: power row of this lane's frame, M + 1 + NPAD
+  // floats are written.
+  template <int NPAD>
+  __device__ __forceinline__ void transform(const StftArgs& a, float2 (&v)[32], float* scr, float* prow) const {
     // window: 0.5*w (zero outside its support) from this lane's TMEM row, next chunk in flight
     // window folded into the first butterfly stage of pass 1: samples A and A + 16 meet in stage 1
     // (registers bitrev(A) = 2m and 2m + 1), so a' = xa*wa + xb*wb, b' = xa*wa - xb*wb is one FMUL2
@@ -780,6 +793,7 @@ k_stft_fb(const StftArgs a) {
   if (warp == 0) tile_meta(blockIdx.x, 0);
   __syncthreads();
 
+
 #ifdef AAD_PHASE_TIMING
   long long tmark = clock64();
 #endif
@@ -791,15 +805,10 @@ k_stft_fb(const StftArgs a) {
 
     // ---- FFT phase ---------------------------------------------------------------
     for (int it = warp; it < C::ITERS; it += C::WARPS) {
-      const int fi = it * Q + g;
-      const int b = sMetaB[fi], t = sMetaT[fi];
-      const bool valid = b >= 0;
-      if (!__any_sync(0xffffffffu, valid)) continue;
-      const int len = valid ? __ldg(a.len_c + b) : 0;
-      const char* row = static_cast<const char*>(a.wav) +
-                        (valid ? (a.row_off ? __ldg(a.row_off + b) : (long long)b * a.wav_stride) * (MODE == IN_I16 ? 2 : 4) : 0);
+      float2 v[32];
       // transposes go through the warp's own power rows
-      fft.template run<C::PAD>(a, valid, t, len, row, sP + (it * Q) * SP, sP + fi * SP + C::skew(fi));
+      if (fft.load_iter(a, sMetaB, sMetaT, it, v))
+        fft.template transform<C::PAD>(a, v, sP + (it * Q) * SP, sP + (it * Q + g) * SP + C::skew(it * Q + g));
     }
     AAD_PHASE_MARK(0);
     __syncthreads();
@@ -917,326 +926,6 @@ k_stft_fb(const StftArgs a) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"((uint32_t)s_tmem_base), "r"((uint32_t)TmemCfg<C::CTAS>::COLS) : "memory");
 }
 
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// ---------------------------------------------------------------------------
-// K1 for n_fft 2048, warp-specialised (k_stft_ws).  Same arithmetic up to the power spectrum as k_stft_fb
-// (FrameFft), but the CTA is a pipeline instead of two phases separated by CTA-wide barriers:
-//
-//   12 FFT warps (producers): each takes frames round-robin, transforms one at a time and writes its power
-//       spectrum into a row of a 16-frame tile buffer (the row doubles as the warp's transpose scratch), then
-//       arrives on the buffer's `full` mbarrier.  The next frame's index look-ups are in flight during the
-//       transform, the frame after that is prefetched into L2.
-//   4 filter-bank warps (consumers, one per scheduler): wait for a full 16-frame tile and apply the filter
-//       bank on the TENSOR cores: E[frame][filter] = P[frame][bin] . W[bin][filter] with mma.sync.m16n8k8
-//       TF32 and the 3-term split hi*hi + lo*hi + hi*lo (fp32 accumulate, ~2^-21 per product).  The bank is
-//       banded, so a warp owns a contiguous range of n-tiles (8 filters) and walks only the 16-bin groups
-//       that touch them, with a rolling window of two n-tiles; its B fragments are per-lane constants held in
-//       tensor memory (columns [160, 512) of the warp's own lane quarter) and read with tcgen05.ld.  One
-//       LDS.128 per lane and row delivers the A values of two k-steps (the k index inside a group is
-//       permuted so that a lane's four bins are contiguous).  Then log, store, running maximum as in
-//       k_stft_fb, and the buffer is handed back through its `empty` mbarrier.
-//
-// Nothing in the steady state is a CTA-wide barrier: FFT warps drift apart instead of meeting twice per 32
-// frames, the filter bank costs no FMA-pipe slots, a third of the shared-memory wavefronts and half the
-// issue slots of the SIMT form, and runs next to the transforms instead of between them.
-// ---------------------------------------------------------------------------
-struct WsCfg {
-#ifdef AAD_WS_NBUF  // dev builds only
-  static constexpr int TILE = 16, NBUF = AAD_WS_NBUF;
-#else
-  static constexpr int TILE = 16, NBUF = 3;
-#endif
-#if defined(AAD_WS_FFTW) && defined(AAD_WS_FBW)  // dev builds only (warp split experiments)
-  static constexpr int FFT_WARPS = AAD_WS_FFTW, FB_WARPS = AAD_WS_FBW;
-#else
-  static constexpr int FFT_WARPS = 12, FB_WARPS = 4;
-#endif
-  static constexpr int WARPS = FFT_WARPS + FB_WARPS;
-  static constexpr int M = 1024;
-  static constexpr int GROUP = 16;                      // bins per filter-bank step (two mma k-steps)
-  static constexpr int NGROUPS = (M + 1 + GROUP - 1) / GROUP;  // 65
-  static constexpr int KPAD = NGROUPS * GROUP;          // bins incl. zeroed padding (1040)
-  // power-row stride in words: = 16 (mod 32) so that the A-fragment LDS.128 of 8 consecutive lanes
-  // (two rows x four 16-byte pieces) covers all 32 banks; holds the padded bins and the 32 x 33 scratch
-  static constexpr int SPW = 1072;
-  static constexpr int TMEM_FB0 = 160;                  // first TMEM column of the filter-bank fragments
-  static constexpr int MAXG = (512 - TMEM_FB0) / 16;    // groups per filter-bank warp (16 columns each)
-  static constexpr int OFF_META = NBUF * TILE * SPW;    // int b[NBUF][TILE], t[NBUF][TILE]
-  static constexpr int OFF_BAR = OFF_META + 2 * NBUF * TILE;  // full[NBUF], empty[NBUF] (8 bytes each)
-  static constexpr int OFF_TMEM = OFF_BAR + 4 * NBUF;
-  static constexpr size_t SMEM_BYTES = size_t(OFF_TMEM + 4) * 4;
-  static_assert(SPW % 32 == 16 && SPW >= KPAD && SPW >= 32 * 33, "power row stride");
-  static_assert(OFF_BAR % 2 == 0, "mbarriers are 8-byte aligned");
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  } while (!done);
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(WsCfg::WARPS * 32, 1) k_stft_ws(const StftArgs a) {
-  using W = WsCfg;
-  using FFT = FrameFft<32, MODE, false, 32>;
-  constexpr int N = 2048;
-  extern __shared__ __align__(16) float smem[];
-  float* sP = smem;
-  int* sMeta = reinterpret_cast<int*>(smem + W::OFF_META);
-  const uint32_t bar0 = smem_u32(smem + W::OFF_BAR);
-  auto full_bar = [&](int buf) { return bar0 + 8u * (uint32_t)buf; };
-  auto empty_bar = [&](int buf) { return bar0 + 8u * (uint32_t)(W::NBUF + buf); };
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  // set-up: tensor memory (all 512 columns: this kernel is alone on its SM), tables, mbarriers
-  volatile uint32_t& s_tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + W::OFF_TMEM);
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 :: "r"(smem_u32(smem + W::OFF_TMEM)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (tid == 32) {
-    for (int i = 0; i < W::NBUF; ++i) {
-      mbar_init(full_bar(i), W::TILE);       // one arrival per frame row
-      mbar_init(empty_bar(i), W::FB_WARPS > 0 ? W::FB_WARPS : 1);  // one arrival per filter-bank warp
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_row = s_tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);
-  if (warp < 4) {
-    FFT::fill_tables(a, tmem_row, lane);
-  } else if (warp >= W::FFT_WARPS) {
-    const int q = warp - W::FFT_WARPS;
-    const int ng = __ldg(&a.ws_ctl[q].y);
-    const float4* src = a.ws_frag + ((size_t)q * W::MAXG * 32 + lane) * 4;
-    for (int i = 0; i < ng; ++i, src += 32 * 4) {
-      float2 w8[8];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float4 f = __ldg(src + c);
-        w8[2 * c] = make_float2(f.x, f.y);
-        w8[2 * c + 1] = make_float2(f.z, f.w);
-      }
-      tmem_st16(tmem_row + W::TMEM_FB0 + 16 * i, w8);
-    }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-  const int total = __ldg(a.frame_off + a.B);
-  const int n_tiles = (total + W::TILE - 1) / W::TILE;
-  const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-
-  if (warp < W::FFT_WARPS) {
-    // ---------------- producers: one frame at a time ----------------
-    FFT fft;
-    fft.init(a, lane, tmem_row, nullptr);
-    constexpr int ES = MODE == IN_I16 ? 2 : 4;
-    const int n_slots = my_tiles * W::TILE;  // slot s = (tile s / 16 of this CTA, row s % 16)
-    struct Slot {
-      int b, t, len;
-      const char* row;
-    };
-    auto slot_meta = [&](int s) {
-      Slot m;
-      m.b = -1; m.t = 0; m.len = 0; m.row = static_cast<const char*>(a.wav);
-      if (s < n_slots) {
-        const int tile = (int)blockIdx.x + (s >> 4) * (int)gridDim.x;
-        const int gf = tile * W::TILE + (s & 15);
-        if (gf < total) {
-          int b = __ldg(a.tile_b0 + tile);
-          int nxt = __ldg(a.frame_off + b + 1);
-          while (gf >= nxt) nxt = __ldg(a.frame_off + (++b) + 1);
-          m.t = gf - __ldg(a.frame_off + b);
-          m.b = b;
-          m.len = __ldg(a.len_c + b);
-          m.row += (a.row_off ? __ldg(a.row_off + b) : (long long)b * a.wav_stride) * ES;
-        }
-      }
-      return m;
-    };
-    auto l2_prefetch = [&](const Slot& m) {  // the samples this frame adds to its predecessor's
-      if (m.b >= 0 && lane == 0) {
-        long long s_lo = (long long)m.t * a.hop - a.s_off + (m.t == 0 ? 0 : N - a.hop);
-        long long s_hi = (long long)m.t * a.hop - a.s_off + N;
-        if (s_lo < 0) s_lo = 0;
-        if (s_hi > m.len) s_hi = m.len;
-        uintptr_t p0 = ((uintptr_t)(m.row + s_lo * ES) + 15) & ~(uintptr_t)15;
-        uintptr_t p1 = (uintptr_t)(m.row + s_hi * ES) & ~(uintptr_t)15;
-        if (p1 > p0)
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"((unsigned)(p1 - p0)) : "memory");
-      }
-    };
-    Slot cur = slot_meta(warp), nx1 = slot_meta(warp + W::FFT_WARPS);
-    for (int s = warp; s < n_slots; s += W::FFT_WARPS) {
-      const Slot nx2 = slot_meta(s + 2 * W::FFT_WARPS);  // consumed two frames from now: never waited for
-      l2_prefetch(nx1);
-      const int tl = s >> 4, r = s & 15, buf = tl % W::NBUF, use = tl / W::NBUF;
-#ifndef AAD_WS_NOFB
-      if (use > 0) mbar_wait(empty_bar(buf), (uint32_t)(use - 1) & 1u);  // the consumers are done with the previous tile here
-#endif
-      float* prow = sP + (buf * W::TILE + r) * W::SPW;
-      if (cur.b >= 0) fft.template run<W::KPAD - W::M - 1>(a, true, cur.t, cur.len, cur.row, prow, prow);
-      if (lane == 0) {
-        sMeta[buf * 2 * W::TILE + r] = cur.b;
-        sMeta[buf * 2 * W::TILE + W::TILE + r] = cur.t;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar(buf));
-      cur = nx1;
-      nx1 = nx2;
-    }
-  } else {
-#ifndef AAD_WS_NOFB
-    // ---------------- consumers: filter bank of one 16-frame tile on the tensor cores ----------------
-    const int q = warp - W::FFT_WARPS;
-    const int4 ctl = __ldg(a.ws_ctl + q);
-    const unsigned long long emit_bits = __ldg(a.ws_emit + q);
-    const int g = lane >> 2, tq = lane & 3;
-    const bool is_db = a.log_type == 0;
-    const float lscale = is_db ? 3.01029995663981195f : 0.69314718055994531f;
-    const float amin_n = fmaxf(a.amin, 1.17549435e-38f);  // keeps MUFU.LG2 off the denormal path
-    const long long estep = a.e_stride_f;
-    for (int tl = 0; tl < my_tiles; ++tl) {
-      const int buf = tl % W::NBUF, use = tl / W::NBUF;
-      mbar_wait(full_bar(buf), (uint32_t)use & 1u);
-      const int* mb = sMeta + buf * 2 * W::TILE;
-      const int b0 = mb[g], t0 = mb[W::TILE + g], b1 = mb[g + 8], t1 = mb[W::TILE + g + 8];
-      const float* r0 = sP + (buf * W::TILE + g) * W::SPW + W::GROUP * ctl.x + 4 * tq;
-      const float* r1 = r0 + 8 * W::SPW;
-      // filter f of the frames in rows g / g + 8 goes to e0[f * estep] / e1[f * estep]
-      float* e0 = a.E + (b0 >= 0 ? (long long)b0 * a.e_stride_b + t0 : 0);
-      float* e1 = a.E + (b1 >= 0 ? (long long)b1 * a.e_stride_b + t1 : 0);
-      float acc[2][2][4];  // [window slot][k-step of the group][fragment]
-#pragma unroll
-      for (int i = 0; i < 16; ++i) (&acc[0][0][0])[i] = 0.f;
-      int nt = ctl.z;      // n-tile in window slot 0
-      unsigned long long eb = emit_bits;
-      float vmax0 = -INFINITY, vmax1 = -INFINITY, chk0 = 0.f, chk1 = 0.f;
-      uint32_t wcol = tmem_row + W::TMEM_FB0;
-#pragma unroll 1
-      for (int i = 0; i < ctl.y; ++i, r0 += W::GROUP, r1 += W::GROUP, wcol += 16, eb >>= 2) {
-        TmemChunk wc;
-        wc.issue(wcol);
-        const float4 x0 = *reinterpret_cast<const float4*>(r0), x1 = *reinterpret_cast<const float4*>(r1);
-        // A fragments of the two k-steps: (row g, k tq), (row g + 8, k tq), (row g, k tq + 4), (row g + 8, k tq + 4)
-        // with k tq <-> bin 4 tq + 2 ks, k tq + 4 <-> bin 4 tq + 2 ks + 1 of the group
-        const float xs[8] = {x0.x, x1.x, x0.y, x1.y, x0.z, x1.z, x0.w, x1.w};
-        unsigned hi[2][4], lo[2][4];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const unsigned h = __float_as_uint(xs[u]) & 0xffffe000u;  // what the tensor core keeps of xs[u]
-          hi[u >> 2][u & 3] = h;
-          lo[u >> 2][u & 3] = __float_as_uint(xs[u] - __uint_as_float(h));
-        }
-        wc.wait();
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-          for (int sl = 0; sl < 2; ++sl) {
-            const unsigned bh0 = wc.r[(ks * 2 + sl) * 4], bh1 = wc.r[(ks * 2 + sl) * 4 + 1];
-            const unsigned bl0 = wc.r[(ks * 2 + sl) * 4 + 2], bl1 = wc.r[(ks * 2 + sl) * 4 + 3];
-#ifdef AAD_WS_NOMMA  // dev only: timing without the tensor-core work (results wrong)
-            acc[sl][ks][0] += __uint_as_float(hi[ks][0] ^ bh0) + __uint_as_float(lo[ks][1] ^ bl1);
-            acc[sl][ks][2] += __uint_as_float(hi[ks][2] ^ bh1) + __uint_as_float(lo[ks][3] ^ bl0);
-#else
-            mma_tf32(acc[sl][ks], hi[ks], bh0, bh1);
-            mma_tf32(acc[sl][ks], lo[ks], bh0, bh1);
-            mma_tf32(acc[sl][ks], hi[ks], bl0, bl1);
-#endif
-          }
-        for (int ne = (int)(eb & 3ull); ne > 0; --ne) {  // n-tile nt is complete: log, store, slide the window
-          const int f = 8 * nt + 2 * tq;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float en = acc[0][0][e] + acc[0][1][e];
-            float val, bad = en;  // dB: max(amin, NaN) hides a NaN energy, so the energy itself is the poison source
-            if (is_db) {
-              float l2;
-              asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(amin_n, en)));
-              val = lscale * l2;
-            } else {
-              val = lscale * __log2f(en == 0.f ? a.eps : en);
-              bad = val;
-            }
-            const int ff = f + (e & 1);
-            if (ff < a.n_filt) {
-              if (e < 2) {
-                if (b0 >= 0) e0[ff * estep] = val;
-                vmax0 = fmaxf(vmax0, val);
-                chk0 = __fmaf_rn(bad, 0.f, chk0);
-              } else {
-                if (b1 >= 0) e1[ff * estep] = val;
-                vmax1 = fmaxf(vmax1, val);
-                chk1 = __fmaf_rn(bad, 0.f, chk1);
-              }
-            }
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            acc[0][0][e] = acc[1][0][e];
-            acc[0][1][e] = acc[1][1][e];
-            acc[1][0][e] = 0.f;
-            acc[1][1][e] = 0.f;
-          }
-          ++nt;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar(buf));  // every power value of this tile has been consumed
-      // per-utterance running maximum (ref=np.max / top_db) and NaN / Inf poison: reduce over the quad,
-      // then one atomic per utterance among the eight quad leaders
-#pragma unroll
-      for (int o = 1; o <= 2; o <<= 1) {
-        vmax0 = fmaxf(vmax0, __shfl_xor_sync(0xffffffffu, vmax0, o));
-        vmax1 = fmaxf(vmax1, __shfl_xor_sync(0xffffffffu, vmax1, o));
-        chk0 += __shfl_xor_sync(0xffffffffu, chk0, o);
-        chk1 += __shfl_xor_sync(0xffffffffu, chk1, o);
-      }
-      if (tq == 0) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int b = h ? b1 : b0;
-          const float vm = h ? vmax1 : vmax0, ck = h ? chk1 : chk0;
-          if (a.utt_max) {
-            const unsigned peers = __match_any_sync(0x11111111u, b);
-            const int enc = __reduce_max_sync(peers, enc_ordered(vm));
-            if (b >= 0 && (int)(__ffs(peers) - 1) == lane) atomicMax(a.utt_max + b, enc);
-          }
-          if (b >= 0 && ck != ck) a.status[b] = 5;
-        }
-      }
-    }
-#endif
-  }
-  // every warp is past its last tcgen05.ld
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"((uint32_t)s_tmem_base), "r"(512u) : "memory");
-}
-
 #ifndef AAD_STFT_ONLY
 // ---------------------------------------------------------------------------
 // K2: dB reference / floor + DCT-II + deltas + layout
@@ -1269,6 +958,12 @@ struct CepArgs {
   int tile_out;           // output frames per tile when T > CEP_TS
   int tiles_per_utt;      // grid.x = B * tiles_per_utt
 };
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 
 // One CTA = (utterance, tile of <= 128 frames).  Three phases:
 //  load : E tile -> sE[m][t] with the dB reference / floor applied (float4 along t, warp w owns the

@@ -44,21 +44,6 @@ stft_kernel_t AAD_CAT(pick_stft_L, AAD_INST_L)(int mode, bool pre, bool pair) {
 #endif
 }
 
-#if AAD_INST_L == 32
-// warp-specialised n_fft 2048 kernel (no pre-emphasis variants: LFCC plans use n_fft 512)
-stft_kernel_t pick_stft_ws(int mode) {
-#if AAD_ABLATE || defined(AAD_DEV_BUILD)
-  return mode == 0 ? k_stft_ws<IN_F32> : nullptr;
-#else
-  switch (mode) {
-    case 0: return k_stft_ws<IN_F32>;
-    case 1: return k_stft_ws<IN_F32_Q16>;
-    default: return k_stft_ws<IN_I16>;
-  }
-#endif
-}
-#endif
-
 }  // namespace aad
 
 #if defined(AAD_PHASE_TIMING) && AAD_INST_L == 32

@@ -13,6 +13,4 @@ stft_kernel_t pick_stft_L4(int mode, bool pre, bool pair);
 stft_kernel_t pick_stft_L8(int mode, bool pre, bool pair);
 stft_kernel_t pick_stft_L16(int mode, bool pre, bool pair);
 stft_kernel_t pick_stft_L32(int mode, bool pre, bool pair);
-// k_stft_ws<mode>: n_fft 2048, warp-specialised (FFT producer warps, tensor-core filter-bank consumer warps)
-stft_kernel_t pick_stft_ws(int mode);
 }  // namespace aad
