@@ -87,11 +87,16 @@ SYMBOLS = {
     "aad_detector_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_size_t, C.c_void_p]),
     "aad_scaler_accumulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "aad_scaler_accumulate_ragged": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]),
     "aad_scaler_apply": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
     "aad_extract_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int,
                                    C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                    C.c_void_p, C.c_int]),
+    "aad_host_reserve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int32, C.c_int]),
+    "aad_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]),
+    "aad_host_free": (C.c_int, [C.c_void_p]),
     "aad_plan_table": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "aad_plan_launches": (C.c_int, [C.c_void_p]),
     "aad_plan_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),

@@ -68,6 +68,20 @@ struct aad_plan {
   int h_stage_cap = 0;
 };
 
+// Entry points that must run on the plan's device select it and restore the caller's current device on every exit
+// path (single-process multi-GPU programs: torch's current device must not flip under the caller).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) err = cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 static const double kPiD = 3.141592653589793238462643383279502884;
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -136,7 +150,7 @@ static int build_filterbank(const aad_params& p, int K, std::vector<float>& fb) 
       }
     }
   } else if (p.fb_type == AAD_FB_LINEAR_INTBIN) {
-    // spafe 0.3.x linear_filter_banks (scale="constant")
+    // spafe 0.1.x / python_speech_features style: triangles on integer FFT bins
     std::vector<double> pts = linspace(fmin, fmax, nf + 2), bins(nf + 2);
     for (int i = 0; i < nf + 2; ++i) bins[i] = std::floor((p.n_fft + 1) * pts[i] / sr);
     for (int j = 0; j < nf; ++j) {
@@ -147,7 +161,11 @@ static int build_filterbank(const aad_params& p, int K, std::vector<float>& fb) 
         fb[(size_t)j * K + i] = (float)(std::fabs(((int)b2 - i) / (b2 - b1)) * pscale);
     }
   } else if (p.fb_type == AAD_FB_LINEAR_CONT) {
-    std::vector<double> edges = linspace(fmin, fmax, nf + 2), freqs = linspace(0.0, sr / 2, K);
+    // spafe 0.3.x linear_filter_banks (scale="constant"): edges low + k |high - low| / (nfilts + 1), bin
+    // frequencies np.linspace(low, high, K), inclusive masks on both slopes (the falling slope wins at a centre)
+    const double delta = std::fabs(fmax - fmin) / (nf + 1);
+    std::vector<double> edges(nf + 2), freqs = linspace(fmin, fmax, K);
+    for (int i = 0; i < nf + 2; ++i) edges[i] = fmin + delta * i;
     for (int j = 0; j < nf; ++j) {
       const double lo = edges[j], ce = edges[j + 1], hi = edges[j + 2];
       for (int k = 0; k < K; ++k) {
@@ -347,7 +365,7 @@ int aad_params_default(aad_params* p, int kind, int sample_rate) {
     p->quantize_i16 = 1;
     p->pre_emph = 0.97f;
     p->n_filt = 24;
-    p->fb_type = AAD_FB_LINEAR_INTBIN;
+    p->fb_type = AAD_FB_LINEAR_CONT;  /* spafe ~= 0.3.3 (requirements.txt:5); see oracle/spafe_ref.py */
     p->power_scale = 1.0f / 512.0f;
     p->log_type = AAD_LOG_LN;
     p->ref_type = AAD_REF_ONE;
@@ -362,7 +380,7 @@ int aad_params_default(aad_params* p, int kind, int sample_rate) {
 
 int aad_plan_destroy(aad_plan* pl) {
   if (!pl) return AAD_OK;
-  cudaSetDevice(pl->device);
+  DeviceGuard guard(pl->device);
   cudaFree(pl->d_window);
   cudaFree(pl->d_window_i16);
   cudaFree(pl->d_tw1);
@@ -393,7 +411,9 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   if (pp->struct_size != (int32_t)sizeof(aad_params)) return AAD_ERR_INVALID_ARG;
   const aad_params& p = *pp;
   if (p.n_fft != 256 && p.n_fft != 512 && p.n_fft != 1024 && p.n_fft != 2048) return AAD_ERR_UNSUPPORTED;
-  if (p.win_length <= 0 || p.win_length > p.n_fft || p.hop_length <= 0) return AAD_ERR_INVALID_ARG;
+  // win_length > n_fft is spafe's behaviour above 20.48 kHz (25 ms frames, np.fft.fft(frames, 512) keeps the first
+  // n_fft windowed samples): allowed without centring only
+  if (p.win_length <= 0 || p.hop_length <= 0 || (p.win_length > p.n_fft && p.center)) return AAD_ERR_INVALID_ARG;
   if (p.n_filt <= 0 || p.n_filt > 512 || p.sample_rate <= 0) return AAD_ERR_INVALID_ARG;
   if (p.n_ceps < 0 || p.n_ceps > p.n_filt) return AAD_ERR_INVALID_ARG;
   if (p.n_delta < 0 || p.n_delta > 2) return AAD_ERR_INVALID_ARG;
@@ -405,7 +425,8 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   if (p.fmax > 0 && p.fmax > p.sample_rate / 2.0f + 1e-3f) return AAD_ERR_INVALID_ARG;
   if (p.znorm && p.time_mean) return AAD_ERR_INVALID_ARG;
 
-  CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  CUDA_TRY(guard.err);
   aad_plan* pl = new (std::nothrow) aad_plan();
   if (!pl) return AAD_ERR_INVALID_ARG;
   pl->p = p;
@@ -437,7 +458,7 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   const int win_off = p.center ? (N - p.win_length) / 2 : 0;
   pl->h_window.assign(N, 0.f);
   std::vector<float> win_half(N, 0.f);
-  for (int n = 0; n < p.win_length; ++n) {
+  for (int n = 0; n < std::min(p.win_length, N); ++n) {  // a window longer than n_fft is cut at n_fft (see above)
     pl->h_window[win_off + n] = (float)w[n];
     win_half[win_off + n] = 0.5f * (float)w[n];
   }
@@ -756,7 +777,7 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
   StftArgs sa;
   sa.wav = wav; sa.wav_stride = wav_stride; sa.row_off = reinterpret_cast<const long long*>(row_off); sa.len_c = d_len; sa.frame_off = d_frame_off; sa.B = B;
   sa.hop = p.hop_length; sa.s_off = p.center ? p.n_fft / 2 : 0;
-  sa.win_off = p.center ? (p.n_fft - p.win_length) / 2 : 0; sa.win_len = p.win_length;
+  sa.win_off = p.center ? (p.n_fft - p.win_length) / 2 : 0; sa.win_len = std::min(p.win_length, p.n_fft);
   sa.pre_emph = p.pre_emph;
   sa.window = wav_dtype == AAD_I16 ? pl->d_window_i16 : pl->d_window; sa.tw1 = pl->d_tw1; sa.twp = pl->d_twp;
   sa.filt_hdr = pl->d_filt_hdr; sa.filt_w = pl->d_filt_w; sa.n_hdr = pl->n_hdr; sa.n_w4 = pl->n_w4;
@@ -942,7 +963,19 @@ int aad_scaler_accumulate(const float* x, int64_t n_rows, int32_t W, int64_t row
   const long long nblk = (n_rows + SC_ROWS - 1) / SC_ROWS;
   if (nblk > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
   (void)cudaGetLastError();
-  k_col_stats<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(x, n_rows, W, row_stride, stats);
+  k_col_stats<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(x, n_rows, W, row_stride, stats, nullptr, nullptr, 1);
+  LAUNCH_CHECK("k_col_stats launch");
+  return AAD_OK;
+}
+
+int aad_scaler_accumulate_ragged(const float* x, int B, int32_t rows_per_utt, int32_t W, int64_t row_stride,
+                                 const int32_t* n_frames, const int32_t* status, double* stats, void* stream) {
+  if (!x || !stats || !n_frames || B <= 0 || rows_per_utt <= 0 || W <= 0 || row_stride < W) return AAD_ERR_INVALID_ARG;
+  const long long n_rows = (long long)B * rows_per_utt;
+  const long long nblk = (n_rows + SC_ROWS - 1) / SC_ROWS;
+  if (nblk > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
+  (void)cudaGetLastError();
+  k_col_stats<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(x, n_rows, W, row_stride, stats, n_frames, status, rows_per_utt);
   LAUNCH_CHECK("k_col_stats launch");
   return AAD_OK;
 }
@@ -989,7 +1022,8 @@ int64_t aad_plan_table(const aad_plan* pl, int which, float* host_out, int64_t c
 
 int aad_plan_set_profiling(aad_plan* pl, int enable) {
   if (!pl) return AAD_ERR_INVALID_ARG;
-  CUDA_TRY(cudaSetDevice(pl->device));
+  DeviceGuard guard(pl->device);
+  CUDA_TRY(guard.err);
   if (enable)
     for (auto& e : pl->ev)
       if (!e) CUDA_TRY(cudaEventCreate(&e));
@@ -1008,7 +1042,8 @@ int aad_plan_kernel_times(const aad_plan* pl, float* ms_out) {
 
 int aad_fp32_peak(int device, int iters, double* tflops_out) {
   if (!tflops_out || iters <= 0) return AAD_ERR_INVALID_ARG;
-  CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  CUDA_TRY(guard.err);
   int sms = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   float* sink = nullptr;
@@ -1048,22 +1083,18 @@ static int ensure(void** p, size_t* cap, size_t need) {
   return AAD_OK;
 }
 
-int aad_extract_host(aad_plan* pl, const void* wav_host, int wav_dtype, int64_t wav_stride,
-                     const int32_t* lengths_host, int B, int64_t max_len, float* out_host,
-                     int64_t out_stride_b, int32_t t_alloc, int32_t* n_frames_host,
-                     int32_t* status_host, int chunk_utts) {
-  if (!pl || !wav_host || !lengths_host || !out_host || !n_frames_host || !status_host)
-    return AAD_ERR_INVALID_ARG;
-  if (B <= 0 || max_len <= 0 || max_len > wav_stride || t_alloc <= 0) return AAD_ERR_INVALID_ARG;
-  CUDA_TRY(cudaSetDevice(pl->device));
+// internal buffers of the host path: three {stream, device wav / out / lengths / n_frames / status / workspace}
+// sets sized for one chunk, and the pinned staging of the per-utterance arrays.  Grown, never shrunk.
+static int host_reserve_impl(aad_plan* pl, int wav_dtype, int B, int64_t max_len, int32_t t_alloc, int chunk_utts,
+                             int* chunk_out) {
   const size_t esz = wav_dtype == AAD_I16 ? 2 : 4;
   const int64_t row_out = pl->p.time_mean ? pl->c_out : (int64_t)pl->c_out * t_alloc;
-  if (out_stride_b == 0) out_stride_b = row_out;
   if (chunk_utts <= 0) {
     // ~32 MB of samples per chunk keeps both copy engines and the SMs busy
     chunk_utts = (int)std::max<int64_t>(1, (32ll << 20) / (int64_t)(max_len * esz));
   }
   chunk_utts = std::min(chunk_utts, B);
+  *chunk_out = chunk_utts;
   int t_max = 0;
   size_t ws_need = 0;
   int rc = aad_query(pl, chunk_utts, max_len, &t_max, nullptr, &ws_need);
@@ -1090,35 +1121,86 @@ int aad_extract_host(aad_plan* pl, const void* wav_host, int wav_dtype, int64_t 
     CUDA_TRY(cudaHostAlloc((void**)&pl->h_stage, (size_t)3 * B * sizeof(int32_t), cudaHostAllocDefault));
     pl->h_stage_cap = B;
   }
+  return AAD_OK;
+}
+
+int aad_host_reserve(aad_plan* pl, int wav_dtype, int B, int64_t max_len, int32_t t_alloc, int chunk_utts) {
+  if (!pl || B <= 0 || max_len <= 0 || t_alloc <= 0) return AAD_ERR_INVALID_ARG;
+  if (wav_dtype != AAD_F32 && wav_dtype != AAD_I16) return AAD_ERR_INVALID_ARG;
+  DeviceGuard guard(pl->device);
+  CUDA_TRY(guard.err);
+  int chunk = 0;
+  return host_reserve_impl(pl, wav_dtype, B, max_len, t_alloc, chunk_utts, &chunk);
+}
+
+int aad_host_alloc(void** ptr, size_t bytes, int write_combined) {
+  if (!ptr || bytes == 0) return AAD_ERR_INVALID_ARG;
+  *ptr = nullptr;
+  CUDA_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+  return AAD_OK;
+}
+
+int aad_host_free(void* ptr) {
+  if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+  return AAD_OK;
+}
+
+int aad_extract_host(aad_plan* pl, const void* wav_host, int wav_dtype, int64_t wav_stride,
+                     const int32_t* lengths_host, int B, int64_t max_len, float* out_host,
+                     int64_t out_stride_b, int32_t t_alloc, int32_t* n_frames_host,
+                     int32_t* status_host, int chunk_utts) {
+  if (!pl || !wav_host || !lengths_host || !out_host || !n_frames_host || !status_host)
+    return AAD_ERR_INVALID_ARG;
+  if (B <= 0 || max_len <= 0 || max_len > wav_stride || t_alloc <= 0) return AAD_ERR_INVALID_ARG;
+  if (wav_dtype != AAD_F32 && wav_dtype != AAD_I16) return AAD_ERR_INVALID_ARG;
+  DeviceGuard guard(pl->device);
+  CUDA_TRY(guard.err);
+  const size_t esz = wav_dtype == AAD_I16 ? 2 : 4;
+  const int64_t row_out = pl->p.time_mean ? pl->c_out : (int64_t)pl->c_out * t_alloc;
+  if (out_stride_b == 0) out_stride_b = row_out;
+  int rc = host_reserve_impl(pl, wav_dtype, B, max_len, t_alloc, chunk_utts, &chunk_utts);  // no-op once warm
+  if (rc != AAD_OK) return rc;
   int32_t* st_len = pl->h_stage;
   int32_t* st_nf = pl->h_stage + pl->h_stage_cap;
   int32_t* st_st = pl->h_stage + 2 * (size_t)pl->h_stage_cap;
   std::memcpy(st_len, lengths_host, (size_t)B * sizeof(int32_t));
+  // on any failure: wait for the copies already in flight (they target the caller's buffers and the pinned stage)
+  auto drain = [&](int code) {
+    for (auto& h : pl->hb)
+      if (h.stream) cudaStreamSynchronize(h.stream);
+    return code;
+  };
+#define HOST_TRY(expr)                                              \
+  do {                                                              \
+    cudaError_t e__ = (expr);                                       \
+    if (e__ != cudaSuccess) return drain(cuda_fail(e__, #expr));    \
+  } while (0)
   int ci = 0;
   for (int b0 = 0; b0 < B; b0 += chunk_utts, ++ci) {
     aad_plan::HostBuf& h = pl->hb[ci % 3];
     const int nb = std::min(chunk_utts, B - b0);
     const char* src = (const char*)wav_host + (size_t)b0 * wav_stride * esz;
     if (wav_stride == max_len)
-      CUDA_TRY(cudaMemcpyAsync(h.d_wav, src, (size_t)nb * max_len * esz, cudaMemcpyHostToDevice, h.stream));
+      HOST_TRY(cudaMemcpyAsync(h.d_wav, src, (size_t)nb * max_len * esz, cudaMemcpyHostToDevice, h.stream));
     else
-      CUDA_TRY(cudaMemcpy2DAsync(h.d_wav, (size_t)max_len * esz, src, (size_t)wav_stride * esz,
+      HOST_TRY(cudaMemcpy2DAsync(h.d_wav, (size_t)max_len * esz, src, (size_t)wav_stride * esz,
                                  (size_t)max_len * esz, nb, cudaMemcpyHostToDevice, h.stream));
-    CUDA_TRY(cudaMemcpyAsync(h.d_len, st_len + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, h.stream));
+    HOST_TRY(cudaMemcpyAsync(h.d_len, st_len + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, h.stream));
     // rows with non-zero status are left untouched by the kernels: start from zeros
-    CUDA_TRY(cudaMemsetAsync(h.d_out, 0, (size_t)nb * row_out * 4, h.stream));
+    HOST_TRY(cudaMemsetAsync(h.d_out, 0, (size_t)nb * row_out * 4, h.stream));
     rc = aad_extract(pl, h.d_wav, wav_dtype, max_len, h.d_len, nb, max_len, h.d_out, row_out, t_alloc,
                      h.d_nf, h.d_st, h.d_ws, h.ws_bytes, h.stream);
-    if (rc != AAD_OK) return rc;
+    if (rc != AAD_OK) return drain(rc);
     if (out_stride_b == row_out)
-      CUDA_TRY(cudaMemcpyAsync(out_host + (size_t)b0 * out_stride_b, h.d_out, (size_t)nb * row_out * 4,
+      HOST_TRY(cudaMemcpyAsync(out_host + (size_t)b0 * out_stride_b, h.d_out, (size_t)nb * row_out * 4,
                                cudaMemcpyDeviceToHost, h.stream));
     else
-      CUDA_TRY(cudaMemcpy2DAsync(out_host + (size_t)b0 * out_stride_b, (size_t)out_stride_b * 4, h.d_out,
+      HOST_TRY(cudaMemcpy2DAsync(out_host + (size_t)b0 * out_stride_b, (size_t)out_stride_b * 4, h.d_out,
                                  (size_t)row_out * 4, (size_t)row_out * 4, nb, cudaMemcpyDeviceToHost, h.stream));
-    CUDA_TRY(cudaMemcpyAsync(st_nf + b0, h.d_nf, (size_t)nb * 4, cudaMemcpyDeviceToHost, h.stream));
-    CUDA_TRY(cudaMemcpyAsync(st_st + b0, h.d_st, (size_t)nb * 4, cudaMemcpyDeviceToHost, h.stream));
+    HOST_TRY(cudaMemcpyAsync(st_nf + b0, h.d_nf, (size_t)nb * 4, cudaMemcpyDeviceToHost, h.stream));
+    HOST_TRY(cudaMemcpyAsync(st_st + b0, h.d_st, (size_t)nb * 4, cudaMemcpyDeviceToHost, h.stream));
   }
+#undef HOST_TRY
   for (auto& h : pl->hb) CUDA_TRY(cudaStreamSynchronize(h.stream));
   std::memcpy(n_frames_host, st_nf, (size_t)B * sizeof(int32_t));
   std::memcpy(status_host, st_st, (size_t)B * sizeof(int32_t));

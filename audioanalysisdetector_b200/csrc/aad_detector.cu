@@ -239,6 +239,21 @@ static void det_layout(const aad_detector* d, int B, int* Bp, size_t* off_x0, si
   *total = o;
 }
 
+namespace {
+// select the object's device for the call and restore the caller's current device afterwards
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) err = cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+}  // namespace
+
 extern "C" {
 
 int aad_detector_create(const aad_detector_weights* w, int device, aad_detector** out) {
@@ -248,7 +263,8 @@ int aad_detector_create(const aad_detector_weights* w, int device, aad_detector*
                          w->w_ih_r, w->w_hh_r, w->b_ih_r, w->b_hh_r, w->ln_b, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b};
   for (const float* p : need)
     if (!p) return AAD_ERR_INVALID_ARG;
-  if (cudaSetDevice(device) != cudaSuccess) return AAD_ERR_CUDA;
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return AAD_ERR_CUDA;
   aad_detector* d = new aad_detector;
   d->device = device;
   d->F = w->feature_dim;
@@ -307,7 +323,7 @@ int aad_detector_create(const aad_detector_weights* w, int device, aad_detector*
 
 int aad_detector_destroy(aad_detector* d) {
   if (!d) return AAD_OK;
-  cudaSetDevice(d->device);
+  DeviceGuard guard(d->device);
   cudaFree(d->d_wt);
   cudaFree(d->d_ss);
   cudaFree(d->d_blob);

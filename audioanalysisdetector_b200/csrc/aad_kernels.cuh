@@ -1145,13 +1145,16 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
     float* ob = a.out + (long long)b * a.out_stride_b + (long long)t * a.out_stride_t + (long long)half * a.out_stride_c;
     const long long cstep = 2ll * a.out_stride_c, dstep = (long long)C * a.out_stride_c;
     const int te = min(max(t, h), T - 1 - h) - lo;  // stencil centre (edges replicate the interior fit)
-    // taps centred in a fixed 9-wide window (zero outside the delta width): immediate offsets
+    // taps centred in a fixed 9-wide window: immediate offsets.  Positions outside the delta width are neither read
+    // nor accumulated (they lie in the slack in front of a row or in its pad columns, which nothing writes: a
+    // zero tap times a NaN bit pattern left there would poison the result)
     float2 tp[CEP_MAXW];
 #pragma unroll
     for (int i = 0; i < CEP_MAXW; ++i) {
       const int src = i - (CEP_MAXW / 2) + h;
       tp[i] = (src >= 0 && src < a.width) ? make_float2(a.taps[0][src], a.taps[1][src]) : make_float2(0.f, 0.f);
     }
+    const int i_lo = CEP_MAXW / 2 - h, i_hi = CEP_MAXW / 2 + h;
     const float* row = sC + half * sc_stride;
     for (int k = half; k < C; k += 2, row += 2 * sc_stride, ob += cstep) {
       ob[0] = row[col];
@@ -1159,7 +1162,11 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
         const float* rc = row + te - CEP_MAXW / 2;
         float2 d12 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < CEP_MAXW; ++i) d12 = __ffma2_rn(make_float2(rc[i], rc[i]), tp[i], d12);
+        for (int i = 0; i < CEP_MAXW; ++i)
+          if (i >= i_lo && i <= i_hi) {
+            const float x = rc[i];
+            d12 = __ffma2_rn(make_float2(x, x), tp[i], d12);
+          }
         ob[dstep] = d12.x;
         if (a.n_delta > 1) ob[2 * dstep] = d12.y;
       }
@@ -1274,16 +1281,31 @@ __global__ void __launch_bounds__(256) k_znorm(const ZnArgs a) {
 // W valid columns; stats = {sum[W], sumsq[W]} in double (atomicAdd per CTA; all-reduced across ranks by
 // the host before the apply pass).  Thread (col = tid % 64, lane row = tid / 64): coalesced row reads.
 constexpr int SC_ROWS = 256;  // rows per CTA
+// Ragged batches (time-major [B][rows_per_utt][W] with n_frames[b] valid rows): n_frames != null masks the padding
+// rows and the rows of utterances with a non-zero status, and the CTA adds its number of valid rows to
+// stats[2 W] (np.vstack of the per-utterance arrays stacks valid frames only).
 __global__ void __launch_bounds__(256) k_col_stats(const float* x, long long n_rows, int W, long long row_stride,
-                                                   double* stats) {
+                                                   double* stats, const int32_t* n_frames, const int32_t* status,
+                                                   int rows_per_utt) {
   __shared__ double red[2][4][64];
   const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
   const long long r0 = (long long)blockIdx.x * SC_ROWS, r1 = min(n_rows, r0 + SC_ROWS);
+  auto row_ok = [&](long long r) {
+    if (!n_frames) return true;
+    const long long b = r / rows_per_utt;
+    return (int)(r - b * rows_per_utt) < __ldg(n_frames + b) && (!status || __ldg(status + b) == 0);
+  };
+  if (n_frames && threadIdx.x == 0) {
+    int cnt = 0;
+    for (long long r = r0; r < r1; ++r) cnt += row_ok(r) ? 1 : 0;
+    atomicAdd(stats + 2 * W, (double)cnt);
+  }
   for (int c0 = 0; c0 < W; c0 += 64) {
     const int c = c0 + cl;
     double s1 = 0.0, s2 = 0.0;
     if (c < W)
       for (long long r = r0 + rl; r < r1; r += 4) {
+        if (!row_ok(r)) continue;
         const double v = (double)__ldg(x + r * row_stride + c);
         s1 += v;
         s2 += v * v;

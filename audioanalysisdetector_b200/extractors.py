@@ -63,6 +63,21 @@ def _prepare_clip(filepath, chunk_start, chunk_end, sr, augment):
     return np.ascontiguousarray(y, dtype=np.float32), sr
 
 
+_STAGE: dict = {}   # per host thread: one pinned staging buffer, grown geometrically (a cudaHostAlloc per call
+#                      would dominate the per-file `func(path)` form of the reference's extractors)
+
+
+def _pinned_stage(n_elems: int) -> torch.Tensor:
+    import threading
+    key = threading.get_ident()
+    buf = _STAGE.get(key)
+    if buf is None or buf.numel() < n_elems:
+        buf = torch.empty(max(n_elems, 2 * (buf.numel() if buf is not None else 0), 1 << 16), dtype=torch.float32,
+                          pin_memory=True)
+        _STAGE[key] = buf
+    return buf
+
+
 def _run_batch(params: FrontendParams, clips: Sequence[np.ndarray]):
     """Pad clips to one [B, Lmax] batch, run the plan, return per-clip arrays (None on item error)."""
     fe = get_frontend(params)
@@ -70,13 +85,14 @@ def _run_batch(params: FrontendParams, clips: Sequence[np.ndarray]):
     lens = np.array([len(c) for c in clips], dtype=np.int32)
     Lmax = max(int(lens.max()), 1)
     Lmax = (Lmax + 3) // 4 * 4          # keeps rows 16-byte aligned for the vector loads
-    host = torch.zeros((B, Lmax), dtype=torch.float32, pin_memory=True)
+    host = _pinned_stage(B * Lmax)[:B * Lmax].view(B, Lmax)
     hv = host.numpy()
     for i, c in enumerate(clips):
         hv[i, :len(c)] = c
+        hv[i, len(c):] = 0.0
     wav = host.to(fe.device, non_blocking=True)
     feats, n_frames, status = fe(wav, torch.from_numpy(lens).to(fe.device))
-    feats, n_frames, status = feats.cpu().numpy(), n_frames.cpu().numpy(), status.cpu().numpy()
+    feats, n_frames, status = feats.cpu().numpy(), n_frames.cpu().numpy(), status.cpu().numpy()   # syncs: the stage is free again
     out: List[Optional[np.ndarray]] = []
     for i in range(B):
         if status[i] != 0:

@@ -68,7 +68,7 @@ class FrontendParams:
 
     @classmethod
     def lfcc(cls, sample_rate, n_ceps=13, nfilts=24, nfft=512, win_len=0.025, win_hop=0.01,
-             pre_emph=0.97, quantize_i16=True, layout=L.LAYOUT_TC, fb_type=L.FB_LINEAR_INTBIN, **kw):
+             pre_emph=0.97, quantize_i16=True, layout=L.LAYOUT_TC, fb_type=L.FB_LINEAR_CONT, **kw):
         """(y*32767).astype(int16) + spafe lfcc(num_ceps, nfilts=24, nfft=512, 25/10 ms hamming)."""
         sr = int(sample_rate)
         return cls(kind=L.KIND_LFCC, sample_rate=sr, n_fft=nfft, win_length=int(win_len * sr),
@@ -363,16 +363,20 @@ class Frontend:
         t_max, c_out, _ = self.query(B, Lmax)
         t_alloc = max(t_max, 1)
         p = self.params
+        if p.time_mean:
+            shape = (B, c_out)
+        elif p.layout == L.LAYOUT_CT:
+            shape = (B, c_out, t_alloc)
+        else:
+            shape = (B, t_alloc, c_out)
         if out is None:
-            if p.time_mean:
-                shape = (B, c_out)
-            elif p.layout == L.LAYOUT_CT:
-                shape = (B, c_out, t_alloc)
-            else:
-                shape = (B, t_alloc, c_out)
             out = np.zeros(shape, dtype=np.float32)
-        elif isinstance(out, torch.Tensor):
-            out = out.numpy()
+        else:
+            if isinstance(out, torch.Tensor):
+                out = out.numpy()
+            # the library writes whole rows through this pointer: shape, dtype and row contiguity must be right
+            if out.dtype != np.float32 or tuple(out.shape) != shape or out[0].strides != np.empty(shape[1:], np.float32).strides:
+                raise L.AadError(f"out must be float32 of shape {shape} with C-contiguous rows, got {out.dtype} {tuple(out.shape)}")
         n_frames = np.empty(B, dtype=np.int32)
         status = np.empty(B, dtype=np.int32)
         rc = self.lib.aad_extract_host(

@@ -30,7 +30,12 @@ def merge_stats(count: int, sums: np.ndarray, sumsq: np.ndarray):
 
 
 class DeviceStandardScaler:
-    """fit / transform with sklearn StandardScaler semantics on [B, R, W] CUDA tensors (W = last axis)."""
+    """fit / transform with sklearn StandardScaler semantics on [B, R, W] CUDA tensors.
+
+    W (the standardised columns) must be the LAST axis, i.e. the extractor's time-major TC layout
+    `[B, T, C]` (or any `[rows, W]` stacking); a CT tensor has to be transposed by the caller.  For ragged
+    batches pass the extractor's `n_frames` (and `status`) to `fit`: the reference fits on
+    `np.vstack(per-utterance arrays)`, valid frames only, so padding rows must not enter the statistics."""
 
     def __init__(self):
         self.mean_: Optional[np.ndarray] = None
@@ -45,18 +50,31 @@ class DeviceStandardScaler:
             raise L.AadError("scaler needs a contiguous float32 CUDA tensor [..., rows, W]")
         return x.numel() // x.shape[-1], x.shape[-1]
 
-    def fit(self, x: torch.Tensor, group=None) -> "DeviceStandardScaler":
+    def fit(self, x: torch.Tensor, group=None, n_frames: Optional[torch.Tensor] = None,
+            status: Optional[torch.Tensor] = None) -> "DeviceStandardScaler":
         """x: this rank's features; with torch.distributed initialised the statistics are those of the
-        union over all ranks of `group` (one all-reduce of 2*W + 1 doubles)."""
+        union over all ranks of `group` (one all-reduce of 2*W + 1 doubles).  n_frames / status (int32 CUDA,
+        [B]): x is a ragged [B, T, W] batch, only the valid rows of utterances with status 0 are counted."""
         import torch.distributed as dist
         lib = L.load()
         n_rows, W = self._rows(x)
         stats = torch.zeros(2 * W + 1, dtype=torch.float64, device=x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         with torch.cuda.device(x.device):
-            L.check(lib.aad_scaler_accumulate(C.c_void_p(x.data_ptr()), n_rows, W, W, C.c_void_p(stats.data_ptr()),
-                                              C.c_void_p(stream)), "aad_scaler_accumulate")
-        stats[2 * W] = float(n_rows)
+            if n_frames is not None:
+                if x.dim() != 3 or n_frames.numel() != x.shape[0]:
+                    raise L.AadError("ragged fit needs x [B, T, W] and n_frames [B]")
+                nf = n_frames.to(device=x.device, dtype=torch.int32).contiguous()
+                st = None if status is None else status.to(device=x.device, dtype=torch.int32).contiguous()
+                L.check(lib.aad_scaler_accumulate_ragged(C.c_void_p(x.data_ptr()), x.shape[0], x.shape[1], W, W,
+                                                         C.c_void_p(nf.data_ptr()),
+                                                         C.c_void_p(st.data_ptr() if st is not None else 0),
+                                                         C.c_void_p(stats.data_ptr()), C.c_void_p(stream)),
+                        "aad_scaler_accumulate_ragged")
+            else:
+                L.check(lib.aad_scaler_accumulate(C.c_void_p(x.data_ptr()), n_rows, W, W, C.c_void_p(stats.data_ptr()),
+                                                  C.c_void_p(stream)), "aad_scaler_accumulate")
+                stats[2 * W] = float(n_rows)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
         h = stats.cpu().numpy()

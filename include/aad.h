@@ -5,9 +5,12 @@
  * IzaP1k/AudioAnalysisDetector.  The reference has no FFI of its own (it is pure
  * Python); each entry point below cites the reference interface it replaces.
  * Signatures are plain C: pointers, sizes, a CUDA stream passed as void*.  All
- * data pointers are DEVICE pointers unless the name says host.  The library
- * never allocates in the hot calls (caller owns inputs, outputs, workspace and
- * status), never synchronises the stream, and never throws across the ABI:
+ * data pointers are DEVICE pointers unless the name says host.  The device
+ * entry points (aad_extract*, aad_logmel / mfcc / lfcc, aad_delta, ...) never
+ * allocate (caller owns inputs, outputs, workspace and status) and never
+ * synchronise the stream; the host convenience path aad_extract_host owns
+ * internal device buffers that grow lazily on first use or up front with
+ * aad_host_reserve, and is synchronous.  Nothing throws across the ABI:
  * every call returns 0 or a negative aad_error; per-utterance problems are
  * reported in status[B] (the reference's "print and return None" convention,
  * ASV_dl_func.py:418-420,437-439,536-538).
@@ -39,8 +42,9 @@ enum aad_window {
 };
 enum aad_fb {
   AAD_FB_MEL_SLANEY = 0,    /* librosa.filters.mel(htk=False, norm='slaney') */
-  AAD_FB_LINEAR_INTBIN = 1, /* spafe 0.3.x linear_filter_banks (integer FFT bins) */
-  AAD_FB_LINEAR_CONT = 2,   /* triangles on continuous bin frequencies */
+  AAD_FB_LINEAR_INTBIN = 1, /* triangles on integer FFT bins (spafe 0.1.x / python_speech_features style) */
+  AAD_FB_LINEAR_CONT = 2,   /* spafe 0.3.x linear_filter_banks: triangles on continuous bin frequencies; the
+                               LFCC default (the reference pins spafe ~= 0.3.3, requirements.txt:5) */
   AAD_FB_CUSTOM = 3         /* caller matrix, at most two adjacent filters per bin */
 };
 enum aad_log {
@@ -217,12 +221,27 @@ int aad_db_reference(float* x, int64_t stride_b, int32_t stride_f, const int32_t
  *   aad_scaler_apply: x = (x - mean[c]) * inv_scale[c] in place. */
 int aad_scaler_accumulate(const float* x, int64_t n_rows, int32_t W, int64_t row_stride, double* stats,
                           void* stream);
+/* The same for a ragged time-major batch x[B][rows_per_utt][row_stride] straight from the extractor (TC
+ * layout): only the n_frames[b] valid rows of utterances with status[b] == 0 (status may be NULL) enter the
+ * sums, as np.vstack of the per-utterance arrays does, and the number of rows that did is added to
+ * stats[2*W] (stats holds 2*W + 1 doubles here; zero it first). */
+int aad_scaler_accumulate_ragged(const float* x, int B, int32_t rows_per_utt, int32_t W, int64_t row_stride,
+                                 const int32_t* n_frames, const int32_t* status, double* stats, void* stream);
 int aad_scaler_apply(float* x, int64_t n_rows, int32_t W, int64_t row_stride, const float* mean,
                      const float* inv_scale, void* stream);
 
 /* Host-buffer convenience path (what the reference-facing Python drop-ins use for
  * host arrays): pinned-or-pageable HOST wav/lengths in, HOST out/n_frames/status back,
- * chunked H2D -> kernels -> D2H pipelined on internal streams.  Synchronous. */
+ * chunked H2D -> kernels -> D2H pipelined on internal streams.  Synchronous.  Its internal
+ * buffers (three chunk-sized device sets + pinned staging for the per-utterance arrays) are
+ * allocated on the first call with a given shape, or ahead of time by aad_host_reserve (same
+ * wav_dtype / B / max_len / t_alloc / chunk_utts as the calls that follow); later calls with
+ * the same or smaller shapes allocate nothing.  aad_host_alloc / aad_host_free hand out pinned
+ * host memory for the caller's buffers (write_combined != 0: faster for the device to read,
+ * slow for the CPU to read back -- input staging only, never the output). */
+int aad_host_reserve(aad_plan* plan, int wav_dtype, int B, int64_t max_len, int32_t t_alloc, int chunk_utts);
+int aad_host_alloc(void** ptr, size_t bytes, int write_combined);
+int aad_host_free(void* ptr);
 int aad_extract_host(aad_plan* plan, const void* wav_host, int wav_dtype, int64_t wav_stride,
                      const int32_t* lengths_host, int B, int64_t max_len, float* out_host,
                      int64_t out_stride_b, int32_t t_alloc, int32_t* n_frames_host,

@@ -15,11 +15,21 @@ spafe/fbanks/linear_fbanks.py), all float64:
   -> (1/nfft) * |X|^2 -> @ linear filterbank^T -> zero_handling (0 -> eps)
   -> np.log -> scipy.fftpack.dct(type=2, norm='ortho', axis=1)[:, :num_ceps].
 
-Least-certain step: the filterbank construction.  `linear_filter_banks`
-restates the integer-FFT-bin triangles of spafe 0.3.x; the continuous-frequency
-construction found in other spafe versions is `linear_filter_banks_continuous`.
-Everything downstream takes the matrix as data, so parity of the CUDA path with
-this oracle holds for either (both are exercised in tests).
+Least-certain step: the filterbank construction.  `linear_filter_banks` restates
+spafe >= 0.2 / 0.3.x (`requirements.txt:5` pins ~= 0.3.3): triangles on the
+CONTINUOUS bin frequencies `np.linspace(low_freq, high_freq, nfft//2 + 1)` with
+`(freqs >= lower) == (freqs <= center)` masks, returning the tuple
+`(fbank, center_freqs)` that `lfcc` unpacks as `lin_fbanks_mat, _ = ...`.  The
+python_speech_features-style construction on integer FFT bins
+(`floor((nfft + 1) * hz / fs)`) belongs to spafe 0.1.x and is kept as
+`linear_filter_banks_intbin`.  Evidence: two independent recollections of the
+0.3.x source (round-1 builder's notes listed it as "a continuous-frequency variant
+exists in other versions", the round-1 review recalled the tuple return and the
+mask expression of 0.3.x); the wheel cannot be opened here (`pip download
+spafe==0.3.3` has no index).  Everything downstream takes the matrix as data, so
+parity of the CUDA path with this oracle holds for either (both are exercised in
+tests), and a deployment that has spafe installed can pass spafe's own matrix as
+a custom bank.
 """
 from __future__ import annotations
 
@@ -73,7 +83,40 @@ def framing(sig, fs=16000, win_len=0.025, win_hop=0.01):
 
 def linear_filter_banks(nfilts=24, nfft=512, fs=16000, low_freq=0, high_freq=None,
                         scale="constant"):
-    """spafe 0.3.x linear_filter_banks: triangles on integer FFT bins, unit peak.
+    """spafe 0.3.x `spafe.fbanks.linear_fbanks.linear_filter_banks` -> (fbank, center_freqs).
+
+    Edge frequencies `low + k * |high - low| / (nfilts + 1)`; bin frequencies
+    `np.linspace(low_freq, high_freq, nfft//2 + 1)` (spafe spaces the bins over the
+    band it was given, which equals the FFT bin centres for the default band
+    0 .. fs/2); rising slope over lower <= f <= center, falling slope over
+    center <= f <= upper, unit peak; `scale="constant"` leaves the heights at 1.
+    """
+    high_freq = high_freq or fs / 2
+    low_freq = low_freq or 0
+    if low_freq < 0 or high_freq > fs / 2:
+        raise ValueError("bad frequency range")
+    delta_hz = abs(high_freq - low_freq) / (nfilts + 1)
+    scale_freqs = low_freq + delta_hz * np.arange(0, nfilts + 2)
+    lower_edges, upper_edges, centers = scale_freqs[:-2], scale_freqs[2:], scale_freqs[1:-1]
+    freqs = np.linspace(low_freq, high_freq, nfft // 2 + 1)
+    fbank = np.zeros((nfilts, nfft // 2 + 1))
+    c = 1.0 if scale in ("descendant", "constant") else 0.0
+    for j, (center, lower, upper) in enumerate(zip(centers, lower_edges, upper_edges)):
+        if scale == "descendant":
+            c -= 1 / nfilts
+            c = c * (c > 0) + 0 * (c < 0)
+        elif scale == "ascendant":
+            c += 1 / nfilts
+            c = c * (c < 1) + 1 * (c > 1)
+        left = (freqs >= lower) == (freqs <= center)
+        fbank[j, left] = c * (freqs[left] - lower) / (center - lower)
+        right = (freqs >= center) == (freqs <= upper)
+        fbank[j, right] = c * (upper - freqs[right]) / (upper - center)
+    return np.abs(fbank), centers
+
+
+def linear_filter_banks_intbin(nfilts=24, nfft=512, fs=16000, low_freq=0, high_freq=None):
+    """spafe 0.1.x (python_speech_features style): triangles on integer FFT bins, unit peak.
 
     bins = floor((nfft + 1) * hz / fs) for nfilts + 2 equally spaced edge
     frequencies; filter j rises over [b_j, b_{j+1}) and falls over [b_{j+1}, b_{j+2}).
@@ -85,35 +128,11 @@ def linear_filter_banks(nfilts=24, nfft=512, fs=16000, low_freq=0, high_freq=Non
     linear_points = np.linspace(low_freq, high_freq, nfilts + 2)
     bins = np.floor((nfft + 1) * linear_points / fs)
     fbank = np.zeros([nfilts, nfft // 2 + 1])
-    c = 1.0 if scale in ("descendant", "constant") else 0.0
     for j in range(nfilts):
         b0, b1, b2 = bins[j], bins[j + 1], bins[j + 2]
-        if scale == "descendant":
-            c -= 1 / nfilts
-            c = c * (c > 0) + 0 * (c < 0)
-        elif scale == "ascendant":
-            c += 1 / nfilts
-            c = c * (c < 1) + 1 * (c > 1)
-        fbank[j, int(b0):int(b1)] = c * (np.arange(int(b0), int(b1)) - int(b0)) / (b1 - b0)
-        fbank[j, int(b1):int(b2)] = c * (int(b2) - np.arange(int(b1), int(b2))) / (b2 - b1)
+        fbank[j, int(b0):int(b1)] = (np.arange(int(b0), int(b1)) - int(b0)) / (b1 - b0)
+        fbank[j, int(b1):int(b2)] = (int(b2) - np.arange(int(b1), int(b2))) / (b2 - b1)
     return np.abs(fbank)
-
-
-def linear_filter_banks_continuous(nfilts=24, nfft=512, fs=16000, low_freq=0,
-                                   high_freq=None):
-    """Alternative construction (triangles on continuous bin frequencies)."""
-    high_freq = high_freq or fs / 2
-    low_freq = low_freq or 0
-    edges = np.linspace(low_freq, high_freq, nfilts + 2)
-    freqs = np.linspace(0, fs / 2, nfft // 2 + 1)
-    fbank = np.zeros((nfilts, nfft // 2 + 1))
-    for j in range(nfilts):
-        lo, ce, hi = edges[j], edges[j + 1], edges[j + 2]
-        left = (freqs >= lo) & (freqs <= ce)
-        fbank[j, left] = (freqs[left] - lo) / (ce - lo)
-        right = (freqs >= ce) & (freqs <= hi)
-        fbank[j, right] = (hi - freqs[right]) / (hi - ce)
-    return fbank
 
 
 def zero_handling(x):
@@ -125,7 +144,7 @@ def linear_spectrogram(sig, fs=16000, pre_emph=True, pre_emph_coeff=0.97,
                        low_freq=0, high_freq=None, fbanks=None):
     """spafe.features.lfcc.linear_spectrogram -> (T, nfilts) float64 energies."""
     if fbanks is None:
-        fbanks = linear_filter_banks(nfilts, nfft, fs, low_freq, high_freq)
+        fbanks, _ = linear_filter_banks(nfilts, nfft, fs, low_freq, high_freq)
     sig = np.asarray(sig)
     if pre_emph:
         sig = pre_emphasis(sig, pre_emph_coeff)

@@ -133,6 +133,7 @@ def test_new_entry_points_validate_their_arguments_before_touching_the_gpu(built
     assert built_lib.aad_db_reference(None, 0, 64, None, None, 1, 64, 63, 1, 80.0, None) == INV
     assert built_lib.aad_scaler_accumulate(None, 10, 13, 13, None, None) == INV
     assert built_lib.aad_scaler_apply(None, 10, 13, 13, None, None, None) == INV
+    assert built_lib.aad_scaler_accumulate_ragged(None, 4, 10, 13, 13, None, None, None, None) == INV
     w = L.AadDetectorWeights()
     h = C.c_void_p()
     assert built_lib.aad_detector_create(C.byref(w), 0, C.byref(h)) == INV            # struct_size not set

@@ -168,6 +168,29 @@ def test_device_standard_scaler_matches_sklearn():
     assert np.abs(got2 - np.stack([ref2.transform(x) for x in lf.cpu().numpy()])).max() <= 1e-4
 
 
+def test_device_standard_scaler_ragged_counts_valid_frames_only():
+    """np.vstack of the per-utterance arrays stacks valid frames only: padding rows of a ragged batch (and rows of
+    utterances with a non-zero status) must not enter mean_ / var_ / n_samples_seen_."""
+    from sklearn.preprocessing import StandardScaler
+    from audioanalysisdetector_b200 import DeviceStandardScaler, Frontend, FrontendParams
+    from helpers import pad_batch
+    dev = torch.device("cuda:0")
+    clips = [noise(90 + i, n) for i, n in enumerate((32000, 17000, 48000, 300, 9000, 24001))]   # one too short
+    w, lens = pad_batch(clips)
+    fl = Frontend(FrontendParams.lfcc(16000, n_ceps=13), dev)
+    lf, nf, st = fl(torch.from_numpy(w).to(dev), torch.from_numpy(lens).to(dev))   # (6, Tmax, 13), time-major
+    nfh, sth, host = nf.cpu().numpy(), st.cpu().numpy(), lf.cpu().numpy()
+    assert sth[3] != 0 and (sth[[0, 1, 2, 4, 5]] == 0).all()
+    valid = [host[i, :nfh[i]] for i in range(len(clips)) if sth[i] == 0]
+    ref = StandardScaler().fit(np.vstack(valid))
+    sc = DeviceStandardScaler().fit(lf, n_frames=nf, status=st)
+    assert sc.n_samples_seen_ == sum(len(v) for v in valid)
+    np.testing.assert_allclose(sc.mean_, ref.mean_, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(sc.scale_, ref.scale_, rtol=1e-6, atol=1e-6)
+    dense = DeviceStandardScaler().fit(lf)                                          # counts the padding: different
+    assert dense.n_samples_seen_ == lf.shape[0] * lf.shape[1] > sc.n_samples_seen_
+
+
 def test_train_fun_extractors_and_dispatcher(files, tmp_path):
     """train_fun.py:69-88 (one averaged vector per file; LFCC averaged over TIME, unlike ASV_dl_func) and the
     `func(path)` loop at :339-344."""

@@ -108,7 +108,7 @@ def test_lfcc_reference_defaults(dev):
         want = oracle.extract_lfcc_ref(c, 16000)
         assert st[i] == 0 and nf[i] == want.shape[0]
         assert np.abs(out[i, :nf[i], :] - want).max() <= TOL_LOG
-    np.testing.assert_allclose(fe.table(LIB().TABLE_FILTERBANK), SR.linear_filter_banks(24, 512, 16000) / 512,
+    np.testing.assert_allclose(fe.table(LIB().TABLE_FILTERBANK), SR.linear_filter_banks(24, 512, 16000)[0] / 512,
                                rtol=1e-6, atol=1e-12)
 
 
@@ -117,19 +117,60 @@ def test_lfcc_config3_int16_with_deltas(dev, fb):
     L = LIB()
     clips = [SR.quantize_int16(noise(20 + i, n)) for i, n in enumerate((16000, 77777, 128000, 31999))]
     kw = dict(n_ceps=20, nfilts=20, win_len=0.02, n_delta=2, layout=L.LAYOUT_CT)
-    if fb == "intbin":
-        p, fbm = FP().lfcc(16000, **kw), SR.linear_filter_banks(20, 512, 16000)
-    elif fb == "cont":
-        p = FP().lfcc(16000, fb_type=L.FB_LINEAR_CONT, **kw)
-        fbm = SR.linear_filter_banks_continuous(20, 512, 16000)
-    else:
-        fbm = SR.linear_filter_banks_continuous(20, 512, 16000)
+    if fb == "intbin":   # spafe 0.1.x construction, selectable
+        p, fbm = FP().lfcc(16000, fb_type=L.FB_LINEAR_INTBIN, **kw), SR.linear_filter_banks_intbin(20, 512, 16000)
+    elif fb == "cont":   # spafe 0.3.x construction, the default
+        p = FP().lfcc(16000, **kw)
+        fbm = SR.linear_filter_banks(20, 512, 16000)[0]
+    else:                # the deployment recipe of INTEGRATION.md: spafe's own matrix as a custom bank
+        fbm = SR.linear_filter_banks(20, 512, 16000)[0]
         p = FP().lfcc(16000, fb_type=L.FB_CUSTOM, custom_fb=fbm.astype(np.float32), **kw)
     out, nf, st, _ = run(p, clips, dev, dtype=np.int16)
     for i, c in enumerate(clips):
         want = oracle.lfcc_with_deltas_ref(c, 16000, fbanks=fbm)
         assert st[i] == 0 and nf[i] == want.shape[1]
         assert np.abs(out[i, :, :nf[i]] - want).max() <= TOL_LOG
+
+
+@pytest.mark.parametrize("sr", [22050, 44100, 48000])
+def test_lfcc_above_20khz_window_longer_than_nfft(dev, sr):
+    """spafe frames with the full 25 ms window (551 / 1102 / 1200 samples) and np.fft.fft(frames, 512) keeps the
+    first 512 windowed samples: the drop-in must return the same LFCCs instead of refusing the plan."""
+    clips = [noise(70, sr), speech(71, int(1.3 * sr) + 7, sr), noise(72, int(0.025 * sr)), noise(73, int(0.025 * sr) - 1)]
+    out, nf, st, fe = run(FP().lfcc(sr, n_ceps=13), clips, dev)
+    assert fe.params.win_length == int(0.025 * sr) > 512
+    for i, c in enumerate(clips[:3]):
+        want = oracle.extract_lfcc_ref(c, sr)
+        assert st[i] == 0 and nf[i] == want.shape[0] == (len(c) - int(0.025 * sr)) // int(0.01 * sr) + 1
+        assert np.abs(out[i, :nf[i], :] - want).max() <= TOL_LOG
+    assert st[3] == 2 and oracle.extract_lfcc_ref(clips[3], sr) is None      # shorter than one frame
+
+
+@pytest.mark.parametrize("width", [3, 5, 7])
+@pytest.mark.parametrize("poison", [False, True])
+def test_fused_deltas_of_narrow_widths(dev, width, poison):
+    """The fused stencil of k_cepstra walks a fixed 9-wide window; the positions outside a narrower delta width lie
+    in the slack in front of a row / in its pad columns and must be neither read into the sum nor multiplied by
+    a zero tap (0 * NaN).  `poison` first runs a batch whose status-5 rows leave NaN patterns behind in shared
+    memory-sized workspaces, then the clean batch."""
+    from audioanalysisdetector_b200.frontend import Frontend
+    p = FP().mfcc(16000, n_mfcc=13, n_delta=2, delta_width=width)
+    clips = [noise(80, 32000), speech(81, 24000), noise(82, 512 * (width - 1) + 1), noise(83, 70000)]
+    if poison:
+        bad = [c.copy() for c in clips]
+        for c in bad:
+            c[::97] = np.nan
+        run(p, bad, dev)
+    out, nf, st, _ = run(p, clips, dev)
+    h = width // 2
+    for i, c in enumerate(clips):
+        want = oracle.mfcc_with_deltas_ref(c, 16000, n_mfcc=13, n_delta=2, width=width)
+        assert st[i] == 0 and nf[i] == want.shape[1]
+        got = out[i, :, :nf[i]]
+        assert np.isfinite(got).all()
+        assert np.abs(got - want).max() <= TOL_LOG
+        for sl in (slice(0, h + 1), slice(nf[i] - 1 - h, nf[i])):                # the edge frames the advisory names
+            assert np.abs(got[:, sl] - want[:, sl]).max() <= TOL_LOG
 
 
 def test_int16_input_equals_float_quantised_input(dev):
@@ -171,7 +212,9 @@ def test_non_banded_custom_filterbank_is_rejected(dev):
 
 
 # ----------------------------------------------------------------------------- golden fixtures
-def test_committed_golden_vectors(dev):
+def test_regression_anchor_oracle_outputs(dev):
+    """oracle_outputs.npz holds the ORACLE's own outputs (tests/golden/make_golden.py): a regression anchor for the
+    restatement and the CUDA path together, not evidence of parity with librosa / spafe."""
     L = LIB()
     g = golden("oracle_outputs.npz")
     for name in ("noise", "speech"):

@@ -28,19 +28,31 @@ def test_pre_emphasis_and_framing():
 
 
 def test_linear_filterbank_structure():
-    for fbk in (SR.linear_filter_banks(24, 512, 16000), SR.linear_filter_banks(20, 512, 16000),
-                SR.linear_filter_banks_continuous(24, 512, 16000)):
+    for fbk in (SR.linear_filter_banks(24, 512, 16000)[0], SR.linear_filter_banks(20, 512, 16000)[0],
+                SR.linear_filter_banks_intbin(24, 512, 16000), SR.linear_filter_banks_intbin(20, 512, 16000)):
         assert fbk.shape[1] == 257 and fbk.min() >= 0 and fbk.max() <= 1.0
         nz = (fbk > 0).sum(axis=0)
         assert nz.max() <= 2
         for k in np.nonzero(nz == 2)[0]:
             j = np.nonzero(fbk[:, k])[0]
             assert j[1] - j[0] == 1
-    fbk = SR.linear_filter_banks(24, 512, 16000)
+    fbk = SR.linear_filter_banks_intbin(24, 512, 16000)
     # unit peaks at the centre bins, adjacent falling/rising slopes sum to one
     bins = np.floor(513 * np.linspace(0, 8000, 26) / 16000).astype(int)
     for j in range(24):
         assert fbk[j, bins[j + 1]] == 1.0
+    # spafe 0.3.x construction (the default): tuple return, centres 320 Hz apart for 24 filters at 16 kHz (10.24
+    # bins: no centre falls on a bin, so no peak reaches 1); inside the band rising + falling slopes sum to 1
+    fbk, centers = SR.linear_filter_banks(24, 512, 16000)
+    np.testing.assert_allclose(centers, 320.0 * np.arange(1, 25))
+    freqs = np.arange(257) * 31.25
+    assert 0.95 < fbk.max(axis=1).min() and fbk.max() < 1.0
+    inside = (freqs >= centers[0]) & (freqs <= centers[-1])
+    np.testing.assert_allclose(fbk.sum(axis=0)[inside], 1.0, atol=1e-12)
+    # triangle values against the closed form on continuous frequencies
+    j = 7
+    want = np.clip(np.minimum((freqs - (centers[j] - 320)) / 320, ((centers[j] + 320) - freqs) / 320), 0, None)
+    np.testing.assert_allclose(fbk[j], want, atol=1e-12)
 
 
 def test_lfcc_known_answers_and_shapes():
@@ -61,10 +73,34 @@ def test_lfcc_matches_direct_dft_formulation():
     fr = e[3 * 160:3 * 160 + 400] * (0.54 - 0.46 * np.cos(2 * np.pi * np.arange(400) / 399))
     n, k = np.arange(400)[None, :], np.arange(257)[:, None]
     X = (fr[None, :] * np.exp(-2j * np.pi * k * n / 512)).sum(axis=1)
-    en = (np.abs(X) ** 2 / 512) @ SR.linear_filter_banks(24, 512, 16000).T
+    en = (np.abs(X) ** 2 / 512) @ SR.linear_filter_banks(24, 512, 16000)[0].T
     m = np.arange(24)
     c = [np.sqrt((1 if q == 0 else 2) / 24) * (np.log(en) * np.cos(np.pi * q * (2 * m + 1) / 48)).sum() for q in range(13)]
     np.testing.assert_allclose(lf[3], c, rtol=1e-9, atol=1e-9)
+
+
+def test_spafe_front_half_matches_scipy_signal():
+    """Independent anchor for the spafe half of the oracle that shares no code with oracle/spafe_ref.py: int16
+    truncation with np.trunc, pre-emphasis as the FIR filter [1, -0.97] (scipy.signal.lfilter, zero initial state
+    => first sample unchanged), framing + symmetric Hamming + FFT by scipy.signal.spectrogram (no padding, tail
+    dropped), |X|^2 / nfft; then spafe's linear bank + ln + DCT-II ortho through scipy.fftpack."""
+    import scipy.fftpack
+    y = noise(21, 9000)
+    q = np.trunc(y.astype(np.float32) * np.float32(32767)).astype(np.int16)
+    np.testing.assert_array_equal(q, SR.quantize_int16(y))
+    e = scipy.signal.lfilter([1.0, -0.97], [1.0], q.astype(np.float64))
+    np.testing.assert_allclose(e, SR.pre_emphasis(q), rtol=0, atol=1e-9)
+    win = scipy.signal.get_window("hamming", 400, fftbins=False)
+    _, _, mag = scipy.signal.spectrogram(e, fs=16000, window=win, nperseg=400, noverlap=240, nfft=512,
+                                         detrend=False, return_onesided=True, scaling="spectrum", mode="magnitude")
+    power = (mag.T * win.sum()) ** 2 / 512                                   # (T, 257)
+    fr, _ = SR.framing(SR.pre_emphasis(q), 16000)
+    own = np.abs(np.fft.fft(np.hamming(400) * fr, 512))[:, :257] ** 2 / 512
+    assert power.shape == own.shape == ((9000 - 400) // 160 + 1, 257)
+    np.testing.assert_allclose(power, own, rtol=1e-9, atol=1e-9 * own.max())
+    fbk = SR.linear_filter_banks(24, 512, 16000)[0]
+    want = scipy.fftpack.dct(np.log(power @ fbk.T), type=2, axis=1, norm="ortho")[:, :13]
+    np.testing.assert_allclose(SR.lfcc(q, fs=16000, num_ceps=13), want, rtol=1e-9, atol=1e-9)
 
 
 def test_delta_taps_and_known_answers():
@@ -92,6 +128,7 @@ def test_delta_interior_matches_torchaudio():
 
 
 def test_oracle_regression_against_committed_outputs():
+    # oracle_outputs.npz = the oracle's own outputs (tests/golden/make_golden.py): regression anchor, not parity evidence
     import oracle
     g = golden("oracle_outputs.npz")
     for name in ("noise", "speech"):

@@ -73,7 +73,7 @@ for i, c in enumerate(clips):
     want = SR.lfcc(SR.quantize_int16(c), fs=16000, num_ceps=13)
     assert nf[i] == want.shape[0] and st[i] == 0, (nf[i], want.shape, st[i])
     report(f"lfcc13 default clip{i}", out[i, :nf[i], :], want, 1e-3)
-print("   lin fb diff", np.abs(fe.table(L.TABLE_FILTERBANK) - SR.linear_filter_banks(24, 512, 16000) / 512).max())
+print("   lin fb diff", np.abs(fe.table(L.TABLE_FILTERBANK) - SR.linear_filter_banks(24, 512, 16000)[0] / 512).max())
 
 # ---- LFCC config 3: int16 in, win 320, 20 filt, 20 ceps, deltas, CT layout
 clips16 = [SR.quantize_int16(noise(n)) for n in (16000, 77777, 128000)]
