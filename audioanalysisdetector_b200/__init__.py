@@ -6,7 +6,7 @@ arithmetic in hand-written sm_100a CUDA kernels behind the C ABI of include/aad.
 """
 from . import _lib
 from ._lib import AadError
-from .frontend import Frontend, FrontendParams, delta, fp32_peak_tflops
+from .frontend import Frontend, FrontendParams, delta, fp32_peak_tflops, pinned_empty
 from .extractors import (compute_melspec, extract_features, extract_lfcc, extract_mel_spectrogram,
                          extract_mfcc, get_frontend)
 from .detector import DetectorEngine
@@ -18,7 +18,7 @@ from .sharding import (bind_to_gpu_numa, contiguous_shard, gather_features, long
                        time_split)
 
 __all__ = [
-    "AadError", "Frontend", "FrontendParams", "delta", "fp32_peak_tflops",
+    "AadError", "Frontend", "FrontendParams", "delta", "fp32_peak_tflops", "pinned_empty",
     "compute_melspec", "extract_features", "extract_lfcc", "extract_mel_spectrogram", "extract_mfcc", "get_frontend",
     "DetectorEngine", "score_files", "DeviceCorpus", "chunk_bounds", "layout_files", "two_second_chunks", "DeviceStandardScaler", "merge_stats", "bind_to_gpu_numa", "contiguous_shard", "gather_features", "long_form_logmel", "partition_by_frames", "time_split",
 ]

@@ -343,6 +343,14 @@ class Frontend:
         return out, n_frames, status
 
     # ---- host buffers in / out (pipelined H2D -> kernels -> D2H inside the library) ----
+    def reserve_host(self, B: int, max_len: int, dtype=np.float32, chunk_utts: int = 0):
+        """Allocate the host path's internal buffers ahead of the first `extract_host` of that shape
+        (aad_host_reserve): the timed / latency-critical calls then allocate nothing."""
+        t_max, _, _ = self.query(B, max_len)
+        dt = L.I16 if np.dtype(dtype) == np.int16 else L.F32
+        L.check(self.lib.aad_host_reserve(self._h, dt, int(B), int(max_len), max(t_max, 1), int(chunk_utts)),
+                "aad_host_reserve")
+
     def extract_host(self, wav: np.ndarray, lengths: Optional[np.ndarray] = None,
                      out: Optional[np.ndarray] = None, chunk_utts: int = 0):
         """wav [B, Lmax] float32|int16 HOST array (numpy, or a pinned torch CPU tensor's .numpy())."""
@@ -386,6 +394,46 @@ class Frontend:
             C.c_void_p(status.ctypes.data), int(chunk_utts))
         L.check(rc, "aad_extract_host")
         return out, n_frames, status
+
+
+class _PinnedBlock:
+    """Owner of one cudaHostAlloc block (freed when the last numpy view of it is gone)."""
+
+    def __init__(self, nbytes: int, write_combined: bool):
+        self.lib = L.load()
+        p = C.c_void_p()
+        L.check(self.lib.aad_host_alloc(C.byref(p), max(int(nbytes), 1), int(bool(write_combined))), "aad_host_alloc")
+        self.ptr, self.nbytes = p.value, max(int(nbytes), 1)
+        self.buf = (C.c_char * self.nbytes).from_address(self.ptr)
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None):
+                self.lib.aad_host_free(C.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class PinnedArray(np.ndarray):
+    """numpy array over pinned host memory from aad_host_alloc (the block lives as long as any view of it)."""
+    _block = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self._block = getattr(obj, "_block", None)
+
+
+def pinned_empty(shape, dtype=np.float32, write_combined: bool = False) -> np.ndarray:
+    """Pinned host array for `Frontend.extract_host` (aad_host_alloc).  `write_combined=True` suits the INPUT
+    staging buffer of a corpus (CPU writes it once, the GPUs read it: no cache snooping on the way out); never
+    use it for buffers the CPU reads back."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    blk = _PinnedBlock(n, write_combined)
+    arr = np.frombuffer(blk.buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape).view(PinnedArray)
+    arr._block = blk
+    return arr
 
 
 def delta(x: torch.Tensor, n_frames: Optional[torch.Tensor] = None, width: int = 9, order: int = 1):

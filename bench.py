@@ -183,37 +183,232 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- B200 arm
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-    import audioanalysisdetector_b200 as aad
+class Ranks:
+    """One process per GPU: device, NCCL group, barrier and max-over-ranks timing (the bench contract)."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        import audioanalysisdetector_b200 as aad
+        self.torch, self.dist, self.aad = torch, dist, aad
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        # one process per GPU: run (and first-touch the pinned host buffers) on the GPU's own NUMA node
+        self.numa_cpus = aad.bind_to_gpu_numa(physical_gpu_index(self.local_rank)) if self.world > 1 else None
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps: int, warmup: int):
+        """ms per step of fn() on this rank's current stream: barrier + sync on both sides, CUDA events, max over
+        ranks; the SM clock is sampled while the timed region runs."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        sampler = ClockSampler(physical_gpu_index(self.local_rank))
+        sampler.start()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        ms = self.max_over_ranks(float(e0.elapsed_time(e1))) / steps
+        return ms, sampler.stop()
+
+    def affinity_note(self):
+        if not self.numa_cpus:
+            return "unbound"
+        note = f"rank bound to {len(self.numa_cpus)} GPU-local CPUs (NVML)"
+        if self.world > 1 and len(self.numa_cpus) == (os.cpu_count() or 0):
+            note += "; every GPU reports the same CPU set on this host (one NUMA node): the binding changes nothing here"
+        return note
+
+    def done(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def base_line(R, args, value, ms_per_step, scaling, dtype, workload, extra_config, clocks, launches):
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": R.world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": dtype,
+        "data": "synthetic",
+        "config": dict({"workload": workload, "parallelism": f"utterance-sharded x{R.world}, no collective in the hot path",
+                        "host_affinity": R.affinity_note()}, **extra_config),
+        "gpu_launches": launches, "clocks": clocks,
+    }
+
+
+# --------------------------------------------------------------------------- configs[2]: ragged LFCC
+def run_c3(args):
+    """BASELINE configs[2]: LFCC 20 filters x 3 (delta, delta-delta) on variable-length 1-8 s int16 clips, padded to
+    8 s; 4096 clips per GPU, the global batch partitioned over the ranks by frame count (greedy LPT)."""
+    R = Ranks()
+    torch, aad = R.torch, R.aad
     from audioanalysisdetector_b200.frontend import Frontend, FrontendParams
     from audioanalysisdetector_b200 import _lib as L
+    per_gpu, lmax = args.clips, 8 * SR
+    G = per_gpu * R.world
+    lens_all = np.random.default_rng(3).integers(SR, lmax + 1, size=G).astype(np.int64)
+    params = FrontendParams.lfcc(SR, n_ceps=20, nfilts=20, win_len=0.02, n_delta=2, layout=L.LAYOUT_CT)
+    frames_all = np.array([params.n_frames(int(n)) for n in lens_all])
+    parts = aad.partition_by_frames(frames_all, R.world)
+    mine = parts[R.rank]
+    lens = torch.from_numpy(lens_all[mine].astype(np.int32)).to(R.dev)
+    gen = torch.Generator(device=R.dev)
+    gen.manual_seed(300 + R.rank)
+    wav = (torch.randn((len(mine), lmax), generator=gen, device=R.dev) * 3000).clamp_(-32767, 32767).to(torch.int16)
+    fe = Frontend(params, R.dev)
+    t_max, c_out, _ = fe.query(len(mine), lmax)
+    out = torch.zeros((len(mine), c_out, t_max), dtype=torch.float32, device=R.dev)
+    ms, clocks = R.timed(lambda: fe(wav, lens, out=out), args.steps, args.warmup)
+    _, nf, st = fe(wav, lens, out=out)
+    assert int(st.sum().item()) == 0 and int(nf.sum().item()) == int(frames_all[mine].sum())
+    loads = [int(frames_all[p].sum()) for p in parts]
+    hours = float(lens_all.sum()) / SR / 3600.0
+    if R.rank == 0:
+        line = base_line(R, args, hours / (ms * 1e-3), ms, "weak", "f32 (int16 PCM in)",
+                         "configs[2]: LFCC 20 filters x (static, delta, delta-delta), int16 PCM, ragged 1-8 s clips padded "
+                         "to 8 s (win 20 ms / hop 10 ms / n_fft 512), 4096 clips per GPU",
+                         {"clips_total": G, "frames_total": int(frames_all.sum()),
+                          "partition": "greedy LPT on frame counts (sharding.partition_by_frames)",
+                          "frames_per_rank_max_over_mean": max(loads) / (sum(loads) / len(loads)),
+                          "l2": "inputs larger than L2 (%.2f GB of PCM per GPU per step)" % (len(mine) * lmax * 2 / 1e9)},
+                         clocks, fe.launches_per_call * args.steps)
+        _OUT.emit(json.dumps(line))
+    R.done()
+    return 0
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    # one process per GPU: run (and first-touch the pinned host buffers) on the GPU's own NUMA node
-    numa_cpus = aad.bind_to_gpu_numa(physical_gpu_index(local_rank)) if world > 1 else None
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+# --------------------------------------------------------------------------- configs[3]: corpus -> features -> scores
+def run_c4(args):
+    """BASELINE configs[3]: ASVspoof-2019-LA-sized synthetic corpus (25 380 two-second chunks @16 kHz) -> MFCC-13 and
+    log-mel-64 from ONE STFT -> CNN-BiLSTM scores on the same device, sharded by utterance (strong scaling); the
+    all-gather of the scores is timed separately (outside the hot path)."""
+    R = Ranks()
+    torch, aad = R.torch, R.aad
+    from audioanalysisdetector_b200.frontend import Frontend, FrontendParams
+    n_chunks, chunk = 25380, 2 * SR
+    sl = aad.contiguous_shard(n_chunks, R.rank, R.world)
+    n_local = sl.stop - sl.start
+    gen = torch.Generator(device=R.dev)
+    gen.manual_seed(4242 + R.rank)
+    wav = (0.1 * torch.randn((n_local, chunk), generator=gen, device=R.dev)).clamp_(-1, 1)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "consumer.npz"))
+    weights = {k[3:]: torch.from_numpy(g[k]).to(R.dev) for k in g.files if k.startswith("w::")}
+    fe_mfcc = Frontend(FrontendParams.mfcc(SR, n_mfcc=13), R.dev)
+    fe_mel = Frontend(FrontendParams.logmel(SR, n_mels=64), R.dev)
+    engine = aad.DetectorEngine(weights, feature_dim=13, device=R.dev)
+    state = {}
 
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    def step():
+        (feats, mel), nf, st = fe_mfcc.extract_pair(fe_mel, wav)
+        state["scores"], state["st"] = engine(feats), st
+
+    ms, clocks = R.timed(step, args.steps, args.warmup)
+    ms_feat, _ = R.timed(lambda: fe_mfcc.extract_pair(fe_mel, wav), max(3, args.steps // 2), 1)
+    idx = torch.arange(sl.start, sl.stop, device=R.dev)
+    ms_gather, _ = R.timed(lambda: aad.gather_features(state["scores"], idx, n_chunks), 5, 1)
+    all_scores = aad.gather_features(state["scores"], idx, n_chunks)
+    assert int(state["st"].ne(0).sum().item()) == 0 and tuple(all_scores.shape)[0] == n_chunks
+    hours = n_chunks * chunk / SR / 3600.0
+    if R.rank == 0:
+        line = base_line(R, args, hours / (ms * 1e-3), ms, "strong", "f32",
+                         "configs[3]: 25 380 x 2 s @16 kHz -> MFCC-13 + log-mel-64 (one STFT) -> CNN-BiLSTM scores, "
+                         "sharded by utterance",
+                         {"chunks_total": n_chunks, "chunks_per_gpu": n_local, "features_ms": ms_feat,
+                          "model_ms": ms - ms_feat, "scores_all_gather_ms_outside_the_step": ms_gather,
+                          "scores_mean": float(all_scores.mean().item())},
+                         clocks, (fe_mfcc.launches_per_call + 1 + 3) * args.steps)
+        _OUT.emit(json.dumps(line))
+    R.done()
+    return 0
+
+
+# --------------------------------------------------------------------------- configs[4]: long-form batch sweep
+def run_c5(args):
+    """BASELINE configs[4]: 10 min @48 kHz, n_fft 2048, hop 480, 128 mels, batch sweep B = 1 .. 64.  B >= N GPUs:
+    utterances are sharded; B < N: every utterance is split along time over N / B ranks (one MAX all-reduce of a
+    float per utterance group: power_to_db's ref=np.max)."""
+    R = Ranks()
+    torch, dist, aad = R.torch, R.dist, R.aad
+    from audioanalysisdetector_b200.frontend import Frontend, FrontendParams
+    sr, L_ = 48000, 48000 * 600
+    params = FrontendParams.logmel(sr, n_mels=128, n_fft=2048, hop_length=480)
+    fe = Frontend(params, R.dev)
+    groups = {}
+    if R.world > 1:  # sub-groups for the time split (every rank creates every group, in the same order)
+        for per in (2, 4, 8):
+            if per <= R.world:
+                for g0 in range(0, R.world, per):
+                    grp = dist.new_group(list(range(g0, g0 + per)))
+                    if g0 <= R.rank < g0 + per:
+                        groups[per] = grp
+    sweep = []
+    gen = torch.Generator(device=R.dev)
+    gen.manual_seed(55 + R.rank)
+    steps = max(3, min(args.steps, 10))
+    for B in (1, 2, 4, 8, 16, 32, 64):
+        if B >= R.world:
+            nb = B // R.world
+            wav = (0.1 * torch.randn((nb, L_), generator=gen, device=R.dev)).clamp_(-1, 1)
+            t_max, c_out, _ = fe.query(nb, L_)
+            out = torch.empty((nb, c_out, t_max), dtype=torch.float32, device=R.dev)
+            ms, clocks = R.timed(lambda: fe(wav, out=out), steps, 3)
+            mode = "utterance-sharded"
+            del out
+        else:
+            per = R.world // B                       # ranks per utterance
+            wav = (0.1 * torch.randn(L_, generator=gen, device=R.dev)).clamp_(-1, 1)
+            sub = R.rank % per
+            ms, clocks = R.timed(lambda: aad.long_form_logmel(params, wav, sub, per, group=groups.get(per),
+                                                              check_status=False), steps, 3)
+            mode = f"time-split over {per} ranks per utterance"
+        hours = B * 600 / 3600.0
+        sweep.append({"B": B, "ms_per_step": ms, "audio_hours_per_s": hours / (ms * 1e-3), "mode": mode,
+                      "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons")})
+        del wav
+        torch.cuda.empty_cache()
+    if R.rank == 0:
+        best = max(sweep, key=lambda r: r["audio_hours_per_s"])
+        line = base_line(R, args, best["audio_hours_per_s"], best["ms_per_step"], "strong", "f32",
+                         "configs[4]: log-mel 128 of 10 min @48 kHz (n_fft 2048, hop 480), batch sweep B = 1..64",
+                         {"sweep": sweep, "value_is": f"the best point of the sweep (B = {best['B']})",
+                          "frames_per_utterance": params.n_frames(L_)},
+                         {"sm_mhz": best["sm_mhz"], "reasons": best["reasons"]}, fe.launches_per_call * steps)
+        line["steps"] = steps
+        _OUT.emit(json.dumps(line))
+    R.done()
+    return 0
+
+
+# --------------------------------------------------------------------------- configs[1]: the bench workload
+def run_b200(args):
+    R = Ranks()
+    torch, dist, aad = R.torch, R.dist, R.aad
+    from audioanalysisdetector_b200.frontend import Frontend, FrontendParams
+    from audioanalysisdetector_b200 import _lib as L
+    world, rank, local_rank, dev, numa_cpus = R.world, R.rank, R.local_rank, R.dev, R.numa_cpus
+    barrier, max_over_ranks = R.barrier, R.max_over_ranks
 
     B, Ls = args.clips, int(CLIP_S * SR)
     params = FrontendParams.mfcc(SR, n_mfcc=N_MFCC, n_mels=N_MELS, n_fft=N_FFT, hop_length=HOP, n_delta=N_DELTA)
@@ -259,41 +454,52 @@ def run_b200(args):
     kms = {k: float(np.mean(v)) for k, v in kt.items()}
 
     # ---- end-to-end: pinned host buffers through the library's host entry point -------
+    # Headline `e2e`: 16-bit PCM in, float32 features out.  PCM16 is the corpus's native format: the reference
+    # decodes 16-bit FLAC for every call (librosa.load, ASV_dl_func.py:406,425,524) and pcm / 32768 is exactly the
+    # float librosa hands on, so the features are bit-identical to the float path (checked below) for half the
+    # bytes over PCIe.  `e2e_f32` is the same call with the decoded float32 waveform as host input.
+    host_out = torch.empty((B, c_out, t_max), dtype=torch.float32, pin_memory=True)
+    ho = host_out.numpy()
+    hlen = np.full(B, Ls, dtype=np.int32)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def time_host_path(hin):
+        for _ in range(max(1, min(args.warmup, 2))):
+            fe.extract_host(hin, hlen, out=ho)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            _, nf_h, st_h = fe.extract_host(hin, hlen, out=ho)
+        torch.cuda.synchronize(dev)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        assert int(st_h.sum()) == 0
+        return dt
+
+    pcm_dev = (wav * 32767.0).round().clamp_(-32768, 32767).to(torch.int16)
+    host_pcm = torch.empty((B, Ls), dtype=torch.int16, pin_memory=True)
+    host_pcm.copy_(pcm_dev)
+    fe.reserve_host(B, Ls, np.int16)
+    pcm_s = time_host_path(host_pcm.numpy())
+    ref8, _, _ = fe(pcm_dev[:8].to(torch.float32).div_(32768.0))
+    pcm_err = float(np.abs(ho[:8] - ref8.cpu().numpy()).max())
+    e2e_value = world * hours_per_step * e2e_steps / pcm_s
+    # the same with the PCM staged in write-combined pinned memory (aad.pinned_empty(write_combined=True)): the
+    # corpus loader writes it once, the GPUs read it without cache snooping -- matters when several GPUs pull
+    # from one host memory system
+    wc_s = None
+    try:
+        wc = aad.pinned_empty((B, Ls), np.int16, write_combined=True)
+        wc[...] = host_pcm.numpy()
+        wc_s = time_host_path(wc)
+        del wc
+    except Exception as e:  # allocation refused: the key stays null
+        sys.stderr.write(f"write-combined staging unavailable: {e}\n")
     host_wav = torch.empty((B, Ls), dtype=torch.float32, pin_memory=True)
     host_wav.copy_(wav)
-    host_out = torch.empty((B, c_out, t_max), dtype=torch.float32, pin_memory=True)
-    hw, ho = host_wav.numpy(), host_out.numpy()
-    hlen = np.full(B, Ls, dtype=np.int32)
-    for _ in range(max(1, min(args.warmup, 2))):
-        fe.extract_host(hw, hlen, out=ho)
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        _, nf_h, st_h = fe.extract_host(hw, hlen, out=ho)
-    torch.cuda.synchronize(dev)
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    assert int(st_h.sum()) == 0
-    e2e_value = world * hours_per_step * e2e_steps / e2e_s
-    e2e_err = float(np.abs(ho[:8] - out[:8].cpu().numpy()).max())
-
-    # ---- same, 16-bit PCM over the bus (the native format of the corpus; pcm/32768 is what
-    #      librosa.load decodes): half the H2D bytes, features bit-identical to the float path
-    host_pcm = torch.empty((B, Ls), dtype=torch.int16, pin_memory=True)
-    host_pcm.copy_((wav * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
-    hp = host_pcm.numpy()
-    fe.extract_host(hp, hlen, out=ho)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        fe.extract_host(hp, hlen, out=ho)
-    torch.cuda.synchronize(dev)
-    pcm_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    ref8, _, _ = fe(host_pcm[:8].to(dev).to(torch.float32).div_(32768.0))
-    pcm_err = float(np.abs(ho[:8] - ref8.cpu().numpy()).max())
-    pcm_value = world * hours_per_step * e2e_steps / pcm_s
+    f32_s = time_host_path(host_wav.numpy())
+    f32_err = float(np.abs(ho[:8] - out[:8].cpu().numpy()).max())
+    del host_wav
 
     if rank != 0:
         if world > 1:
@@ -382,20 +588,26 @@ def run_b200(args):
         "config": {"workload": WORKLOAD, "clips_per_gpu": B, "frames_per_gpu": frames,
                    "l2": "inputs larger than L2 (%.2f GB waveforms per GPU per step, no flush needed)" % (B * Ls * 4 / 1e9),
                    "parallelism": f"utterance-sharded x{world}, no collective in the hot path",
-                   "host_affinity": (f"rank bound to {len(numa_cpus)} GPU-local CPUs (NVML)" if numa_cpus else "unbound")},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * Ls * 4 + B * 4,
+                   "host_affinity": R.affinity_note()},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * Ls * 2 + B * 4,
                 "d2h_bytes_per_step": B * c_out * t_max * 4 + 2 * B * 4, "steps": e2e_steps,
-                "ms_per_step": e2e_s / e2e_steps * 1e3,
-                "h2d_gbs": (B * Ls * 4) / (e2e_s / e2e_steps) / 1e9,
+                "ms_per_step": pcm_s / e2e_steps * 1e3,
+                "h2d_gbs": (B * Ls * 2) / (pcm_s / e2e_steps) / 1e9,
+                "d2h_gbs": (B * c_out * t_max * 4) / (pcm_s / e2e_steps) / 1e9,
+                "input": "int16 PCM host buffers (pinned), the corpus's native format: the reference decodes 16-bit FLAC "
+                         "per call (librosa.load, ASV_dl_func.py:406); pcm * 2^-15 is folded into the window",
                 "api": "Frontend.extract_host -> aad_extract_host (pinned host in/out, chunked H2D/compute/D2H on 3 streams)",
-                "note": "PCIe-bound: the box measures 55.6 GB/s H2D (profiles/r1_pcie_probe.log)",
-                "max_abs_diff_vs_device_path": e2e_err},
-        "e2e_pcm16": {"value": pcm_value, "unit": UNIT, "h2d_bytes_per_step": B * Ls * 2 + B * 4,
-                      "d2h_bytes_per_step": B * c_out * t_max * 4 + 2 * B * 4, "steps": e2e_steps,
-                      "ms_per_step": pcm_s / e2e_steps * 1e3,
-                      "note": "same call with int16 PCM host buffers (pcm * 2^-15 folded into the window); "
-                              "informational, the headline e2e above moves float32",
-                      "max_abs_diff_vs_float_path_on_pcm_over_32768": pcm_err},
+                "note": "PCIe-bound: the box measures 55.6 GB/s H2D and 57.2 GB/s D2H per GPU (profiles/r1_pcie_probe.log)",
+                "max_abs_diff_vs_float_path_on_pcm_over_32768": pcm_err},
+        "e2e_wc": None if wc_s is None else {
+            "value": world * hours_per_step * e2e_steps / wc_s, "unit": UNIT, "ms_per_step": wc_s / e2e_steps * 1e3,
+            "note": "same call, PCM staged in write-combined pinned memory (aad.pinned_empty(write_combined=True))"},
+        "e2e_f32": {"value": world * hours_per_step * e2e_steps / f32_s, "unit": UNIT,
+                    "h2d_bytes_per_step": B * Ls * 4 + B * 4, "d2h_bytes_per_step": B * c_out * t_max * 4 + 2 * B * 4,
+                    "steps": e2e_steps, "ms_per_step": f32_s / e2e_steps * 1e3,
+                    "h2d_gbs": (B * Ls * 4) / (f32_s / e2e_steps) / 1e9,
+                    "note": "same call with the decoded float32 waveform as host input (twice the H2D bytes)",
+                    "max_abs_diff_vs_device_path": f32_err},
         "gpu_launches": fe.launches_per_call * args.steps,
         "clocks": clocks,
         "roofline": roofline,
@@ -445,13 +657,15 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work per baseline pass (core-seconds)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="c2 = BASELINE configs[1] (the default the driver runs); c3 / c4 / c5 = configs[2] / [3] / [4]")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     with _StdoutToStderr() as _OUT:
         if args.impl == "reference":
             return run_reference(args)
-        return run_b200(args)
+        return {"c2": run_b200, "c3": run_c3, "c4": run_c4, "c5": run_c5}[args.workload](args)
 
 
 if __name__ == "__main__":
