@@ -42,6 +42,12 @@ class AadParams(C.Structure):
     ]
 
 
+class AadFlacInfo(C.Structure):
+    """mirrors `aad_flac_info_t` (include/aad.h)"""
+    _fields_ = [("sample_rate", C.c_int32), ("channels", C.c_int32), ("bits_per_sample", C.c_int32),
+                ("total_samples", C.c_int64), ("md5", C.c_uint8 * 16)]
+
+
 class AadDetectorWeights(C.Structure):
     """mirrors `struct aad_detector_weights` (include/aad.h)"""
     _FP = C.POINTER(C.c_float)
@@ -94,6 +100,8 @@ SYMBOLS = {
     "aad_extract_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int,
                                    C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                    C.c_void_p, C.c_int]),
+    "aad_flac_info": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(AadFlacInfo)]),
+    "aad_flac_decode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "aad_host_reserve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int32, C.c_int]),
     "aad_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]),
     "aad_host_free": (C.c_int, [C.c_void_p]),

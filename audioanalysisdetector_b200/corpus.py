@@ -3,10 +3,11 @@
 In the reference every 2-second chunk row (`prepare_dataframe`, ASV_dl_func.py:287-293) calls
 `librosa.load(filepath)` on its whole file and then slices `y[start_sample:end_sample]`
 (ASV_dl_func.py:406-411, 425-429, 524-528), once per feature -- file decode dominates its wall time
-(SURVEY.md section 6).  `DeviceCorpus` decodes each distinct file once (16-bit PCM stays int16: half the
-PCIe bytes), puts all files back to back in ONE pinned buffer, uploads it with one copy, and hands the
-kernels a chunk table (element offset + length per row) instead of padded copies: `aad_extract_indexed`
-(include/aad.h).  Noise augmentation (`augment_audio(mode="noise")`, ASV_dl_func.py:78-93) is applied on
+(SURVEY.md section 6).  `DeviceCorpus` decodes each distinct file once (16-bit PCM, WAV or FLAC, stays int16: half the
+PCIe bytes), lays all files back to back in ONE device buffer -- streamed up through two pinned staging
+buffers, the decode of one segment overlapping the H2D copy of the previous one, so the host never holds the
+whole corpus -- and hands the kernels a chunk table (element offset + length per row) instead of padded
+copies: `aad_extract_indexed` (include/aad.h).  Noise augmentation (`augment_audio(mode="noise")`, ASV_dl_func.py:78-93) is applied on
 the device to the rows that ask for it.
 """
 from __future__ import annotations
@@ -22,6 +23,7 @@ from . import audio_io
 from .frontend import Frontend
 
 FILE_ALIGN = 8          # elements: every file starts on a 16-byte (int16) / 32-byte (float32) boundary
+STAGE_BYTES = 64 << 20  # each of the two pinned staging buffers of the streamed upload
 NOISE_FACTOR = 1.022    # augment_audio's default factor for mode="noise" (ASV_dl_func.py:85-86)
 
 
@@ -62,6 +64,7 @@ class DeviceCorpus:
         self._keep: list = []
         self.sample_rates: List[int] = []
         self.n_samples: List[int] = []
+        self._is_i16: List[bool] = []
         self.base: List[int] = []            # element offset of every file inside the device buffer
         self.pcm: Optional[torch.Tensor] = None
         self._pcm_f32: Optional[torch.Tensor] = None
@@ -69,7 +72,9 @@ class DeviceCorpus:
 
     # ---- building -----------------------------------------------------------------
     def add(self, source) -> int:
-        """Decode `source` (path, or an in-memory (waveform, sr) pair) unless it is already here."""
+        """Register `source` (path, or an in-memory (waveform, sr) pair) unless it is already here.  Files are only
+        measured now (`audio_io.info`: header read, as soundfile.info in ASV_dl_func.py:280) and decoded while the
+        corpus is streamed to the device."""
         if isinstance(source, tuple) and len(source) == 2:
             key = (id(source[0]), int(source[1]))     # the waveform object identifies an in-memory clip
         else:
@@ -77,31 +82,79 @@ class DeviceCorpus:
         idx = self._index.get(key)
         if idx is None:
             self._keep.append(source)                 # ids stay unique while the corpus lives
-            y, sr = audio_io.load_pcm(source)
-            if y.dtype != np.int16:
-                y = np.ascontiguousarray(y, dtype=np.float32)
+            if isinstance(source, tuple):
+                y, sr = audio_io.load_pcm(source)
+                y = y if y.dtype == np.int16 else np.ascontiguousarray(y, dtype=np.float32)
+                n, i16 = len(y), y.dtype == np.int16
+            else:
+                y = None                              # decoded in upload()
+                n, sr, i16 = audio_io.info_ex(source)
             idx = self._index[key] = len(self._host)
             self._host.append(y)
             self.sample_rates.append(int(sr))
-            self.n_samples.append(int(len(y)))
+            self.n_samples.append(int(n))
+            self._is_i16.append(bool(i16))
             self.pcm = None
         return idx
 
-    def upload(self) -> torch.Tensor:
-        """One pinned staging buffer, one H2D copy.  int16 when every file is 16-bit PCM, else float32."""
-        if self.pcm is not None:
+    def _decoded(self, i: int) -> np.ndarray:
+        y = self._host[i]
+        if y is None:
+            y, sr = audio_io.load_pcm(self._keep[i])
+            if len(y) != self.n_samples[i] or int(sr) != self.sample_rates[i]:
+                raise L.AadError(f"{self._keep[i]}: header says {self.n_samples[i]} samples @ {self.sample_rates[i]} Hz, "
+                                 f"decoded {len(y)} @ {sr}")
+        return y
+
+    def upload(self, dtype: Optional[torch.dtype] = None, stage_bytes: int = STAGE_BYTES) -> torch.Tensor:
+        """Stream the corpus to the device: files are decoded into one of two pinned staging buffers while the other
+        one's H2D copy is in flight (copy stream + events), segment after segment.  int16 when every file is 16-bit
+        PCM (or `dtype=torch.int16` is forced), else float32 (int16 / 32768)."""
+        if self.pcm is not None and (dtype is None or self.pcm.dtype == dtype):
             return self.pcm
         if not self._host:
             raise L.AadError("empty corpus")
-        all_i16 = all(y.dtype == np.int16 for y in self._host)
         self.base, total = layout_files(self.n_samples)
-        stage = torch.zeros(total, dtype=torch.int16 if all_i16 else torch.float32, pin_memory=True)
-        sv = stage.numpy()
-        for y, b in zip(self._host, self.base):
-            sv[b:b + len(y)] = y if all_i16 or y.dtype != np.int16 else y.astype(np.float32) / 32768.0
-        self.pcm = stage.to(self.device, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()   # the staging buffer is released below
-        self.h2d_bytes = stage.numel() * stage.element_size()
+        if dtype is None:
+            dtype = torch.int16 if all(self._is_i16) else torch.float32
+        esz = 2 if dtype == torch.int16 else 4
+        seg = max(int(stage_bytes) // esz // FILE_ALIGN * FILE_ALIGN, FILE_ALIGN)
+        dev = torch.empty(total, dtype=dtype, device=self.device)
+        stages = [torch.empty(seg, dtype=dtype, pin_memory=True) for _ in range(2 if total > seg else 1)]
+        views = [st.numpy() for st in stages]
+        events = [None] * len(stages)
+        copy_stream = torch.cuda.Stream(self.device)
+        fi, fpos = 0, 0                                # next file and how much of it has been staged
+        cur = None                                     # decoded samples of file fi
+        for k, s0 in enumerate(range(0, total, seg)):
+            n = min(seg, total - s0)
+            b = k % len(stages)
+            if events[b] is not None:
+                events[b].synchronize()                # the copy that last read this staging buffer is done
+            sv = views[b]
+            sv[:n] = 0
+            while fi < len(self.base) and self.base[fi] < s0 + n:
+                if cur is None:
+                    cur = self._decoded(fi)
+                    if dtype == torch.int16 and cur.dtype != np.int16:
+                        raise L.AadError("int16 upload of a corpus with non-16-bit files")
+                    if dtype == torch.float32 and cur.dtype == np.int16:
+                        cur = cur.astype(np.float32) / np.float32(32768.0)
+                d0 = self.base[fi] + fpos - s0          # destination inside this segment
+                take = min(len(cur) - fpos, n - d0)
+                sv[d0:d0 + take] = cur[fpos:fpos + take]
+                fpos += take
+                if fpos < len(cur):
+                    break                              # the file continues in the next segment
+                fi, fpos, cur = fi + 1, 0, None
+            with torch.cuda.stream(copy_stream):
+                dev[s0:s0 + n].copy_(stages[b][:n], non_blocking=True)
+                events[b] = torch.cuda.Event()
+                events[b].record(copy_stream)
+        torch.cuda.current_stream(self.device).wait_stream(copy_stream)
+        copy_stream.synchronize()                      # the staging buffers are released below
+        self.pcm = dev
+        self.h2d_bytes = total * esz
         self._pcm_f32 = None
         return self.pcm
 

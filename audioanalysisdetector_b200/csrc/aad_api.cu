@@ -322,6 +322,7 @@ const char* aad_strerror(int err) {
     case AAD_ERR_KIND: return "plan kind does not match entry point";
     case AAD_ERR_PAIR: return "plans cannot be paired (different STFT, or the second is not a plain log filter bank)";
     case AAD_ERR_FILTERBANK: return "filterbank is not banded (at most two adjacent filters per bin)";
+    case AAD_ERR_FORMAT: return "malformed or unsupported audio stream";
   }
   return "unknown error";
 }

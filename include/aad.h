@@ -68,7 +68,8 @@ enum aad_error {
   AAD_ERR_WORKSPACE = -4, /* workspace too small */
   AAD_ERR_KIND = -5,      /* plan kind does not match the entry point */
   AAD_ERR_FILTERBANK = -6, /* custom filterbank is not two-adjacent-filters-per-bin */
-  AAD_ERR_PAIR = -7        /* aad_extract_pair: the two plans do not share one STFT, or the second is not a plain log filter bank */
+  AAD_ERR_PAIR = -7,       /* aad_extract_pair: the two plans do not share one STFT, or the second is not a plain log filter bank */
+  AAD_ERR_FORMAT = -8      /* aad_flac_*: not a FLAC stream, or a frame fails its CRC / uses a reserved code */
 };
 
 enum aad_item_status { /* status[b] */
@@ -229,6 +230,22 @@ int aad_scaler_accumulate_ragged(const float* x, int B, int32_t rows_per_utt, in
                                  const int32_t* n_frames, const int32_t* status, double* stats, void* stream);
 int aad_scaler_apply(float* x, int64_t n_rows, int32_t W, int64_t row_stride, const float* mean,
                      const float* inv_scale, void* stream);
+
+/* Compressed-audio decode on the input side of the path (HOST pointers, CPU code).  The
+ * reference's corpus (ASVspoof 2019 / 2021) is 16-bit FLAC read through libsndfile: soundfile.info for the chunk
+ * index (ASV_dl_func.py:280), librosa.load in every extractor call (ASV_dl_func.py:406,425,524).
+ *   aad_flac_info:   STREAMINFO of a FLAC stream held in memory (total_samples is per channel; md5 = MD5 of the
+ *                    interleaved little-endian PCM as the encoder saw it, all zero when absent).
+ *   aad_flac_decode: the whole stream as interleaved int32 samples out[n][channels] (sample / 2^(bits-1) is the
+ *                    float librosa.load returns before its mono mix); capacity_samples >= total_samples.  Every
+ *                    frame is checked against its CRC-8 / CRC-16. */
+typedef struct aad_flac_info_t {
+  int32_t sample_rate, channels, bits_per_sample;
+  int64_t total_samples;
+  uint8_t md5[16];
+} aad_flac_info_t;
+int aad_flac_info(const uint8_t* data, size_t size, aad_flac_info_t* info);
+int aad_flac_decode(const uint8_t* data, size_t size, int32_t* out, int64_t capacity_samples, int64_t* n_decoded);
 
 /* Host-buffer convenience path (what the reference-facing Python drop-ins use for
  * host arrays): pinned-or-pageable HOST wav/lengths in, HOST out/n_frames/status back,

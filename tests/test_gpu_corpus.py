@@ -170,3 +170,47 @@ def test_long_form_time_split_equals_the_unsplit_extraction():
         assert covered[0][0] == 0 and covered[-1][1] == T
         got = torch.cat(pieces, dim=1)
         assert got.shape == (128, T) and torch.equal(got, want[0, :, :T])
+
+
+def test_streamed_upload_of_a_flac_and_wav_corpus(tmp_path):
+    """The corpus goes up through two pinned staging buffers (decode of one segment overlaps the copy of the previous
+    one); with a tiny segment size files span segments.  The device buffer must equal the back-to-back layout of
+    the individually decoded files, whatever the segment size, for FLAC (the ASVspoof container) and WAV alike."""
+    import flac_writer as FW
+    from audioanalysisdetector_b200 import DeviceCorpus, FrontendParams, audio_io, layout_files
+    paths, clips = [], []
+    for i, n in enumerate((33000, 4097, 70001, 16000, 5, 52345)):
+        pcm = np.round(speech(40 + i, n) * 32767 * 0.9).astype(np.int16) if i % 2 else \
+            np.round(noise(40 + i, n) * 32767).astype(np.int16)
+        p = tmp_path / (f"LA_{i}.flac" if i % 3 else f"LA_{i}.wav")
+        if p.suffix == ".flac":
+            p.write_bytes(FW.encode(pcm.astype(np.int64), SR, seed=i))
+        else:
+            with wave.open(str(p), "wb") as w:
+                w.setnchannels(1)
+                w.setsampwidth(2)
+                w.setframerate(SR)
+                w.writeframes(pcm.astype("<i2").tobytes())
+        paths.append(str(p))
+        clips.append(pcm)
+    want, base = _flat(clips, np.int16)
+    ups = []
+    for stage_bytes in (64 << 20, 16 * 1024, 4096):
+        corpus = DeviceCorpus("cuda:0")
+        for p in paths:
+            corpus.add(p)
+        assert corpus.n_samples == [len(c) for c in clips] and corpus._host == [None] * len(paths)   # measured, not decoded
+        dev = corpus.upload(stage_bytes=stage_bytes)
+        assert dev.dtype == torch.int16 and corpus.base == base
+        np.testing.assert_array_equal(dev.cpu().numpy(), want)
+        ups.append(corpus)
+    # and the features over a chunk table equal the per-file path
+    corpus = ups[-1]
+    rows = [(0, 0.0, 2.0), (2, 1.0, 3.0), (5, None, None), (3, 0.0, 1.0)]
+    off, ln = corpus.table(rows)
+    feats, nf, st = corpus.extract(_fe(FrontendParams.mfcc(SR, n_mfcc=13)), off, ln)
+    assert int(st.sum()) == 0
+    for k, (f, cs, ce) in enumerate(rows):
+        y, sr = audio_io.load(paths[f])
+        ref = oracle.extract_mfcc_ref(y, sr, chunk_start=cs, chunk_end=ce)
+        assert np.abs(feats[k, :, :nf[k]].cpu().numpy() - ref).max() <= 1e-3
