@@ -461,6 +461,51 @@ def test_long_form_48k_multi_tile(dev):
         assert np.abs(out[i, :, :nf[i]] - want).max() <= TOL_LOG
 
 
+def test_config5_ten_minutes_at_48k_full_length(dev):
+    """BASELINE configs[4] at its stated length: ONE 10-minute 48 kHz utterance, 60 001 frames = 1 876 tiles of a
+    single utterance (the long-utterance path of k_prepare / k_stft_fb), against the oracle over the whole matrix,
+    with a quiet stretch so that the top_db floor is active."""
+    sr, n = 48000, 48000 * 600
+    rng = np.random.default_rng(51)
+    y = np.clip(0.1 * rng.standard_normal(n), -1, 1).astype(np.float32)
+    y[: 20 * sr] *= 1e-5
+    t = np.arange(5 * sr) / sr
+    y[100 * sr:105 * sr] += (0.5 * np.sin(2 * np.pi * 1000 * t)).astype(np.float32)
+    out, nf, st, _ = run(FP().logmel(sr, n_mels=128, n_fft=2048, hop_length=480), [y], dev)
+    want = LR.logmel_db(y, sr, n_mels=128, n_fft=2048, hop_length=480)
+    assert st[0] == 0 and nf[0] == want.shape[1] == 60001
+    err = np.abs(out[0, :, :nf[0]] - want)
+    assert err.max() <= TOL_LOG, float(err.max())
+    assert (want == want.max() - 80.0).mean() > 0.01 and (out[0] == out[0].max() - 80.0).mean() > 0.01   # floor active
+
+
+def test_config3_ragged_4096_clips_full_size(dev):
+    """BASELINE configs[2] at its stated size: 4096 int16 clips of 1-8 s padded to 8 s, LFCC 20 x 3.  Every clip must
+    equal its own extraction as a batch of one (batch invariance over ~1.8 M ragged frames: tiles span utterances),
+    and a random sample of them the oracle."""
+    from audioanalysisdetector_b200.frontend import Frontend
+    L = LIB()
+    B, lmax = 4096, 128000
+    lens = np.random.default_rng(3).integers(16000, lmax + 1, size=B).astype(np.int32)
+    gen = torch.Generator(device=dev).manual_seed(33)
+    wav = (torch.randn((B, lmax), generator=gen, device=dev) * 3000).clamp_(-32767, 32767).to(torch.int16)
+    p = FP().lfcc(16000, n_ceps=20, nfilts=20, win_len=0.02, n_delta=2, layout=L.LAYOUT_CT)
+    fe = Frontend(p, dev)
+    out, nf, st = fe(wav, torch.from_numpy(lens).to(dev))
+    torch.cuda.synchronize()
+    assert int(st.sum()) == 0
+    nfh = nf.cpu().numpy()
+    assert np.array_equal(nfh, (lens - 320) // 160 + 1)
+    pick = np.random.default_rng(4).choice(B, size=48, replace=False)
+    for i in pick:
+        one, nf1, st1 = fe(wav[i:i + 1, :int(lens[i] + 3) // 4 * 4].contiguous(), torch.from_numpy(lens[i:i + 1]).to(dev))
+        assert int(nf1[0]) == nfh[i] and torch.equal(one[0, :, :nfh[i]], out[i, :, :nfh[i]])
+    host = wav[torch.from_numpy(pick[:12]).to(dev)].cpu().numpy()
+    for k, i in enumerate(pick[:12]):
+        want = oracle.lfcc_with_deltas_ref(host[k, :lens[i]], 16000)
+        assert np.abs(out[i, :, :nfh[i]].cpu().numpy() - want).max() <= TOL_LOG
+
+
 def test_host_path_equals_device_path(dev):
     from audioanalysisdetector_b200.frontend import Frontend
     p = FP().mfcc(16000, n_mfcc=40, n_delta=2)
