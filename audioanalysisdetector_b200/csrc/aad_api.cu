@@ -256,6 +256,26 @@ static cudaError_t upload(T** dptr, const std::vector<T>& h) {
   return cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
 }
 
+// Launch with programmatic dependent launch (PDL): the kernel may be scheduled while its predecessor in the stream
+// is still running and executes its own prologue (tensor-memory allocation, table fills) meanwhile; it reaches the
+// predecessor's results only behind `griddepcontrol.wait`.  Hides the launch gaps and K0 behind K1's set-up, which is
+// what a step on a small batch (BASELINE configs[0]: 64 clips) consists of.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- kernel dispatch table --------------------------------------------------
 static stft_kernel_t pick_stft(int L, int tile, int mode, bool pre, bool pair = false) {
   if (tile != 32) return nullptr;
@@ -803,8 +823,13 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
   stft_kernel_t kern = pick_stft(pl->L, pl->tile, mode, p.pre_emph != 0.f, pl2 != nullptr);
   if (!kern) return pl2 ? AAD_ERR_PAIR : AAD_ERR_UNSUPPORTED;
   const long long max_tiles = w.max_tiles;
-  const int grid1 = (int)std::min<long long>((long long)pl->sm_count * pl->ctas, std::max<long long>(max_tiles, 1));
-  kern<<<grid1, pl->warps * 32, pl->k1_smem + (pl2 ? prog_smem_bytes(pl2) : 0), stream>>>(sa);
+  // persistent CTAs take tiles round-robin: with few tiles per CTA shrink the grid so that every CTA gets the same
+  // number (802 tiles on 592 slots would leave 382 CTAs idle during the second round; 401 CTAs x 2 tiles share the
+  // SMs evenly)
+  const long long slots = (long long)pl->sm_count * pl->ctas, nt1 = std::max<long long>(max_tiles, 1);
+  const long long per_cta = (nt1 + slots - 1) / slots;
+  const int grid1 = (int)std::min<long long>(slots, (nt1 + per_cta - 1) / per_cta);
+  launch_pdl(kern, dim3(grid1), dim3(pl->warps * 32), pl->k1_smem + (pl2 ? prog_smem_bytes(pl2) : 0), stream, !prof, sa);
   LAUNCH_CHECK("k_stft_fb launch");
   if (prof) cudaEventRecord(pl->ev[2], stream);
 
@@ -830,7 +855,7 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
     const int gx = t_max <= CEP_TS ? 1 : (t_max + ca.tile_out - 1) / ca.tile_out;
     if ((long long)B * gx > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
     ca.tiles_per_utt = gx;
-    pick_cep(pl->cep_nt)<<<(unsigned)((long long)B * gx), CEP_THREADS, cep_smem_bytes(pl), stream>>>(ca);
+    launch_pdl(pick_cep(pl->cep_nt), dim3((unsigned)((long long)B * gx)), dim3(CEP_THREADS), cep_smem_bytes(pl), stream, !prof, ca);
     LAUNCH_CHECK("k_cepstra launch");
     if (prof) cudaEventRecord(pl->ev[3], stream);
     if (p.time_mean) {
@@ -846,7 +871,7 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
       const int n_chunks = (std::max(t_max, 1) + FIN_CHUNK - 1) / FIN_CHUNK;
       const long long nblk = (long long)B * n_row_blocks * n_chunks;
       if (nblk > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
-      k_db_finalize<<<(unsigned)nblk, 256, 0, stream>>>(fa, n_row_blocks, n_chunks);
+      launch_pdl(k_db_finalize, dim3((unsigned)nblk), dim3(256), 0, stream, !prof, fa, n_row_blocks, n_chunks);
     }
     if (prof) cudaEventRecord(pl->ev[3], stream);
   }

@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepArgs a) {
   __shared__ int warp_sums[32];
   __shared__ int carry_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // programmatic dependent launch: k_stft_fb may start its set-up now; it waits for this grid before it reads anything
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) carry_s = 0;
   __syncthreads();
   for (int base = 0; base < a.B; base += 1024) {
@@ -758,6 +760,9 @@ k_stft_fb(const StftArgs a) {
   FFT fft;
   fft.init(a, lane, tmem_row, sTwp);
   const int4 wprog = a.warp_prog[warp];
+  // everything above read plan tables only; k_prepare's results (frame_off, tile_b0, len_c, utt_max reset) from here on
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the epilogue kernel may queue up behind this grid
   const int total = a.frame_off[a.B];
   const int n_tiles = (total + C::TILE - 1) / C::TILE;
 
@@ -979,6 +984,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], 
 template <int NT>
 __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
   extern __shared__ __align__(16) float smem[];
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // launched behind k_stft_fb (programmatic dependent launch)
   // grid.x = B * tiles_per_utt, utterance-major: consecutive CTAs read neighbouring tiles of one utterance
   const int b = blockIdx.x / a.tiles_per_utt, tile = blockIdx.x - b * a.tiles_per_utt;
   const int T = a.nf_eff[b];
@@ -1189,6 +1195,7 @@ constexpr int FIN_ROWS = 8;      // filter rows per CTA (one per warp)
 constexpr int FIN_CHUNK = 1024;  // frames per CTA
 // grid.x = B * n_row_blocks * n_chunks (flattened, utterance-major)
 __global__ void __launch_bounds__(256) k_db_finalize(const FinArgs a, int n_row_blocks, int n_chunks) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // a no-op unless launched as a programmatic dependent
   const int per_b = n_row_blocks * n_chunks;
   const int b = blockIdx.x / per_b, r = blockIdx.x - b * per_b;
   const int f = (r / n_chunks) * FIN_ROWS + (threadIdx.x >> 5);

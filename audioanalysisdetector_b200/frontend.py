@@ -244,6 +244,36 @@ class Frontend:
         L.check(rc, "aad_extract")
         return out, n_frames, status
 
+    # ---- repeated shapes: the whole call as one CUDA graph ------------------------------------------
+    def graph(self, wav: torch.Tensor, lengths: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+        """Capture this call (K0 -> K1 -> K2, programmatic-dependent-launch edges included) into a CUDA graph for
+        repeated batches of one shape, e.g. a serving loop on small batches where the three launches and the
+        per-call tensor allocations are a large part of the step.  `wav` / `lengths` / `out` are the STATIC buffers
+        of the graph: copy each new batch into them, then `replay()`.
+
+        Returns an object with `.replay()`, `.out`, `.n_frames`, `.status`, `.wav`, `.lengths`."""
+        B, Lmax = wav.shape
+        if lengths is None:
+            lengths = torch.full((B,), Lmax, dtype=torch.int32, device=self.device)
+        if out is None:
+            out = self(wav, lengths)[0]           # allocates the output (and grows the workspace) outside the capture
+        else:
+            self(wav, lengths, out=out)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.graph(g, stream=side):
+            res = self(wav, lengths, out=out)
+
+        class Graphed:
+            pass
+        r = Graphed()
+        r.graph, r.replay = g, g.replay
+        r.wav, r.lengths = wav, lengths
+        r.out, r.n_frames, r.status = res
+        return r
+
     # ---- one STFT, two features -------------------------------------------------------
     def extract_pair(self, other: "Frontend", wav: torch.Tensor, lengths: Optional[torch.Tensor] = None,
                      offsets: Optional[torch.Tensor] = None, max_len: Optional[int] = None):

@@ -231,3 +231,24 @@ def test_asv_func_signatures_default_to_the_time_mean(files):
     want = oracle.extract_lfcc_ref(y, sr, **kw)
     assert got.shape == want.shape == (198, 13) and np.abs(got - want).max() <= 1e-3
     assert af.extract_lfcc(files[0], chunk_start=100.0, chunk_end=102.0) is None
+
+
+def test_cuda_graph_replay_equals_the_direct_call():
+    """Frontend.graph: K0 -> K1 -> K2 (with their programmatic-dependent-launch edges) captured once, replayed on new
+    contents of the static buffers."""
+    from audioanalysisdetector_b200 import Frontend, FrontendParams
+    dev = torch.device("cuda:0")
+    fe = Frontend(FrontendParams.mfcc(16000, n_mfcc=13, n_delta=2), dev)
+    a = torch.from_numpy(np.stack([noise(200 + i, 24000) for i in range(6)])).to(dev)
+    b = torch.from_numpy(np.stack([speech(300 + i, 24000) for i in range(6)])).to(dev)
+    lens = torch.tensor([24000, 20000, 5000, 24000, 100, 12345], dtype=torch.int32, device=dev)
+    g = fe.graph(a.clone(), lens.clone())
+    for src in (a, b, a):
+        g.wav.copy_(src)
+        g.replay()
+        want, nf, st = fe(src, lens)
+        torch.cuda.synchronize()
+        assert torch.equal(g.n_frames, nf) and torch.equal(g.status, st)
+        for i in range(6):
+            if int(st[i]) == 0:
+                assert torch.equal(g.out[i, :, :int(nf[i])], want[i, :, :int(nf[i])])

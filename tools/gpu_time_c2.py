@@ -34,6 +34,17 @@ if "--quick" in sys.argv:
 timeit("C2b mfcc40+d+dd 512/160/80", FrontendParams.mfcc(16000, n_mfcc=40, n_mels=80, n_fft=512, hop_length=160, n_delta=2), wav)
 timeit("C1 logmel80 512/160 (B=4096)", FrontendParams.logmel(16000, n_mels=80, n_fft=512, hop_length=160), wav)
 timeit("C1 logmel80 512/160 (B=64)", FrontendParams.logmel(16000, n_mels=80, n_fft=512, hop_length=160), wav[:64].contiguous(), iters=50)
+# the same as a CUDA graph replay on static buffers: what the three launches cost without per-call allocations
+fe64 = Frontend(FrontendParams.logmel(16000, n_mels=80, n_fft=512, hop_length=160), dev)
+g64 = fe64.graph(wav[:64].contiguous())
+for _ in range(5): g64.replay()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(200): g64.replay()
+e1.record(); torch.cuda.synchronize()
+ref64 = fe64(wav[:64].contiguous())[0]
+print(f"C1 logmel80 512/160 (B=64) graph   {e0.elapsed_time(e1) / 200:8.4f} ms/step  (replay equals the direct call: {bool(torch.equal(ref64, g64.out))})", flush=True)
 # C3: variable-length int16 LFCC 20x3
 lens = torch.randint(16000, 128001, (4096,), generator=torch.Generator().manual_seed(3)).to(torch.int32)
 w16 = (wav[:, :1].new_empty((4096, 128000)).normal_(generator=g) * 3000).clamp_(-32767, 32767).to(torch.int16)
