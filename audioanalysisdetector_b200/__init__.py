@@ -14,11 +14,12 @@ from .corpus import DeviceCorpus, chunk_bounds, layout_files, two_second_chunks
 from . import asv_func, train_fun  # noqa: F401  (drop-ins for the older ASV_func.py / train_fun.py signatures)
 from .pipeline import score_files
 from .scaler import DeviceStandardScaler, merge_stats
+from .training import DeviceFeatureLoader
 from .sharding import (bind_to_gpu_numa, contiguous_shard, gather_features, long_form_logmel, partition_by_frames,
                        time_split)
 
 __all__ = [
     "AadError", "Frontend", "FrontendParams", "delta", "fp32_peak_tflops", "pinned_empty",
     "compute_melspec", "extract_features", "extract_lfcc", "extract_mel_spectrogram", "extract_mfcc", "get_frontend",
-    "DetectorEngine", "score_files", "DeviceCorpus", "chunk_bounds", "layout_files", "two_second_chunks", "DeviceStandardScaler", "merge_stats", "bind_to_gpu_numa", "contiguous_shard", "gather_features", "long_form_logmel", "partition_by_frames", "time_split",
+    "DetectorEngine", "score_files", "DeviceCorpus", "chunk_bounds", "layout_files", "two_second_chunks", "DeviceStandardScaler", "merge_stats", "DeviceFeatureLoader", "bind_to_gpu_numa", "contiguous_shard", "gather_features", "long_form_logmel", "partition_by_frames", "time_split",
 ]

@@ -233,3 +233,55 @@ def test_detector_weight_packing_validates_the_state_dict():
     with pytest.raises(AadError):
         pack_weights(bad, 13)
     assert set(_SHAPES) == set(_NAMES)
+
+
+def test_device_feature_loader_feeds_a_train_loop_like_the_reference():
+    """DeviceFeatureLoader stands in for CQCCDataset + DataLoader (cnn_bilstm_hybrid.py:4-15) in train_loop
+    (ASV_dl_func.py:751-829): (X [n, F, 63], y [n, 1]) batches, every kept item once per epoch, failed items dropped;
+    one epoch of the reference's loop body (restated: BCE on a sigmoid output) runs on them and learns."""
+    import torch
+    from audioanalysisdetector_b200 import DeviceFeatureLoader
+    from oracle import consumer_ref
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "consumer.npz"))
+    weights = {k[3:]: torch.from_numpy(g[k]).clone() for k in g.files if k.startswith("w::")}
+    for k, w in weights.items():
+        if w.dtype.is_floating_point and "running" not in k:
+            w.requires_grad_(True)
+    rng = np.random.default_rng(0)
+    N = 45
+    labels = rng.integers(0, 2, size=N)
+    feats = torch.from_numpy(rng.standard_normal((N, 13, 63)).astype(np.float32))
+    feats[labels == 1] += 0.8                                       # separable on purpose
+    status = torch.zeros(N, dtype=torch.int32)
+    status[[3, 17]] = 2                                             # extractor returned None for these
+    loader = DeviceFeatureLoader(feats, labels, batch_size=16, shuffle=True, status=status, seed=1)
+    assert len(loader) == 3 and loader.dataset_size == N - 2
+    seen = []
+    for X, y in loader:
+        assert X.shape[1:] == (13, 63) and X.dtype == torch.float32 and y.shape == (X.shape[0], 1) and y.dtype == torch.float32
+        seen.append(X[:, 0, 0])
+    got = torch.sort(torch.cat(seen)).values
+    keep = [i for i in range(N) if i not in (3, 17)]
+    assert torch.equal(got, torch.sort(feats[keep, 0, 0]).values)   # every kept item exactly once
+    flat = DeviceFeatureLoader(feats, labels, batch_size=50, label_shape="flat")
+    (Xa, ya), = list(flat)
+    assert ya.dtype == torch.int64 and ya.shape == (N,) and torch.equal(Xa, feats)
+    # the loop body of train_loop: forward, BCE (the model ends in a sigmoid), backward, step
+    params = [w for w in weights.values() if w.requires_grad]
+    opt = torch.optim.Adam(params, lr=3e-3)
+    crit = torch.nn.BCELoss()
+
+    def epoch():
+        total, n = 0.0, 0
+        for X, y in loader:
+            opt.zero_grad()
+            out = consumer_ref.forward(weights, X)
+            loss = crit(out.reshape(-1, 1), y)
+            loss.backward()
+            opt.step()
+            total, n = total + float(loss) * len(y), n + len(y)
+        return total / n
+    first = epoch()
+    for _ in range(6):
+        last = epoch()
+    assert last < first
