@@ -18,7 +18,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libaad_b200.so")
 # (source, extra defines)
-UNITS = [("aad_api.cu", []), ("aad_detector.cu", []), ("aad_flac.cpp", [])] + [("aad_stft_inst.cu", [f"-DAAD_INST_L={L}"]) for L in (32, 8, 16, 4)]
+UNITS = [("aad_api.cu", []), ("aad_detector.cu", []), ("aad_flac.cpp", []), ("aad_cqcc.cu", [])] + [("aad_stft_inst.cu", [f"-DAAD_INST_L={L}"]) for L in (32, 8, 16, 4)]
 SOURCES = sorted({os.path.join(CSRC, u) for u, _ in UNITS})
 HEADERS = [os.path.join(CSRC, "aad_kernels.cuh"), os.path.join(CSRC, "aad_fft.cuh"), os.path.join(CSRC, "aad_stft_inst.h"),
            os.path.join(os.path.dirname(PKG_DIR), "include", "aad.h")]

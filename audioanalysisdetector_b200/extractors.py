@@ -173,6 +173,51 @@ def extract_lfcc(filepath, chunk_start=None, chunk_end=None, n_ceps=13, mean=Fal
         return None
 
 
+_CQCC_PLANS: dict = {}
+
+
+def get_cqcc_frontend(sr: int, bins_per_octave: int = 12, n_ceps: int = 19, device=None):
+    """Cached CQCC plan per (sample rate, bins per octave, n_ceps, device)."""
+    from .cqcc import CqccFrontend
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (int(sr), int(bins_per_octave), int(n_ceps), str(dev))
+    fe = _CQCC_PLANS.get(key)
+    if fe is None:
+        fe = _CQCC_PLANS[key] = CqccFrontend(sr, bins_per_octave, n_ceps, dev)
+    return fe
+
+
+def extract_cqcc_batch(clips: Sequence[np.ndarray], sr: int, bins_per_octave: int = 12, n_ceps: int = 19):
+    """CQCCs of a list of float32 clips in one GPU call -> list of (n_ceps, T) arrays (None on item error)."""
+    fe = get_cqcc_frontend(sr, bins_per_octave, n_ceps)
+    B = len(clips)
+    lens = np.array([len(c) for c in clips], dtype=np.int32)
+    Lmax = (max(int(lens.max()), 1) + 3) // 4 * 4
+    host = _pinned_stage(B * Lmax)[:B * Lmax].view(B, Lmax)
+    hv = host.numpy()
+    for i, c in enumerate(clips):
+        hv[i, :len(c)] = c
+        hv[i, len(c):] = 0.0
+    feats, n_frames, status = fe(host.to(fe.device, non_blocking=True), torch.from_numpy(lens).to(fe.device))
+    feats, n_frames, status = feats.cpu().numpy(), n_frames.cpu().numpy(), status.cpu().numpy()
+    return [feats[i, :, :n_frames[i]].copy() if status[i] == 0 else None for i in range(B)], status
+
+
+def extract_cqcc(filepath, chunk_start=None, chunk_end=None, sr=None, bins_per_octave=12, n_ceps=19, mean=False,
+                 augment=None):
+    """ASV_dl_func.py:442-481: (n_ceps, T) float32, T = 1 + len(y) // 512 (63 for a 2-second 16 kHz chunk: the
+    `(19, 63)` input of the reference's CNN-BiLSTM), or its time mean; None (and a printed line) on any error."""
+    try:
+        y, sr = _prepare_clip(filepath, chunk_start, chunk_end, sr, augment)
+        out, status = extract_cqcc_batch([y], sr, bins_per_octave, n_ceps)
+        if out[0] is None:
+            raise ValueError(L.ITEM_STATUS_NAMES.get(int(status[0]), "item failed"))
+        return np.mean(out[0], axis=1) if mean else out[0]
+    except Exception as e:
+        print(f"[BŁĄD CQCC] {filepath if isinstance(filepath, str) else '<array>'}: {e}")
+        return None
+
+
 # how extract_features batches each recognised extractor: (params builder, post-processing, tag)
 _BATCHED = {
     extract_mel_spectrogram: ("MEL", lambda sr, mean: _mel_params(sr, 64, None, mean), lambda x, mean: x),
