@@ -55,52 +55,108 @@ __device__ __forceinline__ float load_sample(const void* wav, int i16, long long
              : __ldg(static_cast<const float*>(wav) + idx);
 }
 
+// The resampler's taps are one fixed design (255-tap Kaiser half band): they live in constant memory so that the
+// unrolled filter reads them through the uniform datapath (LDCU -> uniform-register operand of FFMA2), not through
+// the shared-memory pipe.  Only the taps at odd offsets from the centre (and the centre) are non-zero:
+// half[i] = h[2 i], i = 0 .. 127.  The kernel accumulates output PAIRS with packed FMAs, which need (half[i], half[i-1])
+// as one aligned 64-bit operand: c_pa[t] = (R[2 t], R[2 t + 1]), c_pb[t] = (R[2 t + 1], R[2 t + 2]) over the reversed,
+// zero-padded array R[j] = half[128 - j] (R[0] = R[129..] = 0), so that (half[i], half[i-1]) = (R[128 - i], R[129 - i]).
+__constant__ float2 c_pa[66];
+__constant__ float2 c_pb[66];
+__constant__ float c_centre;
+
 // y_out[b][n] = sqrt(2) * sum_k h[k] * y_in[b][2 n + k - 127],  n < ceil(len_in / 2); zero outside [0, len_in).
-// grid (chunks of 256 outputs, B); the 766 inputs of a chunk are staged in shared memory.
-__global__ void __launch_bounds__(256) k_cqt_resample(const void* in, int in_i16, long long in_stride, float* out,
-                                                      long long out_stride, const int32_t* lengths, int shift,
-                                                      const float* taps) {
-  __shared__ float sIn[2 * 256 + kTaps + 1];
-  __shared__ float sH[kTaps + 1];
+// Even k reach odd input offsets: with the inputs de-interleaved (sE[j] = in[base + 2 j + 1], sO[j] = in[base + 2 j + 2],
+// base = 2 n0 - 128) output n0 + m is  sqrt(2) (sum_i half[i] sE[m + i] + c_centre sO[m + 63]).  A thread owns EIGHT
+// consecutive outputs as four packed accumulators: every float4 it reads from sE feeds 16 FFMA2 whose tap pairs are
+// uniform-register operands.  sE is skewed by 4 words per 32 so that the stride-8 float4 reads of a quarter warp
+// fall into 8 bank groups.  Rows of the octave buffers carry pad_in / pad_out zeros in front and n_fft zeros behind
+// the signal (written here), so that every CQT frame of the lower octaves is an interior frame.
+// grid (chunks of 1024 outputs, B), 128 threads.
+constexpr int kRsOut = 1024, kRsPer = 8, kRsIn = kRsOut + 128 + 8;
+__device__ __forceinline__ int rs_skew(int j) { return j + 4 * (j >> 5); }
+__global__ void __launch_bounds__(128) k_cqt_resample(const void* in, int in_i16, long long in_stride, int pad_in, float* out,
+                                                      long long out_stride, int pad_out, int tail_out,
+                                                      const int32_t* lengths, int shift) {
+  __shared__ __align__(16) float sE[kRsIn + 4 * (kRsIn / 32) + 8];
+  __shared__ float sO[kRsIn];
   const int b = blockIdx.y;
   long long len0 = lengths[b];
   if (len0 < 0) len0 = 0;
   long long len_in = len0;
   for (int s = 0; s < shift; ++s) len_in = (len_in + 1) >> 1;  // length at the input octave
   const long long len_out = (len_in + 1) >> 1;
-  const long long n0 = (long long)blockIdx.x * 256;
-  if (n0 >= len_out) return;
-  for (int i = threadIdx.x; i < kTaps; i += 256) sH[i] = taps[i];
-  const long long base = 2 * n0 - (kTaps - 1) / 2;
-  for (int i = threadIdx.x; i < 2 * 256 + kTaps - 1; i += 256) {
-    const long long src = base + i;
-    sIn[i] = (src >= 0 && src < len_in) ? load_sample(in, in_i16, (long long)b * in_stride + src) : 0.f;
+  const long long n0 = (long long)blockIdx.x * kRsOut;
+  float* orow = out + (long long)b * out_stride;
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < pad_out; i += 128) orow[i] = 0.f;
+  if (n0 >= len_out + tail_out) return;
+  if (n0 >= len_out) {  // only zeros behind the signal in this chunk
+    for (int i = threadIdx.x; i < kRsOut; i += 128)
+      if (n0 + i < len_out + tail_out) orow[pad_out + n0 + i] = 0.f;
+    return;
+  }
+  const long long base = 2 * n0 - (kTaps - 1) / 2 - 1;
+  const long long irow = (long long)b * in_stride + pad_in;
+  for (int i = threadIdx.x; i < kRsIn; i += 128) {
+    const long long s0 = base + 2 * i + 1, s1 = s0 + 1;
+    sE[rs_skew(i)] = (s0 >= 0 && s0 < len_in) ? load_sample(in, in_i16, irow + s0) : 0.f;
+    sO[i] = (s1 >= 0 && s1 < len_in) ? load_sample(in, in_i16, irow + s1) : 0.f;
   }
   __syncthreads();
-  const long long n = n0 + threadIdx.x;
-  if (n >= len_out) return;
-  const float* x = sIn + 2 * threadIdx.x;
-  float acc = sH[(kTaps - 1) / 2] * x[(kTaps - 1) / 2];
-#pragma unroll 8
-  for (int k = 0; k < kTaps; k += 2) acc = __fmaf_rn(sH[k], x[k], acc);  // odd offsets from the centre (centre = 127)
-  out[(long long)b * out_stride + n] = 1.41421356237309515f * acc;
+  const int m0 = kRsPer * threadIdx.x;
+  float2 acc[kRsPer / 2];
+#pragma unroll
+  for (int p = 0; p < kRsPer / 2; ++p) acc[p] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int r = 0; r < (128 + kRsPer + 2) / 4; ++r) {
+    const float4 v = *reinterpret_cast<const float4*>(sE + rs_skew(m0 + 4 * r));
+    const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int q = 4 * r + e;  // sE index relative to m0: feeds outputs (2 p, 2 p + 1) with taps (i, i - 1), i = q - 2 p
+#pragma unroll
+      for (int p = 0; p < kRsPer / 2; ++p) {
+        const int i = q - 2 * p;
+        if (i >= 0 && i <= 128) {
+          const int sidx = 128 - i;  // (half[i], half[i - 1]) = (R[sidx], R[sidx + 1])
+          const float2 tp = (sidx & 1) ? c_pb[sidx >> 1] : c_pa[sidx >> 1];
+          acc[p] = __ffma2_rn(make_float2(x[e], x[e]), tp, acc[p]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < kRsPer; ++m) {
+    const float a = (m & 1) ? acc[m >> 1].y : acc[m >> 1].x;
+    const float r = __fmaf_rn(c_centre, sO[m0 + m + 63], a);
+    const long long n = n0 + m0 + m;
+    if (n < len_out) orow[pad_out + n] = 1.41421356237309515f * r;
+    else if (n < len_out + tail_out) orow[pad_out + n] = 0.f;
+  }
 }
 
-// One octave: mag[b][bin0 + k][t] = | sum_n g[k][n] * y[b][t * hop - n_fft / 2 + n] |  for the n_k bins of the octave.
-// grid (frame blocks of 8, B); thread = (frame in block, bin): 8 x n_k <= 96 threads.  The 8 frames are staged in
-// shared memory with an odd row stride (frames are hop apart, a multiple of 32 words in the top octaves).
-constexpr int kFramesPerCta = 8;
-__global__ void __launch_bounds__(128) k_cqt_octave(const void* y, int y_i16, long long y_stride, const int32_t* lengths,
-                                                    int shift, int hop, int n_fft, const float2* g, int n_k, int bin0,
-                                                    float* mag, long long mag_stride_b, int t_alloc, int32_t* utt_max) {
-  extern __shared__ float smem[];
-  float* sY = smem;                                             // [8][n_fft + 1]
-  float2* sG = reinterpret_cast<float2*>(smem + ((kFramesPerCta * (n_fft + 1) + 1) & ~1));  // [n_fft][n_k]
+// One octave: mag[b][bin0 + k][t] = | sum_n g[k][n] * y[b][pad + t * hop - n_fft / 2 + n] |  for the n_k bins of the octave.
+// Thread = (bin k, group of 4 frames); a CTA of 16 x n_k threads covers 64 frames of one utterance.  Only the taps are
+// staged in shared memory (once per CTA); the frames are read where they lie with one 16-byte load per frame and
+// 4 samples -- the n_k threads of a frame group read the same address (one broadcast transaction) and the frames of
+// the lower octaves overlap, so these loads are L1 hits -- which feeds 16 FFMA2 per 8 loads.  The octave buffers are
+// padded (pad = n_fft / 2 zeros in front, n_fft behind), so every frame of octaves >= 1 is interior; in octave 0 (the
+// caller's waveform) the first and the last frames of an utterance take the masked path.  (The first version
+// staged the frames in shared memory as well: two CTAs per SM, two barriers per block, 22 ms for the seven octaves
+// of the 25 380-chunk corpus.)  grid (frame blocks of 64, B).
+constexpr int kOctFrames = 64;
+__global__ void __launch_bounds__(16 * 24) k_cqt_octave(const void* y, int y_i16, long long y_stride, int pad,
+                                                        const int32_t* lengths, int shift, int hop, int n_fft, const float2* g,
+                                                        int n_k, int bin0, float* mag, long long mag_stride_b, int t_alloc,
+                                                        int32_t* utt_max) {
+  extern __shared__ __align__(16) float smem[];
+  float2* sG = reinterpret_cast<float2*>(smem);                  // [n_fft][n_k]
   const int b = blockIdx.y;
-  long long len0 = lengths[b];
+  const long long len0 = lengths[b];
   if (len0 <= 0) return;
   const int T = (int)min((long long)t_alloc, 1 + len0 / kHop);  // frames of the utterance (all octaves are trimmed to it)
-  const int t0 = blockIdx.x * kFramesPerCta;
+  const int t0 = blockIdx.x * kOctFrames;
   if (t0 >= T) return;
   long long len = len0;
   for (int s = 0; s < shift; ++s) len = (len + 1) >> 1;
@@ -108,25 +164,72 @@ __global__ void __launch_bounds__(128) k_cqt_octave(const void* y, int y_i16, lo
     const int n = i / n_k, k = i - n * n_k;
     sG[i] = __ldg(g + (size_t)k * n_fft + n);
   }
-  for (int i = threadIdx.x; i < kFramesPerCta * n_fft; i += blockDim.x) {
-    const int f = i / n_fft, n = i - f * n_fft;
-    const long long src = (long long)(t0 + f) * hop - n_fft / 2 + n;
-    sY[f * (n_fft + 1) + n] = (t0 + f < T && src >= 0 && src < len) ? load_sample(y, y_i16, (long long)b * y_stride + src) : 0.f;
-  }
   __syncthreads();
-  const int f = threadIdx.x / n_k, k = threadIdx.x - f * n_k;
-  if (f >= kFramesPerCta || t0 + f >= T) return;
-  const float* yr = sY + f * (n_fft + 1);
-  float2 a0 = make_float2(0.f, 0.f), a1 = a0;
-  for (int n = 0; n < n_fft; n += 2) {
-    a0 = __ffma2_rn(make_float2(yr[n], yr[n]), sG[n * n_k + k], a0);
-    a1 = __ffma2_rn(make_float2(yr[n + 1], yr[n + 1]), sG[(n + 1) * n_k + k], a1);
+  const int k = threadIdx.x % n_k, fg = threadIdx.x / n_k;       // fg < 16
+  const int tb = t0 + 4 * fg;
+  if (tb >= T) return;
+  float2 acc[4];
+  long long s0[4];  // first sample of each of the thread's frames, relative to the signal's first sample
+  const bool vec_ok = !y_i16 && (y_stride & 3) == 0 && (hop & 3) == 0 && (n_fft & 7) == 0 && (pad & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+  bool fast = vec_ok;
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    acc[f] = make_float2(0.f, 0.f);
+    s0[f] = (long long)(tb + f) * hop - n_fft / 2;
+    if (tb + f >= T) s0[f] = pad > 0 ? 0 : (max(0ll, len - n_fft) & ~3ll);  // a frame that is not stored: read anything valid (aligned)
+    if (pad == 0) fast = fast && s0[f] >= 0 && s0[f] + n_fft <= len;
   }
-  const float re = a0.x + a1.x, im = a0.y + a1.y;
-  const float m = sqrtf(__fmaf_rn(re, re, im * im));
-  mag[(long long)b * mag_stride_b + (long long)(bin0 + k) * t_alloc + t0 + f] = m;
-  if (m == m) atomicMax(utt_max + b, __float_as_int(m));        // non-negative floats order like their bit patterns
-  else atomicMax(utt_max + b, 0x7fc00000);                      // NaN poisons the utterance
+  const long long row = (long long)b * y_stride + pad;
+  if (fast) {
+    const float* yf = static_cast<const float*>(y) + row;
+    for (int n = 0; n < n_fft; n += 4) {
+      float2 gg[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) gg[e] = sG[(n + e) * n_k + k];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(yf + s0[f] + n));
+        acc[f] = __ffma2_rn(make_float2(v.x, v.x), gg[0], acc[f]);
+        acc[f] = __ffma2_rn(make_float2(v.y, v.y), gg[1], acc[f]);
+        acc[f] = __ffma2_rn(make_float2(v.z, v.z), gg[2], acc[f]);
+        acc[f] = __ffma2_rn(make_float2(v.w, v.w), gg[3], acc[f]);
+      }
+    }
+  } else {  // frames touching the zero padding of the caller's waveform, int16 input, unaligned rows
+    for (int n = 0; n < n_fft; n += 4) {
+      float2 gg[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) gg[e] = sG[(n + e) * n_k + k];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const long long src = s0[f] + n;
+        float v[4];
+        if (vec_ok && src >= 0 && src + 4 <= len) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(y) + row + src));
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = (src + e >= 0 && src + e < len) ? load_sample(y, y_i16, row + src + e) : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[f] = __ffma2_rn(make_float2(v[e], v[e]), gg[e], acc[f]);
+      }
+    }
+  }
+  float vmax = 0.f;
+  bool poison = false;
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    if (tb + f < T) {
+      const float m = sqrtf(__fmaf_rn(acc[f].x, acc[f].x, acc[f].y * acc[f].y));
+      mag[(long long)b * mag_stride_b + (long long)(bin0 + k) * t_alloc + tb + f] = m;
+      if (m == m) vmax = fmaxf(vmax, m);
+      else poison = true;
+    }
+  }
+  // non-negative floats order like their bit patterns; a NaN poisons the utterance
+  atomicMax(utt_max + b, poison ? 0x7fc00000 : __float_as_int(vmax));
 }
 
 // dB relative to the utterance maximum (floor -80) -> interpolation onto the uniform frequency grid -> log(x^2 + 1e-12)
@@ -206,7 +309,6 @@ struct aad_cqcc_plan {
   int n_k[kMaxOct] = {0};           // bins of octave i (top first)
   int bin0[kMaxOct] = {0};
   float2* d_g[kMaxOct] = {nullptr}; // [n_k][n_fft] taps of octave i
-  float* d_taps = nullptr;          // resampler
   int32_t* d_interp_lo = nullptr;
   float* d_interp_w = nullptr;
   float* d_dct = nullptr;           // [n_ceps][n_bins]
@@ -219,7 +321,6 @@ int aad_cqcc_plan_destroy(aad_cqcc_plan* pl) {
   if (!pl) return AAD_OK;
   DeviceGuard guard(pl->device);
   for (auto& p : pl->d_g) cudaFree(p);
-  cudaFree(pl->d_taps);
   cudaFree(pl->d_interp_lo);
   cudaFree(pl->d_interp_w);
   cudaFree(pl->d_dct);
@@ -356,10 +457,18 @@ int aad_cqcc_plan_create(int sample_rate, int bins_per_octave, int n_ceps, int d
       h[i] = 0.5 * sinc * bessel_i0(14.0 * std::sqrt(std::max(0.0, 1 - rr * rr))) / bessel_i0(14.0);
       sum += h[i];
     }
-    std::vector<float> hf(kTaps);
-    for (int i = 0; i < kTaps; ++i) hf[i] = (float)(h[i] / sum);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&pl->d_taps, kTaps * sizeof(float));
-    if (e == cudaSuccess) e = cudaMemcpy(pl->d_taps, hf.data(), kTaps * sizeof(float), cudaMemcpyHostToDevice);
+    // R[j] = half[128 - j] = h[2 (128 - j)] / sum for j = 1 .. 128, zero elsewhere
+    std::vector<float> R(134, 0.f);
+    for (int j = 1; j <= 128; ++j) R[j] = (float)(h[2 * (128 - j)] / sum);
+    std::vector<float2> pa(66), pb(66);
+    for (int t = 0; t < 66; ++t) {
+      pa[t] = make_float2(R[2 * t], R[2 * t + 1]);
+      pb[t] = make_float2(R[2 * t + 1], R[2 * t + 2]);
+    }
+    const float centre = (float)(h[(kTaps - 1) / 2] / sum);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_pa, pa.data(), 66 * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_pb, pb.data(), 66 * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_centre, &centre, sizeof(float));
   }
   // interpolation onto np.linspace(f[0], f[-1], n_bins) and the DCT-II (ortho) rows
   {
@@ -386,8 +495,9 @@ int aad_cqcc_plan_create(int sample_rate, int bins_per_octave, int n_ceps, int d
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_dct, dct.data(), dct.size() * sizeof(float), cudaMemcpyHostToDevice);
   }
   if (e == cudaSuccess) {
-    const size_t smem = ((size_t)((kFramesPerCta * (pl->n_fft + 1) + 1) & ~1) + 2 * (size_t)pl->n_fft * bpo) * 4;
-    if (smem > 48 * 1024) e = cudaFuncSetAttribute((const void*)k_cqt_octave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = 2 * (size_t)pl->n_fft * bpo * 4;
+    if (smem > 200 * 1024) e = cudaErrorInvalidValue;
+    else if (smem > 48 * 1024) e = cudaFuncSetAttribute((const void*)k_cqt_octave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
   if (e != cudaSuccess) {
     aad_cqcc_plan_destroy(pl);
@@ -410,7 +520,7 @@ static CqccWs cqcc_ws(const aad_cqcc_plan* pl, int B, int64_t max_len, int t_all
   w.stride[0] = 0; w.off_sig[0] = 0;
   for (int i = 1; i < pl->n_oct; ++i) {
     len = (len + 1) >> 1;
-    w.stride[i] = (len + 3) / 4 * 4;
+    w.stride[i] = (pl->n_fft / 2 + len + pl->n_fft + 3) / 4 * 4;  // zeros in front (n_fft / 2) and behind (n_fft)
     w.off_sig[i] = o; o = up256(o + (size_t)B * w.stride[i] * 4);
   }
   w.off_mag = o; o = up256(o + (size_t)B * pl->n_bins * t_alloc * 4);
@@ -449,19 +559,20 @@ int aad_cqcc(const aad_cqcc_plan* pl, const void* wav, int wav_dtype, int64_t wa
   if (cudaMemsetAsync(d_max, 0, (size_t)B * 4, stream) != cudaSuccess) return AAD_ERR_CUDA;
   const int i16 = wav_dtype == AAD_I16;
   const int frames = std::min(t_max, t_ws);
-  const dim3 grid_oct((frames + kFramesPerCta - 1) / kFramesPerCta, B);
   long long len = max_len;
   for (int i = 0; i < pl->n_oct; ++i) {
     const void* y = i == 0 ? wav : (const void*)(ws + w.off_sig[i]);
     const long long ystride = i == 0 ? wav_stride : w.stride[i];
-    const size_t smem = ((size_t)((kFramesPerCta * (pl->n_fft + 1) + 1) & ~1) + 2 * (size_t)pl->n_fft * pl->n_k[i]) * 4;
-    k_cqt_octave<<<grid_oct, 128, smem, stream>>>(y, i == 0 ? i16 : 0, ystride, lengths, i, kHop >> i, pl->n_fft, pl->d_g[i],
-                                                  pl->n_k[i], pl->bin0[i], d_mag, mag_stride_b, t_ws, d_max);
+    const size_t smem = 2 * (size_t)pl->n_fft * pl->n_k[i] * 4;
+    const dim3 grid_oct((frames + kOctFrames - 1) / kOctFrames, B);
+    const int pad_i = i == 0 ? 0 : pl->n_fft / 2;
+    k_cqt_octave<<<grid_oct, 16 * pl->n_k[i], smem, stream>>>(y, i == 0 ? i16 : 0, ystride, pad_i, lengths, i, kHop >> i, pl->n_fft,
+                                                       pl->d_g[i], pl->n_k[i], pl->bin0[i], d_mag, mag_stride_b, t_ws, d_max);
     if (i + 1 < pl->n_oct) {
       const long long len_out = (len + 1) >> 1;
-      const dim3 grid_rs((unsigned)((len_out + 255) / 256), B);
-      k_cqt_resample<<<grid_rs, 256, 0, stream>>>(y, i == 0 ? i16 : 0, ystride, (float*)(ws + w.off_sig[i + 1]), w.stride[i + 1],
-                                                  lengths, i, pl->d_taps);
+      const dim3 grid_rs((unsigned)((len_out + pl->n_fft + kRsOut - 1) / kRsOut), B);
+      k_cqt_resample<<<grid_rs, 128, 0, stream>>>(y, i == 0 ? i16 : 0, ystride, pad_i, (float*)(ws + w.off_sig[i + 1]),
+                                                  w.stride[i + 1], pl->n_fft / 2, pl->n_fft, lengths, i);
       len = len_out;
     }
   }
