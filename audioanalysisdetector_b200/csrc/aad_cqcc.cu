@@ -68,13 +68,14 @@ __constant__ float c_centre;
 // y_out[b][n] = sqrt(2) * sum_k h[k] * y_in[b][2 n + k - 127],  n < ceil(len_in / 2); zero outside [0, len_in).
 // Even k reach odd input offsets: with the inputs de-interleaved (sE[j] = in[base + 2 j + 1], sO[j] = in[base + 2 j + 2],
 // base = 2 n0 - 128) output n0 + m is  sqrt(2) (sum_i half[i] sE[m + i] + c_centre sO[m + 63]).  A thread owns EIGHT
-// consecutive outputs as four packed accumulators: every float4 it reads from sE feeds 16 FFMA2 whose tap pairs are
-// uniform-register operands.  sE is skewed by 4 words per 32 so that the stride-8 float4 reads of a quarter warp
-// fall into 8 bank groups.  Rows of the octave buffers carry pad_in / pad_out zeros in front and n_fft zeros behind
+// consecutive outputs as four packed accumulators: every float4 it reads from sE feeds up to 16 FFMA2 whose tap pairs
+// are uniform-register operands (16 outputs per thread was measured too: the tap pairs no longer fit the uniform
+// register file and the uniform datapath saturates, 6.8 ms instead of 2.8 ms for the first stage).  sE is skewed by
+// 4 words per 32 so that the stride-8 float4 reads of a quarter warp fall into 8 bank groups.  Rows of the octave buffers carry pad_in / pad_out zeros in front and n_fft zeros behind
 // the signal (written here), so that every CQT frame of the lower octaves is an interior frame.
 // grid (chunks of 1024 outputs, B), 128 threads.
-constexpr int kRsOut = 1024, kRsPer = 8, kRsIn = kRsOut + 128 + 8;
-__device__ __forceinline__ int rs_skew(int j) { return j + 4 * (j >> 5); }
+constexpr int kRsPer = 8, kRsOut = 128 * kRsPer, kRsIn = kRsOut + 128 + 8;
+__device__ __forceinline__ int rs_skew(int j) { return j + 4 * (j >> 5); }  // stride-8 float4 reads: 8 bank groups
 __global__ void __launch_bounds__(128) k_cqt_resample(const void* in, int in_i16, long long in_stride, int pad_in, float* out,
                                                       long long out_stride, int pad_out, int tail_out,
                                                       const int32_t* lengths, int shift) {
@@ -137,84 +138,87 @@ __global__ void __launch_bounds__(128) k_cqt_resample(const void* in, int in_i16
 }
 
 // One octave: mag[b][bin0 + k][t] = | sum_n g[k][n] * y[b][pad + t * hop - n_fft / 2 + n] |  for the n_k bins of the octave.
-// Thread = (bin k, group of 4 frames); a CTA of 16 x n_k threads covers 64 frames of one utterance.  Only the taps are
-// staged in shared memory (once per CTA); the frames are read where they lie with one 16-byte load per frame and
-// 4 samples -- the n_k threads of a frame group read the same address (one broadcast transaction) and the frames of
-// the lower octaves overlap, so these loads are L1 hits -- which feeds 16 FFMA2 per 8 loads.  The octave buffers are
-// padded (pad = n_fft / 2 zeros in front, n_fft behind), so every frame of octaves >= 1 is interior; in octave 0 (the
-// caller's waveform) the first and the last frames of an utterance take the masked path.  (The first version
-// staged the frames in shared memory as well: two CTAs per SM, two barriers per block, 22 ms for the seven octaves
-// of the 25 380-chunk corpus.)  grid (frame blocks of 64, B).
-constexpr int kOctFrames = 64;
-__global__ void __launch_bounds__(16 * 24) k_cqt_octave(const void* y, int y_i16, long long y_stride, int pad,
-                                                        const int32_t* lengths, int shift, int hop, int n_fft, const float2* g,
-                                                        int n_k, int bin0, float* mag, long long mag_stride_b, int t_alloc,
-                                                        int32_t* utt_max) {
+// Thread = (group of 4 bins, group of 4 frames): per 4 samples four 16-byte frame loads and sixteen 8-byte tap loads
+// feed 64 FFMA2 (one bin per thread made the kernel L1-bound at 98 %: the 12 threads of a frame group repeated its
+// loads).  The taps are staged in shared memory once per CTA; the frames are read where they lie -- the octave
+// buffers are padded (pad = n_fft / 2 zeros in front, n_fft behind), so every frame of octaves >= 1 is interior; in
+// octave 0 (the caller's waveform) the first and the last frames of an utterance take the masked path.
+// A CTA covers kOctUtt utterances x 64 frames: (n_k / 4) x 16 threads per utterance.  grid (frame blocks of 64, B / kOctUtt).
+constexpr int kOctFrames = 64, kOctUtt = 4, kOctBins = 4;
+__global__ void __launch_bounds__(kOctUtt * 16 * 6) k_cqt_octave(const void* y, int y_i16, long long y_stride, int pad,
+                                                                 const int32_t* lengths, int B, int shift, int hop, int n_fft,
+                                                                 const float2* g, int n_k, int bin0, float* mag,
+                                                                 long long mag_stride_b, int t_alloc, int32_t* utt_max) {
   extern __shared__ __align__(16) float smem[];
-  float2* sG = reinterpret_cast<float2*>(smem);                  // [n_fft][n_k]
-  const int b = blockIdx.y;
+  float2* sG = reinterpret_cast<float2*>(smem);                  // [n_fft][n_kp], n_kp = n_k rounded up to 4 (zero taps)
+  const int n_bg = (n_k + kOctBins - 1) / kOctBins, n_kp = n_bg * kOctBins;
+  for (int i = threadIdx.x; i < n_fft * n_kp; i += blockDim.x) {
+    const int n = i / n_kp, k = i - n * n_kp;
+    sG[i] = k < n_k ? __ldg(g + (size_t)k * n_fft + n) : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const int per_utt = n_bg * 16;
+  const int u = threadIdx.x / per_utt, r = threadIdx.x - u * per_utt;
+  const int b = blockIdx.y * kOctUtt + u;
+  if (u >= kOctUtt || b >= B) return;
   const long long len0 = lengths[b];
   if (len0 <= 0) return;
   const int T = (int)min((long long)t_alloc, 1 + len0 / kHop);  // frames of the utterance (all octaves are trimmed to it)
-  const int t0 = blockIdx.x * kOctFrames;
-  if (t0 >= T) return;
+  const int kg = r % n_bg, fg = r / n_bg;                        // bin group, frame group (< 16)
+  const int tb = blockIdx.x * kOctFrames + 4 * fg, k0 = kOctBins * kg;
+  if (tb >= T) return;
   long long len = len0;
   for (int s = 0; s < shift; ++s) len = (len + 1) >> 1;
-  for (int i = threadIdx.x; i < n_fft * n_k; i += blockDim.x) {
-    const int n = i / n_k, k = i - n * n_k;
-    sG[i] = __ldg(g + (size_t)k * n_fft + n);
-  }
-  __syncthreads();
-  const int k = threadIdx.x % n_k, fg = threadIdx.x / n_k;       // fg < 16
-  const int tb = t0 + 4 * fg;
-  if (tb >= T) return;
-  float2 acc[4];
+  float2 acc[4][kOctBins];
   long long s0[4];  // first sample of each of the thread's frames, relative to the signal's first sample
   const bool vec_ok = !y_i16 && (y_stride & 3) == 0 && (hop & 3) == 0 && (n_fft & 7) == 0 && (pad & 3) == 0 &&
                       (reinterpret_cast<uintptr_t>(y) & 15) == 0;
   bool fast = vec_ok;
 #pragma unroll
   for (int f = 0; f < 4; ++f) {
-    acc[f] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < kOctBins; ++c) acc[f][c] = make_float2(0.f, 0.f);
     s0[f] = (long long)(tb + f) * hop - n_fft / 2;
     if (tb + f >= T) s0[f] = pad > 0 ? 0 : (max(0ll, len - n_fft) & ~3ll);  // a frame that is not stored: read anything valid (aligned)
     if (pad == 0) fast = fast && s0[f] >= 0 && s0[f] + n_fft <= len;
   }
   const long long row = (long long)b * y_stride + pad;
-  if (fast) {
-    const float* yf = static_cast<const float*>(y) + row;
-    for (int n = 0; n < n_fft; n += 4) {
-      float2 gg[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) gg[e] = sG[(n + e) * n_k + k];
+  const float2* gk = sG + k0;
+  for (int n = 0; n < n_fft; n += 4) {
+    float v[4][4];
+    if (fast) {
+      const float* yf = static_cast<const float*>(y) + row;
 #pragma unroll
       for (int f = 0; f < 4; ++f) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(yf + s0[f] + n));
-        acc[f] = __ffma2_rn(make_float2(v.x, v.x), gg[0], acc[f]);
-        acc[f] = __ffma2_rn(make_float2(v.y, v.y), gg[1], acc[f]);
-        acc[f] = __ffma2_rn(make_float2(v.z, v.z), gg[2], acc[f]);
-        acc[f] = __ffma2_rn(make_float2(v.w, v.w), gg[3], acc[f]);
+        const float4 q = __ldg(reinterpret_cast<const float4*>(yf + s0[f] + n));
+        v[f][0] = q.x; v[f][1] = q.y; v[f][2] = q.z; v[f][3] = q.w;
       }
-    }
-  } else {  // frames touching the zero padding of the caller's waveform, int16 input, unaligned rows
-    for (int n = 0; n < n_fft; n += 4) {
-      float2 gg[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) gg[e] = sG[(n + e) * n_k + k];
+    } else {  // frames touching the zero padding of the caller's waveform, int16 input, unaligned rows
 #pragma unroll
       for (int f = 0; f < 4; ++f) {
         const long long src = s0[f] + n;
-        float v[4];
         if (vec_ok && src >= 0 && src + 4 <= len) {
           const float4 q = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(y) + row + src));
-          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+          v[f][0] = q.x; v[f][1] = q.y; v[f][2] = q.z; v[f][3] = q.w;
         } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] = (src + e >= 0 && src + e < len) ? load_sample(y, y_i16, row + src + e) : 0.f;
+          for (int e = 0; e < 4; ++e) v[f][e] = (src + e >= 0 && src + e < len) ? load_sample(y, y_i16, row + src + e) : 0.f;
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[f] = __ffma2_rn(make_float2(v[e], v[e]), gg[e], acc[f]);
       }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 gg[kOctBins];
+#pragma unroll
+      for (int c = 0; c < kOctBins; c += 2) {  // two bins per 16-byte load
+        const float4 q = *reinterpret_cast<const float4*>(gk + (n + e) * n_kp + c);
+        gg[c] = make_float2(q.x, q.y);
+        gg[c + 1] = make_float2(q.z, q.w);
+      }
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int c = 0; c < kOctBins; ++c) acc[f][c] = __ffma2_rn(make_float2(v[f][e], v[f][e]), gg[c], acc[f][c]);
     }
   }
   float vmax = 0.f;
@@ -222,10 +226,15 @@ __global__ void __launch_bounds__(16 * 24) k_cqt_octave(const void* y, int y_i16
 #pragma unroll
   for (int f = 0; f < 4; ++f) {
     if (tb + f < T) {
-      const float m = sqrtf(__fmaf_rn(acc[f].x, acc[f].x, acc[f].y * acc[f].y));
-      mag[(long long)b * mag_stride_b + (long long)(bin0 + k) * t_alloc + tb + f] = m;
-      if (m == m) vmax = fmaxf(vmax, m);
-      else poison = true;
+#pragma unroll
+      for (int c = 0; c < kOctBins; ++c) {
+        if (k0 + c < n_k) {
+          const float m = sqrtf(__fmaf_rn(acc[f][c].x, acc[f][c].x, acc[f][c].y * acc[f][c].y));
+          mag[(long long)b * mag_stride_b + (long long)(bin0 + k0 + c) * t_alloc + tb + f] = m;
+          if (m == m) vmax = fmaxf(vmax, m);
+          else poison = true;
+        }
+      }
     }
   }
   // non-negative floats order like their bit patterns; a NaN poisons the utterance
@@ -495,8 +504,8 @@ int aad_cqcc_plan_create(int sample_rate, int bins_per_octave, int n_ceps, int d
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_dct, dct.data(), dct.size() * sizeof(float), cudaMemcpyHostToDevice);
   }
   if (e == cudaSuccess) {
-    const size_t smem = 2 * (size_t)pl->n_fft * bpo * 4;
-    if (smem > 200 * 1024) e = cudaErrorInvalidValue;
+    const size_t smem = 2 * (size_t)pl->n_fft * ((bpo + 3) / 4 * 4) * 4;
+    if (smem > 200 * 1024 || (bpo + 3) / 4 > 6) e = cudaErrorInvalidValue;
     else if (smem > 48 * 1024) e = cudaFuncSetAttribute((const void*)k_cqt_octave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
   if (e != cudaSuccess) {
@@ -563,11 +572,12 @@ int aad_cqcc(const aad_cqcc_plan* pl, const void* wav, int wav_dtype, int64_t wa
   for (int i = 0; i < pl->n_oct; ++i) {
     const void* y = i == 0 ? wav : (const void*)(ws + w.off_sig[i]);
     const long long ystride = i == 0 ? wav_stride : w.stride[i];
-    const size_t smem = 2 * (size_t)pl->n_fft * pl->n_k[i] * 4;
-    const dim3 grid_oct((frames + kOctFrames - 1) / kOctFrames, B);
+    const int n_bg = (pl->n_k[i] + kOctBins - 1) / kOctBins;
+    const size_t smem = 2 * (size_t)pl->n_fft * n_bg * kOctBins * 4;
+    const dim3 grid_oct((frames + kOctFrames - 1) / kOctFrames, (B + kOctUtt - 1) / kOctUtt);
     const int pad_i = i == 0 ? 0 : pl->n_fft / 2;
-    k_cqt_octave<<<grid_oct, 16 * pl->n_k[i], smem, stream>>>(y, i == 0 ? i16 : 0, ystride, pad_i, lengths, i, kHop >> i, pl->n_fft,
-                                                       pl->d_g[i], pl->n_k[i], pl->bin0[i], d_mag, mag_stride_b, t_ws, d_max);
+    k_cqt_octave<<<grid_oct, kOctUtt * 16 * n_bg, smem, stream>>>(y, i == 0 ? i16 : 0, ystride, pad_i, lengths, B, i, kHop >> i, pl->n_fft,
+                                                           pl->d_g[i], pl->n_k[i], pl->bin0[i], d_mag, mag_stride_b, t_ws, d_max);
     if (i + 1 < pl->n_oct) {
       const long long len_out = (len + 1) >> 1;
       const dim3 grid_rs((unsigned)((len_out + pl->n_fft + kRsOut - 1) / kRsOut), B);
