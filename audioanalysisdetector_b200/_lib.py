@@ -104,8 +104,8 @@ SYMBOLS = {
     "aad_cqcc_plan_destroy": (C.c_int, [C.c_void_p]),
     "aad_cqcc_query": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                  C.POINTER(C.c_int32), C.POINTER(C.c_size_t)]),
-    "aad_cqcc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64,
-                           C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "aad_cqcc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
+                           C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "aad_flac_info": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(AadFlacInfo)]),
     "aad_flac_decode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "aad_host_reserve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int32, C.c_int]),

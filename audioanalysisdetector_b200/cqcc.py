@@ -52,16 +52,31 @@ class CqccFrontend:
         return t.value, c.value, nb.value, ws.value
 
     def __call__(self, wav: torch.Tensor, lengths: Optional[torch.Tensor] = None, return_cqt: bool = False):
+        """wav [B, Lmax] float32|int16 on this device -> (features [B, n_ceps, Tmax], n_frames, status[, |CQT|])."""
         if wav.dim() != 2 or not wav.is_cuda or wav.device != self.device:
             raise L.AadError(f"wav must be a 2-D tensor on {self.device}")
-        dt = L.F32 if wav.dtype == torch.float32 else (L.I16 if wav.dtype == torch.int16 else None)
-        if dt is None:
-            raise L.AadError("wav must be float32 or int16")
         if wav.stride(1) != 1:
             wav = wav.contiguous()
         B, Lmax = wav.shape
         if lengths is None:
             lengths = torch.full((B,), Lmax, dtype=torch.int32, device=self.device)
+        return self._run(wav, wav.stride(0), None, lengths, B, Lmax, return_cqt)
+
+    def extract_indexed(self, pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, max_len: Optional[int] = None,
+                        return_cqt: bool = False):
+        """pcm: 1-D float32|int16 on this device (decoded files back to back); utterance b is
+        pcm[offsets[b] : offsets[b] + lengths[b]] -- the chunk table of DeviceCorpus, as Frontend.extract_indexed."""
+        if pcm.dim() != 1 or not pcm.is_cuda or pcm.device != self.device or not pcm.is_contiguous():
+            raise L.AadError(f"pcm must be a contiguous 1-D tensor on {self.device}")
+        offsets = offsets.to(device=self.device, dtype=torch.int64).contiguous()
+        B = int(offsets.numel())
+        Lmax = int(max_len) if max_len is not None else max(int(lengths.max()), 1)
+        return self._run(pcm, 0, offsets, lengths, B, Lmax, return_cqt)
+
+    def _run(self, wav, stride, offsets, lengths, B, Lmax, return_cqt):
+        dt = L.F32 if wav.dtype == torch.float32 else (L.I16 if wav.dtype == torch.int16 else None)
+        if dt is None:
+            raise L.AadError("wav must be float32 or int16")
         lengths = lengths.to(device=self.device, dtype=torch.int32).contiguous()
         t_max, n_ceps, n_bins, ws_bytes = self.query(B, Lmax)
         t_alloc = max(t_max, 1)
@@ -73,8 +88,8 @@ class CqccFrontend:
             self._ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            rc = self.lib.aad_cqcc(self._h, _ptr(wav), dt, wav.stride(0), _ptr(lengths), B, Lmax, _ptr(out), out.stride(0),
-                                   t_alloc, _ptr(n_frames), _ptr(status), _ptr(mag), _ptr(self._ws), self._ws.numel(),
-                                   C.c_void_p(stream))
+            rc = self.lib.aad_cqcc(self._h, _ptr(wav), dt, int(stride), _ptr(offsets), _ptr(lengths), B, Lmax, _ptr(out),
+                                   out.stride(0), t_alloc, _ptr(n_frames), _ptr(status), _ptr(mag), _ptr(self._ws),
+                                   self._ws.numel(), C.c_void_p(stream))
         L.check(rc, "aad_cqcc")
         return (out, n_frames, status, mag) if return_cqt else (out, n_frames, status)

@@ -76,8 +76,8 @@ __constant__ float c_centre;
 // grid (chunks of 1024 outputs, B), 128 threads.
 constexpr int kRsPer = 8, kRsOut = 128 * kRsPer, kRsIn = kRsOut + 128 + 8;
 __device__ __forceinline__ int rs_skew(int j) { return j + 4 * (j >> 5); }  // stride-8 float4 reads: 8 bank groups
-__global__ void __launch_bounds__(128) k_cqt_resample(const void* in, int in_i16, long long in_stride, int pad_in, float* out,
-                                                      long long out_stride, int pad_out, int tail_out,
+__global__ void __launch_bounds__(128) k_cqt_resample(const void* in, int in_i16, long long in_stride, const long long* row_off,
+                                                      int pad_in, float* out, long long out_stride, int pad_out, int tail_out,
                                                       const int32_t* lengths, int shift) {
   __shared__ __align__(16) float sE[kRsIn + 4 * (kRsIn / 32) + 8];
   __shared__ float sO[kRsIn];
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(128) k_cqt_resample(const void* in, int in_i16
     return;
   }
   const long long base = 2 * n0 - (kTaps - 1) / 2 - 1;
-  const long long irow = (long long)b * in_stride + pad_in;
+  const long long irow = (row_off ? __ldg(row_off + b) : (long long)b * in_stride) + pad_in;
   for (int i = threadIdx.x; i < kRsIn; i += 128) {
     const long long s0 = base + 2 * i + 1, s1 = s0 + 1;
     sE[rs_skew(i)] = (s0 >= 0 && s0 < len_in) ? load_sample(in, in_i16, irow + s0) : 0.f;
@@ -145,8 +145,9 @@ __global__ void __launch_bounds__(128) k_cqt_resample(const void* in, int in_i16
 // octave 0 (the caller's waveform) the first and the last frames of an utterance take the masked path.
 // A CTA covers kOctUtt utterances x 64 frames: (n_k / 4) x 16 threads per utterance.  grid (frame blocks of 64, B / kOctUtt).
 constexpr int kOctFrames = 64, kOctUtt = 4, kOctBins = 4;
-__global__ void __launch_bounds__(kOctUtt * 16 * 6) k_cqt_octave(const void* y, int y_i16, long long y_stride, int pad,
-                                                                 const int32_t* lengths, int B, int shift, int hop, int n_fft,
+__global__ void __launch_bounds__(kOctUtt * 16 * 6) k_cqt_octave(const void* y, int y_i16, long long y_stride,
+                                                                 const long long* row_off, int pad, const int32_t* lengths,
+                                                                 int B, int shift, int hop, int n_fft,
                                                                  const float2* g, int n_k, int bin0, float* mag,
                                                                  long long mag_stride_b, int t_alloc, int32_t* utt_max) {
   extern __shared__ __align__(16) float smem[];
@@ -171,7 +172,8 @@ __global__ void __launch_bounds__(kOctUtt * 16 * 6) k_cqt_octave(const void* y, 
   for (int s = 0; s < shift; ++s) len = (len + 1) >> 1;
   float2 acc[4][kOctBins];
   long long s0[4];  // first sample of each of the thread's frames, relative to the signal's first sample
-  const bool vec_ok = !y_i16 && (y_stride & 3) == 0 && (hop & 3) == 0 && (n_fft & 7) == 0 && (pad & 3) == 0 &&
+  const long long row = (row_off ? __ldg(row_off + b) : (long long)b * y_stride) + pad;
+  const bool vec_ok = !y_i16 && (row & 3) == 0 && (hop & 3) == 0 && (n_fft & 7) == 0 &&
                       (reinterpret_cast<uintptr_t>(y) & 15) == 0;
   bool fast = vec_ok;
 #pragma unroll
@@ -182,7 +184,6 @@ __global__ void __launch_bounds__(kOctUtt * 16 * 6) k_cqt_octave(const void* y, 
     if (tb + f >= T) s0[f] = pad > 0 ? 0 : (max(0ll, len - n_fft) & ~3ll);  // a frame that is not stored: read anything valid (aligned)
     if (pad == 0) fast = fast && s0[f] >= 0 && s0[f] + n_fft <= len;
   }
-  const long long row = (long long)b * y_stride + pad;
   const float2* gk = sG + k0;
   for (int n = 0; n < n_fft; n += 4) {
     float v[4][4];
@@ -548,11 +549,11 @@ int aad_cqcc_query(const aad_cqcc_plan* pl, int B, int64_t max_len, int32_t* t_m
   return AAD_OK;
 }
 
-int aad_cqcc(const aad_cqcc_plan* pl, const void* wav, int wav_dtype, int64_t wav_stride, const int32_t* lengths, int B,
-             int64_t max_len, float* out, int64_t out_stride_b, int32_t t_alloc, int32_t* n_frames, int32_t* status,
-             float* cqt_mag_out, void* workspace, size_t workspace_bytes, void* stream_) {
+int aad_cqcc(const aad_cqcc_plan* pl, const void* wav, int wav_dtype, int64_t wav_stride, const int64_t* row_off,
+             const int32_t* lengths, int B, int64_t max_len, float* out, int64_t out_stride_b, int32_t t_alloc,
+             int32_t* n_frames, int32_t* status, float* cqt_mag_out, void* workspace, size_t workspace_bytes, void* stream_) {
   if (!pl || !wav || !lengths || !out || !n_frames || !status || !workspace) return AAD_ERR_INVALID_ARG;
-  if (B <= 0 || max_len <= 0 || max_len > wav_stride || t_alloc <= 0) return AAD_ERR_INVALID_ARG;
+  if (B <= 0 || max_len <= 0 || (!row_off && max_len > wav_stride) || t_alloc <= 0) return AAD_ERR_INVALID_ARG;
   if (wav_dtype != AAD_F32 && wav_dtype != AAD_I16) return AAD_ERR_INVALID_ARG;
   const int t_max = (int)(1 + max_len / kHop);
   const int t_ws = std::max(t_alloc, 1);
@@ -576,12 +577,13 @@ int aad_cqcc(const aad_cqcc_plan* pl, const void* wav, int wav_dtype, int64_t wa
     const size_t smem = 2 * (size_t)pl->n_fft * n_bg * kOctBins * 4;
     const dim3 grid_oct((frames + kOctFrames - 1) / kOctFrames, (B + kOctUtt - 1) / kOctUtt);
     const int pad_i = i == 0 ? 0 : pl->n_fft / 2;
-    k_cqt_octave<<<grid_oct, kOctUtt * 16 * n_bg, smem, stream>>>(y, i == 0 ? i16 : 0, ystride, pad_i, lengths, B, i, kHop >> i, pl->n_fft,
+    const long long* roff = i == 0 ? reinterpret_cast<const long long*>(row_off) : nullptr;
+    k_cqt_octave<<<grid_oct, kOctUtt * 16 * n_bg, smem, stream>>>(y, i == 0 ? i16 : 0, ystride, roff, pad_i, lengths, B, i, kHop >> i, pl->n_fft,
                                                            pl->d_g[i], pl->n_k[i], pl->bin0[i], d_mag, mag_stride_b, t_ws, d_max);
     if (i + 1 < pl->n_oct) {
       const long long len_out = (len + 1) >> 1;
       const dim3 grid_rs((unsigned)((len_out + pl->n_fft + kRsOut - 1) / kRsOut), B);
-      k_cqt_resample<<<grid_rs, 128, 0, stream>>>(y, i == 0 ? i16 : 0, ystride, pad_i, (float*)(ws + w.off_sig[i + 1]),
+      k_cqt_resample<<<grid_rs, 128, 0, stream>>>(y, i == 0 ? i16 : 0, ystride, roff, pad_i, (float*)(ws + w.off_sig[i + 1]),
                                                   w.stride[i + 1], pl->n_fft / 2, pl->n_fft, lengths, i);
       len = len_out;
     }

@@ -253,7 +253,7 @@ def extract_features(final_df, feature_extractors_map: Dict[str, Callable], col_
                      mean=False, aug_col="augmentationType", max_batch_samples: int = 1 << 28):
     """Reference dispatcher (ASV_dl_func.py:1031-1049): adds one object column per map key.
 
-    Recognised extractors (the three above) run as batched GPU calls over a `DeviceCorpus`: every
+    Recognised extractors (log-mel, MFCC, LFCC and CQCC) run as batched GPU calls over a `DeviceCorpus`: every
     distinct file is decoded ONCE for all features and uploaded once (16-bit PCM as int16); the chunk
     rows become a table of offsets into that buffer (`aad_extract_indexed`), so no chunk is copied or
     padded on the host; "noise" rows are augmented on the device.  Any other callable in the map is
@@ -270,6 +270,46 @@ def extract_features(final_df, feature_extractors_map: Dict[str, Callable], col_
     paired_mel: Dict[tuple, tuple] = {}      # (sr, start, end) -> (features, n_frames, status) of the mel plan
     for name, func in feature_extractors_map.items():
         print(f"   - Ekstrahuję: {name}")
+        if func is extract_cqcc:
+            # CQCC over the same decoded corpus: one batched call per sample rate through the chunk table
+            results = [None] * len(rows)
+            if corpus is None:
+                corpus = DeviceCorpus()
+                for i, r in enumerate(rows):
+                    src = _row_get(r, col_name)
+                    try:
+                        file_of[i] = corpus.add(src)
+                    except Exception as e:
+                        print(f"[BŁĄD CQCC] {src if isinstance(src, str) else '<array>'}: {e}")
+            by_sr_c: Dict[int, List[int]] = {}
+            for i, r in enumerate(rows):
+                if file_of[i] is None:
+                    continue
+                if _row_get(r, aug_col) is not None:          # augmented rows: per row, as the reference does
+                    results[i] = func(_row_get(r, col_name), chunk_start=_row_get(r, "chunk_start"),
+                                      chunk_end=_row_get(r, "chunk_end"), mean=mean, augment=_row_get(r, aug_col))
+                    continue
+                by_sr_c.setdefault(corpus.sample_rates[file_of[i]], []).append(i)
+            for sr, idxs in by_sr_c.items():
+                cq = get_cqcc_frontend(sr)
+                off, ln = corpus.table([(file_of[i], _row_get(rows[i], "chunk_start"), _row_get(rows[i], "chunk_end"))
+                                        for i in idxs])
+                step = max(1, max_batch_samples // max(int(ln.max()), 1))
+                for a in range(0, len(idxs), step):
+                    try:
+                        o, l = torch.from_numpy(off[a:a + step].copy()), torch.from_numpy(ln[a:a + step].copy())
+                        feats, nf, st = cq.extract_indexed(corpus.upload(), o, l, max_len=max(int(l.max()), 1))
+                        feats, nf, st = feats.cpu().numpy(), nf.cpu().numpy(), st.cpu().numpy()
+                        for k, i in enumerate(idxs[a:a + step]):
+                            if st[k] != 0:
+                                print(f"[BŁĄD CQCC] row {i}: {L.ITEM_STATUS_NAMES.get(int(st[k]), 'item failed')}")
+                            else:
+                                x = feats[k, :, :nf[k]].copy()
+                                results[i] = np.mean(x, axis=1) if mean else x
+                    except Exception as e:
+                        print(f"[BŁĄD CQCC] batch {a}:{a + step}: {e}")
+            final_df[name] = results
+            continue
         if func not in _BATCHED:
             final_df[name] = [
                 func(_row_get(r, col_name), chunk_start=_row_get(r, "chunk_start"),

@@ -26,12 +26,13 @@ def score_files(sources: Sequence[object], state_dict: Mapping[str, object], fea
                 max_rows_per_call: int = 1 << 16) -> Tuple[np.ndarray, List[Tuple[int, float, float]]]:
     """sources: file paths or in-memory (waveform, sr) pairs -> (scores [n_rows], rows [(source index, chunk_start,
     chunk_end)]) for every full `chunk_s`-second chunk, in source order (files shorter than one chunk give no row,
-    as in the reference).  `feature`: "mfcc" (librosa.feature.mfcc, n_features coefficients) or "mel" (log-mel dB,
-    n_features bands) -- the model needs exactly 63 frames per chunk, i.e. 2-second chunks at 16 kHz with the
+    as in the reference).  `feature`: "mfcc" (librosa.feature.mfcc, n_features coefficients), "mel" (log-mel dB,
+    n_features bands) or "cqcc" (extract_cqcc, n_features coefficients: what the reference trains this model on,
+    cnn_bilstm_hybrid.py:6,21 with n_features = 19) -- the model needs exactly 63 frames per chunk, i.e. 2-second chunks at 16 kHz with the
     librosa framing.  `scaler`: a fitted DeviceStandardScaler applied to every chunk's (63, n_features) matrix the
     way the reference standardises time-major rows; None: raw features, as cnn_bilstm_hybrid's training loop uses."""
-    if feature not in ("mfcc", "mel"):
-        raise L.AadError("feature must be 'mfcc' or 'mel'")
+    if feature not in ("mfcc", "mel", "cqcc"):
+        raise L.AadError("feature must be 'mfcc', 'mel' or 'cqcc'")
     corpus = DeviceCorpus(device)
     rows: List[Tuple[int, float, float]] = []
     file_rows = []
@@ -46,15 +47,24 @@ def score_files(sources: Sequence[object], state_dict: Mapping[str, object], fea
     if len(srs) != 1:
         raise L.AadError(f"all sources must share one sample rate, got {sorted(srs)}")
     sr = srs.pop()
-    params = (FrontendParams.mfcc(sr, n_mfcc=n_features) if feature == "mfcc" else FrontendParams.logmel(sr, n_mels=n_features))
-    if params.n_frames(int(chunk_s * sr)) != 63:
+    if 1 + int(chunk_s * sr) // 512 != 63:   # librosa's default hop for all three features
         raise L.AadError("the model's first layer takes 63 frames per chunk (2-second chunks at 16 kHz)")
-    fe = get_frontend(params, corpus.device)
+    if feature == "cqcc":
+        from .extractors import get_cqcc_frontend
+        cq = get_cqcc_frontend(sr, 12, n_features, corpus.device)
+    else:
+        params = (FrontendParams.mfcc(sr, n_mfcc=n_features) if feature == "mfcc" else FrontendParams.logmel(sr, n_mels=n_features))
+        fe = get_frontend(params, corpus.device)
     engine = DetectorEngine(state_dict, feature_dim=n_features, device=corpus.device)
     off, ln = corpus.table(file_rows)
     out = []
     for a in range(0, len(rows), max_rows_per_call):
-        feats, nf, st = corpus.extract(fe, off[a:a + max_rows_per_call], ln[a:a + max_rows_per_call])
+        if feature == "cqcc":
+            o = torch.from_numpy(np.ascontiguousarray(off[a:a + max_rows_per_call]))
+            l = torch.from_numpy(np.ascontiguousarray(ln[a:a + max_rows_per_call]))
+            feats, nf, st = cq.extract_indexed(corpus.upload(), o, l, max_len=max(int(l.max()), 1))
+        else:
+            feats, nf, st = corpus.extract(fe, off[a:a + max_rows_per_call], ln[a:a + max_rows_per_call])
         if int(st.ne(0).sum()) != 0:
             raise L.AadError("a chunk failed in the front-end (non-finite audio?)")
         if scaler is not None:     # time-major rows, columns = coefficients (BiLSTM collate, ASV_dl_func.py:1206-1227)

@@ -235,7 +235,9 @@ int aad_scaler_apply(float* x, int64_t n_rows, int32_t W, int64_t row_stride, co
  * SURVEY 8f row 4): librosa.cqt (hop 512, fmin = C1, n_bins = floor(log2((sr/2 - 100) / fmin)) * bins_per_octave)
  * -> |.| -> amplitude_to_db(ref=np.max) -> per-frame linear interpolation onto a uniform frequency grid
  * -> log(x^2 + 1e-12) -> DCT-II ortho, first n_ceps rows.  out is [B][n_ceps][t_alloc] (T = 1 + len / 512 frames
- * per utterance); status as in aad_extract (1 empty, 4 output too small, 5 non-finite audio).  cqt_mag_out
+ * per utterance); status as in aad_extract (1 empty, 4 output too small, 5 non-finite audio).  row_off (optional,
+ * [B] element offsets): utterance b starts at wav + row_off[b] instead of b * wav_stride -- chunks of decoded files,
+ * as in aad_extract_indexed.  cqt_mag_out
  * (optional, [B][n_bins][t_alloc]) receives |CQT|.  The octave recursion of librosa.cqt is followed; its
  * 'soxr_hq' resampler is replaced by a documented half-band FIR (csrc/aad_cqcc.cu, oracle/cqcc_ref.py). */
 typedef struct aad_cqcc_plan aad_cqcc_plan;
@@ -243,9 +245,9 @@ int aad_cqcc_plan_create(int sample_rate, int bins_per_octave, int n_ceps, int d
 int aad_cqcc_plan_destroy(aad_cqcc_plan* plan);
 int aad_cqcc_query(const aad_cqcc_plan* plan, int B, int64_t max_len, int32_t* t_max, int32_t* n_ceps, int32_t* n_bins,
                    size_t* workspace_bytes);
-int aad_cqcc(const aad_cqcc_plan* plan, const void* wav, int wav_dtype, int64_t wav_stride, const int32_t* lengths,
-             int B, int64_t max_len, float* out, int64_t out_stride_b, int32_t t_alloc, int32_t* n_frames,
-             int32_t* status, float* cqt_mag_out, void* workspace, size_t workspace_bytes, void* stream);
+int aad_cqcc(const aad_cqcc_plan* plan, const void* wav, int wav_dtype, int64_t wav_stride, const int64_t* row_off,
+             const int32_t* lengths, int B, int64_t max_len, float* out, int64_t out_stride_b, int32_t t_alloc,
+             int32_t* n_frames, int32_t* status, float* cqt_mag_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Compressed-audio decode on the input side of the path (HOST pointers, CPU code).  The
  * reference's corpus (ASVspoof 2019 / 2021) is 16-bit FLAC read through libsndfile: soundfile.info for the chunk

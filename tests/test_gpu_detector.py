@@ -103,3 +103,33 @@ def test_score_files_equals_the_reference_flow_chunk_by_chunk(tmp_path):
         want = consumer_ref.forward(weights, torch.from_numpy(np.stack(feats)))[:, 0].numpy()
     assert np.abs(scores - want).max() <= 5e-5       # 1e-3 feature tolerance through the model
     assert score_files([paths[2]], weights)[0].shape == (0,)
+
+
+def test_score_files_with_cqcc_the_feature_the_reference_trains_on(tmp_path):
+    """The reference's own pipeline: FLAC files -> 2-s chunk rows -> CQCC-19 (cnn_bilstm_hybrid.py:6,21) -> model, on
+    the device through the chunk table, against the oracle's CQCC (per-chunk slicing) through the model's restatement."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import flac_writer as FW
+    from oracle import cqcc_ref
+    from audioanalysisdetector_b200 import audio_io, score_files
+    from helpers import noise, speech
+    sr = 16000
+    paths = []
+    for i, n in enumerate((4 * sr + 77, 2 * sr + 1)):                      # 2 chunks + 1 chunk
+        y = speech(50 + i, n) if i % 2 else noise(50 + i, n)
+        p = tmp_path / f"LA_E_{i}.flac"
+        p.write_bytes(FW.encode(np.round(y * 32767).astype(np.int64), sr, seed=i))
+        paths.append(str(p))
+    _, weights = load_fixture()
+    scores, rows = score_files(paths, weights, feature="cqcc", n_features=19)
+    assert rows == [(0, 0.0, 2.0), (0, 2.0, 4.0), (1, 0.0, 2.0)] and scores.shape == (3,)
+    feats = []
+    for i, cs, ce in rows:
+        y, _ = audio_io.load(paths[i])
+        f = cqcc_ref.extract_cqcc_ref(y, sr, chunk_start=cs, chunk_end=ce)
+        assert f.shape == (19, 63)
+        feats.append(f)
+    with torch.no_grad():
+        want = consumer_ref.forward(weights, torch.from_numpy(np.stack(feats)))[:, 0].numpy()
+    assert np.abs(scores - want).max() <= 2e-3       # CQCC cells near 0 dB are ill-conditioned (oracle/cqcc_ref.py)
