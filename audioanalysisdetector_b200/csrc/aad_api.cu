@@ -790,7 +790,7 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
   const bool prof = pl->profile;
   if (prof) cudaEventRecord(pl->ev[0], stream);
   (void)cudaGetLastError();  // clear stale non-sticky state left by earlier calls in this thread
-  k_prepare<<<1, 1024, 0, stream>>>(pa);
+  k_prepare<<<(B + kPrepBlock - 1) / kPrepBlock, kPrepBlock, 0, stream>>>(pa);
   LAUNCH_CHECK("k_prepare launch");
   if (prof) cudaEventRecord(pl->ev[1], stream);
 

@@ -84,89 +84,109 @@ struct PrepArgs {
 };
 
 #ifndef AAD_STFT_ONLY  // the translation units that only instantiate k_stft_fb (aad_stft_inst.cu) skip the other kernels
-__global__ void __launch_bounds__(1024) k_prepare(PrepArgs a) {
-  __shared__ int warp_sums[32];
+// frames of utterance b and its status (the geometry of librosa.stft(center=True) / spafe's framing)
+__device__ __forceinline__ int prep_geometry(const PrepArgs& a, int b, int& st, int& len_c) {
+  long long len = __ldg(a.lengths + b);
+  if (len > a.max_len) len = a.max_len;
+  st = 0;
+  int T = 0;
+  if (len <= 0) {
+    st = 1;
+    len = 0;
+  } else {
+    T = a.center ? (int)(1 + len / a.hop) : (len >= a.win_len ? (int)((len - a.win_len) / a.hop + 1) : 0);
+    if (T == 0) st = 2;
+    else if (a.n_delta > 0 && T < a.delta_width) st = 3;
+    else if (T > a.t_alloc) st = 4;
+  }
+  len_c = (int)len;
+  return T;
+}
+
+// One CTA per kPrepBlock utterances.  The exclusive scan of the frame counts needs the total of all earlier
+// utterances: every CTA recomputes it from the lengths (base / kPrepBlock reads per thread: a few microseconds even for
+// 10^5 utterances) instead of waiting for its predecessors, so the grid has no inter-CTA dependency and the tile table
+// of a large batch (51 000 tiles for 4096 x 4 s at hop 160) is written by many SMs.
+constexpr int kPrepBlock = 256;
+__global__ void __launch_bounds__(kPrepBlock) k_prepare(PrepArgs a) {
+  __shared__ int warp_sums[kPrepBlock / 32];
   __shared__ int carry_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // programmatic dependent launch: k_stft_fb may start its set-up now; it waits for this grid before it reads anything
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (tid == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < a.B; base += 1024) {
-    int b = base + tid;
-    int nf = 0;
-    if (b < a.B) {
-      long long len = a.lengths[b];
-      if (len > a.max_len) len = a.max_len;
-      int st = 0;
-      int T = 0;
-      if (len <= 0) {
-        st = 1;
-        len = 0;
-      } else {
-        T = a.center ? (int)(1 + len / a.hop) : (len >= a.win_len ? (int)((len - a.win_len) / a.hop + 1) : 0);
-        if (T == 0) st = 2;
-        else if (a.n_delta > 0 && T < a.delta_width) st = 3;
-        else if (T > a.t_alloc) st = 4;
-      }
-      nf = st ? 0 : T;
-      a.n_frames[b] = T;
-      a.status[b] = st;
-      a.len_c[b] = (int)len;
-      a.nf_eff[b] = nf;
-      a.utt_max[b] = AAD_ENC_NEG_INF;
-      if (a.utt_max2) a.utt_max2[b] = AAD_ENC_NEG_INF;
-      if (a.zn_stats) {
-        a.zn_stats[2 * b] = 0.0;
-        a.zn_stats[2 * b + 1] = 0.0;
-      }
+  const int base = blockIdx.x * kPrepBlock;
+  {  // frames in front of this CTA's utterances
+    int part = 0;
+    for (int i = tid; i < base; i += kPrepBlock) {
+      int st, lc;
+      const int T = prep_geometry(a, i, st, lc);
+      part += st ? 0 : T;
     }
-    // block exclusive scan of nf
-    int x = nf;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) warp_sums[warp] = x;
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) warp_sums[warp] = part;
     __syncthreads();
-    if (warp == 0) {
-      int w = warp_sums[lane];
+    if (tid == 0) {
+      int c = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int y = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += y;
-      }
-      warp_sums[lane] = w;  // inclusive
+      for (int w = 0; w < kPrepBlock / 32; ++w) c += warp_sums[w];
+      carry_s = c;
     }
-    __syncthreads();
-    int carry = carry_s;
-    int excl = carry + (warp ? warp_sums[warp - 1] : 0) + (x - nf);
-    if (b < a.B) a.frame_off[b] = excl;
-    // tile -> utterance index for k_stft_fb: tile tl (first frame tl*tile) starts inside utterance b
-    // iff frame_off[b] <= tl*tile < frame_off[b+1].  Each thread writes the few tiles of its own
-    // utterance; utterances that own many tiles (long-form audio) are written by the whole warp.
-    {
-      const int t_first = (excl + a.tile - 1) / a.tile, t_end = nf ? (excl + nf + a.tile - 1) / a.tile : t_first;
-      const bool big = t_end - t_first > 32;
-      if (!big)
-        for (int tl = t_first; tl < t_end; ++tl)
-          if (tl < a.max_tiles) a.tile_b0[tl] = b;
-      unsigned todo = __ballot_sync(0xffffffffu, big);
-      while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int f0 = __shfl_sync(0xffffffffu, t_first, src), f1 = __shfl_sync(0xffffffffu, t_end, src);
-        const int b0 = __shfl_sync(0xffffffffu, b, src);
-        for (int tl = f0 + lane; tl < f1; tl += 32)
-          if (tl < a.max_tiles) a.tile_b0[tl] = b0;
-      }
-    }
-    __syncthreads();
-    if (tid == 1023) carry_s = carry + warp_sums[31];
     __syncthreads();
   }
-  if (tid == 0) a.frame_off[a.B] = carry_s;
+  const int b = base + tid;
+  int nf = 0;
+  if (b < a.B) {
+    int st, lc;
+    const int T = prep_geometry(a, b, st, lc);
+    nf = st ? 0 : T;
+    a.n_frames[b] = T;
+    a.status[b] = st;
+    a.len_c[b] = lc;
+    a.nf_eff[b] = nf;
+    a.utt_max[b] = AAD_ENC_NEG_INF;
+    if (a.utt_max2) a.utt_max2[b] = AAD_ENC_NEG_INF;
+    if (a.zn_stats) {
+      a.zn_stats[2 * b] = 0.0;
+      a.zn_stats[2 * b + 1] = 0.0;
+    }
+  }
+  // block exclusive scan of nf
+  int x = nf;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  const int carry = carry_s;
+  __syncthreads();  // warp_sums is reused
+  if (lane == 31) warp_sums[warp] = x;
+  __syncthreads();
+  int before = 0;
+#pragma unroll
+  for (int w = 0; w < kPrepBlock / 32; ++w) before += w < warp ? warp_sums[w] : 0;
+  const int excl = carry + before + (x - nf);
+  if (b < a.B) a.frame_off[b] = excl;
+  if (b == a.B - 1) a.frame_off[a.B] = excl + nf;
+  // tile -> utterance index for k_stft_fb: tile tl (first frame tl*tile) starts inside utterance b
+  // iff frame_off[b] <= tl*tile < frame_off[b+1].  Each thread writes the few tiles of its own
+  // utterance; utterances that own many tiles (long-form audio) are written by the whole warp.
+  {
+    const int t_first = (excl + a.tile - 1) / a.tile, t_end = nf ? (excl + nf + a.tile - 1) / a.tile : t_first;
+    const bool big = t_end - t_first > 32;
+    if (!big)
+      for (int tl = t_first; tl < t_end; ++tl)
+        if (tl < a.max_tiles) a.tile_b0[tl] = b;
+    unsigned todo = __ballot_sync(0xffffffffu, big);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int f0 = __shfl_sync(0xffffffffu, t_first, src), f1 = __shfl_sync(0xffffffffu, t_end, src);
+      const int b0 = __shfl_sync(0xffffffffu, b, src);
+      for (int tl = f0 + lane; tl < f1; tl += 32)
+        if (tl < a.max_tiles) a.tile_b0[tl] = b0;
+    }
+  }
 }
 
 #endif  // AAD_STFT_ONLY
@@ -180,6 +200,9 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepArgs a) {
 // ---------------------------------------------------------------------------
 #ifndef AAD_TWP_TMEM
 #define AAD_TWP_TMEM 1
+#endif
+#ifndef AAD_T64
+#define AAD_T64 1
 #endif
 // columns: [0, 64) window pairs, [64, 128) pass-1 twiddles, [128, 160) split twiddles (only when at
 // most two CTAs share the SM's 512 columns: allocations are powers of two)
@@ -394,6 +417,7 @@ struct FrameFft {
   static constexpr bool TWFOLD = AAD_TWFOLD && L == 32;
   static constexpr bool TWPTM = TmemCfg<C::CTAS>::TWP;
   static constexpr bool TWPGEN = !TWPTM && AAD_TWPGEN && Q <= 4;
+  static constexpr bool T64 = AAD_T64 && Q >= 2 && Q <= 4;   // 64-bit transposes in two halves
 
   int lane, j, g, partner;  // lane = g * L + j: frame-in-iteration g, lane j within the frame's group
   uint32_t tmem_row;        // TMEM address of this thread's row (lane quarter of the warp, column 0 of the tables)
@@ -603,7 +627,30 @@ struct FrameFft {
       }
     }
 
-    // transpose through the warp's scratch (= its own power rows), re then im
+    // transpose through the warp's scratch (= its own power rows)
+    if constexpr (T64) {
+      // n_fft 512 / 1024: complex words, rows kA < 16 then kA >= 16 (a lane's rows j + L q fall into the half q / (Q / 2));
+      // half the instructions of the re / im form below for the same 128 wavefronts.  16 rows x 33 float2 = the scratch.
+      float2* scr2 = reinterpret_cast<float2*>(scr);
+      float2* w2 = scr2 + lane;
+      const float2* r2 = scr2 + j * 33 + g * L;
+      static_for<0, 2>([&](auto h_) {
+        constexpr int H = decltype(h_)::value;
+        static_for<0, 16>([&](auto k_) {
+          constexpr int KA = 16 * H + decltype(k_)::value;
+          w2[(KA - 16 * H) * 33] = v[KA];
+        });
+        __syncwarp();
+        static_for<0, Q / 2>([&](auto q_) {
+          constexpr int QL = decltype(q_)::value, QQ = H * (Q / 2) + QL;
+          static_for<0, L>([&](auto b_) {
+            constexpr int BB = decltype(b_)::value;
+            v[QQ * L + bitrev(BB, LOG2L)] = r2[QL * L * 33 + BB];
+          });
+        });
+        __syncwarp();
+      });
+    } else {
     float* scr_w = scr + lane;
     const float* scr_r = scr + j * 33 + g * L;
     if constexpr (!(ABL & 4)) {
@@ -633,6 +680,7 @@ struct FrameFft {
       });
     });
     __syncwarp();
+    }
     }
 
     // pass 2: Q DFTs of length L over b  ->  v[q*L + kB] = Z[(j + L q) + 32 kB]
