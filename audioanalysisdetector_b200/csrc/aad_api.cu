@@ -278,7 +278,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 // ---- kernel dispatch table --------------------------------------------------
 static stft_kernel_t pick_stft(int L, int tile, int mode, bool pre, bool pair = false) {
-  if (tile != 32) return nullptr;
+  if (tile != stft_tile(L)) return nullptr;
   switch (L) {  // instantiated per transform size in aad_stft_inst.cu
     case 4: return pick_stft_L4(mode, pre, pair);
     case 8: return pick_stft_L8(mode, pre, pair);
@@ -295,7 +295,7 @@ static void stft_cfg_LT(int* warps, int* ctas, size_t* fixed, int* fbu) {
 static void stft_cfg(int L, int* warps, int* ctas, size_t* fixed, int* fbu) {
   switch (L) {
     case 4: stft_cfg_LT<4, 32>(warps, ctas, fixed, fbu); break;
-    case 8: stft_cfg_LT<8, 32>(warps, ctas, fixed, fbu); break;
+    case 8: stft_cfg_LT<8, stft_tile(8)>(warps, ctas, fixed, fbu); break;
     case 16: stft_cfg_LT<16, 32>(warps, ctas, fixed, fbu); break;
     default: stft_cfg_LT<32, 32>(warps, ctas, fixed, fbu);
   }
@@ -456,7 +456,7 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, device);
   pl->L = p.n_fft / 64;
   pl->K = p.n_fft / 2 + 1;
-  pl->tile = 32;  // frames per K1 tile (n_fft 2048: one 16-warp CTA per SM)
+  pl->tile = stft_tile(pl->L);  // frames per K1 tile (n_fft 2048: one 16-warp CTA per SM)
   size_t k1_fixed = 0;
   int fbu = 1;
   stft_cfg(pl->L, &pl->warps, &pl->ctas, &k1_fixed, &fbu);
@@ -560,8 +560,11 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
             for (int i = 0; i < 4; ++i) {
               const int k = k0a + g * 4 + i;
               const bool in = k >= k0 && k < k1;
-              w[2 * i] = in ? fbw[k].x : 0.f;
-              w[2 * i + 1] = in ? fbw[k].y : 0.f;
+              // the warp emits filters f0 .. f1 - 1: the falling taps of its first segment and the rising taps of its
+              // last one belong to the neighbours' filters and are zeroed (k_stft_fb relies on it: entries that emit
+              // nothing evaluate to the log floor)
+              w[2 * i] = in && sgi != f1 ? fbw[k].x : 0.f;
+              w[2 * i + 1] = in && sgi != f0 ? fbw[k].y : 0.f;
             }
             fw4[w_off + ((size_t)g * fbu + u) * 2] = make_float4(w[0], w[1], w[2], w[3]);
             fw4[w_off + ((size_t)g * fbu + u) * 2 + 1] = make_float4(w[4], w[5], w[6], w[7]);
@@ -642,9 +645,9 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   }
   for (int mode = 0; mode < 3 && e == cudaSuccess; ++mode)
     for (int pre = 0; pre < 2 && e == cudaSuccess; ++pre) {
-      const void* fn = (const void*)pick_stft(L, 32, mode, pre != 0);
+      const void* fn = (const void*)pick_stft(L, pl->tile, mode, pre != 0);
       if (fn) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-      const void* fp = (const void*)pick_stft(L, 32, mode, pre != 0, true);
+      const void* fp = (const void*)pick_stft(L, pl->tile, mode, pre != 0, true);
       if (fp && e == cudaSuccess) e = cudaFuncSetAttribute(fp, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     }
   if (e == cudaSuccess && pl->need_ws_E) {
@@ -682,7 +685,7 @@ static WsLayout ws_layout(const aad_plan* pl, int B, int t_max) {
   w.off_max = o;       o = align_up(o + (size_t)B * 4, 256);
   w.off_zn = o;        if (pl->p.znorm) o = align_up(o + (size_t)B * 2 * sizeof(double), 256);
   w.max_tiles = (int)(((long long)B * t_max + pl->tile - 1) / pl->tile);
-  w.off_tile = o;      o = align_up(o + (size_t)(w.max_tiles + 1) * 4, 256);
+  w.off_tile = o;      o = align_up(o + (size_t)(w.max_tiles + 1) * 48, 256);
   w.t_ws = (t_max + 31) / 32 * 32;
   w.off_E = o;
   if (pl->need_ws_E) o = align_up(o + (size_t)B * pl->p.n_filt * w.t_ws * 4, 256);
@@ -785,7 +788,8 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
   pa.utt_max2 = d_max2;
   const int mode = wav_dtype == AAD_I16 ? IN_I16 : (p.quantize_i16 ? IN_F32_Q16 : IN_F32);
   const int k1_tile = pl->tile;
-  pa.tile_b0 = (int32_t*)(ws + w.off_tile); pa.tile = k1_tile; pa.max_tiles = w.max_tiles;
+  pa.tile_rec = (int4*)(ws + w.off_tile); pa.tile = k1_tile; pa.max_tiles = w.max_tiles;
+  pa.row_off = reinterpret_cast<const long long*>(row_off); pa.wav_stride = wav_stride;
   pa.zn_stats = p.znorm ? (double*)(ws + w.off_zn) : nullptr;
   const bool prof = pl->profile;
   if (prof) cudaEventRecord(pl->ev[0], stream);
@@ -802,7 +806,7 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
   sa.pre_emph = p.pre_emph;
   sa.window = wav_dtype == AAD_I16 ? pl->d_window_i16 : pl->d_window; sa.tw1 = pl->d_tw1; sa.twp = pl->d_twp;
   sa.filt_hdr = pl->d_filt_hdr; sa.filt_w = pl->d_filt_w; sa.n_hdr = pl->n_hdr; sa.n_w4 = pl->n_w4;
-  sa.warp_prog = pl->d_warp_prog; sa.tile_b0 = pa.tile_b0; sa.n_filt = p.n_filt;
+  sa.warp_prog = pl->d_warp_prog; sa.tile_rec = pa.tile_rec; sa.n_filt = p.n_filt;
   sa.log_type = p.log_type; sa.amin = p.amin; sa.eps = 2.220446049250313e-16f;
   if (pl->need_ws_E) {
     sa.E = d_E; sa.e_stride_b = (long long)p.n_filt * w.t_ws; sa.e_stride_f = w.t_ws;

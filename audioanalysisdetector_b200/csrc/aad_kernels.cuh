@@ -78,8 +78,10 @@ struct PrepArgs {
   int32_t* frame_off;  // ws: [B+1] exclusive scan of nf_eff
   int32_t* utt_max;    // ws: ordered-int encoded running max, init -inf
   int32_t* utt_max2;   // the same for the second filter bank of a paired call (or null)
-  int32_t* tile_b0;    // ws: [max_tiles] utterance holding the first frame of each K1 tile
+  int4* tile_rec;      // ws: [max_tiles][3] what k_stft_fb needs to place the frames of a tile (see TileRec)
   int tile, max_tiles;
+  const long long* row_off;  // [B] element offsets of the utterances (or null: b * wav_stride)
+  long long wav_stride;
   double* zn_stats;    // ws: [B][2] z-norm accumulators (null when unused)
 };
 
@@ -168,23 +170,50 @@ __global__ void __launch_bounds__(kPrepBlock) k_prepare(PrepArgs a) {
   const int excl = carry + before + (x - nf);
   if (b < a.B) a.frame_off[b] = excl;
   if (b == a.B - 1) a.frame_off[a.B] = excl + nf;
-  // tile -> utterance index for k_stft_fb: tile tl (first frame tl*tile) starts inside utterance b
-  // iff frame_off[b] <= tl*tile < frame_off[b+1].  Each thread writes the few tiles of its own
-  // utterance; utterances that own many tiles (long-form audio) are written by the whole warp.
+  // tile records for k_stft_fb: tile tl (first frame tl*tile) starts inside utterance b iff
+  // frame_off[b] <= tl*tile < frame_off[b+1].  The record carries everything the tile's frames need as long as they
+  // lie in utterances b and b + 1 (frame offsets, clamped lengths, row offsets), so that k_stft_fb places a tile with
+  // one round of independent loads instead of a chain of four dependent ones.  Each thread writes the few tiles of its
+  // own utterance; utterances that own many tiles (long-form audio) are written by the whole warp.
   {
+    int4 r0, r1;
+    longlong2 r2;
+    {
+      int st1 = 1, len1 = 0, nf1 = 0, lc0 = 0, st0;
+      if (b < a.B) prep_geometry(a, b, st0, lc0);
+      if (b + 1 < a.B) {
+        const int T1 = prep_geometry(a, b + 1, st1, len1);
+        nf1 = st1 ? 0 : T1;
+      }
+      r0 = make_int4(b, excl, excl + nf, excl + nf + nf1);
+      r1 = make_int4(lc0, len1, 0, 0);
+      r2.x = b < a.B ? (a.row_off ? __ldg(a.row_off + b) : (long long)b * a.wav_stride) : 0;
+      r2.y = b + 1 < a.B ? (a.row_off ? __ldg(a.row_off + b + 1) : (long long)(b + 1) * a.wav_stride) : 0;
+    }
+    auto put = [&](int tl, const int4& q0, const int4& q1, const longlong2& q2) {
+      if (tl < a.max_tiles) {
+        a.tile_rec[3 * tl] = q0;
+        a.tile_rec[3 * tl + 1] = q1;
+        *reinterpret_cast<longlong2*>(a.tile_rec + 3 * tl + 2) = q2;
+      }
+    };
     const int t_first = (excl + a.tile - 1) / a.tile, t_end = nf ? (excl + nf + a.tile - 1) / a.tile : t_first;
     const bool big = t_end - t_first > 32;
     if (!big)
-      for (int tl = t_first; tl < t_end; ++tl)
-        if (tl < a.max_tiles) a.tile_b0[tl] = b;
+      for (int tl = t_first; tl < t_end; ++tl) put(tl, r0, r1, r2);
     unsigned todo = __ballot_sync(0xffffffffu, big);
     while (todo) {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
       const int f0 = __shfl_sync(0xffffffffu, t_first, src), f1 = __shfl_sync(0xffffffffu, t_end, src);
-      const int b0 = __shfl_sync(0xffffffffu, b, src);
-      for (int tl = f0 + lane; tl < f1; tl += 32)
-        if (tl < a.max_tiles) a.tile_b0[tl] = b0;
+      int4 q0, q1;
+      longlong2 q2;
+      q0.x = __shfl_sync(0xffffffffu, r0.x, src); q0.y = __shfl_sync(0xffffffffu, r0.y, src);
+      q0.z = __shfl_sync(0xffffffffu, r0.z, src); q0.w = __shfl_sync(0xffffffffu, r0.w, src);
+      q1.x = __shfl_sync(0xffffffffu, r1.x, src); q1.y = __shfl_sync(0xffffffffu, r1.y, src);
+      q1.z = 0; q1.w = 0;
+      q2.x = __shfl_sync(0xffffffffu, r2.x, src); q2.y = __shfl_sync(0xffffffffu, r2.y, src);
+      for (int tl = f0 + lane; tl < f1; tl += 32) put(tl, q0, q1, q2);
     }
   }
 }
@@ -250,6 +279,13 @@ struct TmemChunk {
 // ---------------------------------------------------------------------------
 // K1: fused STFT + power + filterbank + log
 // ---------------------------------------------------------------------------
+// frames per k_stft_fb tile.  n_fft 512: 64 (two frames per lane in the filterbank phase: the walk over the program --
+// headers, loop control, weight look-ups -- is paid once per 64 frames, and there is one barrier pair per 64)
+#ifndef AAD_TILE_L8
+#define AAD_TILE_L8 32
+#endif
+__host__ __device__ constexpr int stft_tile(int L) { return L == 8 ? AAD_TILE_L8 : 32; }
+
 template <int L, int TILE_>
 struct StftCfg {
   static constexpr int Q = 32 / L;        // frames per warp-iteration
@@ -286,7 +322,8 @@ struct StftCfg {
 #else
   static constexpr int WARPS = ITERS >= 8 ? ITERS / 2 : 4;
 #endif
-  static constexpr int CTAS = L == 32 ? 1 : (L == 16 ? 2 : 4);
+  static constexpr int FPL = TILE / 32;    // frames per lane in the filterbank phase (lane handles frames lane + 32 f)
+  static constexpr int CTAS = L == 32 ? 1 : (L == 16 || TILE == 64 ? 2 : 4);
   // shared memory carve-up, in floats (the filterbank program follows at OFF_PROG)
   // the window / twiddle tables live in tensor memory (or are generated) and take no shared memory then
   static constexpr bool SMEM_TWP = !(TmemCfg<CTAS>::TWP || (AAD_TWPGEN && Q <= 4));
@@ -296,7 +333,7 @@ struct StftCfg {
   static constexpr int OFF_TMEM = OFF_META + 4 * TILE;        // TMEM base address written by tcgen05.alloc
   static constexpr int OFF_PROG = OFF_TMEM + 4;               // segment headers + tap weights follow
   static constexpr size_t FIXED_BYTES = size_t(OFF_PROG) * 4;
-  static_assert(TILE == 32, "filterbank phase runs with lane = frame");
+  static_assert(TILE == 32 || TILE == 64, "filterbank phase runs with lane = frame (mod 32)");
   static_assert(SKEW ? SP % 32 == 0 : SP % 8 == 4, "LDS.128 over lane = frame needs 8 rows in 8 different 16-byte bank groups");
   static_assert(Q * SP >= 32 * 33, "power rows must hold the transpose scratch");
   static_assert(SP >= K + PAD + (SKEW ? 28 : 0), "row must hold the bins, the zero padding and the skew");
@@ -331,7 +368,7 @@ struct StftArgs {
   const float4* filt_w;     // [n_w4]
   int n_hdr, n_w4;
   const int4* warp_prog;    // [WARPS] {first filter, first entry, n_entries, n_filters}
-  const int32_t* tile_b0;   // [n_tiles] from k_prepare
+  const int4* tile_rec;     // [n_tiles][3] from k_prepare: {b0, off[b0], off[b0+1], off[b0+2]}, {len[b0], len[b0+1]}, {row[b0], row[b0+1]}
   int n_filt;
   int log_type;             // 0 dB, 1 ln
   float amin, eps;
@@ -818,29 +855,47 @@ k_stft_fb(const StftArgs a) {
   // dependent index loads never sit on the critical path, and used to prefetch the next tile's
   // new samples into L2 (bulk prefetch: one instruction per frame)
   auto tile_meta = [&](int tile, int buf) {
-    const int gf = tile * C::TILE + lane;
-    int b = -1, t = 0;
-    if (tile < n_tiles && gf < total) {
-      b = __ldg(a.tile_b0 + tile);
-      int nxt = __ldg(a.frame_off + b + 1);
-      while (gf >= nxt) nxt = __ldg(a.frame_off + (++b) + 1);
-      t = gf - __ldg(a.frame_off + b);
+    int4 r0 = make_int4(0, 0, 0, 0), r1 = r0;
+    longlong2 r2 = make_longlong2(0, 0);
+    if (tile < n_tiles) {
+      r0 = __ldg(a.tile_rec + 3 * tile);
+      r1 = __ldg(a.tile_rec + 3 * tile + 1);
+      r2 = __ldg(reinterpret_cast<const longlong2*>(a.tile_rec + 3 * tile + 2));
     }
-    sMeta[buf * 2 * C::TILE + lane] = b;
-    sMeta[buf * 2 * C::TILE + C::TILE + lane] = t;
-    if (b >= 0) {
-      constexpr int ES = MODE == IN_I16 ? 2 : 4;
-      const long long len = __ldg(a.len_c + b);
-      long long s_lo = (long long)t * a.hop - a.s_off + (t == 0 ? 0 : N - a.hop);
-      long long s_hi = (long long)t * a.hop - a.s_off + N;
-      if (s_lo < 0) s_lo = 0;
-      if (s_hi > len) s_hi = len;
-      const char* row = static_cast<const char*>(a.wav) +
-                        (a.row_off ? __ldg(a.row_off + b) : (long long)b * a.wav_stride) * ES;
-      uintptr_t p0 = ((uintptr_t)(row + s_lo * ES) + 15) & ~(uintptr_t)15;
-      uintptr_t p1 = (uintptr_t)(row + s_hi * ES) & ~(uintptr_t)15;
-      if (p1 > p0)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"((unsigned)(p1 - p0)) : "memory");
+#pragma unroll
+    for (int f = 0; f < C::FPL; ++f) {
+      const int gf = tile * C::TILE + f * 32 + lane;
+      int b = -1, t = 0;
+      long long ro = 0;
+      int len = 0;
+      if (tile < n_tiles && gf < total) {
+        if (gf < r0.z) {
+          b = r0.x; t = gf - r0.y; len = r1.x; ro = r2.x;
+        } else if (gf < r0.w) {
+          b = r0.x + 1; t = gf - r0.z; len = r1.y; ro = r2.y;
+        } else {  // utterances shorter than a tile: walk on (dependent loads, rare)
+          b = r0.x + 1;
+          int nxt = r0.w;
+          while (gf >= nxt) nxt = __ldg(a.frame_off + (++b) + 1);
+          t = gf - __ldg(a.frame_off + b);
+          len = __ldg(a.len_c + b);
+          ro = a.row_off ? __ldg(a.row_off + b) : (long long)b * a.wav_stride;
+        }
+      }
+      sMeta[buf * 2 * C::TILE + f * 32 + lane] = b;
+      sMeta[buf * 2 * C::TILE + C::TILE + f * 32 + lane] = t;
+      if (b >= 0) {
+        constexpr int ES = MODE == IN_I16 ? 2 : 4;
+        long long s_lo = (long long)t * a.hop - a.s_off + (t == 0 ? 0 : N - a.hop);
+        long long s_hi = (long long)t * a.hop - a.s_off + N;
+        if (s_lo < 0) s_lo = 0;
+        if (s_hi > len) s_hi = len;
+        const char* row = static_cast<const char*>(a.wav) + ro * ES;
+        uintptr_t p0 = ((uintptr_t)(row + s_lo * ES) + 15) & ~(uintptr_t)15;
+        uintptr_t p1 = (uintptr_t)(row + s_hi * ES) & ~(uintptr_t)15;
+        if (p1 > p0)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"((unsigned)(p1 - p0)) : "memory");
+      }
     }
   };
   if (warp == 0) tile_meta(blockIdx.x, 0);
@@ -874,87 +929,110 @@ k_stft_fb(const StftArgs a) {
     auto fb_phase = [&](const int4 wprog, const int2* sHdr, const float4* sW4, float* Eout, long long e_stride_b,
                         int e_stride_f, int log_type, float amin, int32_t* utt_max) {
     if (wprog.w > 0 && !(ABL & 8)) {
-      const int b = sMetaB[lane], t = sMetaT[lane];
+      constexpr int FPL = C::FPL;
+      int b[FPL];
+      bool valid[FPL];
+      const char* pbase[FPL];
+      float* eptr[FPL];
+      float vmax[FPL], chk[FPL], rprev[FPL];
+#pragma unroll
+      for (int f = 0; f < FPL; ++f) {
+        b[f] = sMetaB[f * 32 + lane];
+        const int t = sMetaT[f * 32 + lane];
 #ifdef AAD_PHASE_TIMING
-      if (b == 0x7fffffff) return;  // forces the first post-barrier load to complete: the barrier wait ends here
+        if (b[f] == 0x7fffffff) return;  // forces the first post-barrier load to complete: the barrier wait ends here
+#endif
+        valid[f] = b[f] >= 0;
+        pbase[f] = reinterpret_cast<const char*>(sP + (f * 32 + lane) * SP + C::skew(f * 32 + lane));
+        // entry i of the list emits filter wf0 + i - 1
+        eptr[f] = Eout + (valid[f] ? (long long)b[f] * e_stride_b + (long long)(wprog.x - 1) * e_stride_f + t : 0);
+        vmax[f] = -INFINITY;
+        chk[f] = 0.f;
+        rprev[f] = 0.f;
+      }
+#ifdef AAD_PHASE_TIMING
       AAD_PHASE_MARK(1);
 #endif
-      const bool valid = b >= 0;
-      const char* pbase = reinterpret_cast<const char*>(sP + lane * SP + C::skew(lane));
       const char* wbase = reinterpret_cast<const char*>(sW4);
-      // entry i of the list emits filter wf0 + i - 1
-      float* eptr = Eout + (valid ? (long long)b * e_stride_b + (long long)(wprog.x - 1) * e_stride_f + t : 0);
       const long long estep = e_stride_f;
       const bool is_db = log_type == 0;
       const float lscale = is_db ? 3.01029995663981195f : 0.69314718055994531f;
       const float amin_n = fmaxf(amin, 1.17549435e-38f);  // keeps MUFU.LG2 off the denormal path
-      float vmax = -INFINITY, chk = 0.f, rprev = 0.f;
       const int2* hp = sHdr + wprog.y;
       for (int i0 = 0; i0 < wprog.z; i0 += FBU, hp += FBU) {
         int2 hd[FBU];
 #pragma unroll
         for (int u = 0; u < FBU; ++u) hd[u] = hp[u];
-        const char* pp[FBU];
-        float2 acc0[FBU], acc1[FBU];
+        int poff[FBU];
+        float2 acc0[FPL][FBU], acc1[FPL][FBU];
 #pragma unroll
         for (int u = 0; u < FBU; ++u) {
-          pp[u] = pbase + (hd[u].x & 0xffff);
-          acc0[u] = make_float2(0.f, 0.f);
-          acc1[u] = make_float2(0.f, 0.f);
+          poff[u] = hd[u].x & 0xffff;
+#pragma unroll
+          for (int f = 0; f < FPL; ++f) {
+            acc0[f][u] = make_float2(0.f, 0.f);
+            acc1[f][u] = make_float2(0.f, 0.f);
+          }
         }
         const char* wp = wbase + hd[0].y;  // the bundle's weights are interleaved: [round][entry][2 x float4]
         for (int gq = hd[0].x >> 16; gq > 0; --gq) {  // same round count for the whole bundle
 #pragma unroll
           for (int u = 0; u < FBU; ++u) {
-            const float4 p = *reinterpret_cast<const float4*>(pp[u]);
             const float4 wa = *reinterpret_cast<const float4*>(wp + 32 * u);
             const float4 wb = *reinterpret_cast<const float4*>(wp + 32 * u + 16);
-            pp[u] += 16;
-            acc0[u] = __ffma2_rn(make_float2(p.x, p.x), make_float2(wa.x, wa.y), acc0[u]);
-            acc1[u] = __ffma2_rn(make_float2(p.y, p.y), make_float2(wa.z, wa.w), acc1[u]);
-            acc0[u] = __ffma2_rn(make_float2(p.z, p.z), make_float2(wb.x, wb.y), acc0[u]);
-            acc1[u] = __ffma2_rn(make_float2(p.w, p.w), make_float2(wb.z, wb.w), acc1[u]);
+#pragma unroll
+            for (int f = 0; f < FPL; ++f) {
+              const float4 p = *reinterpret_cast<const float4*>(pbase[f] + poff[u]);
+              acc0[f][u] = __ffma2_rn(make_float2(p.x, p.x), make_float2(wa.x, wa.y), acc0[f][u]);
+              acc1[f][u] = __ffma2_rn(make_float2(p.y, p.y), make_float2(wa.z, wa.w), acc1[f][u]);
+              acc0[f][u] = __ffma2_rn(make_float2(p.z, p.z), make_float2(wb.x, wb.y), acc0[f][u]);
+              acc1[f][u] = __ffma2_rn(make_float2(p.w, p.w), make_float2(wb.z, wb.w), acc1[f][u]);
+            }
+            poff[u] += 16;
           }
           wp += 32 * FBU;
         }
-        float val[FBU], bad[FBU];
+        // entries that emit nothing (the first one of the list, the padding behind the last one) have had the taps of
+        // the neighbouring warps' filters zeroed by the plan: their value is log(floor), harmless for the running
+        // maximum and the poison check, so that only the store depends on the entry index
 #pragma unroll
-        for (int u = 0; u < FBU; ++u) {
-          const float2 rf = __fadd2_rn(acc0[u], acc1[u]);  // (R, F) of entry i0 + u
-          const float en = rprev + rf.y;                   // filter wf0 + i0 + u - 1
-          rprev = rf.x;
-          bad[u] = en;  // dB: max(amin, NaN) hides a NaN energy, so the energy itself is the poison source
-          // 10*log10(x) = 3.0103*log2(x), ln(x) = 0.6931*log2(x); MUFU.LG2 is accurate to 2 ulp,
-          // i.e. <= 3e-5 dB / 4e-6 nepers here, far inside the 1e-3 parity tolerance
-          if constexpr (ABL & 256) {
-            val[u] = en;
-          } else if (is_db) {
-            float l2;
-            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(amin_n, en)));
-            val[u] = lscale * l2;
-          } else {
-            val[u] = lscale * __log2f(en == 0.f ? a.eps : en);
-            bad[u] = val[u];  // ln: also catches the log of a negative energy (custom filter banks)
-          }
-        }
+        for (int f = 0; f < FPL; ++f) {
 #pragma unroll
-        for (int u = 0; u < FBU; ++u) {
-          const int fi_ = i0 + u;  // emits filter wf0 + fi_ - 1 when 1 <= fi_ <= n_filters
-          if (fi_ >= 1 && fi_ <= wprog.w) {
-            if (valid) *eptr = val[u];
-            vmax = fmaxf(vmax, val[u]);
-            chk = __fmaf_rn(bad[u], 0.f, chk);  // NaN/Inf poison
+          for (int u = 0; u < FBU; ++u) {
+            const float2 rf = __fadd2_rn(acc0[f][u], acc1[f][u]);  // (R, F) of entry i0 + u
+            const float en = rprev[f] + rf.y;                       // filter wf0 + i0 + u - 1
+            rprev[f] = rf.x;
+            float val, bad = en;  // dB: max(amin, NaN) hides a NaN energy, so the energy itself is the poison source
+            // 10*log10(x) = 3.0103*log2(x), ln(x) = 0.6931*log2(x); MUFU.LG2 is accurate to 2 ulp,
+            // i.e. <= 3e-5 dB / 4e-6 nepers here, far inside the 1e-3 parity tolerance
+            if constexpr (ABL & 256) {
+              val = en;
+            } else if (is_db) {
+              float l2;
+              asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(amin_n, en)));
+              val = lscale * l2;
+            } else {
+              val = lscale * __log2f(en == 0.f ? a.eps : en);
+              bad = val;  // ln: also catches the log of a negative energy (custom filter banks)
+            }
+            const int fi_ = i0 + u;  // emits filter wf0 + fi_ - 1 when 1 <= fi_ <= n_filters
+            if (valid[f] && fi_ >= 1 && fi_ <= wprog.w) eptr[f][u * estep] = val;
+            vmax[f] = fmaxf(vmax[f], val);
+            chk[f] = __fmaf_rn(bad, 0.f, chk[f]);  // NaN/Inf poison
           }
-          eptr += estep;
+          eptr[f] += FBU * estep;
         }
       }
-      if (valid) {
-        if (utt_max) {
-          unsigned peers = __match_any_sync(__activemask(), b);
-          int enc = __reduce_max_sync(peers, enc_ordered(vmax));
-          if ((int)(__ffs(peers) - 1) == lane) atomicMax(utt_max + b, enc);
+#pragma unroll
+      for (int f = 0; f < FPL; ++f) {
+        if (valid[f]) {
+          if (utt_max) {
+            unsigned peers = __match_any_sync(__activemask(), b[f]);
+            int enc = __reduce_max_sync(peers, enc_ordered(vmax[f]));
+            if ((int)(__ffs(peers) - 1) == lane) atomicMax(utt_max + b[f], enc);
+          }
+          if (chk[f] != chk[f]) a.status[b[f]] = 5;
         }
-        if (chk != chk) a.status[b] = 5;
       }
     }
     };

@@ -12,7 +12,7 @@ namespace aad {
 #define AAD_CAT(a, b) AAD_CAT2(a, b)
 
 stft_kernel_t AAD_CAT(pick_stft_L, AAD_INST_L)(int mode, bool pre, bool pair) {
-  constexpr int L = AAD_INST_L, TILE = 32;
+  constexpr int L = AAD_INST_L, TILE = stft_tile(AAD_INST_L);
 #if AAD_ABLATE || defined(AAD_DEV_BUILD)
   // dev builds: one variant
 #if AAD_INST_L == 32
