@@ -959,10 +959,16 @@ k_stft_fb(const StftArgs a) {
       const float lscale = is_db ? 3.01029995663981195f : 0.69314718055994531f;
       const float amin_n = fmaxf(amin, 1.17549435e-38f);  // keeps MUFU.LG2 off the denormal path
       const int2* hp = sHdr + wprog.y;
-      for (int i0 = 0; i0 < wprog.z; i0 += FBU, hp += FBU) {
-        int2 hd[FBU];
+      int2 hd[FBU];
 #pragma unroll
-        for (int u = 0; u < FBU; ++u) hd[u] = hp[u];
+      for (int u = 0; u < FBU; ++u) hd[u] = hp[u];
+      for (int i0 = 0; i0 < wprog.z; i0 += FBU) {
+        // the next bundle's headers travel while this bundle is evaluated (the walk is a chain of dependent
+        // shared-memory reads otherwise: header -> round count / offsets -> taps)
+        hp += (i0 + FBU < wprog.z) ? FBU : 0;
+        int2 hn[FBU];
+#pragma unroll
+        for (int u = 0; u < FBU; ++u) hn[u] = hp[u];
         int poff[FBU];
         float2 acc0[FPL][FBU], acc1[FPL][FBU];
 #pragma unroll
@@ -1022,6 +1028,8 @@ k_stft_fb(const StftArgs a) {
           }
           eptr[f] += FBU * estep;
         }
+#pragma unroll
+        for (int u = 0; u < FBU; ++u) hd[u] = hn[u];
       }
 #pragma unroll
       for (int f = 0; f < FPL; ++f) {
