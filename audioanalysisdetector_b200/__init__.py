@@ -7,7 +7,7 @@ arithmetic in hand-written sm_100a CUDA kernels behind the C ABI of include/aad.
 from . import _lib
 from ._lib import AadError
 from .frontend import Frontend, FrontendParams, delta, fp32_peak_tflops, pinned_empty
-from .extractors import (compute_melspec, extract_cqcc, extract_cqcc_batch, extract_features, extract_lfcc,
+from .extractors import (compute_melspec, extract_cqcc, extract_gtcc, extract_cqcc_batch, extract_features, extract_lfcc,
                          extract_mel_spectrogram, extract_mfcc, get_frontend)
 from .cqcc import CqccFrontend
 from .detector import DetectorEngine
@@ -21,6 +21,6 @@ from .sharding import (bind_to_gpu_numa, contiguous_shard, gather_features, long
 
 __all__ = [
     "AadError", "Frontend", "FrontendParams", "delta", "fp32_peak_tflops", "pinned_empty",
-    "compute_melspec", "extract_cqcc", "extract_cqcc_batch", "CqccFrontend", "extract_features", "extract_lfcc", "extract_mel_spectrogram", "extract_mfcc", "get_frontend",
+    "compute_melspec", "extract_cqcc", "extract_gtcc", "extract_cqcc_batch", "CqccFrontend", "extract_features", "extract_lfcc", "extract_mel_spectrogram", "extract_mfcc", "get_frontend",
     "DetectorEngine", "score_files", "DeviceCorpus", "chunk_bounds", "layout_files", "two_second_chunks", "DeviceStandardScaler", "merge_stats", "DeviceFeatureLoader", "bind_to_gpu_numa", "contiguous_shard", "gather_features", "long_form_logmel", "partition_by_frames", "time_split",
 ]

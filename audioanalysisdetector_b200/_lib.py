@@ -12,11 +12,12 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AAD_LIB_PATH") or os.path.join(_PKG_DIR, "libaad_b200.so")  # override: dev builds only
 
 # enums (mirror include/aad.h)
-KIND_LOGMEL, KIND_MFCC, KIND_LFCC = 0, 1, 2
+KIND_LOGMEL, KIND_MFCC, KIND_LFCC, KIND_GTCC = 0, 1, 2, 3
 F32, I16 = 0, 1
 WIN_HANN_PERIODIC, WIN_HAMMING_SYMMETRIC = 0, 1
-FB_MEL_SLANEY, FB_LINEAR_INTBIN, FB_LINEAR_CONT, FB_CUSTOM = 0, 1, 2, 3
-LOG_DB10, LOG_LN = 0, 1
+FB_MEL_SLANEY, FB_LINEAR_INTBIN, FB_LINEAR_CONT, FB_CUSTOM, FB_GAMMATONE, FB_CUSTOM_DENSE = 0, 1, 2, 3, 4, 5
+LOG_DB10, LOG_LN, LOG_CBRT = 0, 1, 2
+SPEC_POWER, SPEC_MAGNITUDE = 0, 1
 REF_ONE, REF_UTT_MAX = 0, 1
 LAYOUT_CT, LAYOUT_TC = 0, 1
 TABLE_WINDOW, TABLE_FILTERBANK, TABLE_DCT, TABLE_DELTA_TAPS = 0, 1, 2, 3
@@ -39,6 +40,7 @@ class AadParams(C.Structure):
         ("top_db", C.c_float), ("n_ceps", C.c_int32), ("n_delta", C.c_int32),
         ("delta_width", C.c_int32), ("layout", C.c_int32), ("time_mean", C.c_int32),
         ("i16_scale", C.c_float), ("znorm", C.c_int32), ("custom_fb", C.POINTER(C.c_float)),
+        ("spectrum", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -83,6 +85,7 @@ SYMBOLS = {
     "aad_logmel": (C.c_int, _EXTRACT_ARGS),
     "aad_mfcc": (C.c_int, _EXTRACT_ARGS),
     "aad_lfcc": (C.c_int, _EXTRACT_ARGS),
+    "aad_gtcc": (C.c_int, _EXTRACT_ARGS),
     "aad_delta": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int32, C.c_int, C.c_int,
                             C.c_void_p, C.c_void_p]),
     "aad_db_reference": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int32,

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -28,6 +29,7 @@ struct aad_plan {
   int warps = 0, ctas = 0;
   size_t k1_smem = 0;
   int n_w4 = 0, n_hdr = 0;
+  bool dense = false;  // dense filter bank (gammatone / custom dense): k_stft_fb FBM = 1, weights stay in global memory
   int smem_optin = 0;  // device limit of dynamic shared memory per CTA
   int n_ksteps = 0, n_tiles = 0, cep_nt = 1;  // K2: DCT as a GEMM (K steps of 8 filters, N tiles of 8 coefficients)
   int c_feat = 0;     // rows before deltas
@@ -176,7 +178,38 @@ static int build_filterbank(const aad_params& p, int K, std::vector<float>& fb) 
         fb[(size_t)j * K + k] = (float)(w * pscale);
       }
     }
-  } else if (p.fb_type == AAD_FB_CUSTOM) {
+  } else if (p.fb_type == AAD_FB_GAMMATONE) {
+    // spafe 0.3.x gammatone_filter_banks(nfilts, nfft, fs, low_freq, high_freq, scale="constant", order=4): Slaney's
+    // ERB filter cascade evaluated on the unit circle at the FFT bins.  Centre frequencies on the ERB scale
+    // (generate_center_frequencies, ascending after the final reversal), bandwidths B = 1.019 * 2 pi * ERB with
+    // ERB = ((fc / EarQ)^order + minBW^order)^(1 / order), four zeros A_i and a double pole pair; the gain factor and
+    // T^4 cancel against the final "every filter has maximum 1" normalisation, the scale is constant 1.
+    const double EarQ = 9.26449, minBW = 24.7, order = 4.0, PI = 3.141592653589793238462643383279502884;
+    const double T = 1.0 / sr, c = EarQ * minBW;
+    const double smax = std::sqrt(3.0 + std::pow(2.0, 1.5)), smin = std::sqrt(3.0 - std::pow(2.0, 1.5));
+    for (int i = 0; i < nf; ++i) {
+      // center_freqs = (max + c) exp((m / nfilts) log((min + c) / (max + c))) - c, m = 1 .. nfilts, then reversed
+      const int m = nf - i;
+      const double fc = (fmax + c) * std::exp(((double)m / nf) * std::log((fmin + c) / (fmax + c))) - c;
+      const double erb = std::pow(std::pow(fc / EarQ, order) + std::pow(minBW, order), 1.0 / order);
+      const double Bw = 1.019 * 2.0 * PI * erb;
+      const double wT = 2.0 * fc * PI * T, Kx = std::exp(Bw * T);
+      const double co = std::cos(wT), si = std::sin(wT);
+      const double A[4] = {(co + smax * si) / Kx, (co - smax * si) / Kx, (co + smin * si) / Kx, (co - smin * si) / Kx};
+      const std::complex<double> pole = std::polar(1.0 / Kx, wT);
+      std::vector<double> row(K);
+      double mx = 0.0;
+      for (int k = 0; k < K; ++k) {
+        const std::complex<double> u = std::polar(1.0, 2.0 * PI * k / p.n_fft);
+        double num = 1.0;
+        for (int q = 0; q < 4; ++q) num *= std::abs(u - A[q]);
+        const double den = std::abs((u - pole) * (u - std::conj(pole)));
+        row[k] = num * std::pow(den, -4.0);
+        mx = std::max(mx, row[k]);
+      }
+      for (int k = 0; k < K; ++k) fb[(size_t)i * K + k] = (float)(row[k] / mx * pscale);
+    }
+  } else if (p.fb_type == AAD_FB_CUSTOM || p.fb_type == AAD_FB_CUSTOM_DENSE) {
     if (!p.custom_fb) return AAD_ERR_INVALID_ARG;
     for (size_t i = 0; i < (size_t)nf * K; ++i) fb[i] = (float)((double)p.custom_fb[i] * pscale);
   } else {
@@ -277,8 +310,9 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 // ---- kernel dispatch table --------------------------------------------------
-static stft_kernel_t pick_stft(int L, int tile, int mode, bool pre, bool pair = false) {
+static stft_kernel_t pick_stft(int L, int tile, int mode, bool pre, bool pair = false, bool dense = false) {
   if (tile != stft_tile(L)) return nullptr;
+  if (dense) return L == 8 && !pair ? pick_stft_L8_dense(mode, pre) : nullptr;
   switch (L) {  // instantiated per transform size in aad_stft_inst.cu
     case 4: return pick_stft_L4(mode, pre, pair);
     case 8: return pick_stft_L8(mode, pre, pair);
@@ -393,6 +427,25 @@ int aad_params_default(aad_params* p, int kind, int sample_rate) {
     p->top_db = -1.f;
     p->n_ceps = 13;
     p->layout = AAD_LAYOUT_TC;
+  } else if (kind == AAD_KIND_GTCC) {
+    // spafe 0.3.x gfcc as the reference calls it: gfcc(sig=y, fs=sr, num_ceps=n_ceps, nfilts=n_filters) with the
+    // float waveform of librosa.load (no int16 step), n_filters = 40, n_ceps = 13
+    p->n_fft = 512;
+    p->win_length = (int)(0.025 * sample_rate);
+    p->hop_length = (int)(0.01 * sample_rate);
+    p->window = AAD_WIN_HAMMING_SYMMETRIC;
+    p->center = 0;
+    p->quantize_i16 = 0;
+    p->pre_emph = 0.97f;
+    p->n_filt = 40;
+    p->fb_type = AAD_FB_GAMMATONE;
+    p->power_scale = 1.0f / 512.0f;
+    p->spectrum = AAD_SPEC_POWER;
+    p->log_type = AAD_LOG_CBRT;
+    p->ref_type = AAD_REF_ONE;
+    p->top_db = -1.f;
+    p->n_ceps = 13;
+    p->layout = AAD_LAYOUT_TC;
   } else {
     return AAD_ERR_INVALID_ARG;
   }
@@ -441,7 +494,10 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   if (p.n_delta > 0 && (p.delta_width < 3 || p.delta_width > CEP_MAXW || p.delta_width % 2 == 0))
     return AAD_ERR_INVALID_ARG;
   if (p.window != AAD_WIN_HANN_PERIODIC && p.window != AAD_WIN_HAMMING_SYMMETRIC) return AAD_ERR_INVALID_ARG;
-  if (p.log_type != AAD_LOG_DB10 && p.log_type != AAD_LOG_LN) return AAD_ERR_INVALID_ARG;
+  const bool dense_fb = p.fb_type == AAD_FB_GAMMATONE || p.fb_type == AAD_FB_CUSTOM_DENSE;
+  if (p.log_type != AAD_LOG_DB10 && p.log_type != AAD_LOG_LN && !(p.log_type == AAD_LOG_CBRT && dense_fb)) return AAD_ERR_INVALID_ARG;
+  if (p.spectrum != AAD_SPEC_POWER && !(p.spectrum == AAD_SPEC_MAGNITUDE && dense_fb)) return AAD_ERR_INVALID_ARG;
+  if (dense_fb && (p.n_fft != 512 || p.n_filt > 64)) return AAD_ERR_UNSUPPORTED;  // one kernel family carries the dense form
   if (p.layout != AAD_LAYOUT_CT && p.layout != AAD_LAYOUT_TC) return AAD_ERR_INVALID_ARG;
   if (p.fmax > 0 && p.fmax > p.sample_rate / 2.0f + 1e-3f) return AAD_ERR_INVALID_ARG;
   if (p.znorm && p.time_mean) return AAD_ERR_INVALID_ARG;
@@ -460,6 +516,7 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   size_t k1_fixed = 0;
   int fbu = 1;
   stft_cfg(pl->L, &pl->warps, &pl->ctas, &k1_fixed, &fbu);
+  if (dense_fb) fbu = kDenseFbu;
   pl->c_feat = p.n_ceps > 0 ? p.n_ceps : p.n_filt;
   pl->c_out = pl->c_feat * (1 + p.n_delta);
   pl->n_ksteps = (p.n_filt + 7) / 8;
@@ -496,7 +553,8 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   int rc = build_filterbank(p, K, pl->h_fb);
   std::vector<float2> fbw;
   std::vector<int32_t> seg;
-  if (rc == AAD_OK) rc = band_filterbank(pl->h_fb, p.n_filt, K, fbw, seg);
+  pl->dense = dense_fb;
+  if (rc == AAD_OK && !dense_fb) rc = band_filterbank(pl->h_fb, p.n_filt, K, fbw, seg);
   if (rc != AAD_OK) {
     delete pl;
     return rc;
@@ -507,7 +565,42 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   std::vector<int2> fhdr;
   std::vector<float4> fw4;
   std::vector<int4> wprog(pl->warps, make_int4(0, 0, 0, 0));
-  {
+  if (dense_fb) {
+    // Dense form: entry e carries the full rows of filters 2e (x taps) and 2e + 1 (y taps) over all bins, in rounds of
+    // 4 bins from bin 0; warps get contiguous entry ranges; wprog = {first filter, first header, entries, filters}.
+    const int n_ent = (p.n_filt + 1) / 2, rounds = (K + 3) / 4;
+    if (rounds > 0x7fff) {
+      delete pl;
+      return AAD_ERR_UNSUPPORTED;
+    }
+    for (int wi = 0; wi < pl->warps; ++wi) {
+      const int e0 = (int)((long long)n_ent * wi / pl->warps), e1 = (int)((long long)n_ent * (wi + 1) / pl->warps);
+      if (e1 <= e0) continue;
+      std::vector<int> ents;
+      for (int e = e0; e < e1; ++e) ents.push_back(e);
+      while (ents.size() % fbu) ents.push_back(-1);
+      wprog[wi] = make_int4(2 * e0, (int)fhdr.size(), (int)ents.size(), std::min(p.n_filt, 2 * e1) - 2 * e0);
+      for (size_t b0 = 0; b0 < ents.size(); b0 += fbu) {
+        const size_t w_off = fw4.size();
+        fw4.resize(w_off + (size_t)rounds * fbu * 2, make_float4(0.f, 0.f, 0.f, 0.f));
+        for (int u = 0; u < fbu; ++u) {
+          const int e = ents[b0 + u];
+          fhdr.push_back(make_int2(0 | (rounds << 16), (int)(w_off * sizeof(float4))));
+          if (e < 0) continue;
+          for (int g = 0; g < rounds; ++g) {
+            float w[8];
+            for (int i = 0; i < 4; ++i) {
+              const int k = g * 4 + i;
+              w[2 * i] = k < K ? pl->h_fb[(size_t)(2 * e) * K + k] : 0.f;
+              w[2 * i + 1] = k < K && 2 * e + 1 < p.n_filt ? pl->h_fb[(size_t)(2 * e + 1) * K + k] : 0.f;
+            }
+            fw4[w_off + ((size_t)g * fbu + u) * 2] = make_float4(w[0], w[1], w[2], w[3]);
+            fw4[w_off + ((size_t)g * fbu + u) * 2 + 1] = make_float4(w[4], w[5], w[6], w[7]);
+          }
+        }
+      }
+    }
+  } else {
     const int nseg = p.n_filt + 1;
     std::vector<int> sk0(nseg), sk1(nseg), srounds(nseg);
     std::vector<double> cost(nseg);
@@ -575,7 +668,8 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   }
   pl->n_hdr = (int)fhdr.size();
   pl->n_w4 = (int)fw4.size();
-  pl->k1_smem = k1_fixed + (size_t)((2 * fhdr.size() + 3) & ~3) * 4 + fw4.size() * sizeof(float4);
+  // dense plans keep their weights in global memory (read through L1): only the headers go to shared memory
+  pl->k1_smem = k1_fixed + (size_t)((2 * fhdr.size() + 3) & ~3) * 4 + (dense_fb ? 0 : fw4.size() * sizeof(float4));
   // DCT-II ortho (scipy.fftpack.dct type 2 norm='ortho'), first n_ceps rows.  Device layout for K2: the
   // transposed table D^T[filter][coef] as mma.m16n8k8 B fragments, split into tf32 hi + lo parts:
   // [k-step][n-tile][lane = 4 g + t] = {b0 hi, b1 hi, b0 lo, b1 lo}, b0 = D^T[8 ks + t][8 nt + g],
@@ -645,9 +739,9 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   }
   for (int mode = 0; mode < 3 && e == cudaSuccess; ++mode)
     for (int pre = 0; pre < 2 && e == cudaSuccess; ++pre) {
-      const void* fn = (const void*)pick_stft(L, pl->tile, mode, pre != 0);
+      const void* fn = (const void*)pick_stft(L, pl->tile, mode, pre != 0, false, pl->dense);
       if (fn) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-      const void* fp = (const void*)pick_stft(L, pl->tile, mode, pre != 0, true);
+      const void* fp = pl->dense ? nullptr : (const void*)pick_stft(L, pl->tile, mode, pre != 0, true);
       if (fp && e == cudaSuccess) e = cudaFuncSetAttribute(fp, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     }
   if (e == cudaSuccess && pl->need_ws_E) {
@@ -777,7 +871,7 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
         q.center != p.center || q.pre_emph != p.pre_emph || q.quantize_i16 != p.quantize_i16 ||
         q.sample_rate != p.sample_rate || q.i16_scale != p.i16_scale || pl2->warps != pl->warps || pl2->L != pl->L)
       return AAD_ERR_PAIR;
-    if (pl2->need_ws_E || pl2->need_ws_feat || q.znorm || q.layout != AAD_LAYOUT_CT) return AAD_ERR_PAIR;
+    if (pl2->need_ws_E || pl2->need_ws_feat || q.znorm || q.layout != AAD_LAYOUT_CT || pl2->dense) return AAD_ERR_PAIR;
     size_t need2 = 0;
     if ((rc = aad_query(pl2, B, max_len, nullptr, nullptr, &need2)) != AAD_OK) return rc;
     if (pair.ws2_bytes < need2) return AAD_ERR_WORKSPACE;
@@ -807,7 +901,8 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
   sa.window = wav_dtype == AAD_I16 ? pl->d_window_i16 : pl->d_window; sa.tw1 = pl->d_tw1; sa.twp = pl->d_twp;
   sa.filt_hdr = pl->d_filt_hdr; sa.filt_w = pl->d_filt_w; sa.n_hdr = pl->n_hdr; sa.n_w4 = pl->n_w4;
   sa.warp_prog = pl->d_warp_prog; sa.tile_rec = pa.tile_rec; sa.n_filt = p.n_filt;
-  sa.log_type = p.log_type; sa.amin = p.amin; sa.eps = 2.220446049250313e-16f;
+  sa.log_type = p.log_type; sa.amin = p.amin; sa.eps = 2.220446049250313e-16f; sa.spec_mag = p.spectrum == AAD_SPEC_MAGNITUDE;
+  if (pl->dense) sa.n_w4 = 0;  // nothing to stage: the dense weights are read from global memory
   if (pl->need_ws_E) {
     sa.E = d_E; sa.e_stride_b = (long long)p.n_filt * w.t_ws; sa.e_stride_f = w.t_ws;
   } else {
@@ -824,7 +919,8 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
     sa.E2 = pair.out2; sa.e2_stride_b = out2_stride_b; sa.e2_stride_f = t_alloc;
     sa.utt_max2 = q.log_type == AAD_LOG_DB10 ? d_max2 : nullptr;
   }
-  stft_kernel_t kern = pick_stft(pl->L, pl->tile, mode, p.pre_emph != 0.f, pl2 != nullptr);
+  if (pl->dense && pl2) return AAD_ERR_PAIR;
+  stft_kernel_t kern = pick_stft(pl->L, pl->tile, mode, p.pre_emph != 0.f, pl2 != nullptr, pl->dense);
   if (!kern) return pl2 ? AAD_ERR_PAIR : AAD_ERR_UNSUPPORTED;
   const long long max_tiles = w.max_tiles;
   // persistent CTAs take tiles round-robin: with few tiles per CTA shrink the grid so that every CTA gets the same
@@ -950,6 +1046,7 @@ int aad_extract_indexed(const aad_plan* pl, const void* wav, int wav_dtype, cons
 AAD_KIND_ALIAS(aad_logmel, AAD_KIND_LOGMEL)
 AAD_KIND_ALIAS(aad_mfcc, AAD_KIND_MFCC)
 AAD_KIND_ALIAS(aad_lfcc, AAD_KIND_LFCC)
+AAD_KIND_ALIAS(aad_gtcc, AAD_KIND_GTCC)
 
 int aad_delta(const float* x, const int32_t* n_frames, int B, int C, int32_t t_stride, int width,
               int order, float* out, void* stream) {

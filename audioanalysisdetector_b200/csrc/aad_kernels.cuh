@@ -285,6 +285,9 @@ struct TmemChunk {
 #define AAD_TILE_L8 32
 #endif
 __host__ __device__ constexpr int stft_tile(int L) { return L == 8 ? AAD_TILE_L8 : 32; }
+// dense filter banks (k_stft_fb FBM = 1): entries per bundle.  All entries of a bundle read the same bins, so the power
+// group is loaded once per round for the whole bundle; 5 entries = the 10 filters a warp owns of spafe's 40.
+constexpr int kDenseFbu = 5;
 
 template <int L, int TILE_>
 struct StftCfg {
@@ -370,7 +373,8 @@ struct StftArgs {
   const int4* warp_prog;    // [WARPS] {first filter, first entry, n_entries, n_filters}
   const int4* tile_rec;     // [n_tiles][3] from k_prepare: {b0, off[b0], off[b0+1], off[b0+2]}, {len[b0], len[b0+1]}, {row[b0], row[b0+1]}
   int n_filt;
-  int log_type;             // 0 dB, 1 ln
+  int log_type;             // 0 dB, 1 ln, 2 cube root (dense filter banks: spafe gfcc)
+  int spec_mag;             // dense variant only: 1 = the filter bank is applied to |X| instead of |X|^2
   float amin, eps;
   float* E;                 // log-energies out: E[b*stride_b + f*stride_f + t]
   long long e_stride_b;
@@ -622,8 +626,17 @@ struct FrameFft {
   // transform: window, FFT, real-input split, power.  scr: warp-private scratch of >= 32 * 33 floats (may alias prow:
   // the transposes are over before the powers are written).  prow: power row of this lane's frame, M + 1 + NPAD
   // floats are written.
-  template <int NPAD>
+  template <int NPAD, bool MAGOPT = false>
   __device__ __forceinline__ void transform(const StftArgs& a, float2 (&v)[32], float* scr, float* prow) const {
+    // |X|^2, or |X| when the (dense filter bank) plan asks for the magnitude spectrum
+    const bool mag = MAGOPT && a.spec_mag != 0;
+    auto spec = [&](float re, float im) {
+      float pw = __fmaf_rn(re, re, im * im);
+      if constexpr (MAGOPT) {
+        if (mag) asm("sqrt.approx.ftz.f32 %0, %0;" : "+f"(pw));
+      }
+      return pw;
+    };
     // window: 0.5*w (zero outside its support) from this lane's TMEM row, next chunk in flight
     // window folded into the first butterfly stage of pass 1: samples A and A + 16 meet in stage 1
     // (registers bitrev(A) = 2m and 2m + 1), so a' = xa*wa + xb*wb, b' = xa*wa - xb*wb is one FMUL2
@@ -785,14 +798,14 @@ struct FrameFft {
         if constexpr (ABL & 32) {
           if (x1.x * x2.y == 123.456f) prow[k] = x1.y;
         } else {
-        prow[k] = __fmaf_rn(x1.x, x1.x, x1.y * x1.y);
-        prow[M - k] = __fmaf_rn(x2.x, x2.x, x2.y * x2.y);
+        prow[k] = spec(x1.x, x1.y);
+        prow[M - k] = spec(x2.x, x2.y);
         }
       });
     });
     if (j == 0) {
       float2 A = v[L / 2];
-      prow[M / 2] = 4.0f * __fmaf_rn(A.x, A.x, A.y * A.y);
+      prow[M / 2] = mag ? 2.0f * spec(A.x, A.y) : 4.0f * spec(A.x, A.y);
       // padding read by the last tap groups of a segment that reaches the Nyquist bin
 #pragma unroll
       for (int i = 1; i <= NPAD; ++i) prow[M + i] = 0.f;
@@ -800,12 +813,16 @@ struct FrameFft {
   }
 };
 
-template <int L, int MODE, bool PRE, int TILE, bool PAIR = false>
+// FBM: 0 = two-tap banded filter bank (mel / linear triangles), program and weights in shared memory;
+//      1 = dense filter bank (gammatone), entries hold the full rows of TWO filters, weights read from global memory
+//          through L1 (40 x 260 x 4 B do not fit the shared memory of four co-resident CTAs)
+template <int L, int MODE, bool PRE, int TILE, bool PAIR = false, int FBM = 0>
 __global__ void __launch_bounds__(StftCfg<L, TILE>::WARPS * 32, StftCfg<L, TILE>::CTAS)
 k_stft_fb(const StftArgs a) {
+  static_assert(!(PAIR && FBM), "paired plans are banded");
   using C = StftCfg<L, TILE>;
   using FFT = FrameFft<L, MODE, PRE, TILE>;
-  constexpr int Q = C::Q, M = C::M, N = C::N, SP = C::SP, FBU = C::FBU;
+  constexpr int Q = C::Q, M = C::M, N = C::N, SP = C::SP, FBU = FBM ? kDenseFbu : C::FBU;
   extern __shared__ __align__(16) float smem[];
   float* sP = smem + C::OFF_P;
   float2* sTwp = reinterpret_cast<float2*>(smem + C::OFF_TWP);
@@ -820,7 +837,8 @@ k_stft_fb(const StftArgs a) {
   if constexpr (C::SMEM_TWP)
     for (int i = tid; i < M / 2; i += nthr) sTwp[i] = a.twp[i];
   for (int i = tid; i < a.n_hdr; i += nthr) sHdr[i] = a.filt_hdr[i];
-  for (int i = tid; i < a.n_w4; i += nthr) sW4[i] = a.filt_w[i];
+  if constexpr (FBM == 0)
+    for (int i = tid; i < a.n_w4; i += nthr) sW4[i] = a.filt_w[i];
   if constexpr (PAIR) {  // second program behind the first (pointers are re-derived where it runs: no live registers)
     int2* sHdr2 = reinterpret_cast<int2*>(sW4 + a.n_w4);
     float4* sW42 = reinterpret_cast<float4*>(reinterpret_cast<float*>(sHdr2) + ((2 * a.n_hdr2 + 3) & ~3));
@@ -916,7 +934,7 @@ k_stft_fb(const StftArgs a) {
       float2 v[32];
       // transposes go through the warp's own power rows
       if (fft.load_iter(a, sMetaB, sMetaT, it, v))
-        fft.template transform<C::PAD>(a, v, sP + (it * Q) * SP, sP + (it * Q + g) * SP + C::skew(it * Q + g));
+        fft.template transform<C::PAD, FBM != 0>(a, v, sP + (it * Q) * SP, sP + (it * Q + g) * SP + C::skew(it * Q + g));
     }
     AAD_PHASE_MARK(0);
     __syncthreads();
@@ -944,8 +962,8 @@ k_stft_fb(const StftArgs a) {
 #endif
         valid[f] = b[f] >= 0;
         pbase[f] = reinterpret_cast<const char*>(sP + (f * 32 + lane) * SP + C::skew(f * 32 + lane));
-        // entry i of the list emits filter wf0 + i - 1
-        eptr[f] = Eout + (valid[f] ? (long long)b[f] * e_stride_b + (long long)(wprog.x - 1) * e_stride_f + t : 0);
+        // entry i of the list emits filter wf0 + i - 1 (banded) / filters wf0 + 2 i, wf0 + 2 i + 1 (dense)
+        eptr[f] = Eout + (valid[f] ? (long long)b[f] * e_stride_b + (long long)(wprog.x - (FBM ? 0 : 1)) * e_stride_f + t : 0);
         vmax[f] = -INFINITY;
         chk[f] = 0.f;
         rprev[f] = 0.f;
@@ -953,7 +971,7 @@ k_stft_fb(const StftArgs a) {
 #ifdef AAD_PHASE_TIMING
       AAD_PHASE_MARK(1);
 #endif
-      const char* wbase = reinterpret_cast<const char*>(sW4);
+      const char* wbase = FBM ? reinterpret_cast<const char*>(a.filt_w) : reinterpret_cast<const char*>(sW4);
       const long long estep = e_stride_f;
       const bool is_db = log_type == 0;
       const float lscale = is_db ? 3.01029995663981195f : 0.69314718055994531f;
@@ -982,51 +1000,83 @@ k_stft_fb(const StftArgs a) {
         }
         const char* wp = wbase + hd[0].y;  // the bundle's weights are interleaved: [round][entry][2 x float4]
         for (int gq = hd[0].x >> 16; gq > 0; --gq) {  // same round count for the whole bundle
+          float4 pv[FPL];
+          if constexpr (FBM) {  // dense: every entry of the bundle starts at bin 0, one group serves them all
+#pragma unroll
+            for (int f = 0; f < FPL; ++f) pv[f] = *reinterpret_cast<const float4*>(pbase[f] + poff[0]);
+            poff[0] += 16;
+          }
 #pragma unroll
           for (int u = 0; u < FBU; ++u) {
-            const float4 wa = *reinterpret_cast<const float4*>(wp + 32 * u);
-            const float4 wb = *reinterpret_cast<const float4*>(wp + 32 * u + 16);
+            float4 wa, wb;
+            if constexpr (FBM) {
+              wa = __ldg(reinterpret_cast<const float4*>(wp + 32 * u));
+              wb = __ldg(reinterpret_cast<const float4*>(wp + 32 * u + 16));
+            } else {
+              wa = *reinterpret_cast<const float4*>(wp + 32 * u);
+              wb = *reinterpret_cast<const float4*>(wp + 32 * u + 16);
+            }
 #pragma unroll
             for (int f = 0; f < FPL; ++f) {
-              const float4 p = *reinterpret_cast<const float4*>(pbase[f] + poff[u]);
+              float4 p;
+              if constexpr (FBM) p = pv[f];
+              else p = *reinterpret_cast<const float4*>(pbase[f] + poff[u]);
               acc0[f][u] = __ffma2_rn(make_float2(p.x, p.x), make_float2(wa.x, wa.y), acc0[f][u]);
               acc1[f][u] = __ffma2_rn(make_float2(p.y, p.y), make_float2(wa.z, wa.w), acc1[f][u]);
               acc0[f][u] = __ffma2_rn(make_float2(p.z, p.z), make_float2(wb.x, wb.y), acc0[f][u]);
               acc1[f][u] = __ffma2_rn(make_float2(p.w, p.w), make_float2(wb.z, wb.w), acc1[f][u]);
             }
-            poff[u] += 16;
+            if constexpr (!FBM) poff[u] += 16;
           }
           wp += 32 * FBU;
         }
         // entries that emit nothing (the first one of the list, the padding behind the last one) have had the taps of
         // the neighbouring warps' filters zeroed by the plan: their value is log(floor), harmless for the running
         // maximum and the poison check, so that only the store depends on the entry index
+        auto nonlin = [&](float en, float& bad) {
+          float val;
+          bad = en;  // dB: max(amin, NaN) hides a NaN energy, so the energy itself is the poison source
+          // 10*log10(x) = 3.0103*log2(x), ln(x) = 0.6931*log2(x); MUFU.LG2 is accurate to 2 ulp,
+          // i.e. <= 3e-5 dB / 4e-6 nepers here, far inside the 1e-3 parity tolerance
+          if constexpr (ABL & 256) {
+            val = en;
+          } else if (is_db) {
+            float l2;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(amin_n, en)));
+            val = lscale * l2;
+          } else if (FBM && log_type == 2) {
+            val = cbrtf(en);  // spafe gfcc: np.power(features, 1 / 3)
+          } else {
+            val = lscale * __log2f(en == 0.f ? a.eps : en);
+            bad = val;  // ln: also catches the log of a negative energy (custom filter banks)
+          }
+          return val;
+        };
 #pragma unroll
         for (int f = 0; f < FPL; ++f) {
 #pragma unroll
           for (int u = 0; u < FBU; ++u) {
-            const float2 rf = __fadd2_rn(acc0[f][u], acc1[f][u]);  // (R, F) of entry i0 + u
-            const float en = rprev[f] + rf.y;                       // filter wf0 + i0 + u - 1
-            rprev[f] = rf.x;
-            float val, bad = en;  // dB: max(amin, NaN) hides a NaN energy, so the energy itself is the poison source
-            // 10*log10(x) = 3.0103*log2(x), ln(x) = 0.6931*log2(x); MUFU.LG2 is accurate to 2 ulp,
-            // i.e. <= 3e-5 dB / 4e-6 nepers here, far inside the 1e-3 parity tolerance
-            if constexpr (ABL & 256) {
-              val = en;
-            } else if (is_db) {
-              float l2;
-              asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(amin_n, en)));
-              val = lscale * l2;
-            } else {
-              val = lscale * __log2f(en == 0.f ? a.eps : en);
-              bad = val;  // ln: also catches the log of a negative energy (custom filter banks)
+            const float2 rf = __fadd2_rn(acc0[f][u], acc1[f][u]);
+            if constexpr (FBM) {  // the two filters of entry i0 + u
+              float bad0, bad1;
+              const float v0 = nonlin(rf.x, bad0), v1 = nonlin(rf.y, bad1);
+              const int fi_ = 2 * (i0 + u);
+              if (valid[f] && fi_ < wprog.w) eptr[f][(2 * u) * estep] = v0;
+              if (valid[f] && fi_ + 1 < wprog.w) eptr[f][(2 * u + 1) * estep] = v1;
+              vmax[f] = fmaxf(vmax[f], fmaxf(v0, v1));
+              chk[f] = __fmaf_rn(bad0, 0.f, __fmaf_rn(bad1, 0.f, chk[f]));
+            } else {              // (R, F) of entry i0 + u: filter wf0 + i0 + u - 1 = R[i0 + u - 1] + F[i0 + u]
+              const float en = rprev[f] + rf.y;
+              rprev[f] = rf.x;
+              float bad;
+              const float val = nonlin(en, bad);
+              const int fi_ = i0 + u;  // emits filter wf0 + fi_ - 1 when 1 <= fi_ <= n_filters
+              if (valid[f] && fi_ >= 1 && fi_ <= wprog.w) eptr[f][u * estep] = val;
+              vmax[f] = fmaxf(vmax[f], val);
+              chk[f] = __fmaf_rn(bad, 0.f, chk[f]);  // NaN/Inf poison
             }
-            const int fi_ = i0 + u;  // emits filter wf0 + fi_ - 1 when 1 <= fi_ <= n_filters
-            if (valid[f] && fi_ >= 1 && fi_ <= wprog.w) eptr[f][u * estep] = val;
-            vmax[f] = fmaxf(vmax[f], val);
-            chk[f] = __fmaf_rn(bad, 0.f, chk[f]);  // NaN/Inf poison
           }
-          eptr[f] += FBU * estep;
+          eptr[f] += (FBM ? 2 : 1) * FBU * estep;
         }
 #pragma unroll
         for (int u = 0; u < FBU; ++u) hd[u] = hn[u];

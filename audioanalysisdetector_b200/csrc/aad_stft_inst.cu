@@ -44,6 +44,24 @@ stft_kernel_t AAD_CAT(pick_stft_L, AAD_INST_L)(int mode, bool pre, bool pair) {
 #endif
 }
 
+#if AAD_INST_L == 8
+stft_kernel_t pick_stft_L8_dense(int mode, bool pre) {
+#if AAD_ABLATE || defined(AAD_DEV_BUILD)
+  return nullptr;
+#else
+  constexpr int TILE = stft_tile(8);
+  switch (mode * 2 + (pre ? 1 : 0)) {
+    case 0: return k_stft_fb<8, IN_F32, false, TILE, false, 1>;
+    case 1: return k_stft_fb<8, IN_F32, true, TILE, false, 1>;
+    case 2: return k_stft_fb<8, IN_F32_Q16, false, TILE, false, 1>;
+    case 3: return k_stft_fb<8, IN_F32_Q16, true, TILE, false, 1>;
+    case 4: return k_stft_fb<8, IN_I16, false, TILE, false, 1>;
+    default: return k_stft_fb<8, IN_I16, true, TILE, false, 1>;
+  }
+#endif
+}
+#endif
+
 }  // namespace aad
 
 #if defined(AAD_PHASE_TIMING) && AAD_INST_L == 32

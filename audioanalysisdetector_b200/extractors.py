@@ -173,6 +173,23 @@ def extract_lfcc(filepath, chunk_start=None, chunk_end=None, n_ceps=13, mean=Fal
         return None
 
 
+def _gtcc_params(sr, n_filters, n_ceps):
+    return FrontendParams.gtcc(sr, n_ceps=n_ceps, nfilts=n_filters)
+
+
+def extract_gtcc(filepath, chunk_start=None, chunk_end=None, sr=None, n_filters=40, n_ceps=13, mean=False, augment=None):
+    """spafe gfcc of the float waveform (ASV_dl_func.py:484-499) -> (T, n_ceps) float64"""
+    try:
+        y, sr = _prepare_clip(filepath, chunk_start, chunk_end, sr, augment)
+        out, status = _run_batch(_gtcc_params(sr, n_filters, n_ceps), [y])
+        if out[0] is None:
+            raise ValueError(L.ITEM_STATUS_NAMES.get(int(status[0]), "item failed"))
+        return _lfcc_post(out[0], mean)            # same orientation and mean axis as extract_lfcc (:496)
+    except Exception as e:
+        print(f"[BŁĄD GTCC] {filepath if isinstance(filepath, str) else '<array>'}: {e}")
+        return None
+
+
 _CQCC_PLANS: dict = {}
 
 
@@ -223,6 +240,7 @@ _BATCHED = {
     extract_mel_spectrogram: ("MEL", lambda sr, mean: _mel_params(sr, 64, None, mean), lambda x, mean: x),
     extract_mfcc: ("MFCC", lambda sr, mean: _mfcc_params(sr, 13, mean), lambda x, mean: x),
     extract_lfcc: ("LFCC", lambda sr, mean: _lfcc_params(sr, 13), _lfcc_post),
+    extract_gtcc: ("GTCC", lambda sr, mean: _gtcc_params(sr, 40, 13), _lfcc_post),
 }
 
 

@@ -50,7 +50,8 @@ class FrontendParams:
     time_mean: bool = False
     znorm: bool = False          # (x - mean) / std over the utterance's feature matrix (ASV_dataset.ipynb compute_melspec)
     i16_scale: float = 0.0       # int16 input: sample = int16 * i16_scale; 0 -> 1/32768 (log-mel / MFCC), 1 (LFCC)
-    custom_fb: Optional[np.ndarray] = None   # (n_filt, n_fft//2+1) float32, FB_CUSTOM only
+    custom_fb: Optional[np.ndarray] = None   # (n_filt, n_fft//2+1) float32, FB_CUSTOM / FB_CUSTOM_DENSE only
+    spectrum: int = L.SPEC_POWER             # SPEC_MAGNITUDE: filter bank on |X| (dense filter banks only)
 
     # ---- reference presets ---------------------------------------------------
     @classmethod
@@ -77,6 +78,18 @@ class FrontendParams:
                    power_scale=1.0 / nfft, log_type=L.LOG_LN, ref_type=L.REF_ONE, top_db=-1.0,
                    n_ceps=n_ceps, layout=layout, **kw)
 
+    @classmethod
+    def gtcc(cls, sample_rate, n_ceps=13, nfilts=40, nfft=512, win_len=0.025, win_hop=0.01, pre_emph=0.97,
+             layout=L.LAYOUT_TC, fb_type=L.FB_GAMMATONE, spectrum=L.SPEC_POWER, **kw):
+        """spafe gfcc(sig=y, fs, num_ceps, nfilts) as extract_gtcc calls it (ASV_dl_func.py:484-499): float waveform,
+        25/10 ms hamming, gammatone bank on |X|^2 / nfft, cube root, DCT-II ortho."""
+        sr = int(sample_rate)
+        return cls(kind=L.KIND_GTCC, sample_rate=sr, n_fft=nfft, win_length=int(win_len * sr),
+                   hop_length=int(win_hop * sr), window=L.WIN_HAMMING_SYMMETRIC, center=False,
+                   quantize_i16=False, pre_emph=pre_emph, n_filt=nfilts, fb_type=fb_type,
+                   power_scale=(1.0 / nfft if spectrum == L.SPEC_POWER else 1.0), spectrum=spectrum,
+                   log_type=L.LOG_CBRT, ref_type=L.REF_ONE, top_db=-1.0, n_ceps=n_ceps, layout=layout, **kw)
+
     def replace(self, **kw) -> "FrontendParams":
         return dataclasses.replace(self, **kw)
 
@@ -89,7 +102,7 @@ class FrontendParams:
         p = L.AadParams()
         p.struct_size = C.sizeof(L.AadParams)
         for f in ("kind", "sample_rate", "n_fft", "win_length", "hop_length", "window", "n_filt",
-                  "fb_type", "log_type", "ref_type", "n_ceps", "n_delta", "delta_width", "layout"):
+                  "fb_type", "log_type", "ref_type", "n_ceps", "n_delta", "delta_width", "layout", "spectrum"):
             setattr(p, f, int(getattr(self, f)))
         p.center = int(bool(self.center))
         p.quantize_i16 = int(bool(self.quantize_i16))

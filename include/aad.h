@@ -33,7 +33,8 @@ typedef struct aad_plan aad_plan;
 enum aad_kind {        /* which reference extractor the plan mirrors */
   AAD_KIND_LOGMEL = 0, /* extract_mel_spectrogram  ASV_dl_func.py:522-538 */
   AAD_KIND_MFCC = 1,   /* extract_mfcc             ASV_dl_func.py:404-420 */
-  AAD_KIND_LFCC = 2    /* extract_lfcc             ASV_dl_func.py:423-439 */
+  AAD_KIND_LFCC = 2,   /* extract_lfcc             ASV_dl_func.py:423-439 */
+  AAD_KIND_GTCC = 3    /* extract_gtcc (spafe gfcc) ASV_dl_func.py:484-499 */
 };
 enum aad_dtype { AAD_F32 = 0, AAD_I16 = 1 }; /* AAD_I16: see aad_params.i16_scale */
 enum aad_window {
@@ -45,11 +46,20 @@ enum aad_fb {
   AAD_FB_LINEAR_INTBIN = 1, /* triangles on integer FFT bins (spafe 0.1.x / python_speech_features style) */
   AAD_FB_LINEAR_CONT = 2,   /* spafe 0.3.x linear_filter_banks: triangles on continuous bin frequencies; the
                                LFCC default (the reference pins spafe ~= 0.3.3, requirements.txt:5) */
-  AAD_FB_CUSTOM = 3         /* caller matrix, at most two adjacent filters per bin */
+  AAD_FB_CUSTOM = 3,        /* caller matrix, at most two adjacent filters per bin */
+  AAD_FB_GAMMATONE = 4,     /* spafe 0.3.x gammatone_filter_banks (Slaney's ERB filters evaluated on the FFT bins, every
+                               filter scaled to a maximum of 1): a DENSE matrix; n_fft 512 only, n_filt <= 64 */
+  AAD_FB_CUSTOM_DENSE = 5   /* caller matrix without any structure (e.g. spafe's own gammatone / bark matrix);
+                               n_fft 512 only, n_filt <= 64 */
 };
 enum aad_log {
   AAD_LOG_DB10 = 0, /* 10*log10(max(amin, S))            librosa.power_to_db */
-  AAD_LOG_LN = 1    /* ln(S == 0 ? eps : S)              spafe zero_handling + np.log */
+  AAD_LOG_LN = 1,   /* ln(S == 0 ? eps : S)              spafe zero_handling + np.log */
+  AAD_LOG_CBRT = 2  /* S^(1/3)                           spafe gfcc (dense filter banks only) */
+};
+enum aad_spectrum {
+  AAD_SPEC_POWER = 0,    /* filter bank applied to |X|^2 (times power_scale) */
+  AAD_SPEC_MAGNITUDE = 1 /* filter bank applied to |X| (times power_scale); dense filter banks only */
 };
 enum aad_ref {
   AAD_REF_ONE = 0,    /* power_to_db(S) inside librosa.feature.mfcc */
@@ -116,7 +126,9 @@ typedef struct aad_params {
   int32_t znorm;       /* 1: out = (x - mean(x)) / std(x) over all valid elements of the utterance (population
                           std), the compute_melspec variant of the reference (ASV_dataset.ipynb:1151,
                           cell [27]); applied last; not combinable with time_mean */
-  const float* custom_fb; /* HOST pointer, row-major n_filt x (n_fft/2+1); AAD_FB_CUSTOM only */
+  const float* custom_fb; /* HOST pointer, row-major n_filt x (n_fft/2+1); AAD_FB_CUSTOM / AAD_FB_CUSTOM_DENSE only */
+  int32_t spectrum;       /* aad_spectrum */
+  int32_t reserved0;
 } aad_params;
 
 /* Fill *p with the parameters of the named reference extractor:
@@ -124,7 +136,10 @@ typedef struct aad_params {
  *                    + power_to_db(ref=np.max)                    ASV_dl_func.py:533-534
  *   AAD_KIND_MFCC:   librosa.feature.mfcc(n_mfcc 13; 128 mels)    ASV_dl_func.py:416
  *   AAD_KIND_LFCC:   int16 quantise + spafe lfcc(num_ceps 13, 24 filters, nfft 512,
- *                    25 ms / 10 ms hamming, pre-emphasis 0.97), TC layout  ASV_dl_func.py:434-435 */
+ *                    25 ms / 10 ms hamming, pre-emphasis 0.97), TC layout  ASV_dl_func.py:434-435
+ *   AAD_KIND_GTCC:   spafe gfcc(num_ceps 13, 40 gammatone filters as the reference passes them, nfft 512,
+ *                    25 ms / 10 ms hamming, pre-emphasis 0.97, power spectrum / nfft, cube root, DCT-II ortho),
+ *                    float input as librosa.load returns it, TC layout              ASV_dl_func.py:484-499 */
 int aad_params_default(aad_params* p, int kind, int sample_rate);
 
 /* ---- plan life cycle ------------------------------------------------------
@@ -194,6 +209,11 @@ int aad_mfcc(const aad_plan* plan, const void* wav, int wav_dtype, int64_t wav_s
              int32_t t_alloc, int32_t* n_frames, int32_t* status, void* workspace,
              size_t workspace_bytes, void* stream);
 int aad_lfcc(const aad_plan* plan, const void* wav, int wav_dtype, int64_t wav_stride,
+             const int32_t* lengths, int B, int64_t max_len, float* out, int64_t out_stride_b,
+             int32_t t_alloc, int32_t* n_frames, int32_t* status, void* workspace,
+             size_t workspace_bytes, void* stream);
+/* extract_gtcc: spafe gfcc over B in-memory clips (ASV_dl_func.py:484-499) */
+int aad_gtcc(const aad_plan* plan, const void* wav, int wav_dtype, int64_t wav_stride,
              const int32_t* lengths, int B, int64_t max_len, float* out, int64_t out_stride_b,
              int32_t t_alloc, int32_t* n_frames, int32_t* status, void* workspace,
              size_t workspace_bytes, void* stream);

@@ -28,6 +28,7 @@ from .extractors_ref import (  # noqa: F401
     compute_melspec_ref,
     extract_mfcc_ref,
     extract_lfcc_ref,
+    extract_gtcc_ref,
     mfcc_with_deltas_ref,
     lfcc_with_deltas_ref,
 )

@@ -66,6 +66,16 @@ def extract_lfcc_ref(y, sr, chunk_start=None, chunk_end=None, n_ceps=13, mean=Fa
         return None
 
 
+def extract_gtcc_ref(y, sr, chunk_start=None, chunk_end=None, n_filters=40, n_ceps=13, mean=False, **kw):
+    """ASV_dl_func.py:484-499 -> (T, n_ceps) float64 (mean=True: axis 1, as the reference writes it)."""
+    try:
+        y = _slice(np.asarray(y, dtype=np.float32), sr, chunk_start, chunk_end)
+        g = spafe_ref.gfcc(sig=y, fs=sr, num_ceps=n_ceps, nfilts=n_filters, **kw)
+        return np.mean(g, axis=1) if mean else g
+    except Exception:
+        return None
+
+
 def mfcc_with_deltas_ref(y, sr, n_mfcc=40, n_fft=2048, hop_length=512, n_mels=128,
                          n_delta=2, width=9, dtype="ref"):
     """BASELINE.json configs[1]: MFCC + delta + delta-delta -> (3*n_mfcc, T)."""

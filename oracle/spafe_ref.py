@@ -168,3 +168,76 @@ def lfcc(sig, fs=16000, num_ceps=13, pre_emph=True, pre_emph_coeff=0.97,
                                nfilts, nfft, low_freq, high_freq, fbanks)
     log_feats = np.log(zero_handling(feats))
     return scipy.fft.dct(log_feats, type=2, axis=1, norm="ortho")[:, :num_ceps]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# spafe.features.gfcc.gfcc / spafe.fbanks.gammatone_fbanks (extract_gtcc, ASV_dl_func.py:484-499:
+#   gtccs = gfcc(sig=y, fs=sr, num_ceps=n_ceps, nfilts=n_filters)   with the float waveform of librosa.load)
+#
+# PARITY UNPINNED, recalled from the 0.3.x source like the rest of this file.  The chain of 0.3.x `erb_spectrogram`
+# has the same block as `linear_spectrogram` (|fft(windows, nfft)|[:, :nfft//2+1], then (1/nfft) * square) followed by
+# `np.dot(abs_fft_values, fbanks.T)`, `np.power(features, 1/3)` and the ortho DCT-II; spafe 0.1.x multiplied the
+# MAGNITUDE spectrum with the bank instead (`spectrum="magnitude"` here, AAD_SPEC_MAGNITUDE in the library).
+# `gammatone_filter_banks` is Slaney's ERB filter bank (Auditory Toolbox MakeERBFilters) evaluated on the unit circle
+# at the FFT bins, as in D. Ellis' fft2gammatonemx: least certain are the ERB order passed through as `order=4`
+# (Slaney's own value is 1) and the per-filter normalisation to a maximum of 1.  A deployment that has spafe passes
+# spafe's own matrix as AAD_FB_CUSTOM_DENSE, which makes both questions moot.
+# ---------------------------------------------------------------------------------------------------------------
+EAR_Q = 9.26449
+MIN_BW = 24.7
+
+
+def generate_center_frequencies(min_freq, max_freq, nfilts):
+    """ERB-spaced centre frequencies (Slaney's ERBSpace), ascending."""
+    m = np.arange(1, nfilts + 1)
+    c = EAR_Q * MIN_BW
+    cf = (max_freq + c) * np.exp((m / nfilts) * np.log((min_freq + c) / (max_freq + c))) - c
+    return cf[::-1]
+
+
+def gammatone_filter_banks(nfilts=24, nfft=512, fs=16000, low_freq=0, high_freq=None, order=4):
+    """-> (fbank (nfilts, nfft//2 + 1) float64, centre frequencies); scale='constant'."""
+    high_freq = high_freq or fs / 2
+    low_freq = low_freq or 0
+    T = 1.0 / fs
+    u = np.exp(2j * np.pi * np.arange(nfft // 2 + 1) / nfft)[None, :]
+    fcs = generate_center_frequencies(low_freq, high_freq, nfilts)
+    erb = ((fcs / EAR_Q) ** order + MIN_BW ** order) ** (1.0 / order)
+    B = 1.019 * 2 * np.pi * erb
+    wT = 2 * fcs * np.pi * T
+    K = np.exp(B * T)
+    pole = (np.exp(1j * wT) / K)[:, None]
+    smax, smin = np.sqrt(3 + 2 ** 1.5), np.sqrt(3 - 2 ** 1.5)
+    A = [((np.cos(wT) + s * np.sin(wT)) / K)[:, None] for s in (smax, -smax, smin, -smin)]
+    kj = np.exp(1j * wT)
+    G = [2 * T * kj * (a[:, 0] - kj) for a in A]
+    coe = -2 / K ** 2 - 2 * kj ** 2 + 2 * (1 + kj ** 2) / K
+    gain = np.abs(G[0] * G[1] * G[2] * G[3] * coe ** -4)
+    fb = (T ** 4 / gain[:, None]) * np.abs((u - A[0]) * (u - A[1]) * (u - A[2]) * (u - A[3])) \
+        * np.abs((u - pole) * (u - pole.conj())) ** -4.0
+    fb = fb / fb.max(axis=1, keepdims=True)          # "make sure all filters has max value = 1.0"
+    return fb, fcs
+
+
+def erb_spectrogram(sig, fs=16000, pre_emph=True, pre_emph_coeff=0.97, win_len=0.025, win_hop=0.01,
+                    nfilts=24, nfft=512, low_freq=0, high_freq=None, fbanks=None, spectrum="power"):
+    if fbanks is None:
+        fbanks, _ = gammatone_filter_banks(nfilts, nfft, fs, low_freq, high_freq)
+    sig = np.asarray(sig, dtype=np.float64)
+    if pre_emph:
+        sig = pre_emphasis(sig, pre_emph_coeff)
+    frames, frame_length = framing(sig, fs, win_len, win_hop)
+    windows = np.hamming(frame_length) * frames
+    mag = np.absolute(np.fft.fft(windows, nfft))[:, : nfft // 2 + 1]
+    spec = (1.0 / nfft) * np.square(mag) if spectrum == "power" else mag
+    return np.dot(spec, fbanks.T)
+
+
+def gfcc(sig, fs=16000, num_ceps=13, pre_emph=True, pre_emph_coeff=0.97, win_len=0.025, win_hop=0.01,
+         nfilts=24, nfft=512, low_freq=0, high_freq=None, fbanks=None, spectrum="power"):
+    """spafe.features.gfcc.gfcc defaults (dct_type=2, no energy / lifter / normalise) -> float64 (T, num_ceps)."""
+    if nfilts < num_ceps:
+        raise ValueError("nfilts must be >= num_ceps")
+    feats = erb_spectrogram(sig, fs, pre_emph, pre_emph_coeff, win_len, win_hop, nfilts, nfft, low_freq, high_freq,
+                            fbanks, spectrum)
+    return scipy.fft.dct(np.power(feats, 1 / 3), type=2, axis=1, norm="ortho")[:, :num_ceps]

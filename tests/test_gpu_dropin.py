@@ -111,14 +111,17 @@ def test_extract_features_dispatcher(files, tmp_path):
     assert df3["mfcc"].iloc[-1] is None and df3["mel-spect"].iloc[-1] is None
     # the notebook's full map (ASV_deep_learning.ipynb:152-160) has 'cqcc' first: batched over the same corpus
     from oracle import cqcc_ref
-    df4 = aad.extract_features(pd.DataFrame(rows), {"cqcc": aad.extract_cqcc, "mfcc": aad.extract_mfcc})
-    assert df4["cqcc"].iloc[-1] is None
+    df4 = aad.extract_features(pd.DataFrame(rows), {"cqcc": aad.extract_cqcc, "gtcc": aad.extract_gtcc, "mfcc": aad.extract_mfcc})
+    assert df4["cqcc"].iloc[-1] is None and df4["gtcc"].iloc[-1] is None
     for i in range(len(rows) - 1):
         y, sr = cache[rows[i]["filepath"]]
         want = cqcc_ref.extract_cqcc_ref(y, sr, chunk_start=rows[i]["chunk_start"], chunk_end=rows[i]["chunk_end"])
         got = df4["cqcc"].iloc[i]
         assert got.shape == want.shape == (19, 63) and np.median(np.abs(got - want)) <= 2e-3
         assert np.array_equal(df4["mfcc"].iloc[i], df["mfcc"].iloc[i])
+        wg = oracle.extract_gtcc_ref(y, sr, chunk_start=rows[i]["chunk_start"], chunk_end=rows[i]["chunk_end"])
+        gg = df4["gtcc"].iloc[i]
+        assert gg.dtype == np.float64 and gg.shape == wg.shape == (198, 13) and np.abs(gg - wg).max() <= 1e-4 * max(1, np.abs(wg).max())
     # mean=True variant of the dispatcher (ASV_func.py defaults)
     df2 = aad.extract_features(pd.DataFrame(rows[:3]), {"mfcc": aad.extract_mfcc}, mean=True)
     y, sr = cache[rows[0]["filepath"]]

@@ -173,6 +173,55 @@ def test_fused_deltas_of_narrow_widths(dev, width, poison):
             assert np.abs(got[:, sl] - want[:, sl]).max() <= TOL_LOG
 
 
+# ----------------------------------------------------------------------------- GTCC (spafe gfcc, dense gammatone bank)
+@pytest.mark.parametrize("sr", [16000, 22050, 48000])
+@pytest.mark.parametrize("spectrum", ["power", "magnitude"])
+def test_gtcc_matches_oracle(dev, sr, spectrum):
+    """extract_gtcc (ASV_dl_func.py:484-499): gfcc(sig=y, fs=sr, num_ceps=13, nfilts=40) of the float waveform.  The
+    cube root keeps the features linear-ish in the spectrum: tolerance 1e-4 of the utterance's largest coefficient
+    (and the 1e-3 absolute bound of the log features on top)."""
+    L = LIB()
+    clips = [speech(90, 2 * sr, sr), noise(91, int(1.3 * sr) + 5), noise(92, int(0.025 * sr)), speech(93, 3 * sr, sr),
+             noise(94, int(0.025 * sr) - 1)]
+    p = FP().gtcc(sr, spectrum=L.SPEC_POWER if spectrum == "power" else L.SPEC_MAGNITUDE)
+    out, nf, st, fe = run(p, clips, dev)
+    np.testing.assert_allclose(fe.table(L.TABLE_FILTERBANK) * (512 if spectrum == "power" else 1),
+                               SR.gammatone_filter_banks(40, 512, sr)[0], rtol=2e-6, atol=1e-9)
+    for i, c in enumerate(clips[:4]):
+        want = SR.gfcc(c, sr, 13, nfilts=40, spectrum=spectrum)
+        assert st[i] == 0 and nf[i] == want.shape[0]
+        err = np.abs(out[i, :nf[i], :] - want).max()
+        assert err <= TOL_LIN * max(1.0, np.abs(want).max()) and err <= TOL_LOG
+    assert st[4] == 2 and oracle.extract_gtcc_ref(clips[4], sr) is None
+
+
+def test_gtcc_custom_dense_bank_int16_and_ct_layout(dev):
+    """The deployment recipe: spafe's own (dense) matrix as AAD_FB_CUSTOM_DENSE; 16-bit PCM input (value / 32768, as
+    librosa decodes it), feature-major layout, an odd number of filters (the last entry holds one filter)."""
+    L = LIB()
+    rng = np.random.default_rng(5)
+    fbm = np.abs(rng.standard_normal((23, 257))) * np.exp(-np.abs(np.arange(257)[None, :] - np.linspace(5, 250, 23)[:, None]) / 30)
+    pcm = [(c * 32768).astype(np.int16) for c in (speech(95, 24000), noise(96, 16001) * 0.5)]
+    p = FP().gtcc(16000, n_ceps=11, nfilts=23, fb_type=L.FB_CUSTOM_DENSE, custom_fb=fbm.astype(np.float32), layout=L.LAYOUT_CT)
+    out, nf, st, _ = run(p, pcm, dev, dtype=np.int16)
+    for i, c in enumerate(pcm):
+        want = SR.gfcc(c.astype(np.float32) / 32768, 16000, 11, nfilts=23, fbanks=fbm.astype(np.float32).astype(np.float64)).T
+        assert st[i] == 0 and nf[i] == want.shape[1]
+        assert np.abs(out[i, :, :nf[i]] - want).max() <= TOL_LIN * max(1.0, np.abs(want).max())
+
+
+def test_dense_bank_is_limited_to_nfft_512_and_cube_root_to_dense_banks(dev):
+    from audioanalysisdetector_b200.frontend import Frontend
+    from audioanalysisdetector_b200._lib import AadError
+    L = LIB()
+    with pytest.raises(AadError):
+        Frontend(FP().gtcc(16000, nfft=1024), dev)
+    with pytest.raises(AadError):
+        Frontend(FP().lfcc(16000).replace(log_type=L.LOG_CBRT), dev)
+    with pytest.raises(AadError):
+        Frontend(FP().gtcc(16000, nfilts=65, n_ceps=13), dev)
+
+
 def test_int16_input_equals_float_quantised_input(dev):
     clips = [noise(30, 20000), speech(31, 33333)]
     p = FP().lfcc(16000)

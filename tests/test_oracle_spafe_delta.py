@@ -103,6 +103,56 @@ def test_spafe_front_half_matches_scipy_signal():
     np.testing.assert_allclose(SR.lfcc(q, fs=16000, num_ceps=13), want, rtol=1e-9, atol=1e-9)
 
 
+def test_gammatone_bank_structure():
+    """spafe gammatone_filter_banks: ERB-spaced centres from low_freq upwards (Slaney's ERBSpace: equal steps of the
+    ERB-rate EarQ * ln(1 + f / (EarQ * minBW))), every filter peaks (value 1) at the bin next to its centre."""
+    for fs, nf in ((16000, 40), (44100, 24)):
+        fb, fc = SR.gammatone_filter_banks(nf, 512, fs)
+        assert fb.shape == (nf, 257) and abs(fc[0]) < 1e-9 and np.all(np.diff(fc) > 0) and fc[-1] < fs / 2
+        rate = SR.EAR_Q * np.log(1 + fc / (SR.EAR_Q * SR.MIN_BW))
+        np.testing.assert_allclose(np.diff(rate), np.diff(rate)[0], rtol=1e-9)
+        np.testing.assert_allclose(fb.max(axis=1), 1.0)
+        assert np.all(np.abs(np.argmax(fb, axis=1) - fc / (fs / 512)) <= 0.75)
+        assert np.all(fb > 0)                                   # dense: no bin is exactly outside a filter
+
+
+def test_gammatone_rows_follow_the_analytic_gammatone_response():
+    """Independent anchor of the filter shape: the magnitude response of the 4th-order gammatone impulse response
+    t^3 exp(-B t) cos(2 pi fc t), evaluated by a long FFT, normalised like the bank.  Slaney's digital cascade is the
+    impulse-invariant design of exactly that filter, so the rows must follow it where aliasing is negligible."""
+    fs, nf = 16000, 40
+    fb, fc = SR.gammatone_filter_banks(nf, 512, fs)
+    t = np.arange(1 << 15) / fs
+    for i in (12, 20, 28, 34):
+        erb = ((fc[i] / SR.EAR_Q) ** 4 + SR.MIN_BW ** 4) ** 0.25
+        g = t ** 3 * np.exp(-1.019 * 2 * np.pi * erb * t) * np.cos(2 * np.pi * fc[i] * t)
+        H = np.abs(np.fft.rfft(g))[:: (1 << 15) // 512][:257]
+        H /= H.max()
+        sel = fb[i] > 0.03                                       # down to -30 dB around the peak
+        assert sel.sum() >= 5
+        np.testing.assert_allclose(fb[i][sel] / fb[i][sel].max(), H[sel] / H[sel].max(), rtol=0.08)
+
+
+def test_gfcc_chain_matches_an_independent_formulation():
+    """pre-emphasis as an FIR filter, frames + symmetric Hamming + FFT through scipy.signal.spectrogram, the bank as a
+    matrix product, cube root, scipy.fftpack DCT: shares no code with oracle/spafe_ref.py except the bank itself."""
+    import scipy.fftpack
+    fs = 16000
+    y = (noise(7, 20000) * 0.3).astype(np.float32)
+    fb, _ = SR.gammatone_filter_banks(40, 512, fs)
+    x = scipy.signal.lfilter([1.0, -0.97], [1.0], y.astype(np.float64))
+    x[0] = y[0]
+    _, _, Z = scipy.signal.spectrogram(x, fs=fs, window=scipy.signal.get_window("hamming", 400, fftbins=False), nperseg=400,
+                                       noverlap=240, nfft=512, detrend=False, scaling="spectrum", mode="complex",
+                                       return_onesided=True)
+    spec = (np.abs(Z.T) * np.hamming(400).sum()) ** 2 / 512       # undo scipy's window normalisation
+    want = scipy.fftpack.dct(np.cbrt(spec @ fb.T), type=2, axis=1, norm="ortho")[:, :13]
+    got = SR.gfcc(y, fs, 13, nfilts=40)
+    assert got.shape == want.shape == ((20000 - 400) // 160 + 1, 13)
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9)
+    assert SR.gfcc(y, fs, 13, nfilts=40, spectrum="magnitude").shape == want.shape
+
+
 def test_delta_taps_and_known_answers():
     np.testing.assert_allclose(DR.savgol_taps(9, 1) * 60, np.arange(-4, 5), atol=1e-12)
     np.testing.assert_allclose(DR.savgol_taps(9, 2) * 462, [28, 7, -8, -17, -20, -17, -8, 7, 28], atol=1e-10)
