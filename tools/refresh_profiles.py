@@ -4,10 +4,11 @@ import csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, launches, bench, bench_ref = sys.argv[1:5]
 P = lambda *a: os.path.join(ROOT, "profiles", *a)
+R = os.environ.get("AAD_ROUND", "r2")   # file-name prefix of the round
 FRAMES = 516096
 
 # 1. ncu summary
-with open(P("r1_ncu_summary.md"), "w") as f:
+with open(P(f"{R}_ncu_summary.md"), "w") as f:
     subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep], stdout=f, check=True)
 
 # 2. DRAM traffic of k_stft_fb
@@ -20,7 +21,7 @@ for r in rr[2:]:
     if "k_stft_fb" in d["Kernel Name"]:
         rd = float(d["dram__bytes_read.sum"]) * scale[units[hdr.index("dram__bytes_read.sum")]]
         wr = float(d["dram__bytes_write.sum"]) * scale[units[hdr.index("dram__bytes_write.sum")]]
-        json.dump({"kernel": d["Kernel Name"], "source": "profiles/r1_ncu_summary.md (ncu --set full, one launch of the C2 workload: 4096 x 4 s)",
+        json.dump({"kernel": d["Kernel Name"], "source": f"profiles/{R}_ncu_summary.md (ncu --set full, one launch of the C2 workload: 4096 x 4 s)",
                    "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
                    "algorithmic_bytes_per_launch": FRAMES * (4 * 512 + 4 * 128)}, open(P("stft_fb_traffic.json"), "w"), indent=1)
 
@@ -42,14 +43,14 @@ for n, hi in enumerate(his):
                          capture_output=True, text=True).stdout
     out.append(f"# {name}\n# SASS opcode mix, per-section cost (sections split at BAR) and warp-stall reasons; "
                f"ncu --set full --import-source on, C2 workload ({FRAMES} frames per launch); tools/sass_profile.py\n" + txt)
-open(P("r1_sass_stalls.txt"), "w").write("\n".join(out))
+open(P(f"{R}_sass_stalls.txt"), "w").write("\n".join(out))
 
 # 4. launch list
 rows = [r for r in csv.reader(open(launches)) if len(r) > 5]
 h = rows[0]
 ki, vi, bi, gi, ii = (h.index(x) for x in ("Kernel Name", "Metric Value", "Block Size", "Grid Size", "ID"))
 tot = {}
-with open(P("r1_launches.csv"), "w", newline="") as f:
+with open(P(f"{R}_launches.csv"), "w", newline="") as f:
     w = csv.writer(f)
     w.writerow(["id", "kernel", "block", "grid", "gpu__time_duration.sum [ns]"])
     for r in rows[1:]:
@@ -64,8 +65,8 @@ s = sum(tot.values())
 print("launch-list shares:", {k: f"{100 * v / s:.1f}%" for k, v in tot.items()})
 
 # 5. bench lines
-for src_, dst in ((bench, "r1_bench.json"), (bench_ref, "r1_bench_reference.json")):
+for src_, dst in ((bench, f"{R}_bench.json"), (bench_ref, f"{R}_bench_reference.json")):
     line = [l for l in open(src_).read().splitlines() if l.startswith("{")][-1]
     open(P(dst), "w").write(line + "\n")
-d = json.loads(open(P("r1_bench.json")).read())
+d = json.loads(open(P(f"{R}_bench.json")).read())
 print("bench:", d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"], d["roofline"]["kernel_ms"])
