@@ -242,6 +242,128 @@ __global__ void __launch_bounds__(kOctUtt * 16 * 6) k_cqt_octave(const void* y, 
   atomicMax(utt_max + b, poison ? 0x7fc00000 : __float_as_int(vmax));
 }
 
+// ---- the same octave on the tensor cores ------------------------------------------------------------------------
+// D[frame][2 bin + {re, im}] = sum_n y[frame start + n] * G[n][2 bin + {re, im}] is a GEMM with M = frames, K = n_fft,
+// N = 24: mma.sync.m16n8k8 TF32 with the 3-term split (a_hi b_hi + a_lo b_hi + a_hi b_lo: float32-accurate, the same
+// scheme as the DCT of k_cepstra).  At ~12 issue-blocking cycles per HMMA the 9 MMAs of a k-step still beat the 96
+// packed FMAs they replace by 3x.  A warp owns 16 consecutive frames of one utterance and reads them where they lie
+// in the padded octave buffer: lane (g, t) loads 16-byte pieces of rows g and g + 8; the k order inside a 32-tap
+// chunk is permuted so that those pieces ARE its A fragments (k-step j of the chunk: column t = tap 4 t + j, column
+// t + 4 = tap 16 + 4 t + j) -- the plan stores the B fragments (taps, pre-split into hi / lo) in the matching order,
+// one LDS.128 per (k-step, n-tile).  The C fragment holds (re, im) of one bin side by side: the magnitude needs no
+// exchange.  Octaves whose buffers allow aligned 16-byte frame reads (hop % 4 == 0; not the caller's own waveform)
+// take this kernel, the others k_cqt_octave.
+constexpr int kMmaWarps = 8, kMmaNT = 3;   // n-tiles of 8: up to 12 bins per octave
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// GENERIC = false: padded float octave buffer of the library (aligned 16-byte reads, every frame interior).
+// GENERIC = true: the caller's waveform (octave 0): float or int16, any row offset, frames that reach in front of /
+// behind the signal read zeros -- scalar loads, masked only in the tiles that touch an end.
+template <bool GENERIC>
+__global__ void __launch_bounds__(kMmaWarps * 32) k_cqt_octave_mma(const void* __restrict__ yv, int y_i16, long long y_stride,
+                                                                   const long long* __restrict__ row_off, int pad,
+                                                                   const int32_t* __restrict__ lengths, int B, int hop, int n_fft,
+                                                                   const float4* __restrict__ gfrag, int n_k, int bin0,
+                                                                   float* __restrict__ mag, long long mag_stride_b, int t_alloc,
+                                                                   int32_t* utt_max, int mt_per_utt) {
+  const float* y = static_cast<const float*>(yv);
+  extern __shared__ __align__(16) float smem[];
+  float4* sB = reinterpret_cast<float4*>(smem);  // [n_fft / 8][kMmaNT][32] = {b0 hi, b1 hi, b0 lo, b1 lo}
+  const int n_frag = n_fft / 8 * kMmaNT * 32;
+  for (int i = threadIdx.x; i < n_frag; i += blockDim.x) sB[i] = __ldg(gfrag + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+  const long long n_items = (long long)B * mt_per_utt;
+  for (long long item = (long long)blockIdx.x * kMmaWarps + warp; item < n_items; item += (long long)gridDim.x * kMmaWarps) {
+    const int b = (int)(item / mt_per_utt), t0 = 16 * (int)(item - (long long)b * mt_per_utt);
+    const long long len0 = __ldg(lengths + b);
+    if (len0 <= 0) continue;
+    const int T = (int)min((long long)t_alloc, 1 + len0 / kHop);
+    if (t0 >= T) continue;
+    const int ta = t0 + g, tb = t0 + g + 8;
+    const long long row0 = GENERIC ? (row_off ? __ldg(row_off + b) : (long long)b * y_stride) : (long long)b * y_stride + pad;
+    // first sample of this lane's pieces of rows g and g + 8, relative to the signal's first sample (rows that are not
+    // stored re-read the last frame)
+    const long long sa = (long long)min(ta, T - 1) * hop - n_fft / 2 + 4 * tig;
+    const long long sb = (long long)min(tb, T - 1) * hop - n_fft / 2 + 4 * tig;
+    const float* pa = y + row0 + sa;
+    const float* pb = y + row0 + sb;
+    // GENERIC: does any frame of the tile reach outside [0, len0)?  (warp-uniform)
+    const bool edge = GENERIC && ((long long)t0 * hop - n_fft / 2 < 0 || (long long)min(t0 + 15, T - 1) * hop + n_fft / 2 > len0);
+    float acc[kMmaNT][4];
+#pragma unroll
+    for (int nt = 0; nt < kMmaNT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    const float4* bp = sB + lane;
+    for (int c = 0; c < n_fft; c += 32, bp += 4 * kMmaNT * 32) {
+      float xa0[4], xa1[4], xb0[4], xb1[4];
+      if constexpr (GENERIC) {
+        auto piece = [&](long long s, float (&x)[4]) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            x[e] = (!edge || (s + e >= 0 && s + e < len0)) ? load_sample(yv, y_i16, row0 + s + e) : 0.f;
+        };
+        piece(sa + c, xa0); piece(sa + c + 16, xa1); piece(sb + c, xb0); piece(sb + c + 16, xb1);
+      } else {
+        const float4 qa0 = __ldg(reinterpret_cast<const float4*>(pa + c)), qa1 = __ldg(reinterpret_cast<const float4*>(pa + c + 16));
+        const float4 qb0 = __ldg(reinterpret_cast<const float4*>(pb + c)), qb1 = __ldg(reinterpret_cast<const float4*>(pb + c + 16));
+        xa0[0] = qa0.x; xa0[1] = qa0.y; xa0[2] = qa0.z; xa0[3] = qa0.w; xa1[0] = qa1.x; xa1[1] = qa1.y; xa1[2] = qa1.z; xa1[3] = qa1.w;
+        xb0[0] = qb0.x; xb0[1] = qb0.y; xb0[2] = qb0.z; xb0[3] = qb0.w; xb1[0] = qb1.x; xb1[1] = qb1.y; xb1[2] = qb1.z; xb1[3] = qb1.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float av[4] = {xa0[j], xb0[j], xa1[j], xb1[j]};  // (g, t), (g + 8, t), (g, t + 4), (g + 8, t + 4)
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          hi[i] = tf32_rna(av[i]);
+          lo[i] = __float_as_uint(av[i] - __uint_as_float(hi[i]));
+        }
+#pragma unroll
+        for (int nt = 0; nt < kMmaNT; ++nt) {
+          const float4 bf = bp[(j * kMmaNT + nt) * 32];
+          mma_tf32(acc[nt], lo, __float_as_uint(bf.x), __float_as_uint(bf.y));
+          mma_tf32(acc[nt], hi, __float_as_uint(bf.z), __float_as_uint(bf.w));
+          mma_tf32(acc[nt], hi, __float_as_uint(bf.x), __float_as_uint(bf.y));
+        }
+      }
+    }
+    float vmax = 0.f;
+    bool poison = false;
+    float* mrow = mag + (long long)b * mag_stride_b + (long long)bin0 * t_alloc;
+#pragma unroll
+    for (int nt = 0; nt < kMmaNT; ++nt) {
+      const int bin = 4 * nt + tig;
+      if (bin < n_k) {
+        const float m0 = sqrtf(__fmaf_rn(acc[nt][0], acc[nt][0], acc[nt][1] * acc[nt][1]));
+        const float m1 = sqrtf(__fmaf_rn(acc[nt][2], acc[nt][2], acc[nt][3] * acc[nt][3]));
+        if (ta < T) {
+          mrow[(long long)bin * t_alloc + ta] = m0;
+          if (m0 == m0) vmax = fmaxf(vmax, m0);
+          else poison = true;
+        }
+        if (tb < T) {
+          mrow[(long long)bin * t_alloc + tb] = m1;
+          if (m1 == m1) vmax = fmaxf(vmax, m1);
+          else poison = true;
+        }
+      }
+    }
+    int enc = poison ? 0x7fc00000 : __float_as_int(vmax);   // non-negative floats order like their bit patterns
+    enc = __reduce_max_sync(0xffffffffu, enc);
+    if (lane == 0) atomicMax(utt_max + b, enc);
+  }
+}
+
 // dB relative to the utterance maximum (floor -80) -> interpolation onto the uniform frequency grid -> log(x^2 + 1e-12)
 // -> DCT-II ortho.  grid (frame blocks of 32, B), 256 threads.
 constexpr int kEpiFrames = 32;
@@ -315,10 +437,12 @@ std::vector<double> float_window_hann(double n) {  // librosa.filters.__float_wi
 
 struct aad_cqcc_plan {
   int device = 0, sample_rate = 0, bpo = 12, n_ceps = 19, n_bins = 0, n_oct = 0;
+  int sm_count = 148, mma_ctas = 1;  // resident CTAs of k_cqt_octave_mma per SM
   int n_fft = 0;                    // per-octave transform size (the same for every octave: wavelet lengths repeat)
   int n_k[kMaxOct] = {0};           // bins of octave i (top first)
   int bin0[kMaxOct] = {0};
   float2* d_g[kMaxOct] = {nullptr}; // [n_k][n_fft] taps of octave i
+  float4* d_gfrag[kMaxOct] = {nullptr};  // the same taps as pre-split TF32 B fragments (k_cqt_octave_mma), or null
   int32_t* d_interp_lo = nullptr;
   float* d_interp_w = nullptr;
   float* d_dct = nullptr;           // [n_ceps][n_bins]
@@ -331,6 +455,7 @@ int aad_cqcc_plan_destroy(aad_cqcc_plan* pl) {
   if (!pl) return AAD_OK;
   DeviceGuard guard(pl->device);
   for (auto& p : pl->d_g) cudaFree(p);
+  for (auto& p : pl->d_gfrag) cudaFree(p);
   cudaFree(pl->d_interp_lo);
   cudaFree(pl->d_interp_w);
   cudaFree(pl->d_dct);
@@ -446,6 +571,36 @@ int aad_cqcc_plan_create(int sample_rate, int bins_per_octave, int n_ceps, int d
     }
     e = cudaMalloc((void**)&pl->d_g[i], g.size() * sizeof(float2));
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_g[i], g.data(), g.size() * sizeof(float2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && nk <= 4 * kMmaNT && n_fft % 32 == 0) {
+      // B fragments of k_cqt_octave_mma: [k-step][n-tile][lane = 4 gid + tig] = {b0 hi, b1 hi, b0 lo, b1 lo} with
+      // b0 = G[tap(tig)][8 nt + gid], b1 = G[tap(tig + 4)][8 nt + gid]; k-step ks = 4 c + j covers, in column order,
+      // taps 32 c + 4 tig + j (columns 0..3) and 32 c + 16 + 4 tig + j (columns 4..7); G[n][2 bin + {0, 1}] = {re, im}
+      auto tf32 = [](float x) {
+        uint32_t u;
+        std::memcpy(&u, &x, 4);
+        u = (u + 0x1000u) & 0xffffe000u;   // cvt.rna: nearest, ties away from zero (magnitude bits)
+        float r;
+        std::memcpy(&r, &u, 4);
+        return r;
+      };
+      auto G = [&](int tap, int n) {
+        const int bin = n >> 1;
+        if (bin >= nk) return 0.f;
+        const float2 v = g[(size_t)bin * n_fft + tap];
+        return (n & 1) ? v.y : v.x;
+      };
+      std::vector<float4> frag((size_t)n_fft / 8 * kMmaNT * 32);
+      for (int ks = 0; ks < n_fft / 8; ++ks)
+        for (int nt = 0; nt < kMmaNT; ++nt)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int gid = lane >> 2, tig = lane & 3, c = ks / 4, j = ks % 4;
+            const float b0 = G(32 * c + 4 * tig + j, 8 * nt + gid), b1 = G(32 * c + 16 + 4 * tig + j, 8 * nt + gid);
+            const float h0 = tf32(b0), h1 = tf32(b1);
+            frag[((size_t)ks * kMmaNT + nt) * 32 + lane] = make_float4(h0, h1, b0 - h0, b1 - h1);
+          }
+      e = cudaMalloc((void**)&pl->d_gfrag[i], frag.size() * sizeof(float4));
+      if (e == cudaSuccess) e = cudaMemcpy(pl->d_gfrag[i], frag.data(), frag.size() * sizeof(float4), cudaMemcpyHostToDevice);
+    }
     my_sr /= 2.0;
   }
   // resampler taps: 0.5 sinc(n / 2) kaiser(255, 14), unit DC gain
@@ -508,6 +663,16 @@ int aad_cqcc_plan_create(int sample_rate, int bins_per_octave, int n_ceps, int d
     const size_t smem = 2 * (size_t)pl->n_fft * ((bpo + 3) / 4 * 4) * 4;
     if (smem > 200 * 1024 || (bpo + 3) / 4 > 6) e = cudaErrorInvalidValue;
     else if (smem > 48 * 1024) e = cudaFuncSetAttribute((const void*)k_cqt_octave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem_mma = (size_t)pl->n_fft / 8 * kMmaNT * 32 * sizeof(float4);
+    if (e == cudaSuccess && smem_mma > 48 * 1024)
+      e = cudaFuncSetAttribute((const void*)k_cqt_octave_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
+    if (e == cudaSuccess && smem_mma > 48 * 1024)
+      e = cudaFuncSetAttribute((const void*)k_cqt_octave_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
+    cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, device);
+    int occ = 0;
+    if (e == cudaSuccess && smem_mma <= 200 * 1024 &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cqt_octave_mma<true>, kMmaWarps * 32, smem_mma) == cudaSuccess)
+      pl->mma_ctas = std::max(1, occ);   // the generic form needs at least as many registers as the aligned one
   }
   if (e != cudaSuccess) {
     aad_cqcc_plan_destroy(pl);
@@ -578,7 +743,24 @@ int aad_cqcc(const aad_cqcc_plan* pl, const void* wav, int wav_dtype, int64_t wa
     const dim3 grid_oct((frames + kOctFrames - 1) / kOctFrames, (B + kOctUtt - 1) / kOctUtt);
     const int pad_i = i == 0 ? 0 : pl->n_fft / 2;
     const long long* roff = i == 0 ? reinterpret_cast<const long long*>(row_off) : nullptr;
-    k_cqt_octave<<<grid_oct, kOctUtt * 16 * n_bg, smem, stream>>>(y, i == 0 ? i16 : 0, ystride, roff, pad_i, lengths, B, i, kHop >> i, pl->n_fft,
+    const int hop_i = kHop >> i;
+    const size_t smem_mma = (size_t)pl->n_fft / 8 * kMmaNT * 32 * sizeof(float4);
+    if (pl->d_gfrag[i] && (i == 0 || hop_i % 4 == 0) && smem_mma <= 200 * 1024) {
+      // tensor-core form: the library's padded float octave buffers with aligned 16-byte frame reads, the caller's
+      // waveform (octave 0) through the generic loads
+      const int mt_per_utt = (frames + 15) / 16;
+      const long long items = (long long)B * mt_per_utt;
+      const int grid_mma = (int)std::min<long long>((long long)pl->sm_count * pl->mma_ctas, (items + kMmaWarps - 1) / kMmaWarps);
+      if (i == 0)
+        k_cqt_octave_mma<true><<<grid_mma, kMmaWarps * 32, smem_mma, stream>>>(y, i16, ystride, roff, 0, lengths, B, hop_i, pl->n_fft,
+                                                                               pl->d_gfrag[i], pl->n_k[i], pl->bin0[i], d_mag,
+                                                                               mag_stride_b, t_ws, d_max, mt_per_utt);
+      else
+        k_cqt_octave_mma<false><<<grid_mma, kMmaWarps * 32, smem_mma, stream>>>(y, 0, ystride, nullptr, pad_i, lengths, B, hop_i, pl->n_fft,
+                                                                                pl->d_gfrag[i], pl->n_k[i], pl->bin0[i], d_mag,
+                                                                                mag_stride_b, t_ws, d_max, mt_per_utt);
+    } else
+    k_cqt_octave<<<grid_oct, kOctUtt * 16 * n_bg, smem, stream>>>(y, i == 0 ? i16 : 0, ystride, roff, pad_i, lengths, B, i, hop_i, pl->n_fft,
                                                            pl->d_g[i], pl->n_k[i], pl->bin0[i], d_mag, mag_stride_b, t_ws, d_max);
     if (i + 1 < pl->n_oct) {
       const long long len_out = (len + 1) >> 1;
