@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define AAD_VERSION 100 /* 0.1.0 */
+#define AAD_VERSION 200 /* 0.2.0: aad_params grew (spectrum), GTCC / CQCC / FLAC entry points */
 
 typedef struct aad_plan aad_plan;
 

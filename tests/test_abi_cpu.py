@@ -27,7 +27,7 @@ def test_header_symbols_all_exported(built_lib):
 
 
 def test_version_and_strerror(built_lib):
-    assert built_lib.aad_version() == 100
+    assert built_lib.aad_version() == 200
     assert built_lib.aad_strerror(0) == b"ok"
     assert b"workspace" in built_lib.aad_strerror(-4)
 
