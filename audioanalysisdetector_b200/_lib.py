@@ -111,6 +111,8 @@ SYMBOLS = {
                            C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "aad_flac_info": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(AadFlacInfo)]),
     "aad_flac_decode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "aad_flac_decode_pcm16": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
+                                        C.POINTER(C.c_int32)]),
     "aad_host_reserve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int32, C.c_int]),
     "aad_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]),
     "aad_host_free": (C.c_int, [C.c_void_p]),

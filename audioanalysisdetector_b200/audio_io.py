@@ -20,11 +20,24 @@ import numpy as np
 from . import _lib as L
 
 _loader: Optional[Callable[[str], Tuple[np.ndarray, int]]] = None
+_verify_flac_md5 = True
+
+
+def set_flac_md5(verify: bool):
+    """FLAC frames are always CRC-checked; the MD5 of the whole decoded stream (STREAMINFO) is checked on top unless
+    switched off here (a quarter of the decode time of a 16-bit file; libsndfile, the reference's decoder, does not
+    check it either)."""
+    global _verify_flac_md5
+    _verify_flac_md5 = bool(verify)
 
 
 def set_loader(fn: Optional[Callable[[str], Tuple[np.ndarray, int]]]):
     global _loader
     _loader = fn
+
+
+def custom_loader_installed() -> bool:
+    return _loader is not None
 
 
 def _load_wav(path: str, keep_pcm16: bool = False) -> Tuple[np.ndarray, int]:
@@ -47,9 +60,10 @@ def _load_wav(path: str, keep_pcm16: bool = False) -> Tuple[np.ndarray, int]:
 
 
 def decode_flac(data: bytes, verify_md5: bool = True) -> Tuple[np.ndarray, int, int]:
-    """FLAC stream in memory -> (interleaved int32 samples [n, channels], sample_rate, bits_per_sample)."""
+    """FLAC stream in memory -> (interleaved int32 samples [n, channels], sample_rate, bits_per_sample).
+    (16-bit streams come back as an int32 VIEW-compatible array too; `_load_flac` narrows them.)"""
     lib = L.load()
-    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    buf = C.cast(C.c_char_p(data), C.c_void_p)     # no copy: the bytes object outlives the calls below
     info = L.AadFlacInfo()
     L.check(lib.aad_flac_info(buf, len(data), C.byref(info)), "aad_flac_info")
     if info.total_samples <= 0:
@@ -64,9 +78,9 @@ def decode_flac(data: bytes, verify_md5: bool = True) -> Tuple[np.ndarray, int, 
     if verify_md5 and any(md5):
         width = (int(info.bits_per_sample) + 7) // 8
         if width == 2:
-            raw = out.astype("<i2").tobytes()
+            raw = out.astype("<i2")                  # hashed through the buffer protocol (no second copy; GIL released)
         elif width == 4:
-            raw = out.astype("<i4").tobytes()
+            raw = out.astype("<i4")
         else:
             raw = out.astype("<i4").view(np.uint8).reshape(-1, 4)[:, :width].tobytes()
         if hashlib.md5(raw).digest() != md5:
@@ -74,9 +88,35 @@ def decode_flac(data: bytes, verify_md5: bool = True) -> Tuple[np.ndarray, int, 
     return out, int(info.sample_rate), int(info.bits_per_sample)
 
 
+def decode_flac_pcm16(data: bytes) -> Optional[Tuple[np.ndarray, int]]:
+    """Mono 16-bit FLAC stream -> (int16 samples, sample_rate) in ONE library call (decode, narrowing and the MD5 check
+    run without the interpreter lock: this is the call the corpus upload fans out over threads); None when the stream
+    is not mono 16-bit."""
+    lib = L.load()
+    buf = C.cast(C.c_char_p(data), C.c_void_p)
+    info = L.AadFlacInfo()
+    L.check(lib.aad_flac_info(buf, len(data), C.byref(info)), "aad_flac_info")
+    if info.channels != 1 or info.bits_per_sample != 16 or info.total_samples <= 0:
+        return None
+    out = np.empty(int(info.total_samples), dtype=np.int16)
+    n, state = C.c_int64(0), C.c_int32(0)
+    L.check(lib.aad_flac_decode_pcm16(buf, len(data), C.c_void_p(out.ctypes.data), out.size, C.byref(n),
+                                      C.byref(state) if _verify_flac_md5 else None), "aad_flac_decode_pcm16")
+    if n.value != info.total_samples:
+        raise ValueError(f"FLAC stream ends after {n.value} of {info.total_samples} samples")
+    if state.value < 0:
+        raise ValueError("FLAC MD5 mismatch: decoded audio differs from what the encoder saw")
+    return out, int(info.sample_rate)
+
+
 def _load_flac(path: str, keep_pcm16: bool = False) -> Tuple[np.ndarray, int]:
     with open(path, "rb") as f:
-        pcm, sr, bps = decode_flac(f.read())
+        data = f.read()
+    if keep_pcm16:
+        got = decode_flac_pcm16(data)
+        if got is not None:
+            return got
+    pcm, sr, bps = decode_flac(data, verify_md5=_verify_flac_md5)
     if keep_pcm16 and bps == 16 and pcm.shape[1] == 1:
         return pcm[:, 0].astype(np.int16), sr                 # sample value = int16 / 32768
     y = pcm.astype(np.float32) / np.float32(1 << (bps - 1))   # what libsndfile hands to librosa.load
@@ -101,7 +141,7 @@ def info_ex(source) -> Tuple[int, int, bool]:
             head = f.read(1 << 16)
         fi = L.AadFlacInfo()
         lib = L.load()
-        rc = lib.aad_flac_info((C.c_uint8 * len(head)).from_buffer_copy(head), len(head), C.byref(fi))
+        rc = lib.aad_flac_info(C.cast(C.c_char_p(head), C.c_void_p), len(head), C.byref(fi))
         if rc == 0 and fi.total_samples > 0:
             return int(fi.total_samples), int(fi.sample_rate), (fi.bits_per_sample == 16 and fi.channels == 1)
     y, sr = load_pcm(source) if _loader is None else load(source)

@@ -15,6 +15,9 @@ from __future__ import annotations
 import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import os
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 import torch
 
@@ -106,10 +109,14 @@ class DeviceCorpus:
                                  f"decoded {len(y)} @ {sr}")
         return y
 
-    def upload(self, dtype: Optional[torch.dtype] = None, stage_bytes: int = STAGE_BYTES) -> torch.Tensor:
+    def upload(self, dtype: Optional[torch.dtype] = None, stage_bytes: int = STAGE_BYTES,
+               decode_threads: Optional[int] = None) -> torch.Tensor:
         """Stream the corpus to the device: files are decoded into one of two pinned staging buffers while the other
         one's H2D copy is in flight (copy stream + events), segment after segment.  int16 when every file is 16-bit
-        PCM (or `dtype=torch.int16` is forced), else float32 (int16 / 32768)."""
+        PCM (or `dtype=torch.int16` is forced), else float32 (int16 / 32768).
+        Decoding runs `decode_threads` files ahead on a thread pool (default: the host's cores, at most 16): the FLAC
+        decoder and the MD5 check release the GIL, and decoding -- not the copy, not the kernels -- is what a corpus
+        of files costs (1.4 ms per 4-second clip and core against 29 ms of GPU time for 25 380 chunks)."""
         if self.pcm is not None and (dtype is None or self.pcm.dtype == dtype):
             return self.pcm
         if not self._host:
@@ -124,8 +131,38 @@ class DeviceCorpus:
         views = [st.numpy() for st in stages]
         events = [None] * len(stages)
         copy_stream = torch.cuda.Stream(self.device)
-        fi, fpos = 0, 0                                # next file and how much of it has been staged
-        cur = None                                     # decoded samples of file fi
+        n_thr = min(16, os.cpu_count() or 1) if decode_threads is None else max(0, int(decode_threads))
+        if audio_io.custom_loader_installed():
+            n_thr = 0                                  # a caller's loader is not known to be thread-safe
+        pool = ThreadPoolExecutor(n_thr) if n_thr > 1 and any(y is None for y in self._host) else None
+        pending: Dict[int, object] = {}                # file index -> future of its decoded samples
+        ahead = 0                                      # files [0, ahead) have been handed to the pool
+
+        def decoded(i: int) -> np.ndarray:
+            nonlocal ahead
+            if pool is None:
+                return self._decoded(i)
+            while ahead < len(self._host) and ahead < i + 4 * n_thr:
+                if self._host[ahead] is None:
+                    pending[ahead] = pool.submit(self._decoded, ahead)
+                ahead += 1
+            fut = pending.pop(i, None)
+            return self._decoded(i) if fut is None else fut.result()
+
+        try:
+            dev = self._stream_segments(total, seg, dtype, dev, stages, views, events, copy_stream, decoded)
+        finally:
+            if pool is not None:
+                pool.shutdown(wait=True, cancel_futures=True)
+        torch.cuda.current_stream(self.device).wait_stream(copy_stream)
+        copy_stream.synchronize()                      # the staging buffers are released below
+        self.pcm = dev
+        self.h2d_bytes = total * esz
+        self._pcm_f32 = None
+        return self.pcm
+
+    def _stream_segments(self, total, seg, dtype, dev, stages, views, events, copy_stream, decoded):
+        fi, fpos, cur = 0, 0, None
         for k, s0 in enumerate(range(0, total, seg)):
             n = min(seg, total - s0)
             b = k % len(stages)
@@ -135,7 +172,7 @@ class DeviceCorpus:
             sv[:n] = 0
             while fi < len(self.base) and self.base[fi] < s0 + n:
                 if cur is None:
-                    cur = self._decoded(fi)
+                    cur = decoded(fi)
                     if dtype == torch.int16 and cur.dtype != np.int16:
                         raise L.AadError("int16 upload of a corpus with non-16-bit files")
                     if dtype == torch.float32 and cur.dtype == np.int16:
@@ -151,12 +188,7 @@ class DeviceCorpus:
                 dev[s0:s0 + n].copy_(stages[b][:n], non_blocking=True)
                 events[b] = torch.cuda.Event()
                 events[b].record(copy_stream)
-        torch.cuda.current_stream(self.device).wait_stream(copy_stream)
-        copy_stream.synchronize()                      # the staging buffers are released below
-        self.pcm = dev
-        self.h2d_bytes = total * esz
-        self._pcm_f32 = None
-        return self.pcm
+        return dev
 
     def as_float32(self) -> torch.Tensor:
         """The corpus as librosa.load would return it (int16 / 32768 is exact in float32)."""

@@ -284,6 +284,10 @@ typedef struct aad_flac_info_t {
 } aad_flac_info_t;
 int aad_flac_info(const uint8_t* data, size_t size, aad_flac_info_t* info);
 int aad_flac_decode(const uint8_t* data, size_t size, int32_t* out, int64_t capacity_samples, int64_t* n_decoded);
+/* The corpus's own format in one call: a MONO 16-BIT stream straight to int16 PCM (AAD_ERR_UNSUPPORTED otherwise), with the
+ * MD5 of STREAMINFO checked in the library: *md5_state = 1 verified, 0 the stream stores no checksum, -1 mismatch. */
+int aad_flac_decode_pcm16(const uint8_t* data, size_t size, int16_t* out, int64_t capacity_samples, int64_t* n_decoded,
+                          int32_t* md5_state);
 
 /* Host-buffer convenience path (what the reference-facing Python drop-ins use for
  * host arrays): pinned-or-pageable HOST wav/lengths in, HOST out/n_frames/status back,

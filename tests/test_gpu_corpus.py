@@ -195,12 +195,12 @@ def test_streamed_upload_of_a_flac_and_wav_corpus(tmp_path):
         clips.append(pcm)
     want, base = _flat(clips, np.int16)
     ups = []
-    for stage_bytes in (64 << 20, 16 * 1024, 4096):
+    for stage_bytes, threads in ((64 << 20, None), (16 * 1024, 0), (4096, 3), (8192, 1)):   # decode-ahead pool on / off
         corpus = DeviceCorpus("cuda:0")
         for p in paths:
             corpus.add(p)
         assert corpus.n_samples == [len(c) for c in clips] and corpus._host == [None] * len(paths)   # measured, not decoded
-        dev = corpus.upload(stage_bytes=stage_bytes)
+        dev = corpus.upload(stage_bytes=stage_bytes, decode_threads=threads)
         assert dev.dtype == torch.int16 and corpus.base == base
         np.testing.assert_array_equal(dev.cpu().numpy(), want)
         ups.append(corpus)
