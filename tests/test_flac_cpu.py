@@ -82,3 +82,42 @@ def test_load_and_info_like_librosa_and_soundfile(aio, tmp_path):
     q.write_bytes(FW.encode(st, 16000, seed=3))
     y2, _ = aio.load(str(q))
     np.testing.assert_allclose(y2, ((st[:, 0] + st[:, 1]) / 2 / 32768.0).astype(np.float32), atol=1e-7)
+
+
+@pytest.mark.parametrize("force", [None, "lpc8", "lpc12", "lpc32", "fixed3"])
+def test_pcm16_one_call_path_with_md5_in_the_library(aio, force):
+    """aad_flac_decode_pcm16 (what the corpus upload fans out over threads): same samples as the generic decoder, the
+    MD5 of STREAMINFO checked in C (hashlib is the independent reference for the digest), unrolled LPC orders and the
+    generic one (32)."""
+    import hashlib
+    x = _speechlike(2 * 4096 + 1234, 9)
+    data = FW.encode(x, 22050, bps=16, blocksize=4096, seed=5, force=force)
+    y, sr = aio.decode_flac_pcm16(data)
+    assert sr == 22050 and y.dtype == np.int16
+    np.testing.assert_array_equal(y, x)
+    assert hashlib.md5(y.astype("<i2").tobytes()).digest() == data[8 + 18:8 + 34]       # STREAMINFO's MD5 field
+    bad = bytearray(data)
+    bad[8 + 20] ^= 0x5a                                                               # a wrong stored checksum
+    with pytest.raises(ValueError, match="MD5"):
+        aio.decode_flac_pcm16(bytes(bad))
+    aio.set_flac_md5(False)
+    try:
+        np.testing.assert_array_equal(aio.decode_flac_pcm16(bytes(bad))[0], x)        # CRCs still pass: accepted
+    finally:
+        aio.set_flac_md5(True)
+    stereo = FW.encode(np.stack([x, -x], axis=1), 16000, bps=16, blocksize=4096, seed=6)
+    assert aio.decode_flac_pcm16(stereo) is None                                      # not the corpus format: generic path
+    assert aio.decode_flac_pcm16(FW.encode(x // 4, 16000, bps=12, blocksize=1024, seed=7)) is None
+
+
+def test_crc16_slices_agree_with_the_bytewise_definition(aio):
+    """Frames of every length modulo 8 pass their CRC-16 (slicing-by-8 with a byte-wise tail) -- and a flipped bit in
+    the last byte of a frame body is caught."""
+    for n in range(4100, 4116):
+        x = _speechlike(n, n)
+        data = FW.encode(x, 16000, bps=16, blocksize=4096, seed=n, force="verbatim")
+        np.testing.assert_array_equal(aio.decode_flac_pcm16(data)[0], x)
+    bad = bytearray(data)
+    bad[-3] ^= 1
+    with pytest.raises(Exception):
+        aio.decode_flac_pcm16(bytes(bad))
