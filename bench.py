@@ -344,6 +344,50 @@ def run_c4(args):
     return 0
 
 
+# --------------------------------------------------------------------------- the notebook's whole extractor map
+def run_map(args):
+    """The reference notebook's feature_extractors_map (ASV_deep_learning.ipynb:152-160: cqcc, gtcc, mel-spect, mfcc,
+    lfcc) over the configs[3] corpus: 25 380 two-second chunks @16 kHz resident in HBM as int16 PCM, sharded by
+    utterance (strong scaling).  mel-spect and mfcc share one STFT (aad_extract_pair)."""
+    R = Ranks()
+    torch, aad = R.torch, R.aad
+    from audioanalysisdetector_b200.frontend import Frontend, FrontendParams
+    n_chunks, chunk = 25380, 2 * SR
+    sl = aad.contiguous_shard(n_chunks, R.rank, R.world)
+    n_local = sl.stop - sl.start
+    gen = torch.Generator(device=R.dev)
+    gen.manual_seed(777 + R.rank)
+    wav = (3276.8 * torch.randn((n_local, chunk), generator=gen, device=R.dev)).clamp_(-32768, 32767).to(torch.int16)
+    cq = aad.CqccFrontend(SR, device=R.dev)
+    gt = Frontend(FrontendParams.gtcc(SR), R.dev)
+    mf = Frontend(FrontendParams.mfcc(SR, n_mfcc=13), R.dev)
+    ml = Frontend(FrontendParams.logmel(SR, n_mels=64), R.dev)
+    lf = Frontend(FrontendParams.lfcc(SR), R.dev)
+    parts = {"cqcc": lambda: cq(wav), "gtcc": lambda: gt(wav), "mfcc + mel-spect (one STFT)": lambda: mf.extract_pair(ml, wav),
+             "lfcc": lambda: lf(wav)}
+    state = {}
+
+    def step():
+        state["out"] = [f() for f in parts.values()]
+
+    ms, clocks = R.timed(step, args.steps, args.warmup)
+    split = {k: R.timed(f, max(3, args.steps // 2), 1)[0] for k, f in parts.items()}
+    bad = sum(int(o[-1].ne(0).sum().item()) if not isinstance(o[-1], tuple) else 0 for o in
+              [(state["out"][0][2],), (state["out"][1][2],), (state["out"][2][2],), (state["out"][3][2],)])
+    assert bad == 0
+    hours = n_chunks * chunk / SR / 3600.0
+    if R.rank == 0:
+        launches = 14 + 1 + gt.launches_per_call + mf.launches_per_call + 1 + lf.launches_per_call   # cqcc: 7 octaves + 6 resamplers + epilogue (+ memset)
+        line = base_line(R, args, hours / (ms * 1e-3), ms, "strong", "f32 (int16 PCM in; CQT octaves 3xTF32 on the tensor pipe)",
+                         "the reference notebook's whole extractor map (cqcc-19, gtcc-13, mel-spect-64, mfcc-13, lfcc-13) over "
+                         "25 380 x 2 s @16 kHz, sharded by utterance",
+                         {"chunks_total": n_chunks, "chunks_per_gpu": n_local, "ms_per_feature": split,
+                          "reference_minutes_for_28408_chunks_8_workers": 42.2}, clocks, launches * args.steps)
+        _OUT.emit(json.dumps(line))
+    R.done()
+    return 0
+
+
 # --------------------------------------------------------------------------- configs[4]: long-form batch sweep
 def run_c5(args):
     """BASELINE configs[4]: 10 min @48 kHz, n_fft 2048, hop 480, 128 mels, batch sweep B = 1 .. 64.  B >= N GPUs:
@@ -657,15 +701,16 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work per baseline pass (core-seconds)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
-                    help="c2 = BASELINE configs[1] (the default the driver runs); c3 / c4 / c5 = configs[2] / [3] / [4]")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "map"],
+                    help="c2 = BASELINE configs[1] (the default the driver runs); c3 / c4 / c5 = configs[2] / [3] / [4]; "
+                         "map = the reference notebook's five-extractor map over the configs[3] corpus")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     with _StdoutToStderr() as _OUT:
         if args.impl == "reference":
             return run_reference(args)
-        return {"c2": run_b200, "c3": run_c3, "c4": run_c4, "c5": run_c5}[args.workload](args)
+        return {"c2": run_b200, "c3": run_c3, "c4": run_c4, "c5": run_c5, "map": run_map}[args.workload](args)
 
 
 if __name__ == "__main__":
