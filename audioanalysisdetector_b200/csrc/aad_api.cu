@@ -29,7 +29,7 @@ struct aad_plan {
   int warps = 0, ctas = 0;
   size_t k1_smem = 0;
   int n_w4 = 0, n_hdr = 0;
-  bool dense = false;  // dense filter bank (gammatone / custom dense): k_stft_fb FBM = 1, weights stay in global memory
+  bool dense = false;  // dense filter bank (gammatone / custom dense): k_stft_fb FBM = 1 (8 warps, two CTAs per SM)
   int smem_optin = 0;  // device limit of dynamic shared memory per CTA
   int n_ksteps = 0, n_tiles = 0, cep_nt = 1;  // K2: DCT as a GEMM (K steps of 8 filters, N tiles of 8 coefficients)
   int c_feat = 0;     // rows before deltas
@@ -321,12 +321,16 @@ static stft_kernel_t pick_stft(int L, int tile, int mode, bool pre, bool pair = 
   }
   return nullptr;
 }
-template <int L, int TILE>
+template <int L, int TILE, bool DENSE = false>
 static void stft_cfg_LT(int* warps, int* ctas, size_t* fixed, int* fbu) {
-  using C = StftCfg<L, TILE>;
-  *warps = C::WARPS; *ctas = C::CTAS; *fixed = C::FIXED_BYTES; *fbu = C::FBU;
+  using C = StftCfg<L, TILE, DENSE>;
+  *warps = C::WARPS; *ctas = C::CTAS; *fixed = C::FIXED_BYTES; *fbu = DENSE ? kDenseFbu : C::FBU;
 }
-static void stft_cfg(int L, int* warps, int* ctas, size_t* fixed, int* fbu) {
+static void stft_cfg(int L, bool dense, int* warps, int* ctas, size_t* fixed, int* fbu) {
+  if (dense) {  // n_fft 512 only (checked by the caller)
+    stft_cfg_LT<8, stft_tile(8), true>(warps, ctas, fixed, fbu);
+    return;
+  }
   switch (L) {
     case 4: stft_cfg_LT<4, 32>(warps, ctas, fixed, fbu); break;
     case 8: stft_cfg_LT<8, stft_tile(8)>(warps, ctas, fixed, fbu); break;
@@ -515,8 +519,7 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   pl->tile = stft_tile(pl->L);  // frames per K1 tile (n_fft 2048: one 16-warp CTA per SM)
   size_t k1_fixed = 0;
   int fbu = 1;
-  stft_cfg(pl->L, &pl->warps, &pl->ctas, &k1_fixed, &fbu);
-  if (dense_fb) fbu = kDenseFbu;
+  stft_cfg(pl->L, dense_fb, &pl->warps, &pl->ctas, &k1_fixed, &fbu);
   pl->c_feat = p.n_ceps > 0 ? p.n_ceps : p.n_filt;
   pl->c_out = pl->c_feat * (1 + p.n_delta);
   pl->n_ksteps = (p.n_filt + 7) / 8;
@@ -573,8 +576,12 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
       delete pl;
       return AAD_ERR_UNSUPPORTED;
     }
-    for (int wi = 0; wi < pl->warps; ++wi) {
-      const int e0 = (int)((long long)n_ent * wi / pl->warps), e1 = (int)((long long)n_ent * (wi + 1) / pl->warps);
+    // The phase is bound by shared-memory wavefronts: 4 per warp and round for the power group, 2 per entry and round
+    // for the weights.  Four of the eight warps therefore take all the entries (5 each for 40 filters: 56 wavefronts
+    // per round instead of 80); the other four go straight to the barrier.
+    const int fb_warps = std::min(pl->warps, 4);
+    for (int wi = 0; wi < fb_warps; ++wi) {
+      const int e0 = (int)((long long)n_ent * wi / fb_warps), e1 = (int)((long long)n_ent * (wi + 1) / fb_warps);
       if (e1 <= e0) continue;
       std::vector<int> ents;
       for (int e = e0; e < e1; ++e) ents.push_back(e);
@@ -668,8 +675,7 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   }
   pl->n_hdr = (int)fhdr.size();
   pl->n_w4 = (int)fw4.size();
-  // dense plans keep their weights in global memory (read through L1): only the headers go to shared memory
-  pl->k1_smem = k1_fixed + (size_t)((2 * fhdr.size() + 3) & ~3) * 4 + (dense_fb ? 0 : fw4.size() * sizeof(float4));
+  pl->k1_smem = k1_fixed + (size_t)((2 * fhdr.size() + 3) & ~3) * 4 + fw4.size() * sizeof(float4);
   // DCT-II ortho (scipy.fftpack.dct type 2 norm='ortho'), first n_ceps rows.  Device layout for K2: the
   // transposed table D^T[filter][coef] as mma.m16n8k8 B fragments, split into tf32 hi + lo parts:
   // [k-step][n-tile][lane = 4 g + t] = {b0 hi, b1 hi, b0 lo, b1 lo}, b0 = D^T[8 ks + t][8 nt + g],
@@ -902,7 +908,7 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
   sa.filt_hdr = pl->d_filt_hdr; sa.filt_w = pl->d_filt_w; sa.n_hdr = pl->n_hdr; sa.n_w4 = pl->n_w4;
   sa.warp_prog = pl->d_warp_prog; sa.tile_rec = pa.tile_rec; sa.n_filt = p.n_filt;
   sa.log_type = p.log_type; sa.amin = p.amin; sa.eps = 2.220446049250313e-16f; sa.spec_mag = p.spectrum == AAD_SPEC_MAGNITUDE;
-  if (pl->dense) sa.n_w4 = 0;  // nothing to stage: the dense weights are read from global memory
+
   if (pl->need_ws_E) {
     sa.E = d_E; sa.e_stride_b = (long long)p.n_filt * w.t_ws; sa.e_stride_f = w.t_ws;
   } else {

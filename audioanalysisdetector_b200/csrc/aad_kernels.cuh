@@ -286,10 +286,11 @@ struct TmemChunk {
 #endif
 __host__ __device__ constexpr int stft_tile(int L) { return L == 8 ? AAD_TILE_L8 : 32; }
 // dense filter banks (k_stft_fb FBM = 1): entries per bundle.  All entries of a bundle read the same bins, so the power
-// group is loaded once per round for the whole bundle; 5 entries = the 10 filters a warp owns of spafe's 40.
+// group is loaded once per round for the whole bundle; with 8 warps a warp owns 2 or 3 of the 20 entries of spafe's 40
+// filters.
 constexpr int kDenseFbu = 5;
 
-template <int L, int TILE_>
+template <int L, int TILE_, bool DENSE = false>
 struct StftCfg {
   static constexpr int Q = 32 / L;        // frames per warp-iteration
   static constexpr int M = 32 * L;        // complex FFT length (n_fft / 2)
@@ -323,10 +324,11 @@ struct StftCfg {
 #ifdef AAD_WARPS_DEV
   static constexpr int WARPS = AAD_WARPS_DEV;
 #else
-  static constexpr int WARPS = ITERS >= 8 ? ITERS / 2 : 4;
+  // dense filter banks keep their 42 KB of weights in shared memory: two 8-warp CTAs per SM instead of four 4-warp ones
+  static constexpr int WARPS = DENSE ? 8 : (ITERS >= 8 ? ITERS / 2 : 4);
 #endif
   static constexpr int FPL = TILE / 32;    // frames per lane in the filterbank phase (lane handles frames lane + 32 f)
-  static constexpr int CTAS = L == 32 ? 1 : (L == 16 || TILE == 64 ? 2 : 4);
+  static constexpr int CTAS = L == 32 ? 1 : (L == 16 || TILE == 64 || DENSE ? 2 : 4);
   // shared memory carve-up, in floats (the filterbank program follows at OFF_PROG)
   // the window / twiddle tables live in tensor memory (or are generated) and take no shared memory then
   static constexpr bool SMEM_TWP = !(TmemCfg<CTAS>::TWP || (AAD_TWPGEN && Q <= 4));
@@ -813,14 +815,15 @@ struct FrameFft {
   }
 };
 
-// FBM: 0 = two-tap banded filter bank (mel / linear triangles), program and weights in shared memory;
-//      1 = dense filter bank (gammatone), entries hold the full rows of TWO filters, weights read from global memory
-//          through L1 (40 x 260 x 4 B do not fit the shared memory of four co-resident CTAs)
+// FBM: 0 = two-tap banded filter bank (mel / linear triangles);
+//      1 = dense filter bank (gammatone): entries hold the full rows of TWO filters.  The 42 KB of weights live in shared
+//          memory like the banded program (warp-uniform LDG.128 through L1 cost four wavefronts each and made the
+//          first version L1-bound at 91 %), which is why this variant runs as two 8-warp CTAs per SM.
 template <int L, int MODE, bool PRE, int TILE, bool PAIR = false, int FBM = 0>
-__global__ void __launch_bounds__(StftCfg<L, TILE>::WARPS * 32, StftCfg<L, TILE>::CTAS)
+__global__ void __launch_bounds__(StftCfg<L, TILE, FBM != 0>::WARPS * 32, StftCfg<L, TILE, FBM != 0>::CTAS)
 k_stft_fb(const StftArgs a) {
   static_assert(!(PAIR && FBM), "paired plans are banded");
-  using C = StftCfg<L, TILE>;
+  using C = StftCfg<L, TILE, FBM != 0>;
   using FFT = FrameFft<L, MODE, PRE, TILE>;
   constexpr int Q = C::Q, M = C::M, N = C::N, SP = C::SP, FBU = FBM ? kDenseFbu : C::FBU;
   extern __shared__ __align__(16) float smem[];
@@ -837,8 +840,7 @@ k_stft_fb(const StftArgs a) {
   if constexpr (C::SMEM_TWP)
     for (int i = tid; i < M / 2; i += nthr) sTwp[i] = a.twp[i];
   for (int i = tid; i < a.n_hdr; i += nthr) sHdr[i] = a.filt_hdr[i];
-  if constexpr (FBM == 0)
-    for (int i = tid; i < a.n_w4; i += nthr) sW4[i] = a.filt_w[i];
+  for (int i = tid; i < a.n_w4; i += nthr) sW4[i] = a.filt_w[i];
   if constexpr (PAIR) {  // second program behind the first (pointers are re-derived where it runs: no live registers)
     int2* sHdr2 = reinterpret_cast<int2*>(sW4 + a.n_w4);
     float4* sW42 = reinterpret_cast<float4*>(reinterpret_cast<float*>(sHdr2) + ((2 * a.n_hdr2 + 3) & ~3));
@@ -971,7 +973,7 @@ k_stft_fb(const StftArgs a) {
 #ifdef AAD_PHASE_TIMING
       AAD_PHASE_MARK(1);
 #endif
-      const char* wbase = FBM ? reinterpret_cast<const char*>(a.filt_w) : reinterpret_cast<const char*>(sW4);
+      const char* wbase = reinterpret_cast<const char*>(sW4);
       const long long estep = e_stride_f;
       const bool is_db = log_type == 0;
       const float lscale = is_db ? 3.01029995663981195f : 0.69314718055994531f;
@@ -1008,14 +1010,8 @@ k_stft_fb(const StftArgs a) {
           }
 #pragma unroll
           for (int u = 0; u < FBU; ++u) {
-            float4 wa, wb;
-            if constexpr (FBM) {
-              wa = __ldg(reinterpret_cast<const float4*>(wp + 32 * u));
-              wb = __ldg(reinterpret_cast<const float4*>(wp + 32 * u + 16));
-            } else {
-              wa = *reinterpret_cast<const float4*>(wp + 32 * u);
-              wb = *reinterpret_cast<const float4*>(wp + 32 * u + 16);
-            }
+            const float4 wa = *reinterpret_cast<const float4*>(wp + 32 * u);
+            const float4 wb = *reinterpret_cast<const float4*>(wp + 32 * u + 16);
 #pragma unroll
             for (int f = 0; f < FPL; ++f) {
               float4 p;
