@@ -311,7 +311,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 // ---- kernel dispatch table --------------------------------------------------
 static stft_kernel_t pick_stft(int L, int tile, int mode, bool pre, bool pair = false, bool dense = false) {
-  if (tile != stft_tile(L)) return nullptr;
+  if (tile != stft_tile(L, dense)) return nullptr;
   if (dense) return L == 8 && !pair ? pick_stft_L8_dense(mode, pre) : nullptr;
   switch (L) {  // instantiated per transform size in aad_stft_inst.cu
     case 4: return pick_stft_L4(mode, pre, pair);
@@ -328,7 +328,7 @@ static void stft_cfg_LT(int* warps, int* ctas, size_t* fixed, int* fbu) {
 }
 static void stft_cfg(int L, bool dense, int* warps, int* ctas, size_t* fixed, int* fbu) {
   if (dense) {  // n_fft 512 only (checked by the caller)
-    stft_cfg_LT<8, stft_tile(8), true>(warps, ctas, fixed, fbu);
+    stft_cfg_LT<8, stft_tile(8, true), true>(warps, ctas, fixed, fbu);
     return;
   }
   switch (L) {
@@ -516,7 +516,7 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, device);
   pl->L = p.n_fft / 64;
   pl->K = p.n_fft / 2 + 1;
-  pl->tile = stft_tile(pl->L);  // frames per K1 tile (n_fft 2048: one 16-warp CTA per SM)
+  pl->tile = stft_tile(pl->L, dense_fb);  // frames per K1 tile (n_fft 2048: one 16-warp CTA per SM)
   size_t k1_fixed = 0;
   int fbu = 1;
   stft_cfg(pl->L, dense_fb, &pl->warps, &pl->ctas, &k1_fixed, &fbu);

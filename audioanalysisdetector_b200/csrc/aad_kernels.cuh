@@ -284,7 +284,10 @@ struct TmemChunk {
 #ifndef AAD_TILE_L8
 #define AAD_TILE_L8 32
 #endif
-__host__ __device__ constexpr int stft_tile(int L) { return L == 8 ? AAD_TILE_L8 : 32; }
+#ifndef AAD_TILE_DENSE
+#define AAD_TILE_DENSE 64
+#endif
+__host__ __device__ constexpr int stft_tile(int L, bool dense = false) { return dense ? AAD_TILE_DENSE : (L == 8 ? AAD_TILE_L8 : 32); }
 // dense filter banks (k_stft_fb FBM = 1): entries per bundle.  All entries of a bundle read the same bins, so the power
 // group is loaded once per round for the whole bundle; with 8 warps a warp owns 2 or 3 of the 20 entries of spafe's 40
 // filters.
@@ -314,8 +317,9 @@ struct StftCfg {
   // skew(r) = L (r mod Q) + 4 ((r / Q) mod (8 / Q)) words: the Q rows of an iteration tile the 32 banks
   // and 8 consecutive rows start in 8 different 16-byte bank groups (measured before: 2-way conflicts on
   // every power store of the n_fft 512 shape, 9 % of its shared-memory wavefronts).
-  static constexpr bool SKEW = AAD_ROW_SKEW && (L == 8 || L == 16);
-  static constexpr int SP = L == 4 ? 132 : (L == 8 ? (SKEW ? 288 : 292) : (L == 16 ? (SKEW ? 544 : 548) : 1060));
+  // (dense filter banks with 64-frame tiles: the skewed rows would not leave room for the weights of two CTAs per SM)
+  static constexpr bool SKEW = AAD_ROW_SKEW && (L == 8 || L == 16) && !(DENSE && TILE_ == 64);
+  static constexpr int SP = L == 4 ? 132 : (L == 8 ? (SKEW ? 288 : (DENSE ? 268 : 292)) : (L == 16 ? (SKEW ? 544 : 548) : 1060));
   __host__ __device__ static constexpr int skew(int r) {
     return SKEW ? L * (r & (Q - 1)) + 4 * ((r / Q) & (8 / Q - 1)) : 0;
   }

@@ -49,7 +49,7 @@ stft_kernel_t pick_stft_L8_dense(int mode, bool pre) {
 #if AAD_ABLATE || defined(AAD_DEV_BUILD)
   return nullptr;
 #else
-  constexpr int TILE = stft_tile(8);
+  constexpr int TILE = stft_tile(8, true);
   switch (mode * 2 + (pre ? 1 : 0)) {
     case 0: return k_stft_fb<8, IN_F32, false, TILE, false, 1>;
     case 1: return k_stft_fb<8, IN_F32, true, TILE, false, 1>;
