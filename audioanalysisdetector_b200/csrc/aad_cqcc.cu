@@ -80,7 +80,9 @@ __global__ void __launch_bounds__(128) k_cqt_resample(const void* in, int in_i16
                                                       int pad_in, float* out, long long out_stride, int pad_out, int tail_out,
                                                       const int32_t* lengths, int shift) {
   __shared__ __align__(16) float sE[kRsIn + 4 * (kRsIn / 32) + 8];
-  __shared__ float sO[kRsIn];
+  // sO is stored one position late and skewed like sE: the eight centre-tap inputs of a thread, sO[m0 + 63 .. m0 + 70],
+  // are then two aligned float4 (as scalars the stride-8 reads of a warp were 8-way bank conflicts)
+  __shared__ __align__(16) float sO[kRsIn + 4 * (kRsIn / 32) + 16];
   const int b = blockIdx.y;
   long long len0 = lengths[b];
   if (len0 < 0) len0 = 0;
@@ -99,10 +101,25 @@ __global__ void __launch_bounds__(128) k_cqt_resample(const void* in, int in_i16
   }
   const long long base = 2 * n0 - (kTaps - 1) / 2 - 1;
   const long long irow = (row_off ? __ldg(row_off + b) : (long long)b * in_stride) + pad_in;
-  for (int i = threadIdx.x; i < kRsIn; i += 128) {
-    const long long s0 = base + 2 * i + 1, s1 = s0 + 1;
-    sE[rs_skew(i)] = (s0 >= 0 && s0 < len_in) ? load_sample(in, in_i16, irow + s0) : 0.f;
-    sO[i] = (s1 >= 0 && s1 < len_in) ? load_sample(in, in_i16, irow + s1) : 0.f;
+  // in[base + 4 q + {0, 1, 2, 3}] = sO[2 q - 1], sE[2 q], sO[2 q], sE[2 q + 1]: one aligned 16-byte load per four samples
+  // when the row allows it (the library's own octave buffers always do), scalar masked loads otherwise
+  const bool vec = !in_i16 && ((irow + base) & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  for (int q = threadIdx.x; q <= kRsIn / 2; q += 128) {
+    const long long s = base + 4 * q;
+    float v[4];
+    if (vec && s >= 0 && s + 4 <= len_in) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(in) + irow + s));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = (s + e >= 0 && s + e < len_in) ? load_sample(in, in_i16, irow + s + e) : 0.f;
+    }
+    if (q > 0) sO[rs_skew(2 * q)] = v[0];                 // sO[2 q - 1], stored one late
+    if (2 * q < kRsIn) {
+      sE[rs_skew(2 * q)] = v[1];
+      sO[rs_skew(2 * q + 1)] = v[2];                       // sO[2 q]
+    }
+    if (2 * q + 1 < kRsIn) sE[rs_skew(2 * q + 1)] = v[3];
   }
   __syncthreads();
   const int m0 = kRsPer * threadIdx.x;
@@ -127,13 +144,27 @@ __global__ void __launch_bounds__(128) k_cqt_resample(const void* in, int in_i16
       }
     }
   }
+  float res[kRsPer];
+  {
+    const float4 c0 = *reinterpret_cast<const float4*>(sO + rs_skew(m0 + 64)), c1 = *reinterpret_cast<const float4*>(sO + rs_skew(m0 + 68));
+    const float cen[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};   // sO[m0 + 63 + m]
 #pragma unroll
-  for (int m = 0; m < kRsPer; ++m) {
-    const float a = (m & 1) ? acc[m >> 1].y : acc[m >> 1].x;
-    const float r = __fmaf_rn(c_centre, sO[m0 + m + 63], a);
-    const long long n = n0 + m0 + m;
-    if (n < len_out) orow[pad_out + n] = 1.41421356237309515f * r;
-    else if (n < len_out + tail_out) orow[pad_out + n] = 0.f;
+    for (int m = 0; m < kRsPer; ++m) {
+      const float a = (m & 1) ? acc[m >> 1].y : acc[m >> 1].x;
+      res[m] = 1.41421356237309515f * __fmaf_rn(c_centre, cen[m], a);
+    }
+  }
+  const long long nb = n0 + m0;
+  float* op = orow + pad_out + nb;
+  if (nb + kRsPer <= len_out && ((pad_out | out_stride) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    *reinterpret_cast<float4*>(op) = make_float4(res[0], res[1], res[2], res[3]);
+    *reinterpret_cast<float4*>(op + 4) = make_float4(res[4], res[5], res[6], res[7]);
+  } else {
+#pragma unroll
+    for (int m = 0; m < kRsPer; ++m) {
+      if (nb + m < len_out) op[m] = res[m];
+      else if (nb + m < len_out + tail_out) op[m] = 0.f;
+    }
   }
 }
 
