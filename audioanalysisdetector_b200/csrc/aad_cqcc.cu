@@ -403,8 +403,9 @@ __global__ void __launch_bounds__(256) k_cqcc_epilogue(const float* mag, long lo
                                                        const float* interp_w, const float* dct, int n_ceps, float* out,
                                                        long long out_stride_b, int32_t* n_frames, int32_t* status) {
   extern __shared__ float smem[];
+  const int w0 = max(kEpiFrames + 1, (n_ceps + 3) & ~3);   // the first region later holds the transposed DCT matrix
   float* sDb = smem;                                // [n_bins][33]
-  float* sLp = smem + n_bins * (kEpiFrames + 1);    // [n_bins][33]
+  float* sLp = smem + n_bins * w0;                  // [n_bins][33]
   const int b = blockIdx.y;
   const long long len0 = lengths[b];
   int T = len0 > 0 ? (int)(1 + len0 / kHop) : 0;
@@ -426,14 +427,17 @@ __global__ void __launch_bounds__(256) k_cqcc_epilogue(const float* mag, long lo
   // librosa.amplitude_to_db(S, ref=np.max): power_to_db(S^2, ref=max^2, amin=1e-10, top_db=80), float32
   const float amin2 = 1e-5f * 1e-5f;
   const float vmax = __int_as_float(mx);
-  const float ref_db = 10.0f * log10f(fmaxf(amin2, vmax * vmax));
+  // 10 log10(x) = 3.0103 log2(x), ln(x) = 0.6931 log2(x) with MUFU.LG2 (2^-22 absolute error in log2: 7e-7 dB, below the
+  // float32 rounding of the dB values themselves); the reference cell is exact: the same expression of the same number
+  const float kDb = 3.01029995663981195f, kLn = 0.69314718055994531f;
+  const float ref_db = kDb * __log2f(fmaxf(amin2, vmax * vmax));
   const float* mb = mag + (long long)b * mag_stride_b;
   for (int i = threadIdx.x; i < n_bins * kEpiFrames; i += 256) {
     const int k = i / kEpiFrames, f = i - k * kEpiFrames;
     float v = 0.f;
     if (f < nt) {
       const float m = mb[(long long)k * t_alloc + t0 + f];
-      v = fmaxf(10.0f * log10f(fmaxf(amin2, m * m)) - ref_db, -80.0f);   // the maximum of log_spec is 0 (the reference)
+      v = fmaxf(kDb * __log2f(fmaxf(amin2, m * m)) - ref_db, -80.0f);   // the maximum of log_spec is 0 (the reference)
     }
     sDb[k * (kEpiFrames + 1) + f] = v;
   }
@@ -443,16 +447,35 @@ __global__ void __launch_bounds__(256) k_cqcc_epilogue(const float* mag, long lo
     const int lo = interp_lo[k];
     const float x0 = sDb[lo * (kEpiFrames + 1) + f], x1 = sDb[(lo + 1) * (kEpiFrames + 1) + f];
     const float x = __fmaf_rn(interp_w[k], x1 - x0, x0);
-    sLp[k * (kEpiFrames + 1) + f] = logf(__fmaf_rn(x, x, 1e-12f));
+    sLp[k * (kEpiFrames + 1) + f] = kLn * __log2f(__fmaf_rn(x, x, 1e-12f));
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n_ceps * kEpiFrames; i += 256) {
-    const int c = i / kEpiFrames, f = i - c * kEpiFrames;
+  // DCT: a thread owns one frame and four coefficients: per bin one LDS of the frame's value and one broadcast LDS.128
+  // of the four DCT entries (sDb is free again: it holds the transposed matrix [bin][n_c4], n_c4 = n_ceps rounded up to 4)
+  const int n_c4 = (n_ceps + 3) & ~3;
+  float* sDt = sDb;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_bins * n_c4; i += 256) {
+    const int k = i / n_c4, c = i - k * n_c4;
+    sDt[i] = c < n_ceps ? __ldg(dct + (size_t)c * n_bins + k) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (n_c4 / 4) * kEpiFrames; i += 256) {
+    const int cg = i / kEpiFrames, f = i - cg * kEpiFrames;
     if (f >= nt) continue;
-    const float* d = dct + (size_t)c * n_bins;
-    float acc = 0.f;
-    for (int k = 0; k < n_bins; ++k) acc = __fmaf_rn(__ldg(d + k), sLp[k * (kEpiFrames + 1) + f], acc);
-    out[(long long)b * out_stride_b + (long long)c * t_alloc + t0 + f] = acc;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* dt = reinterpret_cast<const float4*>(sDt) + cg;
+    for (int k = 0; k < n_bins; ++k) {
+      const float x = sLp[k * (kEpiFrames + 1) + f];
+      const float4 d = dt[k * (n_c4 / 4)];
+      acc.x = __fmaf_rn(d.x, x, acc.x); acc.y = __fmaf_rn(d.y, x, acc.y);
+      acc.z = __fmaf_rn(d.z, x, acc.z); acc.w = __fmaf_rn(d.w, x, acc.w);
+    }
+    float* o = out + (long long)b * out_stride_b + (long long)(4 * cg) * t_alloc + t0 + f;
+    const float r[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * cg + j < n_ceps) o[(long long)j * t_alloc] = r[j];
   }
 }
 
@@ -802,7 +825,7 @@ int aad_cqcc(const aad_cqcc_plan* pl, const void* wav, int wav_dtype, int64_t wa
     }
   }
   const dim3 grid_epi((frames + kEpiFrames - 1) / kEpiFrames, B);
-  const size_t smem_epi = 2 * (size_t)pl->n_bins * (kEpiFrames + 1) * 4;
+  const size_t smem_epi = (size_t)pl->n_bins * (std::max(kEpiFrames + 1, (pl->n_ceps + 3) & ~3) + kEpiFrames + 1) * 4;
   k_cqcc_epilogue<<<grid_epi, 256, smem_epi, stream>>>(d_mag, mag_stride_b, t_ws, pl->n_bins, lengths, d_max, pl->d_interp_lo,
                                                        pl->d_interp_w, pl->d_dct, pl->n_ceps, out, out_stride_b, n_frames, status);
   cudaError_t e = cudaGetLastError();
