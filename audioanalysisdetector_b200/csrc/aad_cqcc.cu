@@ -299,7 +299,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 // GENERIC = true: the caller's waveform (octave 0): float or int16, any row offset, frames that reach in front of /
 // behind the signal read zeros -- scalar loads, masked only in the tiles that touch an end.
 template <bool GENERIC>
-__global__ void __launch_bounds__(kMmaWarps * 32) k_cqt_octave_mma(const void* __restrict__ yv, int y_i16, long long y_stride,
+__global__ void __launch_bounds__(kMmaWarps * 32, 3) k_cqt_octave_mma(const void* __restrict__ yv, int y_i16, long long y_stride,
                                                                    const long long* __restrict__ row_off, int pad,
                                                                    const int32_t* __restrict__ lengths, int B, int hop, int n_fft,
                                                                    const float4* __restrict__ gfrag, int n_k, int bin0,
@@ -359,13 +359,17 @@ __global__ void __launch_bounds__(kMmaWarps * 32) k_cqt_octave_mma(const void* _
           hi[i] = tf32_rna(av[i]);
           lo[i] = __float_as_uint(av[i] - __uint_as_float(hi[i]));
         }
+        // the three terms of an accumulator are dependent MMAs: issue them n-tile by n-tile per term, so that two
+        // independent MMAs sit between an MMA and the next one into the same accumulator
+        float4 bf[kMmaNT];
 #pragma unroll
-        for (int nt = 0; nt < kMmaNT; ++nt) {
-          const float4 bf = bp[(j * kMmaNT + nt) * 32];
-          mma_tf32(acc[nt], lo, __float_as_uint(bf.x), __float_as_uint(bf.y));
-          mma_tf32(acc[nt], hi, __float_as_uint(bf.z), __float_as_uint(bf.w));
-          mma_tf32(acc[nt], hi, __float_as_uint(bf.x), __float_as_uint(bf.y));
-        }
+        for (int nt = 0; nt < kMmaNT; ++nt) bf[nt] = bp[(j * kMmaNT + nt) * 32];
+#pragma unroll
+        for (int nt = 0; nt < kMmaNT; ++nt) mma_tf32(acc[nt], lo, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
+#pragma unroll
+        for (int nt = 0; nt < kMmaNT; ++nt) mma_tf32(acc[nt], hi, __float_as_uint(bf[nt].z), __float_as_uint(bf[nt].w));
+#pragma unroll
+        for (int nt = 0; nt < kMmaNT; ++nt) mma_tf32(acc[nt], hi, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
       }
     }
     float vmax = 0.f;
@@ -726,7 +730,7 @@ int aad_cqcc_plan_create(int sample_rate, int bins_per_octave, int n_ceps, int d
     int occ = 0;
     if (e == cudaSuccess && smem_mma <= 200 * 1024 &&
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cqt_octave_mma<true>, kMmaWarps * 32, smem_mma) == cudaSuccess)
-      pl->mma_ctas = std::max(1, occ);   // the generic form needs at least as many registers as the aligned one
+      pl->mma_ctas = std::max(1, occ);   // both instantiations are compiled for three CTAs per SM (launch bounds)
   }
   if (e != cudaSuccess) {
     aad_cqcc_plan_destroy(pl);
