@@ -103,13 +103,19 @@ __global__ void __launch_bounds__(128) k_cqt_resample(const void* in, int in_i16
   const long long irow = (row_off ? __ldg(row_off + b) : (long long)b * in_stride) + pad_in;
   // in[base + 4 q + {0, 1, 2, 3}] = sO[2 q - 1], sE[2 q], sO[2 q], sE[2 q + 1]: one aligned 16-byte load per four samples
   // when the row allows it (the library's own octave buffers always do), scalar masked loads otherwise
-  const bool vec = !in_i16 && ((irow + base) & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  const bool vec = ((irow + base) & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
   for (int q = threadIdx.x; q <= kRsIn / 2; q += 128) {
     const long long s = base + 4 * q;
     float v[4];
     if (vec && s >= 0 && s + 4 <= len_in) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(in) + irow + s));
-      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      if (in_i16) {
+        const short4 t = __ldg(reinterpret_cast<const short4*>(static_cast<const short*>(in) + irow + s));
+        v[0] = (float)t.x * (1.0f / 32768.0f); v[1] = (float)t.y * (1.0f / 32768.0f);
+        v[2] = (float)t.z * (1.0f / 32768.0f); v[3] = (float)t.w * (1.0f / 32768.0f);
+      } else {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(in) + irow + s));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      }
     } else {
 #pragma unroll
       for (int e = 0; e < 4; ++e) v[e] = (s + e >= 0 && s + e < len_in) ? load_sample(in, in_i16, irow + s + e) : 0.f;
@@ -329,6 +335,8 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) k_cqt_octave_mma(const void
     const float* pb = y + row0 + sb;
     // GENERIC: does any frame of the tile reach outside [0, len0)?  (warp-uniform)
     const bool edge = GENERIC && ((long long)t0 * hop - n_fft / 2 < 0 || (long long)min(t0 + 15, T - 1) * hop + n_fft / 2 > len0);
+    const bool vec4 = GENERIC && !edge && (row0 & 3) == 0 && (hop & 3) == 0 && (n_fft & 7) == 0 &&
+                      (reinterpret_cast<uintptr_t>(yv) & 15) == 0;
     float acc[kMmaNT][4];
 #pragma unroll
     for (int nt = 0; nt < kMmaNT; ++nt)
@@ -338,10 +346,22 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) k_cqt_octave_mma(const void
     for (int c = 0; c < n_fft; c += 32, bp += 4 * kMmaNT * 32) {
       float xa0[4], xa1[4], xb0[4], xb1[4];
       if constexpr (GENERIC) {
+        // interior tiles of rows that start on a 4-sample boundary: one 16-byte (float) or 8-byte (int16) load per piece
         auto piece = [&](long long s, float (&x)[4]) {
+          if (vec4) {
+            if (y_i16) {
+              const short4 q = __ldg(reinterpret_cast<const short4*>(static_cast<const short*>(yv) + row0 + s));
+              x[0] = (float)q.x * (1.0f / 32768.0f); x[1] = (float)q.y * (1.0f / 32768.0f);
+              x[2] = (float)q.z * (1.0f / 32768.0f); x[3] = (float)q.w * (1.0f / 32768.0f);
+            } else {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(y + row0 + s));
+              x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+            }
+          } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            x[e] = (!edge || (s + e >= 0 && s + e < len0)) ? load_sample(yv, y_i16, row0 + s + e) : 0.f;
+            for (int e = 0; e < 4; ++e)
+              x[e] = (!edge || (s + e >= 0 && s + e < len0)) ? load_sample(yv, y_i16, row0 + s + e) : 0.f;
+          }
         };
         piece(sa + c, xa0); piece(sa + c + 16, xa1); piece(sb + c, xb0); piece(sb + c + 16, xb1);
       } else {
