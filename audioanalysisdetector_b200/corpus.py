@@ -116,7 +116,7 @@ class DeviceCorpus:
         PCM (or `dtype=torch.int16` is forced), else float32 (int16 / 32768).
         Decoding runs `decode_threads` files ahead on a thread pool (default: the host's cores, at most 16): the FLAC
         decoder and the MD5 check release the GIL, and decoding -- not the copy, not the kernels -- is what a corpus
-        of files costs (1.4 ms per 4-second clip and core against 25 ms of GPU time for 25 380 chunks)."""
+        of files costs (1.4 ms per 4-second clip and core against 24 ms of GPU time for 25 380 chunks)."""
         if self.pcm is not None and (dtype is None or self.pcm.dtype == dtype):
             return self.pcm
         if not self._host:
