@@ -74,8 +74,12 @@ __constant__ float c_centre;
 // 4 words per 32 so that the stride-8 float4 reads of a quarter warp fall into 8 bank groups.  Rows of the octave buffers carry pad_in / pad_out zeros in front and n_fft zeros behind
 // the signal (written here), so that every CQT frame of the lower octaves is an interior frame.
 // grid (chunks of 1024 outputs, B), 128 threads.
-constexpr int kRsPer = 8, kRsOut = 128 * kRsPer, kRsIn = kRsOut + 128 + 8;
-__device__ __forceinline__ int rs_skew(int j) { return j + 4 * (j >> 5); }  // stride-8 float4 reads: 8 bank groups
+#ifndef AAD_RS_PER
+#define AAD_RS_PER 8
+#endif
+constexpr int kRsPer = AAD_RS_PER, kRsOut = 128 * kRsPer, kRsIn = kRsOut + 128 + 8;
+// stride-8 float4 reads of a quarter warp need a skew to fall into 8 bank groups; stride 12 (48 bytes) does by itself
+__device__ __forceinline__ int rs_skew(int j) { return kRsPer == 8 ? j + 4 * (j >> 5) : j; }
 __global__ void __launch_bounds__(128) k_cqt_resample(const void* in, int in_i16, long long in_stride, const long long* row_off,
                                                       int pad_in, float* out, long long out_stride, int pad_out, int tail_out,
                                                       const int32_t* lengths, int shift) {
@@ -152,8 +156,12 @@ __global__ void __launch_bounds__(128) k_cqt_resample(const void* in, int in_i16
   }
   float res[kRsPer];
   {
-    const float4 c0 = *reinterpret_cast<const float4*>(sO + rs_skew(m0 + 64)), c1 = *reinterpret_cast<const float4*>(sO + rs_skew(m0 + 68));
-    const float cen[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};   // sO[m0 + 63 + m]
+    float cen[kRsPer];   // sO[m0 + 63 + m]
+#pragma unroll
+    for (int q = 0; q < kRsPer / 4; ++q) {
+      const float4 c = *reinterpret_cast<const float4*>(sO + rs_skew(m0 + 64 + 4 * q));
+      cen[4 * q] = c.x; cen[4 * q + 1] = c.y; cen[4 * q + 2] = c.z; cen[4 * q + 3] = c.w;
+    }
 #pragma unroll
     for (int m = 0; m < kRsPer; ++m) {
       const float a = (m & 1) ? acc[m >> 1].y : acc[m >> 1].x;
@@ -163,8 +171,8 @@ __global__ void __launch_bounds__(128) k_cqt_resample(const void* in, int in_i16
   const long long nb = n0 + m0;
   float* op = orow + pad_out + nb;
   if (nb + kRsPer <= len_out && ((pad_out | out_stride) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-    *reinterpret_cast<float4*>(op) = make_float4(res[0], res[1], res[2], res[3]);
-    *reinterpret_cast<float4*>(op + 4) = make_float4(res[4], res[5], res[6], res[7]);
+#pragma unroll
+    for (int q = 0; q < kRsPer / 4; ++q) *reinterpret_cast<float4*>(op + 4 * q) = make_float4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
   } else {
 #pragma unroll
     for (int m = 0; m < kRsPer; ++m) {
