@@ -144,3 +144,47 @@ def test_new_entry_points_validate_their_arguments_before_touching_the_gpu(built
     assert built_lib.aad_detector_forward(None, None, 0, 63, 8, None, None, 0, None) == INV
     assert built_lib.aad_detector_destroy(None) == 0
     assert b"paired" in built_lib.aad_strerror(-7)
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(built_lib, tmp_path):
+    """The boundary is a C ABI: include/aad.h must compile as C99 on its own, and a C program (no C++, no Python) must
+    link against libaad_b200.so and get the reference defaults of every plan kind without touching a GPU."""
+    import shutil
+    import subprocess
+    from audioanalysisdetector_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "include")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                    os.path.join(inc, "aad.h")], check=True)
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "aad.h"
+int main(void) {
+  aad_params p;
+  int kinds[4] = {AAD_KIND_LOGMEL, AAD_KIND_MFCC, AAD_KIND_LFCC, AAD_KIND_GTCC};
+  for (int i = 0; i < 4; ++i) {
+    if (aad_params_default(&p, kinds[i], 16000) != AAD_OK) return 1;
+    if (p.struct_size != (int)sizeof(aad_params) || p.kind != kinds[i]) return 2;
+    printf("%d %d %d %d %d\n", p.kind, p.n_fft, p.hop_length, p.n_filt, p.n_ceps);
+  }
+  if (aad_params_default(&p, 99, 16000) != AAD_ERR_INVALID_ARG) return 3;
+  if (aad_plan_create(NULL, 0, NULL) != AAD_ERR_INVALID_ARG) return 4;
+  if (aad_flac_info((const unsigned char*)"nope", 4, NULL) != AAD_ERR_INVALID_ARG) return 5;
+  if (strcmp(aad_strerror(AAD_ERR_FORMAT), "malformed or unsupported audio stream") != 0) return 6;
+  return aad_version() == AAD_VERSION ? 0 : 7;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe), "-L", libdir,
+                    "-l:libaad_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    assert out[0].split() == ["0", "2048", "512", "64", "0"]        # extract_mel_spectrogram
+    assert out[1].split() == ["1", "2048", "512", "128", "13"]      # extract_mfcc
+    assert out[2].split() == ["2", "512", "160", "24", "13"]        # extract_lfcc
+    assert out[3].split() == ["3", "512", "160", "40", "13"]        # extract_gtcc
