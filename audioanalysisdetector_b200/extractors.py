@@ -277,41 +277,47 @@ def extract_features(final_df, feature_extractors_map: Dict[str, Callable], col_
     padded on the host; "noise" rows are augmented on the device.  Any other callable in the map is
     called per row, as the reference does."""
     from .corpus import DeviceCorpus
-    rows = [row for _, row in final_df.iterrows()]
+    n_rows = len(final_df)
+
+    def column(name):   # one pass per column (a pandas look-up per row and field costs more than the GPU work)
+        if name not in final_df.columns:
+            return [None] * n_rows
+        return [None if (isinstance(v, float) and math.isnan(v)) else v for v in final_df[name].tolist()]
+
+    srcs, c_start, c_end, augs = column(col_name), column("chunk_start"), column("chunk_end"), column(aug_col)
+    rows = range(n_rows)
     corpus: Optional[DeviceCorpus] = None
-    file_of: List[Optional[int]] = [None] * len(rows)
+    file_of: List[Optional[int]] = [None] * n_rows
     funcs = list(feature_extractors_map.values())
     # MFCC and log-mel over the same rows share one STFT: the second one rides on the first one's kernel launch
     pair_ok = (extract_mfcc in funcs and extract_mel_spectrogram in funcs and
                funcs.index(extract_mfcc) < funcs.index(extract_mel_spectrogram) and
-               not any(_row_get(r, aug_col) == "noise" for r in rows))
+               not any(a == "noise" for a in augs))
     paired_mel: Dict[tuple, tuple] = {}      # (sr, start, end) -> (features, n_frames, status) of the mel plan
     for name, func in feature_extractors_map.items():
         print(f"   - Ekstrahuję: {name}")
         if func is extract_cqcc:
             # CQCC over the same decoded corpus: one batched call per sample rate through the chunk table
-            results = [None] * len(rows)
+            results = [None] * n_rows
             if corpus is None:
                 corpus = DeviceCorpus()
-                for i, r in enumerate(rows):
-                    src = _row_get(r, col_name)
+                for i in rows:
+                    src = srcs[i]
                     try:
                         file_of[i] = corpus.add(src)
                     except Exception as e:
                         print(f"[BŁĄD CQCC] {src if isinstance(src, str) else '<array>'}: {e}")
             by_sr_c: Dict[int, List[int]] = {}
-            for i, r in enumerate(rows):
+            for i in rows:
                 if file_of[i] is None:
                     continue
-                if _row_get(r, aug_col) is not None:          # augmented rows: per row, as the reference does
-                    results[i] = func(_row_get(r, col_name), chunk_start=_row_get(r, "chunk_start"),
-                                      chunk_end=_row_get(r, "chunk_end"), mean=mean, augment=_row_get(r, aug_col))
+                if augs[i] is not None:                       # augmented rows: per row, as the reference does
+                    results[i] = func(srcs[i], chunk_start=c_start[i], chunk_end=c_end[i], mean=mean, augment=augs[i])
                     continue
                 by_sr_c.setdefault(corpus.sample_rates[file_of[i]], []).append(i)
             for sr, idxs in by_sr_c.items():
                 cq = get_cqcc_frontend(sr)
-                off, ln = corpus.table([(file_of[i], _row_get(rows[i], "chunk_start"), _row_get(rows[i], "chunk_end"))
-                                        for i in idxs])
+                off, ln = corpus.table([(file_of[i], c_start[i], c_end[i]) for i in idxs])
                 step = max(1, max_batch_samples // max(int(ln.max()), 1))
                 for a in range(0, len(idxs), step):
                     try:
@@ -329,26 +335,24 @@ def extract_features(final_df, feature_extractors_map: Dict[str, Callable], col_
             final_df[name] = results
             continue
         if func not in _BATCHED:
-            final_df[name] = [
-                func(_row_get(r, col_name), chunk_start=_row_get(r, "chunk_start"),
-                     chunk_end=_row_get(r, "chunk_end"), mean=mean, augment=_row_get(r, aug_col))
-                for r in rows]
+            final_df[name] = [func(srcs[i], chunk_start=c_start[i], chunk_end=c_end[i], mean=mean, augment=augs[i])
+                              for i in rows]
             continue
         tag, mk_params, post = _BATCHED[func]
-        results: List[Optional[np.ndarray]] = [None] * len(rows)
+        results: List[Optional[np.ndarray]] = [None] * n_rows
         if corpus is None:                      # decode each distinct file once, for every feature
             corpus = DeviceCorpus()
-            for i, r in enumerate(rows):
-                src = _row_get(r, col_name)
+            for i in rows:
+                src = srcs[i]
                 try:
                     file_of[i] = corpus.add(src)
                 except Exception as e:
                     print(f"[BŁĄD {tag}] {src if isinstance(src, str) else '<array>'}: {e}")
         by_sr: Dict[int, List[int]] = {}
-        for i, r in enumerate(rows):
+        for i in rows:
             if file_of[i] is None:
                 continue
-            aug = _row_get(r, aug_col)
+            aug = augs[i]
             if aug == "change pitch":
                 print(f"[BŁĄD {tag}] row {i}: pitch-shift augmentation is outside the spectral front-end")
                 continue
@@ -356,8 +360,7 @@ def extract_features(final_df, feature_extractors_map: Dict[str, Callable], col_
         for sr, idxs in by_sr.items():
             params = mk_params(sr, mean)
             fe = get_frontend(params)
-            off, ln = corpus.table([(file_of[i], _row_get(rows[i], "chunk_start"), _row_get(rows[i], "chunk_end"))
-                                    for i in idxs])
+            off, ln = corpus.table([(file_of[i], c_start[i], c_end[i]) for i in idxs])
             start = 0
             while start < len(idxs):            # bound the output (rows x longest chunk) per GPU call
                 end, lmax = start, 0
@@ -382,7 +385,7 @@ def extract_features(final_df, feature_extractors_map: Dict[str, Callable], col_
                         _split_rows(feats, nf, st, params, post, mean, part, results, tag)
                         start = end
                         continue
-                    noise = [k for k, i in enumerate(part) if _row_get(rows[i], aug_col) == "noise"]
+                    noise = [k for k, i in enumerate(part) if augs[i] == "noise"]
                     feats, nf, st = corpus.extract(fe, off[start:end], ln[start:end], noise_rows=noise)
                     _split_rows(feats, nf, st, params, post, mean, part, results, tag)
                 except Exception as e:
