@@ -676,6 +676,8 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
   pl->n_hdr = (int)fhdr.size();
   pl->n_w4 = (int)fw4.size();
   pl->k1_smem = k1_fixed + (size_t)((2 * fhdr.size() + 3) & ~3) * 4 + fw4.size() * sizeof(float4);
+  if (AAD_TMA_STAGE && pl->L == 32)   // dev switch: staged samples of one tile (+ 16 floats of header)
+    pl->k1_smem += (size_t)(16 + ((pl->tile * p.hop_length + p.n_fft + 8 + 3) & ~3)) * 4;
   // DCT-II ortho (scipy.fftpack.dct type 2 norm='ortho'), first n_ceps rows.  Device layout for K2: the
   // transposed table D^T[filter][coef] as mma.m16n8k8 B fragments, split into tf32 hi + lo parts:
   // [k-step][n-tile][lane = 4 g + t] = {b0 hi, b1 hi, b0 lo, b1 lo}, b0 = D^T[8 ks + t][8 nt + g],

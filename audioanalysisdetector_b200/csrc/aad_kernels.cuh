@@ -233,6 +233,11 @@ __global__ void __launch_bounds__(kPrepBlock) k_prepare(PrepArgs a) {
 #ifndef AAD_T64
 #define AAD_T64 1
 #endif
+// dev switch (profiles/r2_experiments.md 12): samples of a tile staged once in shared memory by a 1-D bulk copy (TMA)
+// issued during the previous tile's filterbank phase; n_fft 2048, float32 input, no pre-emphasis, dense rows
+#ifndef AAD_TMA_STAGE
+#define AAD_TMA_STAGE 0
+#endif
 // columns: [0, 64) window pairs, [64, 128) pass-1 twiddles, [128, 160) split twiddles (only when at
 // most two CTAs share the SM's 512 columns: allocations are powers of two)
 template <int CTAS>
@@ -524,9 +529,20 @@ struct FrameFft {
   // valid / t / len / row: this lane's frame (the L lanes of a frame agree): frame t of an utterance of len samples
   // whose first sample is at `row`.
   __device__ __forceinline__ void load(const StftArgs& a, bool valid, int t, int len, const char* row,
-                                       float2 (&v)[32]) const {
+                                       float2 (&v)[32], const float* stage = nullptr, int stage_a0 = 0) const {
     const int s0 = t * a.hop - a.s_off;
     bool fast = valid && s0 >= (PRE ? 1 : 0) && (s0 + N) <= len;
+    if constexpr (AAD_TMA_STAGE && MODE == IN_F32 && !PRE) {
+      // interior frame of a staged tile: the samples are in shared memory (a0 is a multiple of 4, s0 is even)
+      if (stage != nullptr && __all_sync(0xffffffffu, fast)) {
+        const float2* p = reinterpret_cast<const float2*>(stage + (s0 - stage_a0)) + j;
+        static_for<0, 32>([&](auto a_) {
+          constexpr int A = decltype(a_)::value;
+          v[bitrev(A, 5)] = p[L * A];
+        });
+        return;
+      }
+    }
     if constexpr (MODE == IN_I16) fast = fast && (((uintptr_t)(row + 2ll * s0)) & 3) == 0;
     else fast = fast && (((uintptr_t)(row + 4ll * s0)) & 7) == 0;
 
@@ -617,7 +633,8 @@ struct FrameFft {
   }
 
   // request the samples of warp-iteration `it` of the tile whose meta is (mB, mT); false: no valid frame in it
-  __device__ __forceinline__ bool load_iter(const StftArgs& a, const int* mB, const int* mT, int it, float2 (&v)[32]) const {
+  __device__ __forceinline__ bool load_iter(const StftArgs& a, const int* mB, const int* mT, int it, float2 (&v)[32],
+                                            const float* stage = nullptr, int stage_a0 = 0) const {
     const int fi = it * Q + g;
     const int b = mB[fi], t = mT[fi];
     const bool valid = b >= 0;
@@ -625,7 +642,7 @@ struct FrameFft {
     const int len = valid ? __ldg(a.len_c + b) : 0;
     const char* row = static_cast<const char*>(a.wav) +
                       (valid ? (a.row_off ? __ldg(a.row_off + b) : (long long)b * a.wav_stride) * (MODE == IN_I16 ? 2 : 4) : 0);
-    load(a, valid, t, len, row, v);
+    load(a, valid, t, len, row, v, stage, stage_a0);
     return true;
   }
 
@@ -840,6 +857,21 @@ k_stft_fb(const StftArgs a) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane / L;
+  // TMA staging (dev switch): [mbarrier (8 B) | a0, bytes, src lo, src hi per meta buffer | ... 16 floats] then the samples
+  constexpr bool STAGE = AAD_TMA_STAGE && L == 32 && MODE == IN_F32 && !PRE && !PAIR && FBM == 0;
+  float* sStageHdr = reinterpret_cast<float*>(sW4 + a.n_w4);
+  int* sInfo = reinterpret_cast<int*>(sStageHdr) + 2;
+  float* sS = sStageHdr + 16;
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(sStageHdr);
+  const bool stage_on = STAGE && a.row_off == nullptr && (a.wav_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(a.wav) & 15) == 0;
+  if constexpr (STAGE) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      sInfo[0] = -1;
+      sInfo[4] = -1;
+    }
+  }
 
   if constexpr (C::SMEM_TWP)
     for (int i = tid; i < M / 2; i += nthr) sTwp[i] = a.twp[i];
@@ -921,9 +953,51 @@ k_stft_fb(const StftArgs a) {
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"((unsigned)(p1 - p0)) : "memory");
       }
     }
+    if constexpr (STAGE) {
+      // a tile whose frames all belong to one utterance is staged as ONE contiguous sample range
+      const int b = sMeta[buf * 2 * C::TILE + lane], t = sMeta[buf * 2 * C::TILE + C::TILE + lane];
+      const unsigned vm = __ballot_sync(0xffffffffu, b >= 0);
+      const int b0 = __shfl_sync(0xffffffffu, b, 0), t0 = __shfl_sync(0xffffffffu, t, 0);
+      const bool one = stage_on && vm != 0 && (vm & 1u) && __all_sync(0xffffffffu, b < 0 || b == b0);
+      if (lane == 0) {
+        int a0 = -1, bytes = 0;
+        unsigned long long src = 0;
+        if (one) {
+          const int len = __ldg(a.len_c + b0), t1 = t0 + __popc(vm) - 1;
+          long long lo = (long long)t0 * a.hop - a.s_off, hi = (long long)t1 * a.hop - a.s_off + N;
+          lo = max(lo, 0ll) & ~3ll;
+          hi = min(min(hi, (long long)len) + 3 & ~3ll, a.wav_stride);
+          if (hi > lo) {
+            a0 = (int)lo;
+            bytes = (int)(hi - lo) * 4;
+            src = reinterpret_cast<unsigned long long>(static_cast<const float*>(a.wav) + (long long)b0 * a.wav_stride + lo);
+          }
+        }
+        sInfo[buf * 4] = a0;
+        sInfo[buf * 4 + 1] = bytes;
+        sInfo[buf * 4 + 2] = (int)(unsigned)(src & 0xffffffffull);
+        sInfo[buf * 4 + 3] = (int)(unsigned)(src >> 32);
+      }
+      __syncwarp();
+    }
+  };
+  // issue the bulk copy of the tile whose meta sits in `buf` (thread 0, after the barrier that ended all reads of sS)
+  auto stage_issue = [&](int buf) {
+    if constexpr (STAGE) {
+      if (tid == 0 && sInfo[buf * 4] >= 0) {
+        const unsigned bytes = (unsigned)sInfo[buf * 4 + 1];
+        const unsigned long long src = ((unsigned long long)(unsigned)sInfo[buf * 4 + 3] << 32) | (unsigned)sInfo[buf * 4 + 2];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(sS)), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+      }
+    }
   };
   if (warp == 0) tile_meta(blockIdx.x, 0);
   __syncthreads();
+  stage_issue(0);
+  unsigned stage_phase = 0;
 
 
 #ifdef AAD_PHASE_TIMING
@@ -935,15 +1009,31 @@ k_stft_fb(const StftArgs a) {
     const int* sMetaT = sMetaB + C::TILE;
     if (warp == 0) tile_meta(tile + gridDim.x, buf ^ 1);  // consumed after the bottom barrier
 
+    const float* stage_ptr = nullptr;
+    int stage_a0 = 0;
+    if constexpr (STAGE) {
+      stage_a0 = sInfo[buf * 4];
+      if (stage_a0 >= 0) {  // this tile's samples were requested during the previous tile's filterbank phase
+        unsigned done = 0;
+        for (int spins = 0; !done; ++spins) {
+          asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                       : "=r"(done) : "r"(mbar), "r"(stage_phase) : "memory");
+          if (spins > (1 << 22)) __trap();   // a copy that never lands must not hang the device
+        }
+        stage_phase ^= 1;
+        stage_ptr = sS;
+      }
+    }
     // ---- FFT phase ---------------------------------------------------------------
     for (int it = warp; it < C::ITERS; it += C::WARPS) {
       float2 v[32];
       // transposes go through the warp's own power rows
-      if (fft.load_iter(a, sMetaB, sMetaT, it, v))
+      if (fft.load_iter(a, sMetaB, sMetaT, it, v, stage_ptr, stage_a0))
         fft.template transform<C::PAD, FBM != 0>(a, v, sP + (it * Q) * SP, sP + (it * Q + g) * SP + C::skew(it * Q + g));
     }
     AAD_PHASE_MARK(0);
     __syncthreads();
+    stage_issue(buf ^ 1);   // the next tile's samples travel during this tile's filterbank phase
 
     // ---- filterbank + log phase: lane = frame, warps split the filters ----
     // Entries are walked FBU at a time (one bundle).  Per round and entry: 4 bins (powers: one
