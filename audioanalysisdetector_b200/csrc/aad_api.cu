@@ -309,6 +309,24 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// dB reference / floor pass: rows shorter than 256 frames take the flat kernel (a CTA per 8192 elements of the utterance's
+// block), longer rows the row kernel (a warp per row and 1024-frame chunk)
+static int launch_db_finalize(const FinArgs& fa, int B, int t_max, cudaStream_t stream, bool pdl) {
+  if (fa.stride_f < 256 && (long long)fa.n_filt * fa.stride_f < (1ll << 30)) {
+    const int n_chunks = (int)(((long long)fa.n_filt * fa.stride_f + FIN_FLAT - 1) / FIN_FLAT);
+    const long long nblk = (long long)B * n_chunks;
+    if (nblk > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
+    launch_pdl(k_db_finalize_flat, dim3((unsigned)nblk), dim3(256), 0, stream, pdl, fa, n_chunks);
+    return AAD_OK;
+  }
+  const int n_row_blocks = (fa.n_filt + FIN_ROWS - 1) / FIN_ROWS;
+  const int n_chunks = (std::max(t_max, 1) + FIN_CHUNK - 1) / FIN_CHUNK;
+  const long long nblk = (long long)B * n_row_blocks * n_chunks;
+  if (nblk > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
+  launch_pdl(k_db_finalize, dim3((unsigned)nblk), dim3(256), 0, stream, pdl, fa, n_row_blocks, n_chunks);
+  return AAD_OK;
+}
+
 // ---- kernel dispatch table --------------------------------------------------
 static stft_kernel_t pick_stft(int L, int tile, int mode, bool pre, bool pair = false, bool dense = false) {
   if (tile != stft_tile(L, dense)) return nullptr;
@@ -975,11 +993,7 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
     fa.out = out; fa.stride_b = out_stride_b; fa.stride_f = t_alloc; fa.nf_eff = d_nf; fa.utt_max = d_max; fa.utt_max_f = nullptr;
     fa.n_filt = p.n_filt; fa.ref_type = p.ref_type; fa.top_db = p.top_db;
     if (p.log_type == AAD_LOG_DB10 && (p.ref_type == AAD_REF_UTT_MAX || p.top_db >= 0.f)) {  // else: identity
-      const int n_row_blocks = (p.n_filt + FIN_ROWS - 1) / FIN_ROWS;
-      const int n_chunks = (std::max(t_max, 1) + FIN_CHUNK - 1) / FIN_CHUNK;
-      const long long nblk = (long long)B * n_row_blocks * n_chunks;
-      if (nblk > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
-      launch_pdl(k_db_finalize, dim3((unsigned)nblk), dim3(256), 0, stream, !prof, fa, n_row_blocks, n_chunks);
+      if ((rc = launch_db_finalize(fa, B, t_max, stream, !prof)) != AAD_OK) return rc;
     }
     if (prof) cudaEventRecord(pl->ev[3], stream);
   }
@@ -989,11 +1003,7 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
       FinArgs fb;
       fb.out = pair.out2; fb.stride_b = out2_stride_b; fb.stride_f = t_alloc; fb.nf_eff = d_nf; fb.utt_max = d_max2;
       fb.utt_max_f = nullptr; fb.n_filt = q.n_filt; fb.ref_type = q.ref_type; fb.top_db = q.top_db;
-      const int n_row_blocks = (q.n_filt + FIN_ROWS - 1) / FIN_ROWS;
-      const int n_chunks = (std::max(t_max, 1) + FIN_CHUNK - 1) / FIN_CHUNK;
-      const long long nblk = (long long)B * n_row_blocks * n_chunks;
-      if (nblk > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
-      k_db_finalize<<<(unsigned)nblk, 256, 0, stream>>>(fb, n_row_blocks, n_chunks);
+      if ((rc = launch_db_finalize(fb, B, t_max, stream, false)) != AAD_OK) return rc;
     }
   }
   if (p.znorm) {
@@ -1081,12 +1091,8 @@ int aad_db_reference(float* x, int64_t stride_b, int32_t stride_f, const int32_t
   FinArgs fa;
   fa.out = x; fa.stride_b = stride_b; fa.stride_f = stride_f; fa.nf_eff = n_frames; fa.utt_max = nullptr;
   fa.utt_max_f = utt_max; fa.n_filt = n_filt; fa.ref_type = ref_type; fa.top_db = top_db;
-  const int n_row_blocks = (n_filt + FIN_ROWS - 1) / FIN_ROWS;
-  const int n_chunks = (t_max + FIN_CHUNK - 1) / FIN_CHUNK;
-  const long long nblk = (long long)B * n_row_blocks * n_chunks;
-  if (nblk > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
   (void)cudaGetLastError();
-  k_db_finalize<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(fa, n_row_blocks, n_chunks);
+  if (int rc2 = launch_db_finalize(fa, B, t_max, (cudaStream_t)stream, false)) return rc2;
   LAUNCH_CHECK("k_db_finalize launch");
   return AAD_OK;
 }

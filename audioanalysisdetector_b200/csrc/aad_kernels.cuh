@@ -1492,6 +1492,47 @@ __global__ void __launch_bounds__(256) k_db_finalize(const FinArgs a, int n_row_
   for (; t < t1; t += 32) row[t] = fmaxf(row[t] - ref, floorv);
 }
 
+// The same for SHORT rows (the reference's 2-second chunks: 63 frames): one warp per row leaves a CTA with 2 KB to move
+// and the launch of 200 000 such CTAs costs three times the memory time.  Here a CTA sweeps FIN_FLAT consecutive elements
+// of the utterance's (filter, frame) block -- rows lie back to back at stride_f -- and masks the columns behind T.
+// grid.x = B * n_chunks, n_chunks = ceil(n_filt * stride_f / FIN_FLAT).
+constexpr int FIN_FLAT = 8192;
+__global__ void __launch_bounds__(256) k_db_finalize_flat(const FinArgs a, int n_chunks) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int b = blockIdx.x / n_chunks, ch = blockIdx.x - b * n_chunks;
+  const int T = a.nf_eff[b];
+  const int total = a.n_filt * a.stride_f, i0 = ch * FIN_FLAT;
+  if (T == 0 || i0 >= total) return;
+  const int i1 = min(total, i0 + FIN_FLAT);
+  const float m = a.utt_max_f ? a.utt_max_f[b] : dec_ordered(a.utt_max[b]);
+  const float ref = a.ref_type == 1 ? m : 0.f;
+  const float floorv = a.top_db >= 0.f ? (m - ref) - a.top_db : -INFINITY;
+  float* base = a.out + (long long)b * a.stride_b;
+  int i = i0 + threadIdx.x;
+  int t = i % a.stride_f;                       // column of element i; advanced incrementally below
+  const int step_t = 256 % a.stride_f;          // 256 elements further on: the column moves by 256 mod stride_f
+  for (; i + 768 < i1; i += 1024) {             // four independent coalesced accesses in flight per lane
+    int tc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      tc[u] = t;
+      t += step_t;
+      if (t >= a.stride_f) t -= a.stride_f;
+    }
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = tc[u] < T ? base[i + 256 * u] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (tc[u] < T) base[i + 256 * u] = fmaxf(v[u] - ref, floorv);
+  }
+  for (; i < i1; i += 256) {
+    if (t < T) base[i] = fmaxf(base[i] - ref, floorv);
+    t += step_t;
+    if (t >= a.stride_f) t -= a.stride_f;
+  }
+}
+
 // z-normalisation of an utterance's whole feature matrix (compute_melspec, ASV_dataset.ipynb:1151):
 // pass 1 accumulates sum and sum of squares in double (one atomicAdd pair per CTA), pass 2 applies
 // (x - mean) * rsqrt(var).  grid.x = B * n_chunks, a chunk = ZN_CHUNK consecutive elements of the
