@@ -358,25 +358,29 @@ static void stft_cfg(int L, bool dense, int* warps, int* ctas, size_t* fixed, in
 }
 
 typedef void (*cep_kernel_t)(const CepArgs);
-static cep_kernel_t pick_cep(int nt) {  // coefficient n-tiles per pass
+template <int TS>
+static cep_kernel_t pick_cep_ts(int nt) {  // coefficient n-tiles per pass
   switch (nt) {
-    case 1: return k_cepstra<1>;
-    case 2: return k_cepstra<2>;
-    case 3: return k_cepstra<3>;
-    case 4: return k_cepstra<4>;
-    case 5: return k_cepstra<5>;
-    case 6: return k_cepstra<6>;
-    case 7: return k_cepstra<7>;
-    default: return k_cepstra<8>;
+    case 1: return k_cepstra<1, TS>;
+    case 2: return k_cepstra<2, TS>;
+    case 3: return k_cepstra<3, TS>;
+    case 4: return k_cepstra<4, TS>;
+    case 5: return k_cepstra<5, TS>;
+    case 6: return k_cepstra<6, TS>;
+    case 7: return k_cepstra<7, TS>;
+    default: return k_cepstra<8, TS>;
   }
 }
+// frames per k_cepstra tile: 64 when no utterance of the call is longer (the reference's 2-second chunks: 63 frames)
+static int cep_tile(int t_max) { return t_max <= 64 ? 64 : CEP_TS; }
+static cep_kernel_t pick_cep(int nt, int ts) { return ts == 64 ? pick_cep_ts<64>(nt) : pick_cep_ts<CEP_TS>(nt); }
 
-static size_t cep_smem_bytes(const aad_plan* pl) {
+static size_t cep_smem_bytes(const aad_plan* pl, int ts) {
   const int kf = pl->p.n_ceps > 0 ? 8 * pl->n_ksteps : pl->p.n_filt;
-  size_t f = 4 + (size_t)kf * CEP_SE + 8 * CEP_TS;
+  size_t f = 4 + (size_t)kf * (ts + 8) + 8 * ts;
   if (pl->p.n_ceps > 0) {
     f += (size_t)pl->n_ksteps * pl->n_tiles * 32 * 4 + (size_t)pl->n_tiles * 8;
-    if (pl->n_tiles > CEP_MAXNT) f += (size_t)pl->p.n_ceps * CEP_SC;  // no aliasing with several passes
+    if (pl->n_tiles > CEP_MAXNT) f += (size_t)pl->p.n_ceps * (ts + 4);  // no aliasing with several passes
   }
   return f * 4;
 }
@@ -771,11 +775,13 @@ int aad_plan_create(const aad_params* pp, int device, aad_plan** out) {
       if (fp && e == cudaSuccess) e = cudaFuncSetAttribute(fp, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     }
   if (e == cudaSuccess && pl->need_ws_E) {
-    if (cep_smem_bytes(pl) > (size_t)optin) {
+    if (cep_smem_bytes(pl, CEP_TS) > (size_t)optin) {
       aad_plan_destroy(pl);
       return AAD_ERR_UNSUPPORTED;
     }
-    e = cudaFuncSetAttribute((const void*)pick_cep(pl->cep_nt), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    e = cudaFuncSetAttribute((const void*)pick_cep(pl->cep_nt, CEP_TS), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute((const void*)pick_cep(pl->cep_nt, 64), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   }
   if (e != cudaSuccess) {
     aad_plan_destroy(pl);
@@ -977,11 +983,12 @@ static int extract_impl(const aad_plan* pl, const void* wav, int wav_dtype, int6
     } else {
       ca.out = out; ca.out_stride_b = out_stride_b; ca.out_stride_c = 1; ca.out_stride_t = pl->c_out;
     }
-    ca.tile_out = CEP_TS - (p.n_delta > 0 ? 2 * (p.delta_width / 2) : 0);
-    const int gx = t_max <= CEP_TS ? 1 : (t_max + ca.tile_out - 1) / ca.tile_out;
+    const int cep_ts = cep_tile(t_max);
+    ca.tile_out = cep_ts - (p.n_delta > 0 ? 2 * (p.delta_width / 2) : 0);
+    const int gx = t_max <= cep_ts ? 1 : (t_max + ca.tile_out - 1) / ca.tile_out;
     if ((long long)B * gx > 0x7fffffffLL) return AAD_ERR_UNSUPPORTED;
     ca.tiles_per_utt = gx;
-    launch_pdl(pick_cep(pl->cep_nt), dim3((unsigned)((long long)B * gx)), dim3(CEP_THREADS), cep_smem_bytes(pl), stream, !prof, ca);
+    launch_pdl(pick_cep(pl->cep_nt, cep_ts), dim3((unsigned)((long long)B * gx)), dim3(2 * cep_ts), cep_smem_bytes(pl, cep_ts), stream, !prof, ca);
     LAUNCH_CHECK("k_cepstra launch");
     if (prof) cudaEventRecord(pl->ev[3], stream);
     if (p.time_mean) {

@@ -1255,8 +1255,12 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], 
 //         column sums) and split in registers.  The result overwrites the energy tile.
 //  out  : thread = frame column; static rows and the delta / delta-delta stencils as one FFMA2 per
 //         tap ((d1, d2) accumulated together), coalesced stores along t (CT) or along c (TC)
-template <int NT>
-__global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
+// TS: frames per tile (128, or 64 when no utterance of the batch is longer: the reference's 2-second chunks have 63 frames,
+// and half of a 128-frame tile's warps, shared memory and load lanes would idle); 2 TS threads = TS / 16 warps.
+template <int NT, int TS = CEP_TS>
+__global__ void __launch_bounds__(2 * TS, TS == 128 ? 2 : 4) k_cepstra(const CepArgs a) {
+  constexpr int SE = TS + 8, SC = TS + 4, THREADS = 2 * TS;
+  constexpr int LPR = TS / 4, RPW = 32 / LPR;   // load phase: lanes per row, rows per warp and step (8 rows per CTA step)
   extern __shared__ __align__(16) float smem[];
   asm volatile("griddepcontrol.wait;" ::: "memory");  // launched behind k_stft_fb (programmatic dependent launch)
   // grid.x = B * tiles_per_utt, utterance-major: consecutive CTAs read neighbouring tiles of one utterance
@@ -1264,7 +1268,7 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
   const int T = a.nf_eff[b];
   if (T == 0) return;
   int o0, o1;
-  if (T <= CEP_TS) {
+  if (T <= TS) {
     if (tile > 0) return;
     o0 = 0;
     o1 = T;
@@ -1280,7 +1284,7 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
     lo = min(lo, c0 - h);
     hi = max(hi, c1 + h + 1);
   }
-  const int nload = hi - lo;  // <= CEP_TS by construction
+  const int nload = hi - lo;  // <= TS by construction
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = a.n_ceps > 0 ? a.n_ceps : a.n_filt;
   const int kf = a.n_ceps > 0 ? 8 * a.n_ksteps : a.n_filt;  // energy rows incl. zero padding of K
@@ -1288,12 +1292,12 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
 
   // 4 floats of slack in front: the fixed 9-tap stencil of a narrower delta window may read up to 3
   // columns before a row (with a zero tap)
-  float* sE = smem + 4;                               // [kf][CEP_SE]
-  float* sPart = sE + kf * CEP_SE;                    // [8][CEP_TS] per-warp partial column sums
-  float4* sB = reinterpret_cast<float4*>(sPart + 8 * CEP_TS);  // [n_ksteps][n_tiles][32]
+  float* sE = smem + 4;                               // [kf][SE]
+  float* sPart = sE + kf * SE;                    // [8][TS] per-warp partial column sums
+  float4* sB = reinterpret_cast<float4*>(sPart + 8 * TS);  // [n_ksteps][n_tiles][32]
   float* sCs = reinterpret_cast<float*>(sB + a.n_ksteps * a.n_tiles * 32);  // [n_tiles * 8]
   float* sC = a.n_ceps == 0 ? sE : (alias ? sE : sCs + a.n_tiles * 8);      // [C][sc_stride]
-  const int sc_stride = a.n_ceps == 0 ? CEP_SE : CEP_SC;
+  const int sc_stride = a.n_ceps == 0 ? SE : SC;
 
   // reference / floor (librosa.power_to_db):  ls = E - ref ; ls = max(ls, max(ls) - top_db)
   float ref = 0.f, floorv = -INFINITY;
@@ -1307,11 +1311,11 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
     const float* Eb = a.E + (long long)b * a.e_stride_b + lo;
     const bool vec = ((lo | a.e_stride_f) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.E) & 15) == 0 &&
                      (a.e_stride_b & 3) == 0;
-    const int t4 = 4 * lane;
+    const int t4 = 4 * (lane % LPR), rsub = lane / LPR;   // this lane's 4 columns and its row within the warp's step
     float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
     auto xf = [&](float v, int t) { return t < nload ? fmaxf(v - ref, floorv) : 0.f; };
     if (vec) {
-      int m = warp;
+      int m = warp * RPW + rsub;
       for (; m + 56 < a.n_filt; m += 64) {  // 8 independent 16-byte loads in flight per thread
         float4 v[8];
 #pragma unroll
@@ -1321,7 +1325,7 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           float4 r = make_float4(xf(v[u].x, t4), xf(v[u].y, t4 + 1), xf(v[u].z, t4 + 2), xf(v[u].w, t4 + 3));
-          *reinterpret_cast<float4*>(sE + (m + 8 * u) * CEP_SE + t4) = r;
+          *reinterpret_cast<float4*>(sE + (m + 8 * u) * SE + t4) = r;
           ps.x += r.x; ps.y += r.y; ps.z += r.z; ps.w += r.w;
         }
       }
@@ -1329,28 +1333,28 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
         float4 v = t4 < nload ? __ldg(reinterpret_cast<const float4*>(Eb + (long long)m * a.e_stride_f + t4))
                               : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 r = make_float4(xf(v.x, t4), xf(v.y, t4 + 1), xf(v.z, t4 + 2), xf(v.w, t4 + 3));
-        *reinterpret_cast<float4*>(sE + m * CEP_SE + t4) = r;
+        *reinterpret_cast<float4*>(sE + m * SE + t4) = r;
         ps.x += r.x; ps.y += r.y; ps.z += r.z; ps.w += r.w;
       }
     } else {
-      for (int m = warp; m < a.n_filt; m += 8) {
+      for (int m = warp * RPW + rsub; m < a.n_filt; m += 8) {
         float r[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int t = t4 + u;
           r[u] = t < nload ? fmaxf(__ldg(Eb + (long long)m * a.e_stride_f + t) - ref, floorv) : 0.f;
         }
-        *reinterpret_cast<float4*>(sE + m * CEP_SE + t4) = make_float4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<float4*>(sE + m * SE + t4) = make_float4(r[0], r[1], r[2], r[3]);
         ps.x += r[0]; ps.y += r[1]; ps.z += r[2]; ps.w += r[3];
       }
     }
-    for (int m = a.n_filt + warp; m < kf; m += 8)  // zero rows that pad K to a multiple of 8
-      *reinterpret_cast<float4*>(sE + m * CEP_SE + t4) = make_float4(0.f, 0.f, 0.f, 0.f);
-    *reinterpret_cast<float4*>(sPart + warp * CEP_TS + t4) = ps;
+    for (int m = a.n_filt + warp * RPW + rsub; m < kf; m += 8)  // zero rows that pad K to a multiple of 8
+      *reinterpret_cast<float4*>(sE + m * SE + t4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(sPart + (warp * RPW + rsub) * TS + t4) = ps;
     if (a.n_ceps > 0) {
       const int nb = a.n_ksteps * a.n_tiles * 32;
-      for (int i = tid; i < nb; i += CEP_THREADS) sB[i] = __ldg(a.dct_frag + i);
-      for (int i = tid; i < a.n_tiles * 8; i += CEP_THREADS) sCs[i] = __ldg(a.dct_colsum + i);
+      for (int i = tid; i < nb; i += THREADS) sB[i] = __ldg(a.dct_frag + i);
+      for (int i = tid; i < a.n_tiles * 8; i += THREADS) sCs[i] = __ldg(a.dct_colsum + i);
     }
   }
   __syncthreads();
@@ -1362,13 +1366,13 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
     float mean0 = 0.f, mean1 = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
-      mean0 += sPart[w * CEP_TS + f0];
-      mean1 += sPart[w * CEP_TS + f1];
+      mean0 += sPart[w * TS + f0];
+      mean1 += sPart[w * TS + f1];
     }
     const float inv = 1.0f / (float)a.n_filt;
     mean0 *= inv;
     mean1 *= inv;
-    const float* ea = sE + t * CEP_SE + f0;  // A fragment (row g / g+8 = frame, col t / t+4 = filter)
+    const float* ea = sE + t * SE + f0;  // A fragment (row g / g+8 = frame, col t / t+4 = filter)
     for (int nt0 = 0; nt0 < a.n_tiles; nt0 += NT) {
       float acc[NT][4];
 #pragma unroll
@@ -1378,9 +1382,9 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
       const float4* bp = sB + nt0 * 32 + lane;
 #pragma unroll 2
       for (int ks = 0; ks < a.n_ksteps; ++ks) {
-        const float* e = ea + ks * 8 * CEP_SE;
+        const float* e = ea + ks * 8 * SE;
         // centred energies (small magnitudes: the tf32 split and the fp32 accumulation lose nothing)
-        const float av[4] = {e[0] - mean0, e[8] - mean1, e[4 * CEP_SE] - mean0, e[4 * CEP_SE + 8] - mean1};
+        const float av[4] = {e[0] - mean0, e[8] - mean1, e[4 * SE] - mean0, e[4 * SE + 8] - mean1};
         unsigned ahi[4], alo[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -1405,12 +1409,12 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
         if (nt0 + n < a.n_tiles) {
           const float cs0 = sCs[c], cs1 = sCs[c + 1];
           if (c < a.n_ceps) {
-            sC[c * CEP_SC + f0] = __fmaf_rn(mean0, cs0, acc[n][0]);
-            sC[c * CEP_SC + f1] = __fmaf_rn(mean1, cs0, acc[n][2]);
+            sC[c * SC + f0] = __fmaf_rn(mean0, cs0, acc[n][0]);
+            sC[c * SC + f1] = __fmaf_rn(mean1, cs0, acc[n][2]);
           }
           if (c + 1 < a.n_ceps) {
-            sC[(c + 1) * CEP_SC + f0] = __fmaf_rn(mean0, cs1, acc[n][1]);
-            sC[(c + 1) * CEP_SC + f1] = __fmaf_rn(mean1, cs1, acc[n][3]);
+            sC[(c + 1) * SC + f0] = __fmaf_rn(mean0, cs1, acc[n][1]);
+            sC[(c + 1) * SC + f1] = __fmaf_rn(mean1, cs1, acc[n][3]);
           }
         }
       }
@@ -1419,7 +1423,7 @@ __global__ void __launch_bounds__(CEP_THREADS, 2) k_cepstra(const CepArgs a) {
   }
 
   // ---- static rows + delta stencils + layout -------------------------------------------
-  const int col = tid & (CEP_TS - 1), half = tid >> 7;
+  const int col = tid & (TS - 1), half = tid / TS;
   const int t = lo + col;
   if (t >= o0 && t < o1) {
     float* ob = a.out + (long long)b * a.out_stride_b + (long long)t * a.out_stride_t + (long long)half * a.out_stride_c;

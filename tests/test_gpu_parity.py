@@ -222,6 +222,27 @@ def test_dense_bank_is_limited_to_nfft_512_and_cube_root_to_dense_banks(dev):
         Frontend(FP().gtcc(16000, nfilts=65, n_ceps=13), dev)
 
 
+@pytest.mark.parametrize("width", [9, 5])
+def test_short_utterance_batches_take_the_64_frame_cepstra_tile(dev, width):
+    """No clip longer than 64 frames (the reference's 2-second chunks have 63): k_cepstra runs with 64-frame tiles and
+    four warps.  MFCC + deltas in both layouts, and LFCC (ln, no reference) -- against the oracle like the long tiles."""
+    L = LIB()
+    clips = [noise(120, 32000), speech(121, 31999), noise(122, 512 * 9 + 1), speech(123, 20000), noise(124, 32767)]
+    for layout in (L.LAYOUT_CT, L.LAYOUT_TC):
+        out, nf, st, _ = run(FP().mfcc(16000, n_mfcc=20, n_delta=2, delta_width=width, layout=layout), clips, dev)
+        assert nf.max() <= 64
+        for i, c in enumerate(clips):
+            want = oracle.mfcc_with_deltas_ref(c, 16000, n_mfcc=20, n_delta=2, width=width)
+            got = out[i, :, :nf[i]] if layout == L.LAYOUT_CT else out[i, :nf[i], :].T
+            assert st[i] == 0 and nf[i] == want.shape[1] and np.abs(got - want).max() <= TOL_LOG
+    short = [SR.quantize_int16(noise(125 + i, n)) for i, n in enumerate((10400, 4000, 401, 9999))]   # <= 64 LFCC frames
+    out, nf, st, _ = run(FP().lfcc(16000, n_ceps=13), [c.astype(np.float32) / 32767 for c in short], dev)
+    assert nf.max() <= 64
+    for i, c in enumerate(short):
+        want = SR.lfcc(c, 16000, 13)
+        assert st[i] == 0 and nf[i] == want.shape[0] and np.abs(out[i, :nf[i], :] - want).max() <= TOL_LOG
+
+
 def test_int16_input_equals_float_quantised_input(dev):
     clips = [noise(30, 20000), speech(31, 33333)]
     p = FP().lfcc(16000)
